@@ -1,0 +1,117 @@
+/* sgpe.h — C ABI of the B200 split-step propagator (libsgpe.so).
+ *
+ * The reference (ultracoldYEG/spinor-gpe) is pure Python and has no FFI: its boundary for this path is
+ * the class spinor_gpe/pspinor/tensor_propagator.py:TensorPropagator plus the helpers of
+ * spinor_gpe/pspinor/tensor_tools.py.  Each entry point below names the reference code it replaces.
+ * The Python binding a maintainer would add is shown in INTEGRATION.md (ctypes, ~40 lines).
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative SGPE_E* code otherwise, never throws;
+ *    sgpe_last_error() returns a thread-local message for the last failure;
+ *  - pointers named *_dev are CUDA device pointers owned by the caller; *_host are host pointers;
+ *  - a state is [batch][2][ny][nx] complex, x contiguous (the reference's list of two (Ny,Nx) arrays,
+ *    tensor_propagator.py:118), complex128 (dtype 0) or complex64 (dtype 1), k-space states in the
+ *    reference's fft-shifted order with its dx*dy/2pi scaling (tensor_tools.py:218-226);
+ *  - operator grids (kinetic, potential, coupling) are real float64 [ny][nx] in both precisions, given
+ *    per trajectory with a batch stride in elements (0 = shared by all trajectories);
+ *  - all work is enqueued on the given stream; nothing synchronises the device except the *_host calls;
+ *  - a plan is not thread-safe; distinct plans are independent.
+ */
+#ifndef SGPE_H
+#define SGPE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sgpe_plan sgpe_plan;
+typedef void* sgpe_stream;            /* cudaStream_t */
+
+enum { SGPE_C128 = 0, SGPE_C64 = 1 };
+enum { SGPE_TIME_REAL = 0, SGPE_TIME_IMAG = 1 };
+enum { SGPE_COUPLING_NONE = 0, SGPE_COUPLING_UNIFORM = 1, SGPE_COUPLING_DENSE = 2 };
+enum {
+    SGPE_OK = 0,
+    SGPE_EINVAL = -1,      /* bad argument / unsupported size */
+    SGPE_ECUDA = -2,       /* CUDA runtime error */
+    SGPE_ESTATE = -3,      /* call order (e.g. stepping before operators are set) */
+    SGPE_ENOMEM = -4
+};
+
+const char* sgpe_last_error(void);
+/* library build info: "sgpe <version> sm_100a" (or "... emu" for the CPU test build) */
+const char* sgpe_version(void);
+
+/* nx, ny: powers of two in [32, 4096].  batch >= 1 independent trajectories.
+ * Replaces the tensor set-up of TensorPropagator.__init__ (tensor_propagator.py:111-122). */
+int sgpe_plan_create(sgpe_plan** out, int nx, int ny, int batch, int dtype, int device);
+int sgpe_plan_destroy(sgpe_plan* p);
+
+/* space['dr'], space['dv_r'], space['dv_k'], atom_num (tensor_propagator.py:111, 119-121). */
+int sgpe_set_grid(sgpe_plan* p, double dx, double dy, double dv_r, double dv_k, double atom_num);
+/* g_sc['uu'], ['dd'], ['ud'] (tensor_propagator.py:113, 247-248). */
+int sgpe_set_interactions(sgpe_plan* p, double g_uu, double g_dd, double g_ud);
+/* kin_eng_spin (tensor_propagator.py:114): borrowed device pointers, must outlive the stepping. */
+int sgpe_set_kinetic(sgpe_plan* p, const double* kin0_dev, const double* kin1_dev, int64_t batch_stride);
+/* pot_eng_spin (tensor_propagator.py:116). */
+int sgpe_set_potential(sgpe_plan* p, const double* pot0_dev, const double* pot1_dev, int64_t batch_stride);
+/* coupling / expon (tensor_propagator.py:122-129, tensor_tools.py:563-591).
+ *   mode NONE    : is_coupling False (tensor_propagator.py:252, 258 skipped)
+ *   mode UNIFORM : one Omega per trajectory, omega_dev[batch]
+ *   mode DENSE   : coupling_dev [ny][nx] (+ batch stride)
+ *   eiphi_dev    : exp(+i*expon) along x, nx complex values of the plan's dtype, or NULL when the
+ *                  coupling is in the rotating frame (expon = 0, tensor_propagator.py:126-127). */
+int sgpe_set_coupling(sgpe_plan* p, int mode, const double* coupling_dev, int64_t batch_stride,
+                      const double* omega_dev, const void* eiphi_dev);
+/* time = 'real' | 'imag' and t_step (tensor_propagator.py:96-103): fixes dt_out, dt_in. */
+int sgpe_set_time(sgpe_plan* p, int time_mode, double dt);
+
+/* Copy a k-space state into the plan (self.psik = to_tensor(spin.psik), tensor_propagator.py:118). */
+int sgpe_load_psik(sgpe_plan* p, const void* psik_dev, sgpe_stream st);
+/* Materialise the current normalised k-space state (what self.psik holds after a step,
+ * tensor_propagator.py:271). */
+int sgpe_store_psik(sgpe_plan* p, void* psik_dev, sgpe_stream st);
+
+/* n x TensorPropagator.full_step() (tensor_propagator.py:214-222) with the per-step populations of
+ * prop_loop (tensor_propagator.py:194): pops_dev (nullable) is [batch][pops_stride] doubles, step i
+ * writes pops_dev[b*pops_stride + 2*(pops_first+i) + {0,1}].  Asynchronous. */
+int sgpe_full_steps(sgpe_plan* p, int n, double* pops_dev, int64_t pops_stride, int pops_first,
+                    sgpe_stream st);
+/* One TensorPropagator.single_step (tensor_propagator.py:224-271) of sub-step length dt_sub
+ * (use sgpe_substeps for dt_out / dt_in). */
+int sgpe_single_step(sgpe_plan* p, double dt_sub, sgpe_stream st);
+int sgpe_substeps(const sgpe_plan* p, double* dt_out, double* dt_in);
+
+/* ttools.fft_2d / ifft_2d (tensor_tools.py:201-258) and fft_1d / ifft_1d (:130-198; axis 0 = x,
+ * 1 = y as in the reference) on a [batch][2][ny][nx] array, with the reference's shift and scaling
+ * taken from sgpe_set_grid.  in == out is allowed. */
+int sgpe_fft2d(sgpe_plan* p, const void* in_dev, void* out_dev, int inverse, sgpe_stream st);
+int sgpe_fft1d(sgpe_plan* p, const void* in_dev, void* out_dev, int axis, int inverse, sgpe_stream st);
+
+/* Per-component sum |psi_c|^2 (ttools.norm_sq / calc_pops without the volume element,
+ * tensor_tools.py:437, 482): out_dev[batch][2]. */
+int sgpe_sumsq(sgpe_plan* p, const void* in_dev, double* out_dev, sgpe_stream st);
+/* ttools.norm (tensor_tools.py:289-305): out = in / sqrt(sum(|in|^2) * vol / atom_num). */
+int sgpe_normalise(sgpe_plan* p, const void* in_dev, void* out_dev, double vol, sgpe_stream st);
+
+/* The same path with HOST buffers (pageable or pinned): H2D of the state, n full steps, D2H of the
+ * final normalised state and the populations [batch][n][2]; synchronises the stream before returning.
+ * Equivalent of PSpinor.imaginary()/real() minus file output (pspinor.py:912-925). */
+int sgpe_run_host(sgpe_plan* p, const void* psik_in_host, void* psik_out_host, int n_steps,
+                  double* pops_host, sgpe_stream st);
+
+/* Traffic / launch accounting for one full step of the whole batch:
+ *   algorithmic = 768 B (c128) or 384 B (c64) per grid point;
+ *   actual      = bytes the kernels are designed to move (state + operator grids);
+ *   launches    = kernel launches per full step in steady state. */
+int sgpe_step_accounting(const sgpe_plan* p, uint64_t* algorithmic_bytes, uint64_t* actual_bytes,
+                         int* launches);
+/* Number of kernels this plan has launched since creation. */
+int sgpe_launch_count(const sgpe_plan* p, uint64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGPE_H */

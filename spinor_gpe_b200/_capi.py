@@ -1,0 +1,55 @@
+"""ctypes prototypes of the C ABI declared in include/sgpe.h (one place, shared by the product loader
+``_lib.py`` and by the CPU-emulation test harness)."""
+import ctypes as C
+
+c_plan = C.c_void_p
+c_stream = C.c_void_p
+c_dptr = C.c_void_p            # device (or, in the emulation build, host) pointer passed as an integer
+
+PROTOTYPES = {
+    'sgpe_last_error': (C.c_char_p, []),
+    'sgpe_version': (C.c_char_p, []),
+    'sgpe_plan_create': (C.c_int, [C.POINTER(c_plan), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    'sgpe_plan_destroy': (C.c_int, [c_plan]),
+    'sgpe_set_grid': (C.c_int, [c_plan, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]),
+    'sgpe_set_interactions': (C.c_int, [c_plan, C.c_double, C.c_double, C.c_double]),
+    'sgpe_set_kinetic': (C.c_int, [c_plan, c_dptr, c_dptr, C.c_int64]),
+    'sgpe_set_potential': (C.c_int, [c_plan, c_dptr, c_dptr, C.c_int64]),
+    'sgpe_set_coupling': (C.c_int, [c_plan, C.c_int, c_dptr, C.c_int64, c_dptr, c_dptr]),
+    'sgpe_set_time': (C.c_int, [c_plan, C.c_int, C.c_double]),
+    'sgpe_load_psik': (C.c_int, [c_plan, c_dptr, c_stream]),
+    'sgpe_store_psik': (C.c_int, [c_plan, c_dptr, c_stream]),
+    'sgpe_full_steps': (C.c_int, [c_plan, C.c_int, c_dptr, C.c_int64, C.c_int, c_stream]),
+    'sgpe_single_step': (C.c_int, [c_plan, C.c_double, c_stream]),
+    'sgpe_substeps': (C.c_int, [c_plan, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    'sgpe_fft2d': (C.c_int, [c_plan, c_dptr, c_dptr, C.c_int, c_stream]),
+    'sgpe_fft1d': (C.c_int, [c_plan, c_dptr, c_dptr, C.c_int, C.c_int, c_stream]),
+    'sgpe_sumsq': (C.c_int, [c_plan, c_dptr, c_dptr, c_stream]),
+    'sgpe_normalise': (C.c_int, [c_plan, c_dptr, c_dptr, C.c_double, c_stream]),
+    'sgpe_run_host': (C.c_int, [c_plan, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, c_stream]),
+    'sgpe_step_accounting': (C.c_int, [c_plan, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
+    'sgpe_launch_count': (C.c_int, [c_plan, C.POINTER(C.c_uint64)]),
+}
+
+SGPE_C128, SGPE_C64 = 0, 1
+SGPE_TIME_REAL, SGPE_TIME_IMAG = 0, 1
+SGPE_COUPLING_NONE, SGPE_COUPLING_UNIFORM, SGPE_COUPLING_DENSE = 0, 1, 2
+
+
+class SgpeError(RuntimeError):
+    """A C-ABI call returned a negative status."""
+
+
+def bind(lib):
+    """Attach argtypes / restype for every exported symbol; raises AttributeError if one is missing."""
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def check(lib, rc, what=''):
+    if rc != 0:
+        msg = lib.sgpe_last_error()
+        raise SgpeError(f"{what or 'sgpe call'} failed ({rc}): {msg.decode() if msg else '?'}")

@@ -1,0 +1,264 @@
+// fft_core.cuh — register-resident Stockham FFT building blocks for one CTA.
+//
+// Data model: a "line" is one 1-D transform of length N.  A line is owned by NT = N/E threads; thread j
+// of the line holds the E elements  x[j + m*NT], m = 0..E-1  in registers — the same element set before
+// and after every stage, and before/after the whole transform (natural order in, natural order out).
+// Between stages the CTA exchanges data through shared memory (one write + one read of the line).
+// Shared memory is XOR-swizzled so that both the strided stage writes and the unit-stride reads are
+// bank-conflict free for 16-byte (complex128) and 8-byte (complex64) elements; W lines can be
+// interleaved element-wise ([n][c] layout, c fastest) which is what the column pass uses to turn W
+// adjacent columns into 64/128-byte global-memory segments.
+//
+// Stage s (radix R = min(E, N/Ns), Ns = product of the previous radices) is the textbook Stockham
+// autosort step: butterfly jb in [0, N/R) reads x[jb + t*N/R], multiplies by w_{Ns*R}^{t*(jb mod Ns)},
+// does a DFT_R and writes y[(jb/Ns)*Ns*R + (jb mod Ns) + t*Ns].  A thread runs E/R butterflies
+// (jb = j + b*NT), whose inputs are exactly its E registers.
+//
+// This replaces the library calls torch.fft.fftn / ifftn at reference tensor_tools.py:225, 256.
+#pragma once
+
+#include "emu_or_cuda.h"
+
+namespace sgpe {
+
+template <typename T> struct cx_of;
+template <> struct cx_of<double> { typedef double2 type; };
+template <> struct cx_of<float>  { typedef float2 type; };
+
+#define SGPE_DI __device__ __forceinline__
+
+template <typename C> SGPE_DI C cadd(C a, C b) { a.x += b.x; a.y += b.y; return a; }
+template <typename C> SGPE_DI C csub(C a, C b) { a.x -= b.x; a.y -= b.y; return a; }
+// a * b
+template <typename C> SGPE_DI C cmul(C a, C b) {
+    C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
+}
+// a * conj(b)
+template <typename C> SGPE_DI C cmulc(C a, C b) {
+    C r; r.x = a.x * b.x + a.y * b.y; r.y = a.y * b.x - a.x * b.y; return r;
+}
+template <typename C, typename T> SGPE_DI C cscale(C a, T s) { a.x *= s; a.y *= s; return a; }
+// multiply by DIR*i  (DIR = -1: forward transform, -i;  DIR = +1: inverse, +i)
+template <int DIR, typename C> SGPE_DI C mul_i(C a) {
+    C r;
+    if (DIR < 0) { r.x = a.y; r.y = -a.x; } else { r.x = -a.y; r.y = a.x; }
+    return r;
+}
+
+// ---- constant twiddles exp(DIR * 2*pi*i * M / 16)
+template <typename T> struct W16 {
+    // cos / sin of 2*pi*m/16, m = 0..4
+    static constexpr T C1 = (T)0.92387953251128675613;   // cos(pi/8)
+    static constexpr T S1 = (T)0.38268343236508977173;   // sin(pi/8)
+    static constexpr T H  = (T)0.70710678118654752440;   // sqrt(1/2)
+};
+
+template <int DIR, int M, typename T, typename C> SGPE_DI C mul_w16(C a) {
+    constexpr int m = ((M % 16) + 16) % 16;
+    if constexpr (m == 0) { return a; }
+    else if constexpr (m == 4) { return mul_i<DIR>(a); }
+    else if constexpr (m == 8) { C r; r.x = -a.x; r.y = -a.y; return r; }
+    else if constexpr (m == 12) { return mul_i<-DIR>(a); }
+    else if constexpr (m == 2) {   // (H, DIR*H)
+        C r; r.x = W16<T>::H * (a.x - (T)DIR * a.y); r.y = W16<T>::H * (a.y + (T)DIR * a.x); return r;
+    }
+    else if constexpr (m == 6) {   // (-H, DIR*H)
+        C r; r.x = W16<T>::H * (-a.x - (T)DIR * a.y); r.y = W16<T>::H * ((T)DIR * a.x - a.y); return r;
+    }
+    else if constexpr (m == 10) {  // (-H, -DIR*H)
+        C r; r.x = W16<T>::H * ((T)DIR * a.y - a.x); r.y = W16<T>::H * (-a.y - (T)DIR * a.x); return r;
+    }
+    else if constexpr (m == 14) {  // (H, -DIR*H)
+        C r; r.x = W16<T>::H * (a.x + (T)DIR * a.y); r.y = W16<T>::H * (a.y - (T)DIR * a.x); return r;
+    }
+    else {
+        // odd m: (wr, DIR*wi) with wr = cos(2 pi m/16), wi = sin(2 pi m/16)
+        constexpr T wr = (m == 1 || m == 15) ? W16<T>::C1 : (m == 3 || m == 13) ? W16<T>::S1
+                       : (m == 5 || m == 11) ? -W16<T>::S1 : -W16<T>::C1;
+        constexpr T wi0 = (m == 1 || m == 7) ? W16<T>::S1 : (m == 3 || m == 5) ? W16<T>::C1
+                        : (m == 9 || m == 15) ? -W16<T>::S1 : -W16<T>::C1;
+        constexpr T wi = (T)DIR * wi0;
+        C r; r.x = a.x * wr - a.y * wi; r.y = a.x * wi + a.y * wr; return r;
+    }
+}
+
+// ---- small in-register DFTs, natural order in and out
+template <int DIR, typename C> SGPE_DI void dft2(C& a0, C& a1) {
+    C t = a0; a0 = cadd(t, a1); a1 = csub(t, a1);
+}
+template <int DIR, typename C> SGPE_DI void dft4(C& a0, C& a1, C& a2, C& a3) {
+    C t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_i<DIR>(csub(a1, a3));
+    a0 = cadd(t0, t2); a2 = csub(t0, t2); a1 = cadd(t1, t3); a3 = csub(t1, t3);
+}
+template <int DIR, typename T, typename C> SGPE_DI void dft8(C (&a)[8]) {
+    C e0 = a[0], e1 = a[2], e2 = a[4], e3 = a[6];
+    C o0 = a[1], o1 = a[3], o2 = a[5], o3 = a[7];
+    dft4<DIR>(e0, e1, e2, e3);
+    dft4<DIR>(o0, o1, o2, o3);
+    o1 = mul_w16<DIR, 2, T>(o1);
+    o2 = mul_w16<DIR, 4, T>(o2);
+    o3 = mul_w16<DIR, 6, T>(o3);
+    a[0] = cadd(e0, o0); a[4] = csub(e0, o0);
+    a[1] = cadd(e1, o1); a[5] = csub(e1, o1);
+    a[2] = cadd(e2, o2); a[6] = csub(e2, o2);
+    a[3] = cadd(e3, o3); a[7] = csub(e3, o3);
+}
+template <int DIR, typename T, typename C> SGPE_DI void dft16(C (&a)[16]) {
+    // n = 4*n1 + n2 ; k = k1 + 4*k2
+    dft4<DIR>(a[0], a[4], a[8],  a[12]);
+    dft4<DIR>(a[1], a[5], a[9],  a[13]);
+    dft4<DIR>(a[2], a[6], a[10], a[14]);
+    dft4<DIR>(a[3], a[7], a[11], a[15]);
+    // a[4*k1 + n2] *= w16^(n2*k1)
+    a[5]  = mul_w16<DIR, 1, T>(a[5]);  a[6]  = mul_w16<DIR, 2, T>(a[6]);  a[7]  = mul_w16<DIR, 3, T>(a[7]);
+    a[9]  = mul_w16<DIR, 2, T>(a[9]);  a[10] = mul_w16<DIR, 4, T>(a[10]); a[11] = mul_w16<DIR, 6, T>(a[11]);
+    a[13] = mul_w16<DIR, 3, T>(a[13]); a[14] = mul_w16<DIR, 6, T>(a[14]); a[15] = mul_w16<DIR, 9, T>(a[15]);
+    dft4<DIR>(a[0],  a[1],  a[2],  a[3]);
+    dft4<DIR>(a[4],  a[5],  a[6],  a[7]);
+    dft4<DIR>(a[8],  a[9],  a[10], a[11]);
+    dft4<DIR>(a[12], a[13], a[14], a[15]);
+    // a[4*k1 + k2] holds X[k1 + 4*k2]  -> transpose the 4x4
+    C t;
+    t = a[1];  a[1]  = a[4];  a[4]  = t;
+    t = a[2];  a[2]  = a[8];  a[8]  = t;
+    t = a[3];  a[3]  = a[12]; a[12] = t;
+    t = a[6];  a[6]  = a[9];  a[9]  = t;
+    t = a[7];  a[7]  = a[13]; a[13] = t;
+    t = a[11]; a[11] = a[14]; a[14] = t;
+}
+
+template <int R, int DIR, typename T, int STRIDE, typename C> SGPE_DI void dft_strided(C* p) {
+    if constexpr (R == 2) {
+        dft2<DIR>(p[0], p[STRIDE]);
+    } else if constexpr (R == 4) {
+        dft4<DIR>(p[0], p[STRIDE], p[2 * STRIDE], p[3 * STRIDE]);
+    } else if constexpr (R == 8) {
+        C a[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) a[t] = p[t * STRIDE];
+        dft8<DIR, T>(a);
+#pragma unroll
+        for (int t = 0; t < 8; t++) p[t * STRIDE] = a[t];
+    } else {
+        static_assert(R == 16, "radix must be 2, 4, 8 or 16");
+        C a[16];
+#pragma unroll
+        for (int t = 0; t < 16; t++) a[t] = p[t * STRIDE];
+        dft16<DIR, T>(a);
+#pragma unroll
+        for (int t = 0; t < 16; t++) p[t * STRIDE] = a[t];
+    }
+}
+
+// ---- geometry of one length-N transform held E elements per thread
+template <typename T, int N, int E, int W>
+struct LineGeom {
+    static_assert((N & (N - 1)) == 0 && (E & (E - 1)) == 0 && E <= N, "powers of two");
+    typedef typename cx_of<T>::type C;
+    static constexpr int NT = N / E;                           // threads per line
+    static constexpr int R0 = E;                               // first-stage radix (E <= N)
+    static constexpr int PHASE = 128 / (int)sizeof(C);         // lanes served per shared-memory wavefront
+    static constexpr int MASK = (PHASE / W > 1) ? (PHASE / W - 1) : 0;
+    static constexpr int log2c(int v) { return v <= 1 ? 0 : 1 + log2c(v >> 1); }
+    static constexpr int SH = log2c(R0);
+    SGPE_DI static int swz(int n) { return n ^ ((n >> SH) & MASK); }
+    static constexpr int radix(int Ns) { return (N / Ns) < E ? (N / Ns) : E; }
+};
+
+// twiddle + butterflies of the stage whose previous-radix product is Ns, on one line's registers
+template <typename T, int N, int E, int DIR, int Ns, typename C>
+SGPE_DI void stage_compute(C (&v)[E], int j, const C* __restrict__ tw) {
+    constexpr int R = (N / Ns) < E ? (N / Ns) : E;
+    constexpr int NB = E / R;
+    constexpr int NT = N / E;
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        if constexpr (Ns > 1) {
+            const int k = (j + b * NT) & (Ns - 1);
+            constexpr int TS = N / (Ns * R);
+#pragma unroll
+            for (int t = 1; t < R; t++) {
+                const C w = __ldg(&tw[t * k * TS]);
+                v[b + t * NB] = (DIR < 0) ? cmul(v[b + t * NB], w) : cmulc(v[b + t * NB], w);
+            }
+        }
+        dft_strided<R, DIR, T, NB>(&v[b]);
+    }
+}
+
+// scatter the stage outputs into the line's shared-memory image (element n of column c at swz(n)*W + c)
+template <typename T, int N, int E, int W, int Ns, typename C>
+SGPE_DI void stage_store(const C (&v)[E], int j, int c, C* sm) {
+    typedef LineGeom<T, N, E, W> G;
+    constexpr int R = (N / Ns) < E ? (N / Ns) : E;
+    constexpr int NB = E / R;
+    constexpr int NT = N / E;
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        const int jb = j + b * NT;
+        const int k = jb & (Ns - 1);
+        const int j0 = (jb - k) * R + k;
+#pragma unroll
+        for (int t = 0; t < R; t++) sm[G::swz(j0 + t * Ns) * W + c] = v[b + t * NB];
+    }
+}
+
+template <typename T, int N, int E, int W, typename C>
+SGPE_DI void stage_load(C (&v)[E], int j, int c, const C* sm) {
+    typedef LineGeom<T, N, E, W> G;
+    constexpr int NT = N / E;
+#pragma unroll
+    for (int m = 0; m < E; m++) v[m] = sm[G::swz(j + m * NT) * W + c];
+}
+
+// Full transform of L lines per thread (each with its own shared-memory image); all threads of the
+// CTA must call this together (it contains __syncthreads()).
+template <typename T, int N, int E, int DIR, int W, int L, int Ns, typename C>
+SGPE_DI void cta_fft_from(C (&v)[L][E], int j, int c, C* const (&sm)[L], const C* __restrict__ tw) {
+    constexpr int R = (N / Ns) < E ? (N / Ns) : E;
+#pragma unroll
+    for (int l = 0; l < L; l++) stage_compute<T, N, E, DIR, Ns>(v[l], j, tw);
+    if constexpr (Ns * R < N) {
+#pragma unroll
+        for (int l = 0; l < L; l++) stage_store<T, N, E, W, Ns>(v[l], j, c, sm[l]);
+        __syncthreads();
+#pragma unroll
+        for (int l = 0; l < L; l++) stage_load<T, N, E, W>(v[l], j, c, sm[l]);
+        __syncthreads();
+        cta_fft_from<T, N, E, DIR, W, L, Ns * R>(v, j, c, sm, tw);
+    }
+}
+
+template <typename T, int N, int E, int DIR, int W, int L, typename C>
+SGPE_DI void cta_fft(C (&v)[L][E], int j, int c, C* const (&sm)[L], const C* __restrict__ tw) {
+    cta_fft_from<T, N, E, DIR, W, L, 1>(v, j, c, sm, tw);
+}
+
+// ---- deterministic CTA reduction of NV doubles (warp shuffle, then shared memory in warp order)
+template <int NV>
+SGPE_DI void cta_reduce(double (&val)[NV], double* red /* >= 32*NV doubles of shared memory */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        double x = val[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        val[i] = x;
+    }
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) red[warp * NV + i] = val[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        double s = 0.0;
+        for (int w = 0; w < nwarps; w++) s += red[w * NV + i];
+        val[i] = s;       // every thread holds the CTA total
+    }
+    __syncthreads();
+}
+
+}  // namespace sgpe

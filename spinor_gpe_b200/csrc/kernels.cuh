@@ -1,0 +1,355 @@
+// kernels.cuh — the two fused passes of the split-step propagator, plus small helpers.
+//
+//   col_pass : for W adjacent columns of one component:  [FFT_y] -> [K_a] -> (S = sum |.|^2) -> [K_b]
+//              -> (T = sum |.|^2) -> [iFFT_y].   K_a is the trailing kinetic half-step of single step s,
+//              K_b the leading one of single step s+1 (reference tensor_propagator.py:270 and :242), the
+//              sums are the two global reductions of ttools.norm (tensor_tools.py:303; the real-space
+//              one is taken in k-space via Parseval) and ttools.calc_pops (:482).
+//   row_pass : for one row of both components: [iFFT_x] -> normalise -> I -> C -> P -> C -> I -> [FFT_x]
+//              (reference tensor_propagator.py:243-269).
+//
+// The fftshift/ifftshift of ttools.fft_2d/ifft_2d (tensor_tools.py:226, 255) never appear: for even N
+// they are the sign (-1)^(i+j) on the real-space side, every real-space operator is diagonal in (i,j),
+// and the sign cancels between the inverse and the forward transform.  The stand-alone transforms
+// apply it explicitly (sign_in / sign_out).
+#pragma once
+
+#include "fft_core.cuh"
+
+namespace sgpe {
+
+enum { TM_REAL = 0, TM_IMAG = 1 };
+
+// exp(-i * e * tau), tau = (tr, ti):  real time tau = (dt, 0);  imaginary time tau = (0, -dt)
+template <int TM, typename T, typename C> SGPE_DI C evo(double e, double tr, double ti) {
+    C r;
+    if (TM == TM_REAL) {
+        double s, c;
+        sincos(e * tr, &s, &c);
+        r.x = (T)c; r.y = (T)(-s);
+    } else {
+        r.x = (T)exp(e * ti); r.y = (T)0;
+    }
+    return r;
+}
+
+template <typename T> struct ColArgs {
+    typedef typename cx_of<T>::type C;
+    const C* in;  C* out;          // [B][2][ny][nx]
+    const C* tw;                   // ny roots of unity exp(-2 pi i q / ny)
+    const double* kin0; const double* kin1; long long kin_bstride;   // [ny][nx] each, stored (shifted) k order
+    int nx, ny; long long plane;
+    int do_fwd, do_inv, do_ka, do_kb;
+    int sign_in, sign_out; double scale_out;     // (-1)^y on load / store, output scale (stand-alone 1-D use)
+    double ka_re, ka_im, kb_re, kb_im;
+    double* partials;              // [B][ntiles][2]
+    unsigned* counter;             // [B]
+    double* totals;                // [B][4] : T, S0, S1, -
+    double* pops; long long pops_bstride; int pops_slot;   // [B][n][2], slot < 0: don't record
+    double atom_num;
+};
+
+template <typename T, int N, int E, int W, int TM>
+__global__ void __launch_bounds__(W * N / E) col_pass(ColArgs<T> a) {
+    typedef typename cx_of<T>::type C;
+    constexpr int NT = N / E;
+    SGPE_DYN_SMEM(smem_raw);
+    C* sm = reinterpret_cast<C*>(smem_raw);
+    double* red = reinterpret_cast<double*>(smem_raw + sizeof(C) * (size_t)N * W);
+
+    const int tid = threadIdx.x;
+    const int c = tid % W, j = tid / W;
+    const int tiles_per_comp = a.nx / W;
+    const int ntiles = 2 * tiles_per_comp;
+    const int tile = blockIdx.x;
+    const int comp = tile / tiles_per_comp;
+    const int col = (tile % tiles_per_comp) * W + c;
+    const int b = blockIdx.y;
+    const long long off = ((long long)b * 2 + comp) * a.plane + col;
+
+    C v[1][E];
+#pragma unroll
+    for (int m = 0; m < E; m++) v[0][m] = a.in[off + (long long)(j + m * NT) * a.nx];
+    if (a.sign_in) {
+#pragma unroll
+        for (int m = 0; m < E; m++)
+            if ((j + m * NT) & 1) { v[0][m].x = -v[0][m].x; v[0][m].y = -v[0][m].y; }
+    }
+
+    C* const sms[1] = {sm};
+    if (a.do_fwd) cta_fft<T, N, E, -1, W, 1>(v, j, c, sms, a.tw);
+
+    double acc[2] = {0.0, 0.0};   // S (after K_a), T (after K_b)
+    const bool any_k = a.do_ka || a.do_kb;
+    if (any_k) {
+        const double* kin = (comp == 0 ? a.kin0 : a.kin1) + (long long)b * a.kin_bstride + col;
+        double e[E];
+#pragma unroll
+        for (int m = 0; m < E; m++) e[m] = __ldg(&kin[(long long)(j + m * NT) * a.nx]);
+        if (TM == TM_REAL) {
+            const double tr = (a.do_ka ? a.ka_re : 0.0) + (a.do_kb ? a.kb_re : 0.0);
+#pragma unroll
+            for (int m = 0; m < E; m++) {
+                v[0][m] = cmul(v[0][m], evo<TM, T, C>(e[m], tr, 0.0));
+                const double d = (double)v[0][m].x * v[0][m].x + (double)v[0][m].y * v[0][m].y;
+                acc[0] += d;
+            }
+            acc[1] = acc[0];        // |K| = 1 in real time: S == T
+        } else {
+            const bool same = a.do_ka && a.do_kb && a.ka_im == a.kb_im;
+#pragma unroll
+            for (int m = 0; m < E; m++) {
+                T fa = (T)1, fb = (T)1;
+                if (a.do_ka) fa = (T)exp(e[m] * a.ka_im);
+                if (a.do_kb) fb = same ? fa : (T)exp(e[m] * a.kb_im);
+                C x = cscale(v[0][m], fa);
+                acc[0] += (double)x.x * x.x + (double)x.y * x.y;
+                x = cscale(x, fb);
+                acc[1] += (double)x.x * x.x + (double)x.y * x.y;
+                v[0][m] = x;
+            }
+        }
+    }
+
+    if (a.do_inv) cta_fft<T, N, E, +1, W, 1>(v, j, c, sms, a.tw);
+
+    if (a.sign_out || a.scale_out != 1.0) {
+        const T sc = (T)a.scale_out;
+#pragma unroll
+        for (int m = 0; m < E; m++) {
+            const T s = (a.sign_out && ((j + m * NT) & 1)) ? -sc : sc;
+            v[0][m] = cscale(v[0][m], s);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < E; m++) a.out[off + (long long)(j + m * NT) * a.nx] = v[0][m];
+
+    if (any_k) {
+        cta_reduce<2>(acc, red);
+        if (tid == 0) {
+            double* p = a.partials + ((long long)b * ntiles + tile) * 2;
+            p[0] = acc[0]; p[1] = acc[1];
+            __threadfence();
+            const unsigned ticket = atomicAdd(&a.counter[b], 1u);
+            red[0] = (ticket == (unsigned)(ntiles - 1)) ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        const bool last = red[0] != 0.0;
+        __syncthreads();
+        if (last) {       // the last tile of this trajectory folds the partials in a fixed order
+            __threadfence();
+            double t4[4] = {0.0, 0.0, 0.0, 0.0};     // S0, T0, S1, T1
+            const double* p = a.partials + (long long)b * ntiles * 2;
+            for (int t = tid; t < ntiles; t += blockDim.x) {
+                const int cp = (t >= tiles_per_comp) ? 2 : 0;
+                t4[cp + 0] += __ldcg(&p[2 * t]);
+                t4[cp + 1] += __ldcg(&p[2 * t + 1]);
+            }
+            cta_reduce<4>(t4, red);
+            if (tid == 0) {
+                double* tot = a.totals + (long long)b * 4;
+                tot[0] = t4[1] + t4[3];
+                tot[1] = t4[0];
+                tot[2] = t4[2];
+                if (a.pops != nullptr && a.pops_slot >= 0) {
+                    // calc_pops of the normalised psi_k: N * S_c / (S_0 + S_1)   (tensor_tools.py:482)
+                    double* pp = a.pops + (long long)b * a.pops_bstride + 2LL * a.pops_slot;
+                    const double inv = a.atom_num / (t4[0] + t4[2]);
+                    pp[0] = t4[0] * inv; pp[1] = t4[2] * inv;
+                }
+                a.counter[b] = 0u;
+            }
+        }
+    }
+}
+
+template <typename T> struct RowArgs {
+    typedef typename cx_of<T>::type C;
+    const C* in;  C* out;          // [B][2][ny][nx]
+    const C* tw;                   // nx roots of unity
+    int nx, ny; long long plane;
+    int do_inv, do_pw, do_fwd;
+    int sign_in, sign_out; double scale_out;   // sign bit 1: (-1)^x, bit 2: (-1)^y
+    const double* pot0; const double* pot1; long long pot_bstride;     // [ny][nx]
+    int cpl_mode;                  // 0: none, 1: uniform (omega_b[b]), 2: dense (coupling[ny][nx])
+    const double* coupling; long long cpl_bstride;
+    const double* omega_b;         // [B]
+    const C* eiphi;                // [nx] exp(+i*expon) or null (rotating frame)
+    double g_uu, g_dd, g_ud;
+    double ti_re, ti_im;           // interaction time argument (dt_sub / 2)
+    double tp_re, tp_im;           // potential time argument (dt_sub)
+    double tc;                     // coupling angle per unit Omega (|dt_sub| / 4)
+    const double* totals;          // [B][4], T at [0]
+    double norm_c;                 // N_atoms / (dv_r * nx * ny)
+};
+
+// 2x2 coupling operator (reference tensor_tools.py:586-590) for theta = Omega*tc and exp(i phi) = ph
+template <int TM, typename T, typename C>
+SGPE_DI void coupling_entries(double theta, C ph, T& diag, C& off01, C& off10) {
+    if (TM == TM_REAL) {
+        double s, c;
+        sincos(theta, &s, &c);
+        diag = (T)c;
+        const T sn = (T)s;
+        off01.x = -sn * ph.y; off01.y = -sn * ph.x;     // -i sin(theta) e^{-i phi}
+        off10.x =  sn * ph.y; off10.y = -sn * ph.x;     // -i sin(theta) e^{+i phi}
+    } else {
+        diag = (T)cosh(theta);
+        const T sh = (T)sinh(theta);
+        off01.x = -sh * ph.x; off01.y =  sh * ph.y;     // -sinh(theta) e^{-i phi}
+        off10.x = -sh * ph.x; off10.y = -sh * ph.y;     // -sinh(theta) e^{+i phi}
+    }
+}
+
+template <typename T, int N, int E, int RPC, int TM>
+__global__ void __launch_bounds__(RPC * N / E) row_pass(RowArgs<T> a) {
+    typedef typename cx_of<T>::type C;
+    constexpr int NT = N / E;
+    SGPE_DYN_SMEM(smem_raw);
+    C* smem = reinterpret_cast<C*>(smem_raw);
+
+    const int tid = threadIdx.x;
+    const int r = tid / NT, j = tid % NT;
+    const int y = blockIdx.x * RPC + r;
+    const int b = blockIdx.y;
+    const long long off0 = ((long long)b * 2) * a.plane + (long long)y * a.nx;
+    const long long off1 = off0 + a.plane;
+
+    C v[2][E];
+#pragma unroll
+    for (int m = 0; m < E; m++) {
+        v[0][m] = a.in[off0 + j + m * NT];
+        v[1][m] = a.in[off1 + j + m * NT];
+    }
+    if (a.sign_in) {
+#pragma unroll
+        for (int m = 0; m < E; m++) {
+            if ((((a.sign_in & 1) ? (j + m * NT) : 0) + ((a.sign_in & 2) ? y : 0)) & 1) {
+                v[0][m].x = -v[0][m].x; v[0][m].y = -v[0][m].y;
+                v[1][m].x = -v[1][m].x; v[1][m].y = -v[1][m].y;
+            }
+        }
+    }
+    C* const sms[2] = {smem + (size_t)(2 * r) * N, smem + (size_t)(2 * r + 1) * N};
+
+    if (a.do_inv) cta_fft<T, N, E, +1, 1, 2>(v, j, 0, sms, a.tw);
+
+    if (a.do_pw) {
+        const T alpha = (T)sqrt(a.norm_c / a.totals[(long long)b * 4]);
+        const long long prow = (long long)b * a.pot_bstride + (long long)y * a.nx;
+        const bool same_pot = (a.pot0 == a.pot1);
+        double omega_u = 0.0;
+        if (a.cpl_mode == 1) omega_u = a.omega_b[b];
+#pragma unroll
+        for (int m = 0; m < E; m++) {
+            const int x = j + m * NT;
+            C p = cscale(v[0][m], alpha), q = cscale(v[1][m], alpha);
+            const double n0 = (double)p.x * p.x + (double)p.y * p.y;
+            const double n1 = (double)q.x * q.x + (double)q.y * q.y;
+            const C i0 = evo<TM, T, C>(a.g_uu * n0 + a.g_ud * n1, a.ti_re, a.ti_im);
+            const C i1 = evo<TM, T, C>(a.g_dd * n1 + a.g_ud * n0, a.ti_re, a.ti_im);
+            p = cmul(p, i0); q = cmul(q, i1);
+            T diag = (T)1; C o01, o10;
+            if (a.cpl_mode) {
+                const double om = (a.cpl_mode == 1) ? omega_u
+                                 : __ldg(&a.coupling[(long long)b * a.cpl_bstride + (long long)y * a.nx + x]);
+                C ph; ph.x = (T)1; ph.y = (T)0;
+                if (a.eiphi != nullptr) ph = __ldg(&a.eiphi[x]);
+                coupling_entries<TM, T, C>(om * a.tc, ph, diag, o01, o10);
+                const C p2 = cadd(cscale(p, diag), cmul(o01, q));
+                const C q2 = cadd(cmul(o10, p), cscale(q, diag));
+                p = p2; q = q2;
+            }
+            const double e0 = __ldg(&a.pot0[prow + x]);
+            const C f0 = evo<TM, T, C>(e0, a.tp_re, a.tp_im);
+            const C f1 = same_pot ? f0 : evo<TM, T, C>(__ldg(&a.pot1[prow + x]), a.tp_re, a.tp_im);
+            p = cmul(p, f0); q = cmul(q, f1);
+            if (a.cpl_mode) {
+                const C p2 = cadd(cscale(p, diag), cmul(o01, q));
+                const C q2 = cadd(cmul(o10, p), cscale(q, diag));
+                p = p2; q = q2;
+            }
+            v[0][m] = cmul(p, i0); v[1][m] = cmul(q, i1);
+        }
+    }
+
+    if (a.do_fwd) cta_fft<T, N, E, -1, 1, 2>(v, j, 0, sms, a.tw);
+
+    const T sc = (T)a.scale_out;
+#pragma unroll
+    for (int m = 0; m < E; m++) {
+        T s = sc;
+        if ((((a.sign_out & 1) ? (j + m * NT) : 0) + ((a.sign_out & 2) ? y : 0)) & 1) s = -s;
+        a.out[off0 + j + m * NT] = cscale(v[0][m], s);
+        a.out[off1 + j + m * NT] = cscale(v[1][m], s);
+    }
+}
+
+// out = in * sqrt(N / (dv * (S0 + S1)))  — the trailing ttools.norm of single_step
+// (tensor_propagator.py:271) applied when the k-space state is materialised.
+template <typename T> struct ScaleArgs {
+    typedef typename cx_of<T>::type C;
+    const C* in; C* out; long long per_batch;   // elements per trajectory (2*ny*nx)
+    const double* totals; double atom_over_dv;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) scale_by_norm(ScaleArgs<T> a) {
+    typedef typename cx_of<T>::type C;
+    const int b = blockIdx.y;
+    const double* tot = a.totals + (long long)b * 4;
+    const T beta = (T)sqrt(a.atom_over_dv / (tot[1] + tot[2]));
+    const long long base = (long long)b * a.per_batch;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.per_batch;
+         i += (long long)gridDim.x * blockDim.x)
+        a.out[base + i] = cscale(a.in[base + i], beta);
+}
+
+// per-component sums of |psi|^2 (ttools.calc_pops / norm_sq, tensor_tools.py:437, 482): partials then
+// the last CTA folds them in a fixed order -> totals[b][1], totals[b][2] (and [0] = their sum).
+template <typename T> struct SumsqArgs {
+    typedef typename cx_of<T>::type C;
+    const C* in; long long plane;
+    double* partials; unsigned* counter; double* totals;
+    double* out2;                  // optional [B][2] compact copy of the per-component sums
+};
+template <typename T>
+__global__ void __launch_bounds__(256) sumsq_pass(SumsqArgs<T> a) {
+    typedef typename cx_of<T>::type C;
+    SGPE_DYN_SMEM(smem_raw);
+    double* red = reinterpret_cast<double*>(smem_raw);
+    const int b = blockIdx.y, nblk = gridDim.x, tid = threadIdx.x;
+    double acc[2] = {0.0, 0.0};
+    for (int comp = 0; comp < 2; comp++) {
+        const C* p = a.in + ((long long)b * 2 + comp) * a.plane;
+        for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < a.plane; i += (long long)nblk * blockDim.x) {
+            const C z = p[i];
+            acc[comp] += (double)z.x * z.x + (double)z.y * z.y;
+        }
+    }
+    cta_reduce<2>(acc, red);
+    if (tid == 0) {
+        double* p = a.partials + ((long long)b * nblk + blockIdx.x) * 2;
+        p[0] = acc[0]; p[1] = acc[1];
+        __threadfence();
+        const unsigned ticket = atomicAdd(&a.counter[b], 1u);
+        red[0] = (ticket == (unsigned)(nblk - 1)) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const bool last = red[0] != 0.0;
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        double t2[2] = {0.0, 0.0};
+        const double* p = a.partials + (long long)b * nblk * 2;
+        for (int t = tid; t < nblk; t += blockDim.x) { t2[0] += __ldcg(&p[2 * t]); t2[1] += __ldcg(&p[2 * t + 1]); }
+        cta_reduce<2>(t2, red);
+        if (tid == 0) {
+            double* tot = a.totals + (long long)b * 4;
+            tot[0] = t2[0] + t2[1]; tot[1] = t2[0]; tot[2] = t2[1];
+            if (a.out2 != nullptr) { a.out2[2 * b] = t2[0]; a.out2[2 * b + 1] = t2[1]; }
+            a.counter[b] = 0u;
+        }
+    }
+}
+
+}  // namespace sgpe

@@ -1,0 +1,487 @@
+// sgpe_api.cu — plan object and the C ABI declared in include/sgpe.h.
+//
+// State machine of a plan.  The working state buffer is always [B][2][ny][nx] complex and is in one of
+//   KSPACE : a k-space state (reference order), possibly un-normalised; `scale_pending` says whether
+//            totals[b][1..2] hold the sums needed to normalise it (ttools.norm, tensor_propagator.py:271);
+//   MID    : the output of a row pass — (k_x, y) space — with the trailing kinetic half-step of the
+//            sub-step `pending_dt` still to be applied by the next column pass.
+// A single step is  col_pass(FFT_y, K_a(pending), sums, K_b(this), sums, iFFT_y) ; row_pass(...)  i.e.
+// two HBM round trips; the junction is closed (col_pass with FFT_y, K_a only) when the k-space state is
+// needed.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sgpe.h"
+#include "kernels.cuh"
+#include "launch.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define SGPE_CUDA(expr)                                                                             \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(SGPE_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));           \
+    } while (0)
+
+const double kGamma = 1.0 / (2.0 + std::cbrt(2.0));      // tensor_propagator.py:101
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+struct sgpe_plan {
+    int nx = 0, ny = 0, batch = 0, dtype = 0, device = 0;
+    size_t csize = 16;
+    long long plane = 0;
+    void* state = nullptr;
+    void* tw_x = nullptr;
+    void* tw_y = nullptr;
+    double* partials = nullptr;
+    unsigned* counter = nullptr;
+    double* totals = nullptr;       // propagator sums [B][4]
+    double* totals_aux = nullptr;   // sumsq / normalise sums [B][4]
+    double* pops_buf = nullptr; size_t pops_cap = 0;
+    int max_tiles = 0;
+    // problem
+    bool grid_set = false, g_set = false, kin_set = false, pot_set = false, time_set = false;
+    double dx = 1, dy = 1, dv_r = 1, dv_k = 1, atom_num = 1;
+    double g_uu = 0, g_dd = 0, g_ud = 0;
+    const double* kin0 = nullptr; const double* kin1 = nullptr; long long kin_bs = 0;
+    const double* pot0 = nullptr; const double* pot1 = nullptr; long long pot_bs = 0;
+    int cpl_mode = 0; const double* cpl = nullptr; long long cpl_bs = 0;
+    const double* omega = nullptr; const void* eiphi = nullptr;
+    int tm = SGPE_TIME_IMAG; double dt = 0, dt_out = 0, dt_in = 0;
+    // state machine
+    enum Phase { EMPTY, KSPACE, MID } phase = EMPTY;
+    double pending_dt = 0;
+    bool scale_pending = false;
+    double* pend_pops = nullptr; long long pend_stride = 0; int pend_slot = -1;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+using sgpe::ColArgs;
+using sgpe::RowArgs;
+
+template <typename T>
+int upload_twiddles(void** dst, int n) {
+    typedef typename sgpe::cx_of<T>::type C;
+    std::vector<C> h(n);
+    const long double two_pi = 6.283185307179586476925286766559L;
+    for (int q = 0; q < n; q++) {
+        // exact values on the axes / diagonals, long-double elsewhere
+        long double ang = two_pi * (long double)q / (long double)n;
+        long double c = cosl(ang), s = sinl(ang);
+        if (q == 0) { c = 1; s = 0; }
+        if (4 * q == n) { c = 0; s = 1; }
+        if (2 * q == n) { c = -1; s = 0; }
+        if (4 * q == 3 * n) { c = 0; s = -1; }
+        h[q].x = (T)c; h[q].y = (T)(-s);
+    }
+    SGPE_CUDA(cudaMalloc(dst, sizeof(C) * n));
+    SGPE_CUDA(cudaMemcpy(*dst, h.data(), sizeof(C) * n, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// tau for exp(-i E tau): real time (len, 0), imaginary time (0, -len)
+void time_arg(int tm, double len, double* re, double* im) {
+    if (tm == SGPE_TIME_REAL) { *re = len; *im = 0.0; } else { *re = 0.0; *im = -len; }
+}
+
+template <typename T>
+int run_col(sgpe_plan* p, const void* in, void* out, bool fwd, bool ka, double dt_a, bool kb, double dt_b,
+            bool inv, int sign_in, int sign_out, double scale_out, double* pops, long long pops_stride,
+            int pops_slot, cudaStream_t st) {
+    typedef typename sgpe::cx_of<T>::type C;
+    ColArgs<T> a;
+    memset(&a, 0, sizeof(a));
+    a.in = static_cast<const C*>(in); a.out = static_cast<C*>(out);
+    a.tw = static_cast<const C*>(p->tw_y);
+    a.kin0 = p->kin0; a.kin1 = p->kin1; a.kin_bstride = p->kin_bs;
+    a.nx = p->nx; a.ny = p->ny; a.plane = p->plane;
+    a.do_fwd = fwd; a.do_inv = inv; a.do_ka = ka; a.do_kb = kb;
+    a.sign_in = sign_in; a.sign_out = sign_out; a.scale_out = scale_out;
+    time_arg(p->tm, dt_a / 2, &a.ka_re, &a.ka_im);          // exp(-i kin dt/2), tensor_propagator.py:138, 144
+    time_arg(p->tm, dt_b / 2, &a.kb_re, &a.kb_im);
+    a.partials = p->partials; a.counter = p->counter; a.totals = p->totals;
+    a.pops = pops; a.pops_bstride = pops_stride; a.pops_slot = pops_slot;
+    a.atom_num = p->atom_num;
+    int rc = sgpe::launch_col(p->ny, p->dtype, p->tm, &a, p->batch, st);
+    if (rc != 0) return fail(SGPE_EINVAL, "column pass: unsupported geometry");
+    p->launches++;
+    SGPE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+int run_row(sgpe_plan* p, const void* in, void* out, bool inv, bool pw, double dt_sub, bool fwd, int sign_in,
+            int sign_out, double scale_out, cudaStream_t st) {
+    typedef typename sgpe::cx_of<T>::type C;
+    RowArgs<T> a;
+    memset(&a, 0, sizeof(a));
+    a.in = static_cast<const C*>(in); a.out = static_cast<C*>(out);
+    a.tw = static_cast<const C*>(p->tw_x);
+    a.nx = p->nx; a.ny = p->ny; a.plane = p->plane;
+    a.do_inv = inv; a.do_pw = pw; a.do_fwd = fwd;
+    a.sign_in = sign_in; a.sign_out = sign_out; a.scale_out = scale_out;
+    a.pot0 = p->pot0; a.pot1 = p->pot1; a.pot_bstride = p->pot_bs;
+    a.cpl_mode = p->cpl_mode; a.coupling = p->cpl; a.cpl_bstride = p->cpl_bs; a.omega_b = p->omega;
+    a.eiphi = static_cast<const C*>(p->eiphi);
+    a.g_uu = p->g_uu; a.g_dd = p->g_dd; a.g_ud = p->g_ud;
+    time_arg(p->tm, dt_sub / 2, &a.ti_re, &a.ti_im);        // evolution_op(t_step / 2, int_eng), :249
+    time_arg(p->tm, dt_sub, &a.tp_re, &a.tp_im);            // evolution_op(dt, pot_eng_spin), :140, 146
+    a.tc = dt_sub / 4;                                      // coupling_op: Omega * dt_sub / 4, :142-149
+    a.totals = p->totals;
+    a.norm_c = p->atom_num / (p->dv_r * (double)p->nx * (double)p->ny);
+    int rc = sgpe::launch_row(p->nx, p->dtype, p->tm, &a, p->batch, st);
+    if (rc != 0) return fail(SGPE_EINVAL, "row pass: unsupported geometry");
+    p->launches++;
+    SGPE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+#define SGPE_BY_DTYPE(p, fn, ...) ((p)->dtype == SGPE_C128 ? fn<double>(__VA_ARGS__) : fn<float>(__VA_ARGS__))
+
+int ready_to_step(sgpe_plan* p) {
+    if (!p) return fail(SGPE_EINVAL, "null plan");
+    if (!(p->grid_set && p->g_set && p->kin_set && p->pot_set && p->time_set))
+        return fail(SGPE_ESTATE, "set grid, interactions, kinetic, potential and time before stepping");
+    if (p->phase == sgpe_plan::EMPTY) return fail(SGPE_ESTATE, "no state loaded (sgpe_load_psik)");
+    return 0;
+}
+
+int single_step_impl(sgpe_plan* p, double dt_sub, cudaStream_t st) {
+    const bool mid = (p->phase == sgpe_plan::MID);
+    int rc = SGPE_BY_DTYPE(p, run_col, p, p->state, p->state, mid, mid, p->pending_dt, true, dt_sub, true, 0, 0,
+                           1.0, mid ? p->pend_pops : nullptr, p->pend_stride, mid ? p->pend_slot : -1, st);
+    if (rc) return rc;
+    if (mid) p->pend_slot = -1;
+    rc = SGPE_BY_DTYPE(p, run_row, p, p->state, p->state, true, true, dt_sub, true, 0, 0, 1.0, st);
+    if (rc) return rc;
+    p->phase = sgpe_plan::MID;
+    p->pending_dt = dt_sub;
+    p->scale_pending = false;
+    return 0;
+}
+
+int close_junction(sgpe_plan* p, cudaStream_t st) {
+    if (p->phase != sgpe_plan::MID) return 0;
+    int rc = SGPE_BY_DTYPE(p, run_col, p, p->state, p->state, true, true, p->pending_dt, false, 0.0, false, 0, 0,
+                           1.0, p->pend_pops, p->pend_stride, p->pend_slot, st);
+    if (rc) return rc;
+    p->pend_slot = -1;
+    p->phase = sgpe_plan::KSPACE;
+    p->scale_pending = true;
+    return 0;
+}
+
+template <typename T>
+int run_scale(sgpe_plan* p, const void* in, void* out, const double* totals, double atom_over_dv, cudaStream_t st) {
+    typedef typename sgpe::cx_of<T>::type C;
+    sgpe::ScaleArgs<T> a;
+    a.in = static_cast<const C*>(in); a.out = static_cast<C*>(out);
+    a.per_batch = 2 * p->plane; a.totals = totals; a.atom_over_dv = atom_over_dv;
+    long long blocks = (a.per_batch + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    dim3 grid((unsigned)blocks, p->batch), block(256);
+    SGPE_LAUNCH((sgpe::scale_by_norm<T>), grid, block, 0, st, a);
+    p->launches++;
+    SGPE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+int run_sumsq(sgpe_plan* p, const void* in, double* out2, cudaStream_t st) {
+    typedef typename sgpe::cx_of<T>::type C;
+    sgpe::SumsqArgs<T> a;
+    a.in = static_cast<const C*>(in); a.plane = p->plane;
+    a.partials = p->partials; a.counter = p->counter; a.totals = p->totals_aux; a.out2 = out2;
+    long long blocks = (p->plane + 256 * 8 - 1) / (256 * 8);
+    if (blocks > p->max_tiles) blocks = p->max_tiles;
+    if (blocks < 1) blocks = 1;
+    dim3 grid((unsigned)blocks, p->batch), block(256);
+    SGPE_LAUNCH((sgpe::sumsq_pass<T>), grid, block, 32 * 2 * sizeof(double), st, a);
+    p->launches++;
+    SGPE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sgpe_last_error(void) { return g_err.c_str(); }
+
+const char* sgpe_version(void) {
+#ifdef SGPE_EMU
+    return "sgpe 0.1 emu";
+#else
+    return "sgpe 0.1 sm_100a";
+#endif
+}
+
+int sgpe_plan_create(sgpe_plan** out, int nx, int ny, int batch, int dtype, int device) {
+    if (!out) return fail(SGPE_EINVAL, "null output pointer");
+    *out = nullptr;
+    if (!sgpe::supported_length(nx) || !sgpe::supported_length(ny))
+        return fail(SGPE_EINVAL, "mesh sizes must be powers of two in [32, 4096]");
+    if (batch < 1) return fail(SGPE_EINVAL, "batch must be >= 1");
+    if (dtype != SGPE_C128 && dtype != SGPE_C64) return fail(SGPE_EINVAL, "dtype must be 0 (c128) or 1 (c64)");
+    DeviceGuard guard(device);
+    sgpe_plan* p = new sgpe_plan();
+    p->nx = nx; p->ny = ny; p->batch = batch; p->dtype = dtype; p->device = device;
+    p->csize = dtype == SGPE_C128 ? 16 : 8;
+    p->plane = (long long)nx * ny;
+    int w = sgpe::col_tile_width(ny, dtype);
+    p->max_tiles = 2 * nx / w;
+    if (p->max_tiles < 1024) p->max_tiles = 1024;
+    int rc = 0;
+    do {
+        if (cudaMalloc(&p->state, (size_t)batch * 2 * p->plane * p->csize) != cudaSuccess) { rc = SGPE_ENOMEM; break; }
+        if (cudaMalloc((void**)&p->partials, sizeof(double) * 2 * (size_t)p->max_tiles * batch) != cudaSuccess) { rc = SGPE_ENOMEM; break; }
+        if (cudaMalloc((void**)&p->counter, sizeof(unsigned) * batch) != cudaSuccess) { rc = SGPE_ENOMEM; break; }
+        if (cudaMalloc((void**)&p->totals, sizeof(double) * 4 * batch) != cudaSuccess) { rc = SGPE_ENOMEM; break; }
+        if (cudaMalloc((void**)&p->totals_aux, sizeof(double) * 4 * batch) != cudaSuccess) { rc = SGPE_ENOMEM; break; }
+        cudaMemset(p->counter, 0, sizeof(unsigned) * batch);
+        cudaMemset(p->totals, 0, sizeof(double) * 4 * batch);
+        cudaMemset(p->totals_aux, 0, sizeof(double) * 4 * batch);
+        rc = dtype == SGPE_C128 ? upload_twiddles<double>(&p->tw_x, nx) : upload_twiddles<float>(&p->tw_x, nx);
+        if (rc) break;
+        rc = dtype == SGPE_C128 ? upload_twiddles<double>(&p->tw_y, ny) : upload_twiddles<float>(&p->tw_y, ny);
+    } while (0);
+    if (rc) {
+        if (rc == SGPE_ENOMEM) fail(rc, "device allocation failed");
+        sgpe_plan_destroy(p);
+        return rc;
+    }
+    *out = p;
+    return 0;
+}
+
+int sgpe_plan_destroy(sgpe_plan* p) {
+    if (!p) return 0;
+    DeviceGuard guard(p->device);
+    cudaFree(p->state); cudaFree(p->tw_x); cudaFree(p->tw_y); cudaFree(p->partials);
+    cudaFree(p->counter); cudaFree(p->totals); cudaFree(p->totals_aux); cudaFree(p->pops_buf);
+    delete p;
+    return 0;
+}
+
+int sgpe_set_grid(sgpe_plan* p, double dx, double dy, double dv_r, double dv_k, double atom_num) {
+    if (!p) return fail(SGPE_EINVAL, "null plan");
+    if (!(dx > 0 && dy > 0 && dv_r > 0 && dv_k > 0 && atom_num > 0)) return fail(SGPE_EINVAL, "grid values must be positive");
+    p->dx = dx; p->dy = dy; p->dv_r = dv_r; p->dv_k = dv_k; p->atom_num = atom_num; p->grid_set = true;
+    return 0;
+}
+
+int sgpe_set_interactions(sgpe_plan* p, double g_uu, double g_dd, double g_ud) {
+    if (!p) return fail(SGPE_EINVAL, "null plan");
+    p->g_uu = g_uu; p->g_dd = g_dd; p->g_ud = g_ud; p->g_set = true;
+    return 0;
+}
+
+int sgpe_set_kinetic(sgpe_plan* p, const double* kin0, const double* kin1, int64_t bs) {
+    if (!p || !kin0 || !kin1) return fail(SGPE_EINVAL, "null argument");
+    p->kin0 = kin0; p->kin1 = kin1; p->kin_bs = bs; p->kin_set = true;
+    return 0;
+}
+
+int sgpe_set_potential(sgpe_plan* p, const double* pot0, const double* pot1, int64_t bs) {
+    if (!p || !pot0 || !pot1) return fail(SGPE_EINVAL, "null argument");
+    p->pot0 = pot0; p->pot1 = pot1; p->pot_bs = bs; p->pot_set = true;
+    return 0;
+}
+
+int sgpe_set_coupling(sgpe_plan* p, int mode, const double* coupling, int64_t bs, const double* omega,
+                      const void* eiphi) {
+    if (!p) return fail(SGPE_EINVAL, "null plan");
+    if (mode == SGPE_COUPLING_UNIFORM && !omega) return fail(SGPE_EINVAL, "uniform coupling needs omega_dev[batch]");
+    if (mode == SGPE_COUPLING_DENSE && !coupling) return fail(SGPE_EINVAL, "dense coupling needs coupling_dev");
+    if (mode < 0 || mode > 2) return fail(SGPE_EINVAL, "bad coupling mode");
+    p->cpl_mode = mode; p->cpl = coupling; p->cpl_bs = bs; p->omega = omega; p->eiphi = eiphi;
+    return 0;
+}
+
+int sgpe_set_time(sgpe_plan* p, int time_mode, double dt) {
+    if (!p) return fail(SGPE_EINVAL, "null plan");
+    if (time_mode != SGPE_TIME_REAL && time_mode != SGPE_TIME_IMAG) return fail(SGPE_EINVAL, "bad time mode");
+    if (p->phase == sgpe_plan::MID && time_mode != p->tm)
+        return fail(SGPE_ESTATE, "store the state before switching between real and imaginary time");
+    p->tm = time_mode; p->dt = dt;
+    p->dt_out = dt * kGamma;                 // tensor_propagator.py:102
+    p->dt_in = dt * (1.0 - 2.0 * kGamma);    // tensor_propagator.py:103
+    p->time_set = true;
+    return 0;
+}
+
+int sgpe_substeps(const sgpe_plan* p, double* dt_out, double* dt_in) {
+    if (!p || !p->time_set) return fail(SGPE_ESTATE, "time not set");
+    if (dt_out) *dt_out = p->dt_out;
+    if (dt_in) *dt_in = p->dt_in;
+    return 0;
+}
+
+int sgpe_load_psik(sgpe_plan* p, const void* psik, sgpe_stream st) {
+    if (!p || !psik) return fail(SGPE_EINVAL, "null argument");
+    DeviceGuard guard(p->device);
+    SGPE_CUDA(cudaMemcpyAsync(p->state, psik, (size_t)p->batch * 2 * p->plane * p->csize, cudaMemcpyDeviceToDevice,
+                              (cudaStream_t)st));
+    p->phase = sgpe_plan::KSPACE; p->scale_pending = false; p->pend_slot = -1;
+    return 0;
+}
+
+int sgpe_store_psik(sgpe_plan* p, void* psik, sgpe_stream st) {
+    if (!p || !psik) return fail(SGPE_EINVAL, "null argument");
+    if (p->phase == sgpe_plan::EMPTY) return fail(SGPE_ESTATE, "no state loaded");
+    DeviceGuard guard(p->device);
+    int rc = close_junction(p, (cudaStream_t)st);
+    if (rc) return rc;
+    if (p->scale_pending) {
+        rc = SGPE_BY_DTYPE(p, run_scale, p, p->state, psik, p->totals, p->atom_num / p->dv_k, (cudaStream_t)st);
+        if (rc) return rc;
+        if (psik == p->state) p->scale_pending = false;
+    } else if (psik != p->state) {
+        SGPE_CUDA(cudaMemcpyAsync(psik, p->state, (size_t)p->batch * 2 * p->plane * p->csize,
+                                  cudaMemcpyDeviceToDevice, (cudaStream_t)st));
+    }
+    return 0;
+}
+
+int sgpe_single_step(sgpe_plan* p, double dt_sub, sgpe_stream st) {
+    int rc = ready_to_step(p);
+    if (rc) return rc;
+    DeviceGuard guard(p->device);
+    return single_step_impl(p, dt_sub, (cudaStream_t)st);
+}
+
+int sgpe_full_steps(sgpe_plan* p, int n, double* pops, int64_t pops_stride, int pops_first, sgpe_stream st) {
+    int rc = ready_to_step(p);
+    if (rc) return rc;
+    if (n < 0) return fail(SGPE_EINVAL, "negative step count");
+    DeviceGuard guard(p->device);
+    cudaStream_t s = (cudaStream_t)st;
+    for (int i = 0; i < n; i++) {                       // tensor_propagator.py:220-222
+        if ((rc = single_step_impl(p, p->dt_out, s))) return rc;
+        if ((rc = single_step_impl(p, p->dt_in, s))) return rc;
+        if ((rc = single_step_impl(p, p->dt_out, s))) return rc;
+        p->pend_pops = pops; p->pend_stride = pops_stride; p->pend_slot = pops ? pops_first + i : -1;
+    }
+    // close the last junction so that the populations of the final step are recorded before returning
+    if (n > 0 && (rc = close_junction(p, s))) return rc;
+    return 0;
+}
+
+int sgpe_fft2d(sgpe_plan* p, const void* in, void* out, int inverse, sgpe_stream st) {
+    if (!p || !in || !out) return fail(SGPE_EINVAL, "null argument");
+    if (!p->grid_set) return fail(SGPE_ESTATE, "grid not set");
+    DeviceGuard guard(p->device);
+    cudaStream_t s = (cudaStream_t)st;
+    const double norm = p->dx * p->dy / (2.0 * M_PI);     // tensor_tools.py:218, 248
+    int rc;
+    if (!inverse) {
+        rc = SGPE_BY_DTYPE(p, run_row, p, in, out, false, false, 0.0, true, 3, 0, norm, s);
+        if (rc) return rc;
+        return SGPE_BY_DTYPE(p, run_col, p, out, out, true, false, 0.0, false, 0.0, false, 0, 0, 1.0, nullptr, 0, -1, s);
+    }
+    rc = SGPE_BY_DTYPE(p, run_col, p, in, out, false, false, 0.0, false, 0.0, true, 0, 0, 1.0, nullptr, 0, -1, s);
+    if (rc) return rc;
+    return SGPE_BY_DTYPE(p, run_row, p, out, out, true, false, 0.0, false, 0, 3,
+                         1.0 / (norm * (double)p->nx * (double)p->ny), s);
+}
+
+int sgpe_fft1d(sgpe_plan* p, const void* in, void* out, int axis, int inverse, sgpe_stream st) {
+    if (!p || !in || !out) return fail(SGPE_EINVAL, "null argument");
+    if (!p->grid_set) return fail(SGPE_ESTATE, "grid not set");
+    if (axis != 0 && axis != 1) return fail(SGPE_EINVAL, "axis must be 0 (x) or 1 (y)");
+    DeviceGuard guard(p->device);
+    cudaStream_t s = (cudaStream_t)st;
+    const double norm = (axis == 0 ? p->dx : p->dy) / std::sqrt(2.0 * M_PI);   // tensor_tools.py:151, 188
+    const int n = axis == 0 ? p->nx : p->ny;
+    if (axis == 0) {
+        if (!inverse) return SGPE_BY_DTYPE(p, run_row, p, in, out, false, false, 0.0, true, 1, 0, norm, s);
+        return SGPE_BY_DTYPE(p, run_row, p, in, out, true, false, 0.0, false, 0, 1, 1.0 / (norm * n), s);
+    }
+    if (!inverse)
+        return SGPE_BY_DTYPE(p, run_col, p, in, out, true, false, 0.0, false, 0.0, false, 1, 0, norm, nullptr, 0, -1, s);
+    return SGPE_BY_DTYPE(p, run_col, p, in, out, false, false, 0.0, false, 0.0, true, 0, 1, 1.0 / (norm * n), nullptr,
+                         0, -1, s);
+}
+
+int sgpe_sumsq(sgpe_plan* p, const void* in, double* out, sgpe_stream st) {
+    if (!p || !in || !out) return fail(SGPE_EINVAL, "null argument");
+    DeviceGuard guard(p->device);
+    return SGPE_BY_DTYPE(p, run_sumsq, p, in, out, (cudaStream_t)st);
+}
+
+int sgpe_normalise(sgpe_plan* p, const void* in, void* out, double vol, sgpe_stream st) {
+    if (!p || !in || !out) return fail(SGPE_EINVAL, "null argument");
+    if (!p->grid_set) return fail(SGPE_ESTATE, "grid not set (atom number)");
+    DeviceGuard guard(p->device);
+    int rc = SGPE_BY_DTYPE(p, run_sumsq, p, in, nullptr, (cudaStream_t)st);
+    if (rc) return rc;
+    return SGPE_BY_DTYPE(p, run_scale, p, in, out, p->totals_aux, p->atom_num / vol, (cudaStream_t)st);
+}
+
+int sgpe_run_host(sgpe_plan* p, const void* psik_in, void* psik_out, int n_steps, double* pops_host, sgpe_stream st) {
+    if (!p || !psik_in || !psik_out) return fail(SGPE_EINVAL, "null argument");
+    if (!(p->grid_set && p->g_set && p->kin_set && p->pot_set && p->time_set))
+        return fail(SGPE_ESTATE, "set grid, interactions, kinetic, potential and time before stepping");
+    DeviceGuard guard(p->device);
+    cudaStream_t s = (cudaStream_t)st;
+    const size_t bytes = (size_t)p->batch * 2 * p->plane * p->csize;
+    const size_t pops_n = (size_t)p->batch * n_steps * 2;
+    if (pops_host && pops_n > p->pops_cap) {
+        cudaFree(p->pops_buf); p->pops_buf = nullptr; p->pops_cap = 0;
+        SGPE_CUDA(cudaMalloc((void**)&p->pops_buf, sizeof(double) * pops_n));
+        p->pops_cap = pops_n;
+    }
+    SGPE_CUDA(cudaMemcpyAsync(p->state, psik_in, bytes, cudaMemcpyHostToDevice, s));
+    p->phase = sgpe_plan::KSPACE; p->scale_pending = false; p->pend_slot = -1;
+    int rc = sgpe_full_steps(p, n_steps, pops_host ? p->pops_buf : nullptr, 2LL * n_steps, 0, st);
+    if (rc) return rc;
+    rc = sgpe_store_psik(p, p->state, st);
+    if (rc) return rc;
+    SGPE_CUDA(cudaMemcpyAsync(psik_out, p->state, bytes, cudaMemcpyDeviceToHost, s));
+    if (pops_host && pops_n)
+        SGPE_CUDA(cudaMemcpyAsync(pops_host, p->pops_buf, sizeof(double) * pops_n, cudaMemcpyDeviceToHost, s));
+    SGPE_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int sgpe_step_accounting(const sgpe_plan* p, uint64_t* algorithmic, uint64_t* actual, int* launches) {
+    if (!p) return fail(SGPE_EINVAL, "null plan");
+    const uint64_t pts = (uint64_t)p->plane * p->batch;
+    if (algorithmic) *algorithmic = pts * (p->dtype == SGPE_C128 ? 768u : 384u);
+    if (actual) {
+        // per single step: 2 passes x (read + write) x 2 components x csize, plus the operator grids
+        uint64_t per_pt = 2 * 2 * 2 * p->csize;
+        per_pt += 2 * 8;                                             // kin0, kin1 (column pass)
+        per_pt += (p->pot0 == p->pot1) ? 8 : 16;                     // potential (row pass)
+        if (p->cpl_mode == SGPE_COUPLING_DENSE) per_pt += 8;
+        *actual = 3 * per_pt * pts;
+    }
+    if (launches) *launches = 6;
+    return 0;
+}
+
+int sgpe_launch_count(const sgpe_plan* p, uint64_t* launches) {
+    if (!p || !launches) return fail(SGPE_EINVAL, "null argument");
+    *launches = p->launches;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,172 @@
+"""TEST INFRASTRUCTURE: drives tests/emu/libsgpe_emu.so (the kernel sources compiled for the CPU fibre
+model) through the *same* C ABI as the CUDA library, with numpy arrays standing in for device memory.
+Lets the index math / algebra of the kernels be checked against the oracle on a box without a GPU."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from spinor_gpe_b200 import _capi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def emu_lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(HERE, 'emu', 'libsgpe_emu.so')
+        subprocess.run(['make', '-s', '-j8', '-C', os.path.join(HERE, 'emu')], check=True)
+        _LIB = _capi.bind(ctypes.CDLL(so))
+        assert b'emu' in _LIB.sgpe_version()
+    return _LIB
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None else None
+
+
+class EmuPlan:
+    """Thin numpy-level wrapper.  Problem arrays follow oracle.Problem (psik (B,2,Ny,Nx) or (2,Ny,Nx))."""
+
+    def __init__(self, nx, ny, batch=1, dtype=np.complex128):
+        self.lib = emu_lib()
+        self.nx, self.ny, self.batch = nx, ny, batch
+        self.cdtype = np.dtype(dtype)
+        self.h = ctypes.c_void_p()
+        code = _capi.SGPE_C128 if self.cdtype == np.complex128 else _capi.SGPE_C64
+        _capi.check(self.lib, self.lib.sgpe_plan_create(ctypes.byref(self.h), nx, ny, batch, code, 0), 'plan_create')
+        self.keep = {}
+
+    def close(self):
+        if self.h:
+            self.lib.sgpe_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _chk(self, rc, what):
+        _capi.check(self.lib, rc, what)
+
+    def set_grid(self, dx, dy, dv_r, dv_k, atom_num):
+        self._chk(self.lib.sgpe_set_grid(self.h, dx, dy, dv_r, dv_k, atom_num), 'set_grid')
+
+    def set_interactions(self, g):
+        self._chk(self.lib.sgpe_set_interactions(self.h, *[float(v) for v in g]), 'set_interactions')
+
+    def _f64(self, key, arr):
+        a = np.ascontiguousarray(arr, dtype=np.float64)
+        self.keep[key] = a
+        return a
+
+    def set_kinetic(self, kin, batched=False):
+        a = self._f64('kin', kin)      # (2,Ny,Nx) or (B,2,Ny,Nx)
+        plane = self.nx * self.ny
+        k0 = ctypes.c_void_p(a.ctypes.data)
+        k1 = ctypes.c_void_p(a.ctypes.data + 8 * plane)
+        self._chk(self.lib.sgpe_set_kinetic(self.h, k0, k1, 2 * plane if batched else 0), 'set_kinetic')
+
+    def set_potential(self, pot, batched=False, share=False):
+        a = self._f64('pot', pot)
+        plane = self.nx * self.ny
+        p0 = ctypes.c_void_p(a.ctypes.data)
+        p1 = p0 if share else ctypes.c_void_p(a.ctypes.data + 8 * plane)
+        self._chk(self.lib.sgpe_set_potential(self.h, p0, p1, 2 * plane if batched else 0), 'set_potential')
+
+    def set_coupling(self, mode, coupling=None, omega=None, eiphi=None, batched=False):
+        c = self._f64('cpl', coupling) if coupling is not None else None
+        o = self._f64('omega', omega) if omega is not None else None
+        e = None
+        if eiphi is not None:
+            e = np.ascontiguousarray(eiphi, dtype=self.cdtype)
+            self.keep['eiphi'] = e
+        self._chk(self.lib.sgpe_set_coupling(self.h, mode, _ptr(c), self.nx * self.ny if batched else 0,
+                                             _ptr(o), _ptr(e)), 'set_coupling')
+
+    def set_time(self, mode, dt):
+        code = _capi.SGPE_TIME_IMAG if mode == 'imag' else _capi.SGPE_TIME_REAL
+        self._chk(self.lib.sgpe_set_time(self.h, code, dt), 'set_time')
+
+    def substeps(self):
+        a, b = ctypes.c_double(), ctypes.c_double()
+        self._chk(self.lib.sgpe_substeps(self.h, ctypes.byref(a), ctypes.byref(b)), 'substeps')
+        return a.value, b.value
+
+    def _state(self, arr):
+        return np.ascontiguousarray(arr, dtype=self.cdtype).reshape(self.batch, 2, self.ny, self.nx)
+
+    def load(self, psik):
+        a = self._state(psik)
+        self._chk(self.lib.sgpe_load_psik(self.h, _ptr(a), None), 'load')
+
+    def store(self):
+        out = np.empty((self.batch, 2, self.ny, self.nx), dtype=self.cdtype)
+        self._chk(self.lib.sgpe_store_psik(self.h, _ptr(out), None), 'store')
+        return out
+
+    def single_step(self, dt_sub):
+        self._chk(self.lib.sgpe_single_step(self.h, dt_sub, None), 'single_step')
+
+    def full_steps(self, n, want_pops=True):
+        pops = np.zeros((self.batch, n, 2)) if want_pops else None
+        self._chk(self.lib.sgpe_full_steps(self.h, n, _ptr(pops), 2 * n, 0, None), 'full_steps')
+        return pops
+
+    def fft2d(self, arr, inverse=False):
+        a = self._state(arr)
+        out = np.empty_like(a)
+        self._chk(self.lib.sgpe_fft2d(self.h, _ptr(a), _ptr(out), int(inverse), None), 'fft2d')
+        return out
+
+    def fft1d(self, arr, axis, inverse=False):
+        a = self._state(arr)
+        out = np.empty_like(a)
+        self._chk(self.lib.sgpe_fft1d(self.h, _ptr(a), _ptr(out), axis, int(inverse), None), 'fft1d')
+        return out
+
+    def sumsq(self, arr):
+        a = self._state(arr)
+        out = np.zeros((self.batch, 2))
+        self._chk(self.lib.sgpe_sumsq(self.h, _ptr(a), _ptr(out), None), 'sumsq')
+        return out
+
+    def normalise(self, arr, vol):
+        a = self._state(arr)
+        out = np.empty_like(a)
+        self._chk(self.lib.sgpe_normalise(self.h, _ptr(a), _ptr(out), vol, None), 'normalise')
+        return out
+
+    def run_host(self, psik, n):
+        a = self._state(psik)
+        out = np.empty_like(a)
+        pops = np.zeros((self.batch, n, 2))
+        self._chk(self.lib.sgpe_run_host(self.h, _ptr(a), _ptr(out), n, _ptr(pops), None), 'run_host')
+        return out, pops
+
+
+def plan_from_problem(prob, mode, dt, dtype=np.complex128):
+    """Configure an EmuPlan from an oracle.Problem the way the product host code configures a CUDA plan
+    (dense operators; uniform coupling detected; exp(i*expon) along x)."""
+    ny, nx = prob.psik.shape[-2:]
+    pl = EmuPlan(nx, ny, 1, dtype)
+    pl.set_grid(prob.dr[0], prob.dr[1], prob.dv_r, prob.dv_k, prob.atom_num)
+    pl.set_interactions((prob.g_uu, prob.g_dd, prob.g_ud))
+    pl.set_kinetic(prob.kin.numpy())
+    pot = prob.pot.numpy()
+    pl.set_potential(pot, share=bool(np.array_equal(pot[0], pot[1])))
+    if prob.is_coupling:
+        cpl = prob.coupling.numpy()
+        eiphi = None
+        if prob.expon.ndim == 2:
+            eiphi = np.exp(1j * prob.expon.numpy()[0])
+        if np.all(cpl == cpl.flat[0]):
+            pl.set_coupling(_capi.SGPE_COUPLING_UNIFORM, omega=np.array([cpl.flat[0]]), eiphi=eiphi)
+        else:
+            pl.set_coupling(_capi.SGPE_COUPLING_DENSE, coupling=cpl, eiphi=eiphi)
+    else:
+        pl.set_coupling(_capi.SGPE_COUPLING_NONE)
+    pl.set_time(mode, dt)
+    pl.load(prob.psik.numpy())
+    return pl
