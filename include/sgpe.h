@@ -96,6 +96,13 @@ int sgpe_sumsq(sgpe_plan* p, const void* in_dev, double* out_dev, sgpe_stream st
 /* ttools.norm (tensor_tools.py:289-305): out = in / sqrt(sum(|in|^2) * vol / atom_num). */
 int sgpe_normalise(sgpe_plan* p, const void* in_dev, void* out_dev, double vol, sgpe_stream st);
 
+/* TensorPropagator.eng_expect (tensor_propagator.py:273-324): [E_total, E_kin, E_pot, E_int] as raw grid
+ * sums, out_dev[batch][4].  psik_dev == NULL evaluates the plan's current state.  kl_term is
+ * 2*kL_recoil*is_coupling (:311).  unwrap_mode 0 leaves the wrapped phase as is (the variant pinned
+ * against the reference), 1 differentiates with locally wrapped differences. */
+int sgpe_energy(sgpe_plan* p, const void* psik_dev, int unwrap_mode, double kl_term, double* out_dev,
+                sgpe_stream st);
+
 /* The same path with HOST buffers (pageable or pinned): H2D of the state, n full steps, D2H of the
  * final normalised state and the populations [batch][n][2]; synchronises the stream before returning.
  * Equivalent of PSpinor.imaginary()/real() minus file output (pspinor.py:912-925). */

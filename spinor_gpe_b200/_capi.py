@@ -26,6 +26,7 @@ PROTOTYPES = {
     'sgpe_fft1d': (C.c_int, [c_plan, c_dptr, c_dptr, C.c_int, C.c_int, c_stream]),
     'sgpe_sumsq': (C.c_int, [c_plan, c_dptr, c_dptr, c_stream]),
     'sgpe_normalise': (C.c_int, [c_plan, c_dptr, c_dptr, C.c_double, c_stream]),
+    'sgpe_energy': (C.c_int, [c_plan, c_dptr, C.c_int, C.c_double, c_dptr, c_stream]),
     'sgpe_run_host': (C.c_int, [c_plan, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, c_stream]),
     'sgpe_step_accounting': (C.c_int, [c_plan, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     'sgpe_launch_count': (C.c_int, [c_plan, C.POINTER(C.c_uint64)]),

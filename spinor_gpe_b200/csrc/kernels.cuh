@@ -352,4 +352,174 @@ __global__ void __launch_bounds__(256) sumsq_pass(SumsqArgs<T> a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Energy expectation (reference TensorPropagator.eng_expect, tensor_propagator.py:298-324) on the
+// real-space state.  Pass 1: per-component max density (the mask threshold of phase_comp,
+// tensor_tools.py:538).  Pass 2: per pixel the np.gradient stencils (2nd-order central, 1st-order at
+// the edges, tensor_tools.py:342) of sqrt(n) and of the masked phase, the potential / interaction /
+// coupling terms, summed over the grid with no volume element (:322-324).  Reference quirks kept:
+// the first np.gradient output (d/d axis 0, i.e. along y) uses spacing dr[0] and is what the Raman
+// term multiplies; the interaction term has no 1/2; the coupling term ignores the Raman phase.
+template <typename T> struct MaxDensArgs {
+    typedef typename cx_of<T>::type C;
+    const C* psi; long long plane;
+    double* partials; unsigned* counter; double* maxdens;   // maxdens [B][2]
+};
+template <typename T>
+__global__ void __launch_bounds__(256) maxdens_pass(MaxDensArgs<T> a) {
+    typedef typename cx_of<T>::type C;
+    SGPE_DYN_SMEM(smem_raw);
+    double* red = reinterpret_cast<double*>(smem_raw);
+    const int b = blockIdx.y, nblk = gridDim.x, tid = threadIdx.x;
+    double mx[2] = {0.0, 0.0};
+    for (int comp = 0; comp < 2; comp++) {
+        const C* p = a.psi + ((long long)b * 2 + comp) * a.plane;
+        for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < a.plane; i += (long long)nblk * blockDim.x) {
+            const C z = p[i];
+            const double d = (double)z.x * z.x + (double)z.y * z.y;
+            mx[comp] = d > mx[comp] ? d : mx[comp];
+        }
+    }
+    // max-reduce through shared memory (order independent)
+    red[tid * 2] = mx[0]; red[tid * 2 + 1] = mx[1];
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (tid < s) {
+            red[tid * 2] = red[tid * 2] > red[(tid + s) * 2] ? red[tid * 2] : red[(tid + s) * 2];
+            red[tid * 2 + 1] = red[tid * 2 + 1] > red[(tid + s) * 2 + 1] ? red[tid * 2 + 1] : red[(tid + s) * 2 + 1];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        double* p = a.partials + ((long long)b * nblk + blockIdx.x) * 2;
+        p[0] = red[0]; p[1] = red[1];
+        __threadfence();
+        red[2] = (atomicAdd(&a.counter[b], 1u) == (unsigned)(nblk - 1)) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    if (red[2] != 0.0 && tid == 0) {
+        __threadfence();
+        const double* p = a.partials + (long long)b * nblk * 2;
+        double m0 = 0.0, m1 = 0.0;
+        for (int t = 0; t < nblk; t++) {
+            const double v0 = __ldcg(&p[2 * t]), v1 = __ldcg(&p[2 * t + 1]);
+            m0 = v0 > m0 ? v0 : m0; m1 = v1 > m1 ? v1 : m1;
+        }
+        a.maxdens[2 * b] = m0; a.maxdens[2 * b + 1] = m1;
+        a.counter[b] = 0u;
+    }
+}
+
+template <typename T> struct EnergyArgs {
+    typedef typename cx_of<T>::type C;
+    const C* psi; int nx, ny; long long plane;
+    const double* pot0; const double* pot1; long long pot_bstride;
+    int cpl_mode; const double* coupling; long long cpl_bstride; const double* omega_b;
+    double g_uu, g_dd, g_ud;
+    double kl2;                 // 2 * kL_recoil * is_coupling
+    double inv_h0, inv_h1;      // 1/dr[0] (used along axis 0 = y!) and 1/dr[1] (axis 1 = x)
+    int unwrap_mode;            // 0: identity (wrapped phase as is), 1: local wrapped differences
+    const double* maxdens;
+    double* partials; unsigned* counter; double* out;        // out [B][4]: total, kin, pot, int
+};
+
+SGPE_DI double sgpe_wrap_pi(double d) {
+    const double pi = 3.14159265358979323846;
+    if (d > pi) d -= 2 * pi;
+    if (d < -pi) d += 2 * pi;
+    return d;
+}
+// np.gradient along one axis from the values at i-1, i, i+1 (clamped loads at the edges)
+SGPE_DI double sgpe_grad3(double fm, double f0, double fp, int i, int n, double inv_h) {
+    if (i == 0) return (fp - f0) * inv_h;
+    if (i == n - 1) return (f0 - fm) * inv_h;
+    return (fp - fm) * (0.5 * inv_h);
+}
+SGPE_DI double sgpe_grad3_wrapped(double fm, double f0, double fp, int i, int n, double inv_h) {
+    if (i == 0) return sgpe_wrap_pi(fp - f0) * inv_h;
+    if (i == n - 1) return sgpe_wrap_pi(f0 - fm) * inv_h;
+    return (sgpe_wrap_pi(fp - f0) + sgpe_wrap_pi(f0 - fm)) * (0.5 * inv_h);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) energy_pass(EnergyArgs<T> a) {
+    typedef typename cx_of<T>::type C;
+    SGPE_DYN_SMEM(smem_raw);
+    double* red = reinterpret_cast<double*>(smem_raw);
+    const int b = blockIdx.y, nblk = gridDim.x, tid = threadIdx.x;
+    const int tx = tid & 31, ty = tid >> 5;                 // 32 x 8 pixel tiles
+    const int tiles_x = a.nx / 32, tiles_y = a.ny / 8;
+    const long long ntiles = (long long)tiles_x * tiles_y;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (long long t = blockIdx.x; t < ntiles; t += nblk) {
+        const int i = (int)(t / tiles_x) * 8 + ty;          // axis 0 (y)
+        const int j = (int)(t % tiles_x) * 32 + tx;         // axis 1 (x)
+        const int im = i > 0 ? i - 1 : 0, ip = i < a.ny - 1 ? i + 1 : a.ny - 1;
+        const int jm = j > 0 ? j - 1 : 0, jp = j < a.nx - 1 ? j + 1 : a.nx - 1;
+        double kin = 0.0, dens[2];
+        C ctr[2];
+        for (int comp = 0; comp < 2; comp++) {
+            const C* p = a.psi + ((long long)b * 2 + comp) * a.plane;
+            const double thr = a.maxdens[2 * b + comp] * 1e-6;
+            const C z[5] = {p[(long long)i * a.nx + j], p[(long long)im * a.nx + j], p[(long long)ip * a.nx + j],
+                            p[(long long)i * a.nx + jm], p[(long long)i * a.nx + jp]};
+            double n[5], r[5], ph[5];
+#pragma unroll
+            for (int q = 0; q < 5; q++) {
+                n[q] = (double)z[q].x * z[q].x + (double)z[q].y * z[q].y;
+                r[q] = sqrt(n[q]);
+                ph[q] = (n[q] < thr) ? 0.0 : atan2((double)z[q].y, (double)z[q].x);
+            }
+            const double r0 = sgpe_grad3(r[1], r[0], r[2], i, a.ny, a.inv_h0);
+            const double r1 = sgpe_grad3(r[3], r[0], r[4], j, a.nx, a.inv_h1);
+            double g0, g1;
+            if (a.unwrap_mode == 0) {
+                g0 = sgpe_grad3(ph[1], ph[0], ph[2], i, a.ny, a.inv_h0);
+                g1 = sgpe_grad3(ph[3], ph[0], ph[4], j, a.nx, a.inv_h1);
+            } else {
+                g0 = sgpe_grad3_wrapped(ph[1], ph[0], ph[2], i, a.ny, a.inv_h0);
+                g1 = sgpe_grad3_wrapped(ph[3], ph[0], ph[4], j, a.nx, a.inv_h1);
+            }
+            kin += (r0 * r0 + r1 * r1) + n[0] * (g0 * g0 + g1 * g1) + n[0] * g0 * a.kl2;
+            dens[comp] = n[0];
+            ctr[comp] = z[0];
+        }
+        kin *= 0.5;
+        const long long pix = (long long)i * a.nx + j;
+        const double pot = dens[0] * __ldg(&a.pot0[(long long)b * a.pot_bstride + pix])
+                         + dens[1] * __ldg(&a.pot1[(long long)b * a.pot_bstride + pix]);
+        const double inter = a.g_uu * dens[0] * dens[0] + a.g_dd * dens[1] * dens[1] + a.g_ud * dens[0] * dens[1];
+        double om = 0.0;
+        if (a.cpl_mode == 1) om = a.omega_b[b];
+        else if (a.cpl_mode == 2) om = __ldg(&a.coupling[(long long)b * a.cpl_bstride + pix]);
+        const double coupl = ((double)ctr[0].x * ctr[1].x + (double)ctr[0].y * ctr[1].y) * om;   // Re(conj(p0) p1) * Omega
+        acc[0] += kin + pot + inter + coupl; acc[1] += kin; acc[2] += pot; acc[3] += inter;
+    }
+    cta_reduce<4>(acc, red);
+    if (tid == 0) {
+        double* p = a.partials + ((long long)b * nblk + blockIdx.x) * 4;
+        p[0] = acc[0]; p[1] = acc[1]; p[2] = acc[2]; p[3] = acc[3];
+        __threadfence();
+        red[0] = (atomicAdd(&a.counter[b], 1u) == (unsigned)(nblk - 1)) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const bool last = red[0] != 0.0;
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        double t4[4] = {0.0, 0.0, 0.0, 0.0};
+        const double* p = a.partials + (long long)b * nblk * 4;
+        for (int t = tid; t < nblk; t += blockDim.x) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) t4[q] += __ldcg(&p[4 * t + q]);
+        }
+        cta_reduce<4>(t4, red);
+        if (tid == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) a.out[4 * b + q] = t4[q];
+            a.counter[b] = 0u;
+        }
+    }
+}
+
 }  // namespace sgpe

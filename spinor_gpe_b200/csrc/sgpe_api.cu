@@ -54,6 +54,8 @@ struct sgpe_plan {
     double* totals = nullptr;       // propagator sums [B][4]
     double* totals_aux = nullptr;   // sumsq / normalise sums [B][4]
     double* pops_buf = nullptr; size_t pops_cap = 0;
+    void* scratch = nullptr;        // state-sized work buffer (energy), allocated on first use
+    double* maxdens = nullptr;
     int max_tiles = 0;
     // problem
     bool grid_set = false, g_set = false, kin_set = false, pot_set = false, time_set = false;
@@ -220,6 +222,40 @@ int run_sumsq(sgpe_plan* p, const void* in, double* out2, cudaStream_t st) {
     return 0;
 }
 
+template <typename T>
+int run_energy(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, double* out, cudaStream_t st) {
+    typedef typename sgpe::cx_of<T>::type C;
+    sgpe::MaxDensArgs<T> m;
+    m.psi = static_cast<const C*>(psi); m.plane = p->plane;
+    m.partials = p->partials; m.counter = p->counter; m.maxdens = p->maxdens;
+    long long blocks = (p->plane + 256 * 8 - 1) / (256 * 8);
+    if (blocks > 1024) blocks = 1024;
+    {
+        dim3 grid((unsigned)blocks, p->batch), block(256);
+        SGPE_LAUNCH((sgpe::maxdens_pass<T>), grid, block, 256 * 2 * sizeof(double), st, m);
+        p->launches++;
+        SGPE_CUDA(cudaGetLastError());
+    }
+    sgpe::EnergyArgs<T> a;
+    memset(&a, 0, sizeof(a));
+    a.psi = static_cast<const C*>(psi); a.nx = p->nx; a.ny = p->ny; a.plane = p->plane;
+    a.pot0 = p->pot0; a.pot1 = p->pot1; a.pot_bstride = p->pot_bs;
+    a.cpl_mode = p->cpl_mode; a.coupling = p->cpl; a.cpl_bstride = p->cpl_bs; a.omega_b = p->omega;
+    a.g_uu = p->g_uu; a.g_dd = p->g_dd; a.g_ud = p->g_ud;
+    a.kl2 = kl_term;
+    a.inv_h0 = 1.0 / p->dx;        // np.gradient(f, dx, dy): dx goes with axis 0 (tensor_tools.py:342)
+    a.inv_h1 = 1.0 / p->dy;
+    a.unwrap_mode = unwrap_mode;
+    a.maxdens = p->maxdens; a.partials = p->partials; a.counter = p->counter; a.out = out;
+    long long tiles = (long long)(p->nx / 32) * (p->ny / 8);
+    blocks = tiles < 512 ? tiles : 512;
+    dim3 grid((unsigned)blocks, p->batch), block(256);
+    SGPE_LAUNCH((sgpe::energy_pass<T>), grid, block, 32 * 4 * sizeof(double), st, a);
+    p->launches++;
+    SGPE_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -277,6 +313,7 @@ int sgpe_plan_destroy(sgpe_plan* p) {
     DeviceGuard guard(p->device);
     cudaFree(p->state); cudaFree(p->tw_x); cudaFree(p->tw_y); cudaFree(p->partials);
     cudaFree(p->counter); cudaFree(p->totals); cudaFree(p->totals_aux); cudaFree(p->pops_buf);
+    cudaFree(p->scratch); cudaFree(p->maxdens);
     delete p;
     return 0;
 }
@@ -434,6 +471,27 @@ int sgpe_normalise(sgpe_plan* p, const void* in, void* out, double vol, sgpe_str
     int rc = SGPE_BY_DTYPE(p, run_sumsq, p, in, nullptr, (cudaStream_t)st);
     if (rc) return rc;
     return SGPE_BY_DTYPE(p, run_scale, p, in, out, p->totals_aux, p->atom_num / vol, (cudaStream_t)st);
+}
+
+int sgpe_energy(sgpe_plan* p, const void* psik, int unwrap_mode, double kl_term, double* out, sgpe_stream st) {
+    if (!p || !out) return fail(SGPE_EINVAL, "null argument");
+    if (!(p->grid_set && p->g_set && p->pot_set)) return fail(SGPE_ESTATE, "set grid, interactions and potential first");
+    if (unwrap_mode != 0 && unwrap_mode != 1) return fail(SGPE_EINVAL, "unwrap_mode must be 0 or 1");
+    DeviceGuard guard(p->device);
+    const size_t bytes = (size_t)p->batch * 2 * p->plane * p->csize;
+    if (!p->scratch) {
+        if (cudaMalloc(&p->scratch, bytes) != cudaSuccess) return fail(SGPE_ENOMEM, "scratch allocation failed");
+        if (cudaMalloc((void**)&p->maxdens, sizeof(double) * 2 * p->batch) != cudaSuccess)
+            return fail(SGPE_ENOMEM, "scratch allocation failed");
+    }
+    int rc;
+    if (psik == nullptr) {
+        if (p->phase == sgpe_plan::EMPTY) return fail(SGPE_ESTATE, "no state loaded");
+        if ((rc = sgpe_store_psik(p, p->scratch, st))) return rc;
+        psik = p->scratch;
+    }
+    if ((rc = sgpe_fft2d(p, psik, p->scratch, 1, st))) return rc;
+    return SGPE_BY_DTYPE(p, run_energy, p, p->scratch, unwrap_mode, kl_term, out, (cudaStream_t)st);
 }
 
 int sgpe_run_host(sgpe_plan* p, const void* psik_in, void* psik_out, int n_steps, double* pops_host, sgpe_stream st) {

@@ -1,0 +1,197 @@
+"""``Plan`` — torch-tensor level wrapper of one ``sgpe_plan`` (the C ABI of include/sgpe.h).
+
+PyTorch is used for device memory and streams only; all arithmetic happens in libsgpe.so."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._lib import lib, require_cuda
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _dp(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class Plan:
+    """One propagator plan on one GPU for ``batch`` independent trajectories of an (ny, nx) mesh."""
+
+    def __init__(self, nx, ny, batch=1, dtype=torch.complex128, device='cuda'):
+        require_cuda()
+        self.lib = lib()
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise ValueError("spinor_gpe_b200 plans live on CUDA devices only (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        self.nx, self.ny, self.batch = int(nx), int(ny), int(batch)
+        self.cdtype = dtype
+        self.rdtype = torch.float64
+        code = _capi.SGPE_C128 if dtype == torch.complex128 else _capi.SGPE_C64
+        self.h = ctypes.c_void_p()
+        self._chk(self.lib.sgpe_plan_create(ctypes.byref(self.h), self.nx, self.ny, self.batch, code,
+                                            self.device.index), 'sgpe_plan_create')
+        self.keep = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def _chk(self, rc, what):
+        _capi.check(self.lib, rc, what)
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.sgpe_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _f64(self, key, arr):
+        t = torch.as_tensor(np.asarray(arr) if not isinstance(arr, torch.Tensor) else arr)
+        t = t.to(device=self.device, dtype=torch.float64).contiguous()
+        self.keep[key] = t
+        return t
+
+    def _state(self, t):
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(np.asarray(t))
+        t = t.to(device=self.device, dtype=self.cdtype).contiguous()
+        if t.numel() != self.batch * 2 * self.ny * self.nx:
+            raise ValueError(f"state has {t.numel()} elements, plan needs "
+                             f"{self.batch}x2x{self.ny}x{self.nx}")
+        return t
+
+    def new_state(self):
+        return torch.empty((self.batch, 2, self.ny, self.nx), dtype=self.cdtype, device=self.device)
+
+    @property
+    def stream(self):
+        return _stream_ptr(self.device)
+
+    # ------------------------------------------------------------------ problem definition
+    def set_grid(self, dx, dy, dv_r, dv_k, atom_num):
+        self._chk(self.lib.sgpe_set_grid(self.h, float(dx), float(dy), float(dv_r), float(dv_k),
+                                         float(atom_num)), 'sgpe_set_grid')
+
+    def set_interactions(self, g_uu, g_dd, g_ud):
+        self._chk(self.lib.sgpe_set_interactions(self.h, float(g_uu), float(g_dd), float(g_ud)),
+                  'sgpe_set_interactions')
+
+    def set_kinetic(self, kin0, kin1, batched=False):
+        """kin_c: (ny,nx) or, batched, (B,ny,nx) float64."""
+        k = self._f64('kin', torch.stack([torch.as_tensor(np.asarray(kin0)) if not isinstance(kin0, torch.Tensor) else kin0,
+                                          torch.as_tensor(np.asarray(kin1)) if not isinstance(kin1, torch.Tensor) else kin1]))
+        plane = self.nx * self.ny
+        per = k[0].numel()
+        self._chk(self.lib.sgpe_set_kinetic(self.h, _dp(k[0]), ctypes.c_void_p(k.data_ptr() + 8 * per),
+                                            plane if batched else 0), 'sgpe_set_kinetic')
+
+    def set_potential(self, pot0, pot1, batched=False, shared=False):
+        p0 = self._f64('pot0', pot0)
+        p1 = p0 if shared else self._f64('pot1', pot1)
+        self._chk(self.lib.sgpe_set_potential(self.h, _dp(p0), _dp(p1),
+                                              self.nx * self.ny if batched else 0), 'sgpe_set_potential')
+
+    def set_coupling(self, mode, coupling=None, omega=None, eiphi=None, batched=False):
+        c = self._f64('coupling', coupling) if coupling is not None else None
+        o = self._f64('omega', omega) if omega is not None else None
+        e = None
+        if eiphi is not None:
+            e = torch.as_tensor(np.asarray(eiphi) if not isinstance(eiphi, torch.Tensor) else eiphi)
+            e = e.to(device=self.device, dtype=self.cdtype).contiguous()
+            self.keep['eiphi'] = e
+        self._chk(self.lib.sgpe_set_coupling(self.h, int(mode), _dp(c), self.nx * self.ny if batched else 0,
+                                             _dp(o), _dp(e)), 'sgpe_set_coupling')
+
+    def set_time(self, mode, dt):
+        code = _capi.SGPE_TIME_IMAG if mode == 'imag' else _capi.SGPE_TIME_REAL
+        self._chk(self.lib.sgpe_set_time(self.h, code, float(dt)), 'sgpe_set_time')
+
+    def substeps(self):
+        a, b = ctypes.c_double(), ctypes.c_double()
+        self._chk(self.lib.sgpe_substeps(self.h, ctypes.byref(a), ctypes.byref(b)), 'sgpe_substeps')
+        return a.value, b.value
+
+    # ------------------------------------------------------------------ state and stepping
+    def load(self, psik):
+        t = self._state(psik)
+        self._chk(self.lib.sgpe_load_psik(self.h, _dp(t), self.stream), 'sgpe_load_psik')
+
+    def store(self, out=None):
+        if out is None:
+            out = self.new_state()
+        self._chk(self.lib.sgpe_store_psik(self.h, _dp(out), self.stream), 'sgpe_store_psik')
+        return out
+
+    def single_step(self, dt_sub):
+        self._chk(self.lib.sgpe_single_step(self.h, float(dt_sub), self.stream), 'sgpe_single_step')
+
+    def full_steps(self, n, pops=None, first=0):
+        """pops: optional float64 CUDA tensor (B, n_total, 2); step i writes row first+i."""
+        stride = 0
+        if pops is not None:
+            assert pops.is_cuda and pops.dtype == torch.float64 and pops.is_contiguous()
+            stride = pops.shape[1] * 2
+        self._chk(self.lib.sgpe_full_steps(self.h, int(n), _dp(pops), stride, int(first), self.stream),
+                  'sgpe_full_steps')
+
+    def run_host(self, psik_host, n_steps, want_pops=True):
+        """Host-buffer path (H2D + steps + D2H inside the call).  psik_host: CPU tensor/ndarray."""
+        a = torch.as_tensor(np.asarray(psik_host) if not isinstance(psik_host, torch.Tensor) else psik_host)
+        a = a.to(dtype=self.cdtype).contiguous()
+        out = torch.empty_like(a, pin_memory=True)
+        pops = torch.zeros((self.batch, n_steps, 2), dtype=torch.float64, pin_memory=True) if want_pops else None
+        self._chk(self.lib.sgpe_run_host(self.h, _dp(a), _dp(out), int(n_steps), _dp(pops), self.stream),
+                  'sgpe_run_host')
+        return out, pops
+
+    # ------------------------------------------------------------------ helpers of tensor_tools
+    def fft2d(self, t, inverse=False, out=None):
+        t = self._state(t)
+        out = torch.empty_like(t) if out is None else out
+        self._chk(self.lib.sgpe_fft2d(self.h, _dp(t), _dp(out), int(inverse), self.stream), 'sgpe_fft2d')
+        return out
+
+    def fft1d(self, t, axis, inverse=False):
+        t = self._state(t)
+        out = torch.empty_like(t)
+        self._chk(self.lib.sgpe_fft1d(self.h, _dp(t), _dp(out), int(axis), int(inverse), self.stream), 'sgpe_fft1d')
+        return out
+
+    def sumsq(self, t):
+        t = self._state(t)
+        out = torch.zeros((self.batch, 2), dtype=torch.float64, device=self.device)
+        self._chk(self.lib.sgpe_sumsq(self.h, _dp(t), _dp(out), self.stream), 'sgpe_sumsq')
+        return out
+
+    def normalise(self, t, vol):
+        t = self._state(t)
+        out = torch.empty_like(t)
+        self._chk(self.lib.sgpe_normalise(self.h, _dp(t), _dp(out), float(vol), self.stream), 'sgpe_normalise')
+        return out
+
+    def energy(self, psik=None, kl_term=0.0, unwrap='none'):
+        """[E_total, E_kin, E_pot, E_int] per trajectory, (B,4) float64 CUDA tensor."""
+        t = self._state(psik) if psik is not None else None
+        out = torch.zeros((self.batch, 4), dtype=torch.float64, device=self.device)
+        mode = {'none': 0, 'local': 1}[unwrap]
+        self._chk(self.lib.sgpe_energy(self.h, _dp(t), mode, float(kl_term), _dp(out), self.stream), 'sgpe_energy')
+        return out
+
+    def accounting(self):
+        a, b, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_int()
+        self._chk(self.lib.sgpe_step_accounting(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)),
+                  'sgpe_step_accounting')
+        return dict(algorithmic_bytes=a.value, actual_bytes=b.value, launches=c.value)
+
+    def launch_count(self):
+        n = ctypes.c_uint64()
+        self._chk(self.lib.sgpe_launch_count(self.h, ctypes.byref(n)), 'sgpe_launch_count')
+        return n.value

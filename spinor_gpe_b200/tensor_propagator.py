@@ -1,0 +1,308 @@
+"""Drop-in for the reference's ``TensorPropagator`` (spinor_gpe/pspinor/tensor_propagator.py).
+
+Same constructor, methods and attributes; the time stepping runs in the fused sm_100a kernels of
+``libsgpe.so``.  There is no CPU path: ``device`` must be a CUDA device.
+
+Differences a user can observe (all documented in DESIGN.md):
+
+* ``psik`` is materialised lazily — between ``full_step()`` calls the state lives in the kernels'
+  internal (k_x, y) layout and un-normalised; reading ``prop.psik`` closes the junction and returns
+  the normalised k-space state the reference would hold (tensor_propagator.py:271).
+* ``eng_out`` / ``eng_in`` are views that build the explicit operator tables (tensor_propagator.py:138-149)
+  only when indexed; the kernels evaluate the operators in registers.
+* ``eng_expect`` runs on the GPU; the phase unwrapping of the reference (skimage) is replaced by
+  ``unwrap='none'`` (default, wrapped phase) or ``'local'``.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import _capi
+from . import tensor_tools as ttools
+from .plan import Plan
+from .prop_result import PropResult
+
+try:                                        # progress bar as in the reference (tensor_propagator.py:185)
+    from tqdm import tqdm as _tqdm
+except ImportError:                         # pragma: no cover
+    _tqdm = None
+
+MAGIC_GAMMA = 1 / (2 + 2 ** (1 / 3))        # tensor_propagator.py:101
+
+
+def next_available_path(file_name, trial_name, ext=''):
+    """First ``<file_name><i>-<trial_name><ext>`` (i = 1, 2, ...) that does not exist yet
+    (reference plotting_tools.py:13-37; decides the name of the sampled-wavefunction file)."""
+    idx = 1
+    while os.path.exists(f'{file_name}{idx}-{trial_name}{ext}'):
+        idx += 1
+    return f'{file_name}{idx}-{trial_name}{ext}'
+
+
+class _LazyTensors(dict):
+    """dict whose values are uploaded to the GPU on first access."""
+
+    def __init__(self, source, keys, device):
+        super().__init__()
+        self._source, self._keys, self._device = source, tuple(keys), device
+
+    def __missing__(self, key):
+        if key not in self._keys:
+            raise KeyError(key)
+        val = torch.tensor(np.asarray(self._source[key]), device=self._device)
+        self[key] = val
+        return val
+
+    def keys(self):
+        return list(self._keys)
+
+    def __contains__(self, key):
+        return key in self._keys
+
+
+class _OperatorView:
+    """``eng_out`` / ``eng_in``: behaves like the reference's dict {'kin', 'pot', 'coupl'} of explicit
+    operator tables, built on demand (never used by the fused kernels)."""
+
+    def __init__(self, prop, dt_sub, outer):
+        self._prop, self.dt_sub, self.outer = prop, dt_sub, outer
+        self._cache = {}
+
+    def __getitem__(self, key):
+        if key not in self._cache:
+            p = self._prop
+            if key == 'kin':
+                self._cache[key] = ttools.evolution_op(self.dt_sub / 2, p.kin_eng_spin)
+            elif key == 'pot':
+                self._cache[key] = ttools.evolution_op(self.dt_sub, p.pot_eng_spin)
+            elif key == 'coupl':
+                if self.outer:      # tensor_propagator.py:142-143
+                    self._cache[key] = ttools.coupling_op(self.dt_sub, p.coupling / 2, p.expon)
+                else:               # tensor_propagator.py:148-149
+                    self._cache[key] = ttools.coupling_op(self.dt_sub / 2, p.coupling, p.expon)
+            else:
+                raise KeyError(key)
+        return self._cache[key]
+
+    def keys(self):
+        return ['kin', 'pot', 'coupl']
+
+
+class TensorPropagator:
+    """GPU propagator of the pseudospin-1/2 GPE (see the module docstring; attributes as in the
+    reference, tensor_propagator.py:14-59)."""
+
+    # pylint: disable=too-many-instance-attributes
+    def __init__(self, spin, t_step, n_steps, device='cuda', time='imag', is_sampling=False, n_samples=1,
+                 precision='c128', progress=False):
+        dev = torch.device(device)
+        if dev.type != 'cuda':
+            raise RuntimeError(f"device={device!r}: the B200 propagator has no CPU path; pass a CUDA device")
+        if dev.index is None:
+            dev = torch.device('cuda', torch.cuda.current_device())
+        self.n_steps = n_steps
+        self.device = device
+        self._dev = dev
+        self.paths = spin.paths
+        self._progress = progress
+
+        if time == 'imag':                                  # tensor_propagator.py:96-99
+            self.t_step = -1.0j * t_step
+        elif time == 'real':
+            self.t_step = t_step
+        else:
+            raise ValueError("time must be 'imag' or 'real'")
+        self._time = time
+        self._dt = float(t_step)
+        self.dt_out = self.t_step * MAGIC_GAMMA             # :102
+        self.dt_in = self.t_step * (1 - 2 * MAGIC_GAMMA)    # :103
+
+        self.rand_seed = spin.rand_seed
+        if self.rand_seed is not None:
+            torch.manual_seed(self.rand_seed)               # :105-107 (no RNG is consumed afterwards)
+        self.is_sampling = is_sampling
+
+        self.atom_num = spin.atom_num
+        self.is_coupling = spin.is_coupling
+        self.g_sc = spin.g_sc
+        self.kL_recoil = spin.kL_recoil                     # pylint: disable=invalid-name
+        self._rot_coupling = bool(spin.rot_coupling)
+        cdtype = {'c128': torch.complex128, 'c64': torch.complex64}[precision]
+        self._cdtype = cdtype
+
+        psik0 = np.asarray(spin.psik)
+        ny, nx = psik0.shape[-2:]
+        self.kin_eng_spin = ttools.to_tensor([np.asarray(k) for k in spin.kin_eng_spin], dev=dev)
+        pot_shared = spin.pot_eng_spin[0] is spin.pot_eng_spin[1] or np.array_equal(spin.pot_eng_spin[0],
+                                                                                    spin.pot_eng_spin[1])
+        if pot_shared:
+            p0 = ttools.to_tensor(np.asarray(spin.pot_eng_spin[0]), dev=dev)
+            self.pot_eng_spin = [p0, p0]
+        else:
+            self.pot_eng_spin = ttools.to_tensor([np.asarray(p) for p in spin.pot_eng_spin], dev=dev)
+        keys_space = ['dr', 'dk', 'x_mesh', 'y_mesh', 'dv_r', 'dv_k']
+        self.space = _LazyTensors(spin.space, keys_space, dev)
+        self._dr = (float(spin.space['dr'][0]), float(spin.space['dr'][1]))
+        self._dv_r, self._dv_k = float(spin.space['dv_r']), float(spin.space['dv_k'])
+        cpl_np = np.asarray(spin.coupling, dtype=np.float64)
+        self.coupling = ttools.to_tensor(cpl_np, dev=dev)
+
+        if self.is_sampling:                                # :131-134
+            assert self.n_steps % n_samples == 0, (
+                f"The number of samples requested {n_samples} does not evenly "
+                f"divide the total number of steps {self.n_steps}.")
+        self.sample_rate = self.n_steps / n_samples         # :136
+
+        # ---- the plan
+        self._plan = pl = Plan(nx, ny, 1, cdtype, dev)
+        pl.set_grid(self._dr[0], self._dr[1], self._dv_r, self._dv_k, self.atom_num)
+        pl.set_interactions(self.g_sc['uu'], self.g_sc['dd'], self.g_sc['ud'])
+        self._bind_operators(cpl_np, spin)
+        pl.set_time(time, self._dt)
+        self._psik_cache = None
+        self.psik = ttools.to_tensor([psik0[0], psik0[1]], dev=dev, dtype=128)
+
+        self.eng_out = _OperatorView(self, self.dt_out, outer=True)      # :138-143
+        self.eng_in = _OperatorView(self, self.dt_in, outer=False)       # :144-149
+
+    # ------------------------------------------------------------------ set-up helpers
+    def _bind_operators(self, cpl_np, spin):
+        import ctypes
+        pl = self._plan
+        k0, k1 = self.kin_eng_spin
+        pl._chk(pl.lib.sgpe_set_kinetic(pl.h, ctypes.c_void_p(k0.data_ptr()), ctypes.c_void_p(k1.data_ptr()), 0),
+                'sgpe_set_kinetic')
+        p0, p1 = self.pot_eng_spin
+        pl._chk(pl.lib.sgpe_set_potential(pl.h, ctypes.c_void_p(p0.data_ptr()), ctypes.c_void_p(p1.data_ptr()), 0),
+                'sgpe_set_potential')
+        eiphi = None
+        if self.is_coupling and not self._rot_coupling:
+            # expon = 2 kL x_mesh (tensor_propagator.py:129) depends on x only: ship exp(i expon) along x
+            x_mesh = np.asarray(spin.space['x_mesh'])
+            if not np.array_equal(x_mesh, np.broadcast_to(x_mesh[0], x_mesh.shape)):
+                raise NotImplementedError("x_mesh must be constant along y (a meshgrid of space['x'])")
+            eiphi = np.exp(1j * 2 * self.kL_recoil * x_mesh[0])
+        self._eiphi = eiphi
+        if not self.is_coupling or not np.any(cpl_np):
+            # Omega == 0 everywhere: the coupling operator is exactly the identity (cos 0 = 1, sin 0 = 0)
+            pl.set_coupling(_capi.SGPE_COUPLING_NONE)
+        elif np.all(cpl_np == cpl_np.flat[0]):
+            pl.set_coupling(_capi.SGPE_COUPLING_UNIFORM, omega=np.array([cpl_np.flat[0]]), eiphi=eiphi)
+        else:
+            pl.keep['coupling_ref'] = self.coupling
+            pl._chk(pl.lib.sgpe_set_coupling(pl.h, _capi.SGPE_COUPLING_DENSE,
+                                             ctypes.c_void_p(self.coupling.data_ptr()), 0, None,
+                                             ctypes.c_void_p(self._upload_eiphi(eiphi))), 'sgpe_set_coupling')
+
+    def _upload_eiphi(self, eiphi):
+        if eiphi is None:
+            return None
+        t = torch.as_tensor(eiphi).to(device=self._dev, dtype=self._cdtype).contiguous()
+        self._plan.keep['eiphi'] = t
+        return t.data_ptr()
+
+    @property
+    def expon(self):
+        """tensor_propagator.py:126-129."""
+        if self._rot_coupling:
+            return torch.tensor(0.0, device=self._dev)
+        return 2 * self.kL_recoil * self.space['x_mesh']
+
+    # ------------------------------------------------------------------ state
+    @property
+    def psik(self):
+        """The normalised k-space wavefunction (list of two (Ny, Nx) CUDA tensors)."""
+        if self._psik_cache is None:
+            out = self._plan.store()
+            if out.dtype != torch.complex128:
+                out = out.to(torch.complex128)
+            self._psik_cache = [out[0, 0], out[0, 1]]
+        return self._psik_cache
+
+    @psik.setter
+    def psik(self, value):
+        if isinstance(value, (list, tuple)):
+            comps = [torch.as_tensor(v) if not isinstance(v, torch.Tensor) else v for v in value]
+            value = torch.stack([c.to(self._dev) for c in comps])
+        self._plan.load(value.reshape(1, 2, *value.shape[-2:]))
+        self._psik_cache = None
+
+    # ------------------------------------------------------------------ stepping
+    def full_step(self):
+        """tensor_propagator.py:214-222 — three single steps with the magic-gamma sub-steps."""
+        self._plan.full_steps(1)
+        self._psik_cache = None
+
+    def single_step(self, t_step, eng=None):
+        """tensor_propagator.py:224-271.  ``t_step`` is ``self.dt_out`` / ``self.dt_in`` (or any sub-step of
+        the propagator's time kind); ``eng`` must be this propagator's ``eng_out`` / ``eng_in`` view (the
+        fused kernels evaluate those operators themselves) or None."""
+        if eng is not None and not isinstance(eng, _OperatorView):
+            raise NotImplementedError("custom operator tables are not supported by the fused kernels; pass "
+                                      "prop.eng_out / prop.eng_in (or None)")
+        ts = complex(t_step)
+        if self._time == 'imag':
+            if abs(ts.real) > 0:
+                raise ValueError("imaginary-time propagator: t_step must be -1j * dt")
+            dt_sub = -ts.imag
+        else:
+            if abs(ts.imag) > 0:
+                raise ValueError("real-time propagator: t_step must be real")
+            dt_sub = ts.real
+        self._plan.single_step(dt_sub)
+        self._psik_cache = None
+
+    def prop_loop(self, n_steps):
+        """tensor_propagator.py:151-212 — step loop with per-step populations, optional sampling, final
+        energy; returns a PropResult."""
+        pop_times = np.linspace(0, self.n_steps * np.abs(self.t_step), n_steps)
+        pops_dev = torch.zeros((1, max(n_steps, 1), 2), dtype=torch.float64, device=self._dev)
+        done = 0
+        if self.is_sampling:
+            n_samples = int(n_steps / self.sample_rate)
+            rate = int(self.sample_rate)
+            shape = (n_samples, 2, self._plan.ny, self._plan.nx)
+            sampled_host = torch.empty(shape, dtype=torch.complex128, pin_memory=True)
+            sampled_times = np.linspace(0, self.n_steps * np.abs(self.t_step), n_samples)
+            chunks = range(n_samples)
+            if self._progress and _tqdm is not None:
+                chunks = _tqdm(chunks)
+            for idx in chunks:                               # sample BEFORE the step (:186-189)
+                snap = self._plan.store()
+                sampled_host[idx].copy_(snap[0].to(torch.complex128), non_blocking=True)
+                self._plan.full_steps(rate, pops_dev, first=done)
+                done += rate
+        if done < n_steps:
+            self._plan.full_steps(n_steps - done, pops_dev, first=done)
+        self._psik_cache = None
+
+        energy = self.eng_expect(None)
+        vals = pops_dev[0, :n_steps].cpu().numpy().copy()
+        pops = {'times': pop_times, 'vals': vals}
+
+        if self.is_sampling:                                 # :198-204
+            torch.cuda.synchronize(self._dev)
+            test_name = self.paths['trial'] + 'psik_sampled'
+            file_name = next_available_path(test_name, self.paths['folder'], '.npz')
+            np.savez(file_name, psiks=sampled_host.numpy(), times=sampled_times)
+        else:
+            file_name = None
+
+        psik_dev = self.psik
+        psi_dev = ttools.ifft_2d(psik_dev, self._dr)
+        psik = ttools.to_numpy(psik_dev)
+        psi = ttools.to_numpy(psi_dev)
+        return PropResult(psi, psik, energy, pops, file_name)
+
+    def eng_expect(self, psik=None, unwrap='none'):
+        """tensor_propagator.py:273-324 — [<total>, <kin>, <pot>, <int>] (raw grid sums), on the GPU."""
+        if psik is not None:
+            assert len(psik) == 2, ("Requires two spinor components to calculate "
+                                    "the energy expectation value.")
+            comps = [torch.as_tensor(p) if not isinstance(p, torch.Tensor) else p for p in psik]
+            psik = torch.stack([c.to(self._dev) for c in comps]).reshape(1, 2, self._plan.ny, self._plan.nx)
+        kl_term = 2 * self.kL_recoil * float(bool(self.is_coupling))
+        # the coupling energy uses the full coupling grid even where the step skips an all-zero one
+        out = self._plan.energy(psik, kl_term=kl_term, unwrap=unwrap)
+        return [float(v) for v in out[0].cpu().numpy()]

@@ -138,6 +138,12 @@ class EmuPlan:
         self._chk(self.lib.sgpe_normalise(self.h, _ptr(a), _ptr(out), vol, None), 'normalise')
         return out
 
+    def energy(self, psik=None, kl_term=0.0, unwrap=0):
+        a = self._state(psik) if psik is not None else None
+        out = np.zeros((self.batch, 4))
+        self._chk(self.lib.sgpe_energy(self.h, _ptr(a), unwrap, kl_term, _ptr(out), None), 'energy')
+        return out
+
     def run_host(self, psik, n):
         a = self._state(psik)
         out = np.empty_like(a)
