@@ -57,6 +57,18 @@ int sgpe_set_interactions(sgpe_plan* p, double g_uu, double g_dd, double g_ud);
 int sgpe_set_kinetic(sgpe_plan* p, const double* kin0_dev, const double* kin1_dev, int64_t batch_stride);
 /* pot_eng_spin (tensor_propagator.py:116). */
 int sgpe_set_potential(sgpe_plan* p, const double* pot0_dev, const double* pot1_dev, int64_t batch_stride);
+/* Separable fast path for the same two operators: kin_c[ky][kx] = kin_x[c][kx] + kin_y[c][ky] and
+ * pot_c[y][x] = pot_x[c][x] + pot_y[c][y] (true for the reference's harmonic trap, free / Raman-shifted
+ * dispersion, linear detuning gradients: pspinor.py:426-430, 496-501, 574-575).  kin_x_dev / pot_x_dev are
+ * [2][nx], kin_y_dev / pot_y_dev [2][ny] (component-major); batch strides are 0 (shared) or 2*nx / 2*ny.
+ * The library turns them into 1-D factor tables exp(-i e tau) per sub-step, so the passes multiply by
+ * table products instead of evaluating exp / sincos per grid point.  The host decides whether the grids
+ * are separable (spinor_gpe_b200.tensor_propagator does it to 1e-13 relative); the dense setters remain
+ * the general path. */
+int sgpe_set_kinetic_separable(sgpe_plan* p, const double* kin_x_dev, const double* kin_y_dev,
+                               int64_t x_batch_stride, int64_t y_batch_stride);
+int sgpe_set_potential_separable(sgpe_plan* p, const double* pot_x_dev, const double* pot_y_dev,
+                                 int64_t x_batch_stride, int64_t y_batch_stride);
 /* coupling / expon (tensor_propagator.py:122-129, tensor_tools.py:563-591).
  *   mode NONE    : is_coupling False (tensor_propagator.py:252, 258 skipped)
  *   mode UNIFORM : one Omega per trajectory, omega_dev[batch]
@@ -65,6 +77,9 @@ int sgpe_set_potential(sgpe_plan* p, const double* pot0_dev, const double* pot1_
  *                  coupling is in the rotating frame (expon = 0, tensor_propagator.py:126-127). */
 int sgpe_set_coupling(sgpe_plan* p, int mode, const double* coupling_dev, int64_t batch_stride,
                       const double* omega_dev, const void* eiphi_dev);
+/* Tuning knobs.  "col_tile": 0 = default column-tile width (64-byte global segments, one CTA per SM at
+ * 2048 points), 2 = half width (two CTAs per SM). */
+int sgpe_set_option(sgpe_plan* p, const char* name, int value);
 /* time = 'real' | 'imag' and t_step (tensor_propagator.py:96-103): fixes dt_out, dt_in. */
 int sgpe_set_time(sgpe_plan* p, int time_mode, double dt);
 
@@ -115,6 +130,11 @@ int sgpe_run_host(sgpe_plan* p, const void* psik_in_host, void* psik_out_host, i
  *   launches    = kernel launches per full step in steady state. */
 int sgpe_step_accounting(const sgpe_plan* p, uint64_t* algorithmic_bytes, uint64_t* actual_bytes,
                          int* launches);
+/* Per-kernel timing with CUDA events on the launching stream: between begin and end every column /
+ * row pass is bracketed by an event pair; end synchronises and returns the summed milliseconds and the
+ * launch counts per kind (used by bench.py for the roofline of the dominant kernel). */
+int sgpe_profile_begin(sgpe_plan* p);
+int sgpe_profile_end(sgpe_plan* p, double* ms_col, uint64_t* n_col, double* ms_row, uint64_t* n_row);
 /* Number of kernels this plan has launched since creation. */
 int sgpe_launch_count(const sgpe_plan* p, uint64_t* launches);
 

@@ -15,7 +15,10 @@ PROTOTYPES = {
     'sgpe_set_interactions': (C.c_int, [c_plan, C.c_double, C.c_double, C.c_double]),
     'sgpe_set_kinetic': (C.c_int, [c_plan, c_dptr, c_dptr, C.c_int64]),
     'sgpe_set_potential': (C.c_int, [c_plan, c_dptr, c_dptr, C.c_int64]),
+    'sgpe_set_kinetic_separable': (C.c_int, [c_plan, c_dptr, c_dptr, C.c_int64, C.c_int64]),
+    'sgpe_set_potential_separable': (C.c_int, [c_plan, c_dptr, c_dptr, C.c_int64, C.c_int64]),
     'sgpe_set_coupling': (C.c_int, [c_plan, C.c_int, c_dptr, C.c_int64, c_dptr, c_dptr]),
+    'sgpe_set_option': (C.c_int, [c_plan, C.c_char_p, C.c_int]),
     'sgpe_set_time': (C.c_int, [c_plan, C.c_int, C.c_double]),
     'sgpe_load_psik': (C.c_int, [c_plan, c_dptr, c_stream]),
     'sgpe_store_psik': (C.c_int, [c_plan, c_dptr, c_stream]),
@@ -29,6 +32,9 @@ PROTOTYPES = {
     'sgpe_energy': (C.c_int, [c_plan, c_dptr, C.c_int, C.c_double, c_dptr, c_stream]),
     'sgpe_run_host': (C.c_int, [c_plan, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, c_stream]),
     'sgpe_step_accounting': (C.c_int, [c_plan, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
+    'sgpe_profile_begin': (C.c_int, [c_plan]),
+    'sgpe_profile_end': (C.c_int, [c_plan, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double),
+                                   C.POINTER(C.c_uint64)]),
     'sgpe_launch_count': (C.c_int, [c_plan, C.POINTER(C.c_uint64)]),
 }
 

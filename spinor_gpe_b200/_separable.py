@@ -1,0 +1,22 @@
+"""Host-side detection of separable operator grids (one-off set-up, NumPy).
+
+A grid g[c, y, x] is separable when g[c, y, x] = gx[c, x] + gy[c, y]; that holds for everything the
+reference's PSpinor builds by default: the harmonic trap (pspinor.py:426-428), the free and Raman-shifted
+dispersions (:429-430, :496-501) and uniform / linear-gradient detunings (:574-575, :660, :678).  For such
+grids the kernels multiply by products of 1-D factor tables instead of evaluating exp / sincos per point.
+"""
+import numpy as np
+
+RTOL = 1e-13
+
+
+def split_separable(grids, rtol=RTOL):
+    """(2, Ny, Nx) -> (gx (2, Nx), gy (2, Ny)) with grids == gx[:, None, :] + gy[:, :, None] to within
+    ``rtol`` of the largest entry, or None when the grids are not separable."""
+    g = np.asarray(grids, dtype=np.float64)
+    gx = g[:, 0, :].copy()
+    gy = g[:, :, 0] - g[:, 0, 0][:, None]
+    err = np.abs(g - (gx[:, None, :] + gy[:, :, None])).max()
+    if err <= rtol * max(float(np.abs(g).max()), 1e-300):
+        return gx, gy
+    return None

@@ -37,11 +37,16 @@ template <typename T> struct ColArgs {
     typedef typename cx_of<T>::type C;
     const C* in;  C* out;          // [B][2][ny][nx]
     const C* tw;                   // ny roots of unity exp(-2 pi i q / ny)
-    const double* kin0; const double* kin1; long long kin_bstride;   // [ny][nx] each, stored (shifted) k order
     int nx, ny; long long plane;
-    int do_fwd, do_inv, do_ka, do_kb;
+    int do_fwd, do_inv;
+    // k-space factors: v <- v*FA (then S = sum|v|^2), v <- v*FB (then T = sum|v|^2)
+    int has_a, has_b;
+    int kin_mode;                  // 0: dense kin grids, factors evaluated here; 1: separable tables
+    const double* kin0; const double* kin1; long long kin_bstride;   // dense: [ny][nx], stored (shifted) k order
+    double ka_re, ka_im, kb_re, kb_im;                               // dense: time arguments of FA / FB
+    const C* xa; const C* ya; const C* xb; const C* yb;              // separable: [2][nx] / [2][ny] factor tables
+    long long sepx_bstride, sepy_bstride;
     int sign_in, sign_out; double scale_out;     // (-1)^y on load / store, output scale (stand-alone 1-D use)
-    double ka_re, ka_im, kb_re, kb_im;
     double* partials;              // [B][ntiles][2]
     unsigned* counter;             // [B]
     double* totals;                // [B][4] : T, S0, S1, -
@@ -49,8 +54,18 @@ template <typename T> struct ColArgs {
     double atom_num;
 };
 
+// multiply by a factor: in imaginary time every factor is real (only .x is meaningful)
+template <int TM, typename C> SGPE_DI C mul_factor(C v, C f) {
+    if (TM == TM_REAL) return cmul(v, f);
+    return cscale(v, f.x);
+}
+template <int TM, typename C> SGPE_DI C combine_factor(C f, C g) {
+    if (TM == TM_REAL) return cmul(f, g);
+    C r; r.x = f.x * g.x; r.y = 0; return r;
+}
+
 template <typename T, int N, int E, int W, int TM>
-__global__ void __launch_bounds__(W * N / E) col_pass(ColArgs<T> a) {
+__global__ void __launch_bounds__(W * N / E, (W * N / E <= 256) ? 2 : 1) col_pass(ColArgs<T> a) {
     typedef typename cx_of<T>::type C;
     constexpr int NT = N / E;
     SGPE_DYN_SMEM(smem_raw);
@@ -79,36 +94,50 @@ __global__ void __launch_bounds__(W * N / E) col_pass(ColArgs<T> a) {
     C* const sms[1] = {sm};
     if (a.do_fwd) cta_fft<T, N, E, -1, W, 1>(v, j, c, sms, a.tw);
 
-    double acc[2] = {0.0, 0.0};   // S (after K_a), T (after K_b)
-    const bool any_k = a.do_ka || a.do_kb;
+    double acc[2] = {0.0, 0.0};   // S (after FA), T (after FB)
+    const bool any_k = a.has_a || a.has_b;
     if (any_k) {
-        const double* kin = (comp == 0 ? a.kin0 : a.kin1) + (long long)b * a.kin_bstride + col;
-        double e[E];
+        if (a.kin_mode == 0) {
+            const double* kin = (comp == 0 ? a.kin0 : a.kin1) + (long long)b * a.kin_bstride + col;
+            double e[E];
 #pragma unroll
-        for (int m = 0; m < E; m++) e[m] = __ldg(&kin[(long long)(j + m * NT) * a.nx]);
-        if (TM == TM_REAL) {
-            const double tr = (a.do_ka ? a.ka_re : 0.0) + (a.do_kb ? a.kb_re : 0.0);
+            for (int m = 0; m < E; m++) e[m] = __ldg(&kin[(long long)(j + m * NT) * a.nx]);
 #pragma unroll
             for (int m = 0; m < E; m++) {
-                v[0][m] = cmul(v[0][m], evo<TM, T, C>(e[m], tr, 0.0));
-                const double d = (double)v[0][m].x * v[0][m].x + (double)v[0][m].y * v[0][m].y;
-                acc[0] += d;
+                C x = v[0][m];
+                if (a.has_a) {
+                    x = mul_factor<TM>(x, evo<TM, T, C>(e[m], a.ka_re, a.ka_im));
+                    acc[0] += (double)x.x * x.x + (double)x.y * x.y;
+                }
+                if (a.has_b) {
+                    x = mul_factor<TM>(x, evo<TM, T, C>(e[m], a.kb_re, a.kb_im));
+                    acc[1] += (double)x.x * x.x + (double)x.y * x.y;
+                }
+                v[0][m] = x;
             }
-            acc[1] = acc[0];        // |K| = 1 in real time: S == T
         } else {
-            const bool same = a.do_ka && a.do_kb && a.ka_im == a.kb_im;
+            const long long ox = (long long)b * a.sepx_bstride + (long long)comp * a.nx + col;
+            const long long oy = (long long)b * a.sepy_bstride + (long long)comp * a.ny + j;
+            C fxa, fxb;
+            fxa.x = (T)1; fxa.y = (T)0; fxb = fxa;
+            if (a.has_a) fxa = __ldg(&a.xa[ox]);
+            if (a.has_b) fxb = __ldg(&a.xb[ox]);
 #pragma unroll
             for (int m = 0; m < E; m++) {
-                T fa = (T)1, fb = (T)1;
-                if (a.do_ka) fa = (T)exp(e[m] * a.ka_im);
-                if (a.do_kb) fb = same ? fa : (T)exp(e[m] * a.kb_im);
-                C x = cscale(v[0][m], fa);
-                acc[0] += (double)x.x * x.x + (double)x.y * x.y;
-                x = cscale(x, fb);
-                acc[1] += (double)x.x * x.x + (double)x.y * x.y;
+                C x = v[0][m];
+                if (a.has_a) {
+                    x = mul_factor<TM>(x, combine_factor<TM>(fxa, __ldg(&a.ya[oy + m * NT])));
+                    acc[0] += (double)x.x * x.x + (double)x.y * x.y;
+                }
+                if (a.has_b) {
+                    x = mul_factor<TM>(x, combine_factor<TM>(fxb, __ldg(&a.yb[oy + m * NT])));
+                    acc[1] += (double)x.x * x.x + (double)x.y * x.y;
+                }
                 v[0][m] = x;
             }
         }
+        if (!a.has_b) acc[1] = acc[0];
+        if (!a.has_a) acc[0] = acc[1];
     }
 
     if (a.do_inv) cta_fft<T, N, E, +1, W, 1>(v, j, c, sms, a.tw);
@@ -171,6 +200,8 @@ template <typename T> struct RowArgs {
     int do_inv, do_pw, do_fwd;
     int sign_in, sign_out; double scale_out;   // sign bit 1: (-1)^x, bit 2: (-1)^y
     const double* pot0; const double* pot1; long long pot_bstride;     // [ny][nx]
+    int pot_mode;                  // 0: dense grids, 1: separable factor tables px[2][nx], py[2][ny]
+    const C* px; const C* py; long long sepx_bstride, sepy_bstride;
     int cpl_mode;                  // 0: none, 1: uniform (omega_b[b]), 2: dense (coupling[ny][nx])
     const double* coupling; long long cpl_bstride;
     const double* omega_b;         // [B]
@@ -238,8 +269,20 @@ __global__ void __launch_bounds__(RPC * N / E) row_pass(RowArgs<T> a) {
         const T alpha = (T)sqrt(a.norm_c / a.totals[(long long)b * 4]);
         const long long prow = (long long)b * a.pot_bstride + (long long)y * a.nx;
         const bool same_pot = (a.pot0 == a.pot1);
-        double omega_u = 0.0;
-        if (a.cpl_mode == 1) omega_u = a.omega_b[b];
+        T cu_diag = (T)1, cu_s = (T)0;          // uniform coupling: cos/sin (cosh/sinh) once per thread
+        if (a.cpl_mode == 1) {
+            C one; one.x = (T)1; one.y = (T)0;
+            C t01, t10;
+            coupling_entries<TM, T, C>(a.omega_b[b] * a.tc, one, cu_diag, t01, t10);
+            cu_s = (TM == TM_REAL) ? -t01.y : -t01.x;       // sin(theta) resp. sinh(theta)
+        }
+        C py0, py1;
+        py0.x = (T)1; py0.y = (T)0; py1 = py0;
+        if (a.pot_mode == 1) {
+            const long long oy = (long long)b * a.sepy_bstride + y;
+            py0 = __ldg(&a.py[oy]);
+            py1 = __ldg(&a.py[oy + a.ny]);
+        }
 #pragma unroll
         for (int m = 0; m < E; m++) {
             const int x = j + m * NT;
@@ -248,28 +291,42 @@ __global__ void __launch_bounds__(RPC * N / E) row_pass(RowArgs<T> a) {
             const double n1 = (double)q.x * q.x + (double)q.y * q.y;
             const C i0 = evo<TM, T, C>(a.g_uu * n0 + a.g_ud * n1, a.ti_re, a.ti_im);
             const C i1 = evo<TM, T, C>(a.g_dd * n1 + a.g_ud * n0, a.ti_re, a.ti_im);
-            p = cmul(p, i0); q = cmul(q, i1);
+            p = mul_factor<TM>(p, i0); q = mul_factor<TM>(q, i1);
             T diag = (T)1; C o01, o10;
             if (a.cpl_mode) {
-                const double om = (a.cpl_mode == 1) ? omega_u
-                                 : __ldg(&a.coupling[(long long)b * a.cpl_bstride + (long long)y * a.nx + x]);
                 C ph; ph.x = (T)1; ph.y = (T)0;
                 if (a.eiphi != nullptr) ph = __ldg(&a.eiphi[x]);
-                coupling_entries<TM, T, C>(om * a.tc, ph, diag, o01, o10);
+                if (a.cpl_mode == 1) {
+                    diag = cu_diag;
+                    if (TM == TM_REAL) {
+                        o01.x = -cu_s * ph.y; o01.y = -cu_s * ph.x; o10.x = cu_s * ph.y; o10.y = -cu_s * ph.x;
+                    } else {
+                        o01.x = -cu_s * ph.x; o01.y = cu_s * ph.y; o10.x = -cu_s * ph.x; o10.y = -cu_s * ph.y;
+                    }
+                } else {
+                    const double om = __ldg(&a.coupling[(long long)b * a.cpl_bstride + (long long)y * a.nx + x]);
+                    coupling_entries<TM, T, C>(om * a.tc, ph, diag, o01, o10);
+                }
                 const C p2 = cadd(cscale(p, diag), cmul(o01, q));
                 const C q2 = cadd(cmul(o10, p), cscale(q, diag));
                 p = p2; q = q2;
             }
-            const double e0 = __ldg(&a.pot0[prow + x]);
-            const C f0 = evo<TM, T, C>(e0, a.tp_re, a.tp_im);
-            const C f1 = same_pot ? f0 : evo<TM, T, C>(__ldg(&a.pot1[prow + x]), a.tp_re, a.tp_im);
-            p = cmul(p, f0); q = cmul(q, f1);
+            C f0, f1;
+            if (a.pot_mode == 0) {
+                f0 = evo<TM, T, C>(__ldg(&a.pot0[prow + x]), a.tp_re, a.tp_im);
+                f1 = same_pot ? f0 : evo<TM, T, C>(__ldg(&a.pot1[prow + x]), a.tp_re, a.tp_im);
+            } else {
+                const long long ox = (long long)b * a.sepx_bstride + x;
+                f0 = combine_factor<TM>(__ldg(&a.px[ox]), py0);
+                f1 = combine_factor<TM>(__ldg(&a.px[ox + a.nx]), py1);
+            }
+            p = mul_factor<TM>(p, f0); q = mul_factor<TM>(q, f1);
             if (a.cpl_mode) {
                 const C p2 = cadd(cscale(p, diag), cmul(o01, q));
                 const C q2 = cadd(cmul(o10, p), cscale(q, diag));
                 p = p2; q = q2;
             }
-            v[0][m] = cmul(p, i0); v[1][m] = cmul(q, i1);
+            v[0][m] = mul_factor<TM>(p, i0); v[1][m] = mul_factor<TM>(q, i1);
         }
     }
 
@@ -283,6 +340,18 @@ __global__ void __launch_bounds__(RPC * N / E) row_pass(RowArgs<T> a) {
         a.out[off0 + j + m * NT] = cscale(v[0][m], s);
         a.out[off1 + j + m * NT] = cscale(v[1][m], s);
     }
+}
+
+// factor table: out[i] = exp(-i * e[i] * tau)   (separable operators: 1-D energy vectors -> 1-D factor tables)
+template <typename T> struct ExpTableArgs {
+    typedef typename cx_of<T>::type C;
+    const double* e; C* out; long long n; double tr, ti; int tm;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) exp_table(ExpTableArgs<T> a) {
+    typedef typename cx_of<T>::type C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x)
+        a.out[i] = (a.tm == TM_REAL) ? evo<TM_REAL, T, C>(a.e[i], a.tr, a.ti) : evo<TM_IMAG, T, C>(a.e[i], a.tr, a.ti);
 }
 
 // out = in * sqrt(N / (dv * (S0 + S1)))  — the trailing ttools.norm of single_step
@@ -414,6 +483,7 @@ template <typename T> struct EnergyArgs {
     typedef typename cx_of<T>::type C;
     const C* psi; int nx, ny; long long plane;
     const double* pot0; const double* pot1; long long pot_bstride;
+    int pot_mode; const double* pot_x; const double* pot_y; long long potx_bstride, poty_bstride;   // separable
     int cpl_mode; const double* coupling; long long cpl_bstride; const double* omega_b;
     double g_uu, g_dd, g_ud;
     double kl2;                 // 2 * kL_recoil * is_coupling
@@ -486,8 +556,17 @@ __global__ void __launch_bounds__(256) energy_pass(EnergyArgs<T> a) {
         }
         kin *= 0.5;
         const long long pix = (long long)i * a.nx + j;
-        const double pot = dens[0] * __ldg(&a.pot0[(long long)b * a.pot_bstride + pix])
-                         + dens[1] * __ldg(&a.pot1[(long long)b * a.pot_bstride + pix]);
+        double v0, v1;
+        if (a.pot_mode == 0) {
+            v0 = __ldg(&a.pot0[(long long)b * a.pot_bstride + pix]);
+            v1 = __ldg(&a.pot1[(long long)b * a.pot_bstride + pix]);
+        } else {
+            const double* px = a.pot_x + (long long)b * a.potx_bstride;
+            const double* py = a.pot_y + (long long)b * a.poty_bstride;
+            v0 = __ldg(&px[j]) + __ldg(&py[i]);
+            v1 = __ldg(&px[a.nx + j]) + __ldg(&py[a.ny + i]);
+        }
+        const double pot = dens[0] * v0 + dens[1] * v1;
         const double inter = a.g_uu * dens[0] * dens[0] + a.g_dd * dens[1] * dens[1] + a.g_ud * dens[0] * dens[1];
         double om = 0.0;
         if (a.cpl_mode == 1) om = a.omega_b[b];

@@ -48,15 +48,28 @@ static int launch_row_t(const RowArgs<T>& a, int batch, cudaStream_t st) {
     return 0;
 }
 
-template <typename T, int N, int TM>
-static int launch_col_t(const ColArgs<T>& a, int batch, cudaStream_t st) {
+template <typename T, int N, int TM, int W>
+static int launch_col_w(const ColArgs<T>& a, int batch, cudaStream_t st) {
     typedef ColCfg<T, N> Cfg;
-    if (a.nx % Cfg::W != 0) return -2;
+    constexpr size_t smem = (size_t)N * W * Cfg::CB + 32 * 4 * sizeof(double);
+    if (a.nx % W != 0) return -2;
     static bool once = false;
-    if (!once) { allow_smem(col_pass<T, N, Cfg::E, Cfg::W, TM>, Cfg::SMEM); once = true; }
-    dim3 grid(2 * a.nx / Cfg::W, batch), block(Cfg::THREADS);
-    SGPE_LAUNCH((col_pass<T, N, Cfg::E, Cfg::W, TM>), grid, block, Cfg::SMEM, st, a);
+    if (!once) { allow_smem(col_pass<T, N, Cfg::E, W, TM>, smem); once = true; }
+    dim3 grid(2 * a.nx / W, batch), block(W * Cfg::NT);
+    SGPE_LAUNCH((col_pass<T, N, Cfg::E, W, TM>), grid, block, smem, st, a);
     return 0;
+}
+
+// wsel: 0 = default tile width (64-byte segments), 2 = narrow tiles (half the shared memory per CTA so
+// that two CTAs share an SM and their load / compute / store phases overlap)
+template <typename T, int N, int TM>
+static int launch_col_t(const ColArgs<T>& a, int batch, int wsel, cudaStream_t st) {
+    typedef ColCfg<T, N> Cfg;
+    constexpr int WN = Cfg::W / 2;
+    if constexpr (WN >= 1 && WN * Cfg::NT >= 32) {
+        if (wsel == 2) return launch_col_w<T, N, TM, WN>(a, batch, st);
+    }
+    return launch_col_w<T, N, TM, Cfg::W>(a, batch, st);
 }
 
 #define SGPE_CAT2(a, b) a##b
@@ -73,15 +86,15 @@ int SGPE_CAT(launch_row_, SGPE_N)(int dtype, int tm, const void* args, int batch
                          : launch_row_t<float, SGPE_N, TM_IMAG>(a, batch, st);
 }
 
-int SGPE_CAT(launch_col_, SGPE_N)(int dtype, int tm, const void* args, int batch, cudaStream_t st) {
+int SGPE_CAT(launch_col_, SGPE_N)(int dtype, int tm, const void* args, int batch, int wsel, cudaStream_t st) {
     if (dtype == 0) {
         const ColArgs<double>& a = *static_cast<const ColArgs<double>*>(args);
-        return tm == TM_REAL ? launch_col_t<double, SGPE_N, TM_REAL>(a, batch, st)
-                             : launch_col_t<double, SGPE_N, TM_IMAG>(a, batch, st);
+        return tm == TM_REAL ? launch_col_t<double, SGPE_N, TM_REAL>(a, batch, wsel, st)
+                             : launch_col_t<double, SGPE_N, TM_IMAG>(a, batch, wsel, st);
     }
     const ColArgs<float>& a = *static_cast<const ColArgs<float>*>(args);
-    return tm == TM_REAL ? launch_col_t<float, SGPE_N, TM_REAL>(a, batch, st)
-                         : launch_col_t<float, SGPE_N, TM_IMAG>(a, batch, st);
+    return tm == TM_REAL ? launch_col_t<float, SGPE_N, TM_REAL>(a, batch, wsel, st)
+                         : launch_col_t<float, SGPE_N, TM_IMAG>(a, batch, wsel, st);
 }
 
 int SGPE_CAT(col_tile_width_, SGPE_N)(int dtype) {

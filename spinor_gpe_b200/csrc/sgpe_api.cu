@@ -63,6 +63,14 @@ struct sgpe_plan {
     double g_uu = 0, g_dd = 0, g_ud = 0;
     const double* kin0 = nullptr; const double* kin1 = nullptr; long long kin_bs = 0;
     const double* pot0 = nullptr; const double* pot1 = nullptr; long long pot_bs = 0;
+    // separable operators: kin_c[ky][kx] = kin_x[c][kx] + kin_y[c][ky], pot_c[y][x] = pot_x[c][x] + pot_y[c][y]
+    int kin_mode = 0, pot_mode = 0;
+    const double* kin_x = nullptr; const double* kin_y = nullptr; long long kin_xbs = 0, kin_ybs = 0;
+    const double* pot_x = nullptr; const double* pot_y = nullptr; long long pot_xbs = 0, pot_ybs = 0;
+    struct FactorTable { bool valid = false; int tm = 0; double tau = 0; void* x = nullptr; void* y = nullptr; uint64_t used = 0; };
+    FactorTable kin_tab[6], pot_tab[4];
+    uint64_t tab_clock = 0;
+    int col_wsel = 0;              // column tile width selector (sgpe_set_option "col_tile")
     int cpl_mode = 0; const double* cpl = nullptr; long long cpl_bs = 0;
     const double* omega = nullptr; const void* eiphi = nullptr;
     int tm = SGPE_TIME_IMAG; double dt = 0, dt_out = 0, dt_in = 0;
@@ -72,12 +80,33 @@ struct sgpe_plan {
     bool scale_pending = false;
     double* pend_pops = nullptr; long long pend_stride = 0; int pend_slot = -1;
     uint64_t launches = 0;
+    // optional per-kernel timing (sgpe_profile_*): event pairs around column (kind 0) / row (kind 1) passes
+    bool prof_on = false;
+#ifndef SGPE_EMU
+    struct ProfRec { int kind; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof;
+#endif
 };
 
 namespace {
 
 using sgpe::ColArgs;
 using sgpe::RowArgs;
+
+#ifndef SGPE_EMU
+struct ProfScope {
+    sgpe_plan* p; cudaStream_t st; int kind; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ProfScope(sgpe_plan* p_, int kind_, cudaStream_t st_) : p(p_), st(st_), kind(kind_) {
+        if (p->prof_on) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+    }
+    ~ProfScope() {
+        if (e0) { cudaEventRecord(e1, st); p->prof.push_back({kind, e0, e1}); }
+    }
+};
+#else
+struct ProfScope { ProfScope(sgpe_plan*, int, cudaStream_t) {} };
+#endif
+
 
 template <typename T>
 int upload_twiddles(void** dst, int n) {
@@ -104,8 +133,47 @@ void time_arg(int tm, double len, double* re, double* im) {
     if (tm == SGPE_TIME_REAL) { *re = len; *im = 0.0; } else { *re = 0.0; *im = -len; }
 }
 
+// factor tables exp(-i * e * tau) of a separable operator for time argument tau (cached per plan)
 template <typename T>
-int run_col(sgpe_plan* p, const void* in, void* out, bool fwd, bool ka, double dt_a, bool kb, double dt_b,
+int factor_table(sgpe_plan* p, sgpe_plan::FactorTable* slots, int nslots, const double* ex, long long xbs,
+                 const double* ey, long long ybs, double tau, cudaStream_t st, sgpe_plan::FactorTable** out) {
+    typedef typename sgpe::cx_of<T>::type C;
+    sgpe_plan::FactorTable* pick = nullptr;
+    for (int i = 0; i < nslots; i++)
+        if (slots[i].valid && slots[i].tm == p->tm && slots[i].tau == tau) { pick = &slots[i]; break; }
+    if (!pick) {
+        pick = &slots[0];
+        for (int i = 0; i < nslots; i++) {
+            if (!slots[i].valid) { pick = &slots[i]; break; }
+            if (slots[i].used < pick->used) pick = &slots[i];
+        }
+        const long long nxe = (xbs ? xbs * p->batch : 2LL * p->nx), nye = (ybs ? ybs * p->batch : 2LL * p->ny);
+        if (!pick->x) {
+            SGPE_CUDA(cudaMalloc(&pick->x, sizeof(C) * (size_t)(2LL * p->nx * p->batch)));
+            SGPE_CUDA(cudaMalloc(&pick->y, sizeof(C) * (size_t)(2LL * p->ny * p->batch)));
+        }
+        sgpe::ExpTableArgs<T> a;
+        a.tm = p->tm;
+        time_arg(p->tm, tau, &a.tr, &a.ti);
+        a.e = ex; a.out = static_cast<C*>(pick->x); a.n = nxe;
+        SGPE_LAUNCH((sgpe::exp_table<T>), dim3((unsigned)((nxe + 255) / 256)), dim3(256), 0, st, a);
+        a.e = ey; a.out = static_cast<C*>(pick->y); a.n = nye;
+        SGPE_LAUNCH((sgpe::exp_table<T>), dim3((unsigned)((nye + 255) / 256)), dim3(256), 0, st, a);
+        p->launches += 2;
+        SGPE_CUDA(cudaGetLastError());
+        pick->valid = true; pick->tm = p->tm; pick->tau = tau;
+    }
+    pick->used = ++p->tab_clock;
+    *out = pick;
+    return 0;
+}
+
+void invalidate_tables(sgpe_plan::FactorTable* slots, int n) { for (int i = 0; i < n; i++) slots[i].valid = false; }
+
+// Column pass.  tau_a / tau_b: time arguments of the k-space factors FA / FB (exp(-i kin tau)); has_a / has_b
+// select them.
+template <typename T>
+int run_col(sgpe_plan* p, const void* in, void* out, bool fwd, bool has_a, double tau_a, bool has_b, double tau_b,
             bool inv, int sign_in, int sign_out, double scale_out, double* pops, long long pops_stride,
             int pops_slot, cudaStream_t st) {
     typedef typename sgpe::cx_of<T>::type C;
@@ -113,16 +181,34 @@ int run_col(sgpe_plan* p, const void* in, void* out, bool fwd, bool ka, double d
     memset(&a, 0, sizeof(a));
     a.in = static_cast<const C*>(in); a.out = static_cast<C*>(out);
     a.tw = static_cast<const C*>(p->tw_y);
-    a.kin0 = p->kin0; a.kin1 = p->kin1; a.kin_bstride = p->kin_bs;
     a.nx = p->nx; a.ny = p->ny; a.plane = p->plane;
-    a.do_fwd = fwd; a.do_inv = inv; a.do_ka = ka; a.do_kb = kb;
+    a.do_fwd = fwd; a.do_inv = inv; a.has_a = has_a; a.has_b = has_b;
     a.sign_in = sign_in; a.sign_out = sign_out; a.scale_out = scale_out;
-    time_arg(p->tm, dt_a / 2, &a.ka_re, &a.ka_im);          // exp(-i kin dt/2), tensor_propagator.py:138, 144
-    time_arg(p->tm, dt_b / 2, &a.kb_re, &a.kb_im);
+    a.kin_mode = p->kin_mode;
+    if (has_a || has_b) {
+        if (p->kin_mode == 0) {
+            a.kin0 = p->kin0; a.kin1 = p->kin1; a.kin_bstride = p->kin_bs;
+            time_arg(p->tm, tau_a, &a.ka_re, &a.ka_im);
+            time_arg(p->tm, tau_b, &a.kb_re, &a.kb_im);
+        } else {
+            sgpe_plan::FactorTable* t = nullptr;
+            int rc;
+            if (has_a) {
+                if ((rc = factor_table<T>(p, p->kin_tab, 6, p->kin_x, p->kin_xbs, p->kin_y, p->kin_ybs, tau_a, st, &t))) return rc;
+                a.xa = static_cast<const C*>(t->x); a.ya = static_cast<const C*>(t->y);
+            }
+            if (has_b) {
+                if ((rc = factor_table<T>(p, p->kin_tab, 6, p->kin_x, p->kin_xbs, p->kin_y, p->kin_ybs, tau_b, st, &t))) return rc;
+                a.xb = static_cast<const C*>(t->x); a.yb = static_cast<const C*>(t->y);
+            }
+            a.sepx_bstride = p->kin_xbs ? p->kin_xbs : 0; a.sepy_bstride = p->kin_ybs ? p->kin_ybs : 0;
+        }
+    }
     a.partials = p->partials; a.counter = p->counter; a.totals = p->totals;
     a.pops = pops; a.pops_bstride = pops_stride; a.pops_slot = pops_slot;
     a.atom_num = p->atom_num;
-    int rc = sgpe::launch_col(p->ny, p->dtype, p->tm, &a, p->batch, st);
+    ProfScope prof(p, 0, st);
+    int rc = sgpe::launch_col(p->ny, p->dtype, p->tm, &a, p->batch, p->col_wsel, st);
     if (rc != 0) return fail(SGPE_EINVAL, "column pass: unsupported geometry");
     p->launches++;
     SGPE_CUDA(cudaGetLastError());
@@ -141,6 +227,14 @@ int run_row(sgpe_plan* p, const void* in, void* out, bool inv, bool pw, double d
     a.do_inv = inv; a.do_pw = pw; a.do_fwd = fwd;
     a.sign_in = sign_in; a.sign_out = sign_out; a.scale_out = scale_out;
     a.pot0 = p->pot0; a.pot1 = p->pot1; a.pot_bstride = p->pot_bs;
+    a.pot_mode = pw ? p->pot_mode : 0;
+    if (pw && p->pot_mode == 1) {
+        sgpe_plan::FactorTable* t = nullptr;
+        int rc0 = factor_table<T>(p, p->pot_tab, 4, p->pot_x, p->pot_xbs, p->pot_y, p->pot_ybs, dt_sub, st, &t);
+        if (rc0) return rc0;
+        a.px = static_cast<const C*>(t->x); a.py = static_cast<const C*>(t->y);
+        a.sepx_bstride = p->pot_xbs; a.sepy_bstride = p->pot_ybs;
+    }
     a.cpl_mode = p->cpl_mode; a.coupling = p->cpl; a.cpl_bstride = p->cpl_bs; a.omega_b = p->omega;
     a.eiphi = static_cast<const C*>(p->eiphi);
     a.g_uu = p->g_uu; a.g_dd = p->g_dd; a.g_ud = p->g_ud;
@@ -149,6 +243,7 @@ int run_row(sgpe_plan* p, const void* in, void* out, bool inv, bool pw, double d
     a.tc = dt_sub / 4;                                      // coupling_op: Omega * dt_sub / 4, :142-149
     a.totals = p->totals;
     a.norm_c = p->atom_num / (p->dv_r * (double)p->nx * (double)p->ny);
+    ProfScope prof(p, 1, st);
     int rc = sgpe::launch_row(p->nx, p->dtype, p->tm, &a, p->batch, st);
     if (rc != 0) return fail(SGPE_EINVAL, "row pass: unsupported geometry");
     p->launches++;
@@ -168,8 +263,23 @@ int ready_to_step(sgpe_plan* p) {
 
 int single_step_impl(sgpe_plan* p, double dt_sub, cudaStream_t st) {
     const bool mid = (p->phase == sgpe_plan::MID);
-    int rc = SGPE_BY_DTYPE(p, run_col, p, p->state, p->state, mid, mid, p->pending_dt, true, dt_sub, true, 0, 0,
-                           1.0, mid ? p->pend_pops : nullptr, p->pend_stride, mid ? p->pend_slot : -1, st);
+    const bool want_s = mid && p->pend_pops != nullptr && p->pend_slot >= 0;
+    int rc;
+    if (!mid) {
+        // leading kinetic half-step only (tensor_propagator.py:242)
+        rc = SGPE_BY_DTYPE(p, run_col, p, p->state, p->state, false, false, 0.0, true, dt_sub / 2, true, 0, 0, 1.0,
+                           nullptr, 0, -1, st);
+    } else if (want_s && p->tm == SGPE_TIME_IMAG) {
+        // the populations need the norms after the trailing half-step: two separate factors
+        rc = SGPE_BY_DTYPE(p, run_col, p, p->state, p->state, true, true, p->pending_dt / 2, true, dt_sub / 2, true,
+                           0, 0, 1.0, p->pend_pops, p->pend_stride, p->pend_slot, st);
+    } else {
+        // trailing half-step of the previous sub-step and leading one of this sub-step as ONE factor
+        // exp(-i kin (dt_a + dt_b)/2); in real time |K| = 1 so the population sums are unaffected
+        rc = SGPE_BY_DTYPE(p, run_col, p, p->state, p->state, true, false, 0.0, true, (p->pending_dt + dt_sub) / 2,
+                           true, 0, 0, 1.0, want_s ? p->pend_pops : nullptr, p->pend_stride,
+                           want_s ? p->pend_slot : -1, st);
+    }
     if (rc) return rc;
     if (mid) p->pend_slot = -1;
     rc = SGPE_BY_DTYPE(p, run_row, p, p->state, p->state, true, true, dt_sub, true, 0, 0, 1.0, st);
@@ -182,7 +292,7 @@ int single_step_impl(sgpe_plan* p, double dt_sub, cudaStream_t st) {
 
 int close_junction(sgpe_plan* p, cudaStream_t st) {
     if (p->phase != sgpe_plan::MID) return 0;
-    int rc = SGPE_BY_DTYPE(p, run_col, p, p->state, p->state, true, true, p->pending_dt, false, 0.0, false, 0, 0,
+    int rc = SGPE_BY_DTYPE(p, run_col, p, p->state, p->state, true, true, p->pending_dt / 2, false, 0.0, false, 0, 0,
                            1.0, p->pend_pops, p->pend_stride, p->pend_slot, st);
     if (rc) return rc;
     p->pend_slot = -1;
@@ -240,6 +350,8 @@ int run_energy(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, d
     memset(&a, 0, sizeof(a));
     a.psi = static_cast<const C*>(psi); a.nx = p->nx; a.ny = p->ny; a.plane = p->plane;
     a.pot0 = p->pot0; a.pot1 = p->pot1; a.pot_bstride = p->pot_bs;
+    a.pot_mode = p->pot_mode; a.pot_x = p->pot_x; a.pot_y = p->pot_y;
+    a.potx_bstride = p->pot_xbs; a.poty_bstride = p->pot_ybs;
     a.cpl_mode = p->cpl_mode; a.coupling = p->cpl; a.cpl_bstride = p->cpl_bs; a.omega_b = p->omega;
     a.g_uu = p->g_uu; a.g_dd = p->g_dd; a.g_ud = p->g_ud;
     a.kl2 = kl_term;
@@ -282,8 +394,7 @@ int sgpe_plan_create(sgpe_plan** out, int nx, int ny, int batch, int dtype, int 
     p->nx = nx; p->ny = ny; p->batch = batch; p->dtype = dtype; p->device = device;
     p->csize = dtype == SGPE_C128 ? 16 : 8;
     p->plane = (long long)nx * ny;
-    int w = sgpe::col_tile_width(ny, dtype);
-    p->max_tiles = 2 * nx / w;
+    p->max_tiles = 2 * nx;                       // covers every column tile width
     if (p->max_tiles < 1024) p->max_tiles = 1024;
     int rc = 0;
     do {
@@ -314,6 +425,8 @@ int sgpe_plan_destroy(sgpe_plan* p) {
     cudaFree(p->state); cudaFree(p->tw_x); cudaFree(p->tw_y); cudaFree(p->partials);
     cudaFree(p->counter); cudaFree(p->totals); cudaFree(p->totals_aux); cudaFree(p->pops_buf);
     cudaFree(p->scratch); cudaFree(p->maxdens);
+    for (auto& t : p->kin_tab) { cudaFree(t.x); cudaFree(t.y); }
+    for (auto& t : p->pot_tab) { cudaFree(t.x); cudaFree(t.y); }
     delete p;
     return 0;
 }
@@ -333,13 +446,27 @@ int sgpe_set_interactions(sgpe_plan* p, double g_uu, double g_dd, double g_ud) {
 
 int sgpe_set_kinetic(sgpe_plan* p, const double* kin0, const double* kin1, int64_t bs) {
     if (!p || !kin0 || !kin1) return fail(SGPE_EINVAL, "null argument");
-    p->kin0 = kin0; p->kin1 = kin1; p->kin_bs = bs; p->kin_set = true;
+    p->kin0 = kin0; p->kin1 = kin1; p->kin_bs = bs; p->kin_set = true; p->kin_mode = 0;
     return 0;
 }
 
 int sgpe_set_potential(sgpe_plan* p, const double* pot0, const double* pot1, int64_t bs) {
     if (!p || !pot0 || !pot1) return fail(SGPE_EINVAL, "null argument");
-    p->pot0 = pot0; p->pot1 = pot1; p->pot_bs = bs; p->pot_set = true;
+    p->pot0 = pot0; p->pot1 = pot1; p->pot_bs = bs; p->pot_set = true; p->pot_mode = 0;
+    return 0;
+}
+
+int sgpe_set_kinetic_separable(sgpe_plan* p, const double* kin_x, const double* kin_y, int64_t xbs, int64_t ybs) {
+    if (!p || !kin_x || !kin_y) return fail(SGPE_EINVAL, "null argument");
+    p->kin_x = kin_x; p->kin_y = kin_y; p->kin_xbs = xbs; p->kin_ybs = ybs; p->kin_mode = 1; p->kin_set = true;
+    invalidate_tables(p->kin_tab, 6);
+    return 0;
+}
+
+int sgpe_set_potential_separable(sgpe_plan* p, const double* pot_x, const double* pot_y, int64_t xbs, int64_t ybs) {
+    if (!p || !pot_x || !pot_y) return fail(SGPE_EINVAL, "null argument");
+    p->pot_x = pot_x; p->pot_y = pot_y; p->pot_xbs = xbs; p->pot_ybs = ybs; p->pot_mode = 1; p->pot_set = true;
+    invalidate_tables(p->pot_tab, 4);
     return 0;
 }
 
@@ -351,6 +478,16 @@ int sgpe_set_coupling(sgpe_plan* p, int mode, const double* coupling, int64_t bs
     if (mode < 0 || mode > 2) return fail(SGPE_EINVAL, "bad coupling mode");
     p->cpl_mode = mode; p->cpl = coupling; p->cpl_bs = bs; p->omega = omega; p->eiphi = eiphi;
     return 0;
+}
+
+int sgpe_set_option(sgpe_plan* p, const char* name, int value) {
+    if (!p || !name) return fail(SGPE_EINVAL, "null argument");
+    if (std::strcmp(name, "col_tile") == 0) {
+        if (value != 0 && value != 2) return fail(SGPE_EINVAL, "col_tile: 0 (default width) or 2 (half width)");
+        p->col_wsel = value;
+        return 0;
+    }
+    return fail(SGPE_EINVAL, std::string("unknown option ") + name);
 }
 
 int sgpe_set_time(sgpe_plan* p, int time_mode, double dt) {
@@ -533,6 +670,35 @@ int sgpe_step_accounting(const sgpe_plan* p, uint64_t* algorithmic, uint64_t* ac
         *actual = 3 * per_pt * pts;
     }
     if (launches) *launches = 6;
+    return 0;
+}
+
+int sgpe_profile_begin(sgpe_plan* p) {
+    if (!p) return fail(SGPE_EINVAL, "null plan");
+    p->prof_on = true;
+    return 0;
+}
+
+int sgpe_profile_end(sgpe_plan* p, double* ms_col, uint64_t* n_col, double* ms_row, uint64_t* n_row) {
+    if (!p) return fail(SGPE_EINVAL, "null plan");
+    p->prof_on = false;
+    double ms[2] = {0.0, 0.0};
+    uint64_t cnt[2] = {0, 0};
+#ifndef SGPE_EMU
+    DeviceGuard guard(p->device);
+    for (auto& r : p->prof) {
+        SGPE_CUDA(cudaEventSynchronize(r.e1));
+        float t = 0.f;
+        SGPE_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+        ms[r.kind] += t; cnt[r.kind]++;
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    }
+    p->prof.clear();
+#endif
+    if (ms_col) *ms_col = ms[0];
+    if (n_col) *n_col = cnt[0];
+    if (ms_row) *ms_row = ms[1];
+    if (n_row) *n_row = cnt[1];
     return 0;
 }
 

@@ -99,6 +99,17 @@ class Plan:
         self._chk(self.lib.sgpe_set_potential(self.h, _dp(p0), _dp(p1),
                                               self.nx * self.ny if batched else 0), 'sgpe_set_potential')
 
+    def set_kinetic_separable(self, kin_x, kin_y, batched=False):
+        """kin_c[ky][kx] = kin_x[c][kx] + kin_y[c][ky]; kin_x (2,nx) / kin_y (2,ny) or, batched, (B,2,n)."""
+        kx, ky = self._f64('kin_x', kin_x), self._f64('kin_y', kin_y)
+        self._chk(self.lib.sgpe_set_kinetic_separable(self.h, _dp(kx), _dp(ky), 2 * self.nx if batched else 0,
+                                                      2 * self.ny if batched else 0), 'sgpe_set_kinetic_separable')
+
+    def set_potential_separable(self, pot_x, pot_y, batched=False):
+        px, py = self._f64('pot_x', pot_x), self._f64('pot_y', pot_y)
+        self._chk(self.lib.sgpe_set_potential_separable(self.h, _dp(px), _dp(py), 2 * self.nx if batched else 0,
+                                                        2 * self.ny if batched else 0), 'sgpe_set_potential_separable')
+
     def set_coupling(self, mode, coupling=None, omega=None, eiphi=None, batched=False):
         c = self._f64('coupling', coupling) if coupling is not None else None
         o = self._f64('omega', omega) if omega is not None else None
@@ -109,6 +120,9 @@ class Plan:
             self.keep['eiphi'] = e
         self._chk(self.lib.sgpe_set_coupling(self.h, int(mode), _dp(c), self.nx * self.ny if batched else 0,
                                              _dp(o), _dp(e)), 'sgpe_set_coupling')
+
+    def set_option(self, name, value):
+        self._chk(self.lib.sgpe_set_option(self.h, name.encode(), int(value)), 'sgpe_set_option')
 
     def set_time(self, mode, dt):
         code = _capi.SGPE_TIME_IMAG if mode == 'imag' else _capi.SGPE_TIME_REAL
@@ -190,6 +204,16 @@ class Plan:
         self._chk(self.lib.sgpe_step_accounting(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)),
                   'sgpe_step_accounting')
         return dict(algorithmic_bytes=a.value, actual_bytes=b.value, launches=c.value)
+
+    def profile_begin(self):
+        self._chk(self.lib.sgpe_profile_begin(self.h), 'sgpe_profile_begin')
+
+    def profile_end(self):
+        a, b = ctypes.c_double(), ctypes.c_double()
+        na, nb = ctypes.c_uint64(), ctypes.c_uint64()
+        self._chk(self.lib.sgpe_profile_end(self.h, ctypes.byref(a), ctypes.byref(na), ctypes.byref(b),
+                                            ctypes.byref(nb)), 'sgpe_profile_end')
+        return dict(col_ms=a.value, col_launches=na.value, row_ms=b.value, row_launches=nb.value)
 
     def launch_count(self):
         n = ctypes.c_uint64()

@@ -10,6 +10,9 @@ Differences a user can observe (all documented in DESIGN.md):
   the normalised k-space state the reference would hold (tensor_propagator.py:271).
 * ``eng_out`` / ``eng_in`` are views that build the explicit operator tables (tensor_propagator.py:138-149)
   only when indexed; the kernels evaluate the operators in registers.
+* when the kinetic / potential grids are separable (``g[y, x] = gx[x] + gy[y]``, true for everything
+  ``PSpinor`` builds by default) the kernels use 1-D factor tables instead of per-point exp / sincos;
+  ``separable=False`` forces the general dense path.
 * ``eng_expect`` runs on the GPU; the phase unwrapping of the reference (skimage) is replaced by
   ``unwrap='none'`` (default, wrapped phase) or ``'local'``.
 """
@@ -22,6 +25,7 @@ from . import _capi
 from . import tensor_tools as ttools
 from .plan import Plan
 from .prop_result import PropResult
+from ._separable import split_separable
 
 try:                                        # progress bar as in the reference (tensor_propagator.py:185)
     from tqdm import tqdm as _tqdm
@@ -95,7 +99,7 @@ class TensorPropagator:
 
     # pylint: disable=too-many-instance-attributes
     def __init__(self, spin, t_step, n_steps, device='cuda', time='imag', is_sampling=False, n_samples=1,
-                 precision='c128', progress=False):
+                 precision='c128', progress=False, separable='auto'):
         dev = torch.device(device)
         if dev.type != 'cuda':
             raise RuntimeError(f"device={device!r}: the B200 propagator has no CPU path; pass a CUDA device")
@@ -106,6 +110,7 @@ class TensorPropagator:
         self._dev = dev
         self.paths = spin.paths
         self._progress = progress
+        self._separable_opt = bool(separable)
 
         if time == 'imag':                                  # tensor_propagator.py:96-99
             self.t_step = -1.0j * t_step
@@ -176,6 +181,17 @@ class TensorPropagator:
         p0, p1 = self.pot_eng_spin
         pl._chk(pl.lib.sgpe_set_potential(pl.h, ctypes.c_void_p(p0.data_ptr()), ctypes.c_void_p(p1.data_ptr()), 0),
                 'sgpe_set_potential')
+        # separable fast path (1-D factor tables) when the grids allow it; the dense path stays general
+        self.separable = {'kin': False, 'pot': False}
+        if self._separable_opt:
+            ksep = split_separable(np.array([np.asarray(k) for k in spin.kin_eng_spin]))
+            if ksep is not None:
+                pl.set_kinetic_separable(*ksep)
+                self.separable['kin'] = True
+            psep = split_separable(np.array([np.asarray(v) for v in spin.pot_eng_spin]))
+            if psep is not None:
+                pl.set_potential_separable(*psep)
+                self.separable['pot'] = True
         eiphi = None
         if self.is_coupling and not self._rot_coupling:
             # expon = 2 kL x_mesh (tensor_propagator.py:129) depends on x only: ship exp(i expon) along x

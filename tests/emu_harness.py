@@ -75,6 +75,16 @@ class EmuPlan:
         p1 = p0 if share else ctypes.c_void_p(a.ctypes.data + 8 * plane)
         self._chk(self.lib.sgpe_set_potential(self.h, p0, p1, 2 * plane if batched else 0), 'set_potential')
 
+    def set_kinetic_separable(self, kin_x, kin_y, batched=False):
+        kx, ky = self._f64('kin_x', kin_x), self._f64('kin_y', kin_y)
+        self._chk(self.lib.sgpe_set_kinetic_separable(self.h, _ptr(kx), _ptr(ky), 2 * self.nx if batched else 0,
+                                                      2 * self.ny if batched else 0), 'set_kinetic_separable')
+
+    def set_potential_separable(self, pot_x, pot_y, batched=False):
+        px, py = self._f64('pot_x', pot_x), self._f64('pot_y', pot_y)
+        self._chk(self.lib.sgpe_set_potential_separable(self.h, _ptr(px), _ptr(py), 2 * self.nx if batched else 0,
+                                                        2 * self.ny if batched else 0), 'set_potential_separable')
+
     def set_coupling(self, mode, coupling=None, omega=None, eiphi=None, batched=False):
         c = self._f64('cpl', coupling) if coupling is not None else None
         o = self._f64('omega', omega) if omega is not None else None
@@ -84,6 +94,9 @@ class EmuPlan:
             self.keep['eiphi'] = e
         self._chk(self.lib.sgpe_set_coupling(self.h, mode, _ptr(c), self.nx * self.ny if batched else 0,
                                              _ptr(o), _ptr(e)), 'set_coupling')
+
+    def set_option(self, name, value):
+        self._chk(self.lib.sgpe_set_option(self.h, name.encode(), int(value)), 'set_option')
 
     def set_time(self, mode, dt):
         code = _capi.SGPE_TIME_IMAG if mode == 'imag' else _capi.SGPE_TIME_REAL
@@ -152,16 +165,27 @@ class EmuPlan:
         return out, pops
 
 
-def plan_from_problem(prob, mode, dt, dtype=np.complex128):
+from spinor_gpe_b200._separable import split_separable  # noqa: E402
+
+
+def plan_from_problem(prob, mode, dt, dtype=np.complex128, separable=False):
     """Configure an EmuPlan from an oracle.Problem the way the product host code configures a CUDA plan
     (dense operators; uniform coupling detected; exp(i*expon) along x)."""
     ny, nx = prob.psik.shape[-2:]
     pl = EmuPlan(nx, ny, 1, dtype)
     pl.set_grid(prob.dr[0], prob.dr[1], prob.dv_r, prob.dv_k, prob.atom_num)
     pl.set_interactions((prob.g_uu, prob.g_dd, prob.g_ud))
-    pl.set_kinetic(prob.kin.numpy())
     pot = prob.pot.numpy()
+    ksep = split_separable(prob.kin.numpy()) if separable else None
+    psep = split_separable(pot) if separable else None
+    if ksep is not None:
+        pl.set_kinetic_separable(*ksep)
+    else:
+        pl.set_kinetic(prob.kin.numpy())
     pl.set_potential(pot, share=bool(np.array_equal(pot[0], pot[1])))
+    if psep is not None:
+        pl.set_potential_separable(*psep)
+    pl.sep_used = (ksep is not None, psep is not None)
     if prob.is_coupling:
         cpl = prob.coupling.numpy()
         eiphi = None

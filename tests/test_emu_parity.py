@@ -25,14 +25,18 @@ def rel(a, b):
     return float(np.linalg.norm((np.asarray(a) - np.asarray(b)).ravel()) / np.linalg.norm(np.asarray(b).ravel()))
 
 
+@pytest.mark.parametrize('separable', [False, True])
 @pytest.mark.parametrize('case', CASES)
-def test_emulated_kernels_vs_golden(case):
+def test_emulated_kernels_vs_golden(case, separable):
+    """separable=False: dense operator grids (general path); True: 1-D factor tables (fast path, every
+    golden case has separable kinetic / potential grids)."""
     z = np.load(os.path.join(GOLDEN, case + '.npz'))
     for r in range(int(z['n_runs'])):
         pre = f'r{r}_'
         prob = orc.Problem.from_golden(z, pre)
         mode, dt, n = str(z[pre + 'mode']), float(z[pre + 'dt']), int(z[pre + 'n_steps'])
-        pl = plan_from_problem(prob, mode, dt)
+        pl = plan_from_problem(prob, mode, dt, separable=separable)
+        assert pl.sep_used == (separable, separable)
         dto, dti = pl.substeps()
         pl.single_step(dto)
         assert rel(pl.store()[0], z[pre + 'psik_single_out']) < 1e-13
@@ -81,6 +85,26 @@ def test_emulated_long_lines():
         pl.set_grid(1.0, 1.0, 1.0, 1.0, 1.0)
         assert rel(pl.fft2d(psi)[0], orc.fft2(torch.as_tensor(psi), (1.0, 1.0)).numpy()) < 1e-14
         pl.close()
+
+
+def test_emulated_half_width_column_tiles():
+    z = np.load(os.path.join(GOLDEN, 'cgrad_64.npz'))
+    pre = 'r0_'
+    prob = orc.Problem.from_golden(z, pre)
+    pl = plan_from_problem(prob, 'real', float(z[pre + 'dt']))
+    pl.set_option('col_tile', 2)
+    pl.full_steps(int(z[pre + 'n_steps']))
+    assert rel(pl.store()[0], z[pre + 'psik_final']) < 1e-12
+    pl.close()
+
+
+def test_separability_detection():
+    from spinor_gpe_b200._separable import split_separable
+    y, x = np.meshgrid(np.linspace(-1, 1, 32), np.linspace(-2, 2, 64), indexing='ij')
+    g = np.stack([x ** 2 + 3 * y, x ** 2 - 3 * y + 1.0])
+    gx, gy = split_separable(g)
+    np.testing.assert_allclose(gx[:, None, :] + gy[:, :, None], g, rtol=0, atol=1e-13)
+    assert split_separable(np.stack([x * y, x + y])) is None
 
 
 def test_emulated_complex64():

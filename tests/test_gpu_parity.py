@@ -1,0 +1,318 @@
+"""GPU parity tests (run on the B200 with ``-m gpu``): the CUDA path, called through the C ABI
+(spinor_gpe_b200.plan.Plan / the TensorPropagator drop-in), against
+
+* the golden fixtures produced by the unmodified reference (tests/golden),
+* the CPU oracle on seeded inputs at sizes it finishes in seconds,
+* size-independent properties at BASELINE.json's full sizes (2048^2, 4096^2).
+
+Tolerances are the north_star's: psi rel-L2 <= 1e-10 (complex128) / 1e-5 (complex64); energy and atom
+number <= 1e-9 relative."""
+import glob
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import spinor_oracle as orc
+from oracle.gen_golden import CASES as GOLDEN_SPECS
+from tests.test_pspinor_setup import build_case
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, '*.npz'))
+               if 'tensor_tools' not in p)
+ENERGY_OK = {('cgrad_64', 0), ('cgrad_64', 1), ('ground_64', 0), ('nocoupl_64', 0), ('raman_64x32', 1)}
+TOL_PSI, TOL_PSI_C64, TOL_SCALAR = 1e-10, 1e-5, 1e-9
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.linalg.norm((a - b).ravel()) / np.linalg.norm(b.ravel()))
+
+
+def problem_of(ps):
+    return orc.Problem(ps.psik, ps.kin_eng_spin, ps.pot_eng_spin, ps.coupling, ps.space['dr'], ps.space['dv_r'],
+                       ps.space['dv_k'], [ps.g_sc['uu'], ps.g_sc['dd'], ps.g_sc['ud']], ps.atom_num,
+                       x=ps.space['x'], kL=ps.kL_recoil, is_coupling=ps.is_coupling, rot_coupling=ps.rot_coupling)
+
+
+def make_ps(mesh, **kw):
+    from spinor_gpe_b200 import PSpinor
+    w0 = 2 * np.pi * 50
+    args = dict(atom_num=1e3, omeg={'x': w0, 'y': w0, 'z': 40 * w0}, g_sc={'uu': 1, 'dd': 1, 'ud': 1.04},
+                pop_frac=(0.5, 0.5), r_sizes=(8, 8), mesh_points=mesh)
+    args.update(kw)
+    tmp = os.path.join(tempfile.mkdtemp(prefix='sgpe_g_'), 'run') + os.sep
+    return PSpinor(tmp, overwrite=True, **args)
+
+
+def test_native_library_is_the_one_running():
+    from spinor_gpe_b200 import _lib
+    assert b'sm_100a' in _lib.lib().sgpe_version()
+    loaded = open('/proc/self/maps').read()
+    assert 'libsgpe.so' in loaded
+
+
+# ------------------------------------------------------------------ golden fixtures (the reference itself)
+@pytest.mark.parametrize('case', CASES)
+def test_golden_through_public_api(case):
+    """Replays every run of the fixture through PSpinor.imaginary()/real() -> TensorPropagator."""
+    z = np.load(os.path.join(GOLDEN, case + '.npz'))
+    spec = GOLDEN_SPECS[case]
+    ps = build_case(spec)
+    run_idx = 0
+    for run in spec['runs']:
+        if run[0] == 'call':
+            from oracle.gen_golden import _resolve
+            getattr(ps, run[1])(*_resolve(ps, run[2]))
+            continue
+        mode, dt, n = run
+        pre = f'r{run_idx}_'
+        from spinor_gpe_b200 import TensorPropagator
+        prop = TensorPropagator(ps, dt, n, 'cuda', time=mode)
+        prop.single_step(prop.dt_out, prop.eng_out)
+        assert rel(np.array([p.cpu().numpy() for p in prop.psik]), z[pre + 'psik_single_out']) < TOL_PSI
+        prop = TensorPropagator(ps, dt, n, 'cuda', time=mode)
+        prop.single_step(prop.dt_in, prop.eng_in)
+        assert rel(np.array([p.cpu().numpy() for p in prop.psik]), z[pre + 'psik_single_in']) < TOL_PSI
+        prop = TensorPropagator(ps, dt, n, 'cuda', time=mode)
+        prop.full_step()
+        assert rel(np.array([p.cpu().numpy() for p in prop.psik]), z[pre + 'psik_full1']) < TOL_PSI
+
+        fn = ps.imaginary if mode == 'imag' else ps.real
+        res, prop = fn(dt, n, 'cuda', is_sampling=True, n_samples=2)
+        assert rel(np.array(res.psik), z[pre + 'psik_final']) < TOL_PSI
+        assert rel(np.array(res.psi), z[pre + 'psi_final']) < TOL_PSI
+        np.testing.assert_allclose(res.pops['vals'], z[pre + 'pops_vals'], rtol=TOL_SCALAR)
+        np.testing.assert_allclose(res.pops['vals'].sum(axis=1), z[pre + 'pops_vals'].sum(axis=1), rtol=TOL_SCALAR)
+        np.testing.assert_array_equal(res.pops['times'], z[pre + 'pops_times'])
+        with np.load(res.sampled_path) as smp:
+            assert rel(smp['psiks'], z[pre + 'sampled_psiks']) < TOL_PSI
+            np.testing.assert_array_equal(smp['times'], z[pre + 'sampled_times'])
+        assert os.path.basename(res.sampled_path) == f"psik_sampled{run_idx + 1}-{ps.paths['folder']}.npz"
+        if (case, run_idx) in ENERGY_OK:
+            np.testing.assert_allclose(res.eng_final, z[pre + 'energy_identity_unwrap'], rtol=TOL_SCALAR)
+        run_idx += 1
+
+
+def test_tensor_tools_vectors_on_gpu():
+    from spinor_gpe_b200 import tensor_tools as tt
+    z = np.load(os.path.join(GOLDEN, 'tensor_tools_vectors.npz'))
+    for tag in 'ab':
+        psi = [torch.as_tensor(p).cuda() for p in z[f'{tag}_psi']]
+        dr = z[f'{tag}_dr']
+        got = lambda lst: np.array([t.cpu().numpy() for t in lst])   # noqa: E731
+        assert rel(got(tt.fft_2d(psi, dr)), z[f'{tag}_fft2']) < 1e-13
+        assert rel(got(tt.ifft_2d(psi, dr)), z[f'{tag}_ifft2']) < 1e-13
+        for ax in (0, 1):
+            assert rel(got(tt.fft_1d(psi, dr, ax)), z[f'{tag}_fft1_ax{ax}']) < 1e-13
+            assert rel(got(tt.ifft_1d(psi, dr, ax)), z[f'{tag}_ifft1_ax{ax}']) < 1e-13
+        pn, dn = tt.norm(psi, 0.125, 1234.5)
+        assert rel(got(pn), z[f'{tag}_norm_psi']) < 1e-13
+        assert rel(got(dn), z[f'{tag}_norm_dens']) < 1e-13
+        np.testing.assert_allclose(tt.calc_pops(psi, 0.125), z[f'{tag}_pops'], rtol=1e-12)
+
+
+def test_reference_fft_invariants_on_gpu():
+    """Port of the reference's own tests (spinor_gpe/tests/fft_func_tests.py:27-472): all-ones grids of
+    128..1024 points, delta_r=(1,1): round trip, 1-D x 1-D == 2-D, Parseval with vol_elem 4 pi^2 / N."""
+    from spinor_gpe_b200 import tensor_tools as tt
+    eps = 10 * 2.2e-16
+    for n in (128, 256, 512, 1024):
+        ones = [torch.ones((n, n), dtype=torch.complex128, device='cuda') for _ in range(2)]
+        dr = (1, 1)
+        back = tt.ifft_2d(tt.fft_2d(ones, dr), dr)
+        assert max(float((b - o).abs().max()) for b, o in zip(back, ones)) < eps
+        for first, second in ((0, 1), (1, 0)):
+            two = tt.fft_1d(tt.fft_1d(ones, dr, first), dr, second)
+            ref = tt.fft_2d(ones, dr)
+            assert max(float((a - b).abs().max()) for a, b in zip(two, ref)) < eps * n * n
+            two = tt.ifft_1d(tt.ifft_1d(ones, dr, first), dr, second)
+            ref = tt.ifft_2d(ones, dr)
+            assert max(float((a - b).abs().max()) for a, b in zip(two, ref)) < eps * n * n
+        n_r = tt.calc_atoms(ones, 1.0)
+        n_k = tt.calc_atoms(tt.fft_2d(ones, dr), 4 * np.pi ** 2 / (n * n))
+        assert abs(n_r - n_k) < eps * n * n
+
+
+# ------------------------------------------------------------------ oracle at larger sizes
+SEEDED = [
+    # mesh (nx, ny), mode, dt, steps, coupling kind, rotating frame, kin_shift
+    ((256, 256), 'imag', 1 / 50, 10, 'zero', True, False),
+    ((512, 256), 'real', 1 / 2000, 8, 'uniform', False, True),
+    ((256, 1024), 'imag', 1 / 50, 6, 'dense', True, True),
+    ((1024, 1024), 'real', 1 / 5000, 4, 'uniform', False, True),
+    ((2048, 128), 'real', 1 / 2000, 4, 'dense', False, True),
+    ((128, 2048), 'imag', 1 / 50, 4, 'none', True, False),
+    ((4096, 64), 'imag', 1 / 50, 3, 'uniform', True, True),
+    ((64, 4096), 'real', 1 / 2000, 3, 'zero', True, False),
+]
+
+
+@pytest.mark.parametrize('separable', [True, False])
+@pytest.mark.parametrize('mesh,mode,dt,n,cpl,rot,kshift', SEEDED)
+def test_against_oracle(mesh, mode, dt, n, cpl, rot, kshift, separable):
+    ps = make_ps(mesh, atom_num=1e4, r_sizes=(16, 16), g_sc={'uu': 1, 'dd': 0.98, 'ud': 1.02})
+    if cpl != 'none':
+        ps.coupling_setup(wavel=790.1e-9, kin_shift=kshift)
+        if kshift:
+            ps.shift_momentum(scale=0.7, frac=(0.3, 0.7))
+        if cpl == 'uniform':
+            ps.coupling_uniform(1.5 * ps.EL_recoil)
+        elif cpl == 'dense':
+            ps.coupling_grad(slope=0.3, offset=2.0, axis=1)
+        ps.detuning_grad(-3.0)
+    ps.rot_coupling = rot
+    rng = np.random.default_rng(99999)          # break the symmetry of the TF state with seeded noise
+    noise = [1 + 0.05 * (rng.standard_normal(p.shape) + 1j * rng.standard_normal(p.shape)) for p in ps.psik]
+    ps.psik = [p * q for p, q in zip(ps.psik, noise)]
+    want = orc.OraclePropagator(problem_of(ps), dt, mode).run(n)
+    res, prop = (ps.imaginary if mode == 'imag' else ps.real)(dt, n, 'cuda', separable=separable)
+    assert prop.separable == {'kin': separable, 'pot': separable}
+    assert rel(np.array(res.psik), want['psik']) < TOL_PSI
+    np.testing.assert_allclose(res.pops['vals'], want['pops_vals'], rtol=TOL_SCALAR)
+    assert abs(res.pops['vals'][-1].sum() / ps.atom_num - 1) < TOL_SCALAR
+
+
+def test_bitwise_reproducible_and_tile_width_independent():
+    """The same propagation repeated gives bit-identical states (fixed-order reductions, no float atomics);
+    the half-width column tiling changes only the summation order of the norms (<= 1e-14)."""
+    from spinor_gpe_b200 import TensorPropagator
+    ps = make_ps((512, 256), atom_num=1e4, r_sizes=(16, 16))
+    ps.coupling_setup(wavel=790.1e-9, kin_shift=True)
+    ps.coupling_uniform(1.5 * ps.EL_recoil)
+    ps.rot_coupling = False
+    outs = []
+    for rep in range(6):
+        prop = TensorPropagator(ps, 1 / 2000, 8, 'cuda', time='real')
+        if rep == 5:
+            prop._plan.set_option('col_tile', 2)
+        prop._plan.full_steps(8)
+        outs.append(torch.stack(prop.psik).clone())
+    for o in outs[1:5]:
+        assert torch.equal(o, outs[0])
+    assert float((outs[5] - outs[0]).abs().max() / outs[0].abs().max()) < 1e-13
+
+
+def test_complex64_against_oracle():
+    ps = make_ps((512, 512))
+    ps.coupling_setup(wavel=790.1e-9, kin_shift=True)
+    ps.coupling_uniform(1.0 * ps.EL_recoil)
+    want = orc.OraclePropagator(problem_of(ps), 1 / 50, 'imag').run(5)
+    res, _ = ps.imaginary(1 / 50, 5, 'cuda', precision='c64')
+    assert rel(np.array(res.psik), want['psik']) < TOL_PSI_C64
+    np.testing.assert_allclose(res.pops['vals'], want['pops_vals'], rtol=1e-5)
+
+
+def test_energy_of_ground_state_against_oracle():
+    """Energy parity where it is pinned (wrapped phase; smooth ground state, rotating frame)."""
+    ps = make_ps((256, 256), atom_num=1e2)
+    ps.coupling_setup(wavel=790.1e-9, kin_shift=False)
+    prob = problem_of(ps)
+    o = orc.OraclePropagator(prob, 1 / 50, 'imag')
+    want = o.run(30)
+    res, prop = ps.imaginary(1 / 50, 30, 'cuda')
+    np.testing.assert_allclose(res.eng_final, want['energy'], rtol=TOL_SCALAR)
+    # 'local' unwrapping agrees with the wrapped phase when there is nothing to unwrap
+    np.testing.assert_allclose(prop.eng_expect(None, unwrap='local'), want['energy'], rtol=1e-6)
+
+
+def test_batched_sweep_matches_individual_runs():
+    """Config-4 style: several trajectories (coupling x detuning sweep) in one plan == one by one."""
+    from spinor_gpe_b200 import _capi
+    from spinor_gpe_b200.plan import Plan
+    base = make_ps((128, 128), atom_num=1e4, r_sizes=(16, 16), g_sc={'uu': 1, 'dd': 0.995, 'ud': 0.995})
+    base.coupling_setup(wavel=804e-9, kin_shift=True)
+    base.shift_momentum(scale=0.6, frac=(0.5, 0.5))
+    omegas = [c * base.EL_recoil for c in (0.5, 2.0, 5.0)]
+    slopes = [-12.0, 0.0, 12.0]
+    pots, wants = [], []
+    for om, sl in zip(omegas, slopes):
+        base.coupling_uniform(om)
+        base.detuning_grad(sl)
+        pots.append(np.array(base.pot_eng_spin))
+        wants.append(orc.OraclePropagator(problem_of(base), 1 / 50, 'imag').run(4))
+    B = len(omegas)
+    pl = Plan(128, 128, B)
+    pl.set_grid(base.space['dr'][0], base.space['dr'][1], base.space['dv_r'], base.space['dv_k'], base.atom_num)
+    pl.set_interactions(base.g_sc['uu'], base.g_sc['dd'], base.g_sc['ud'])
+    pl.set_kinetic(base.kin_eng_spin[0], base.kin_eng_spin[1])
+    pot = np.stack(pots)                                   # (B, 2, ny, nx)
+    pl.set_potential(pot[:, 0].copy(), pot[:, 1].copy(), batched=True)
+    pl.set_coupling(_capi.SGPE_COUPLING_UNIFORM, omega=np.array(omegas))
+    pl.set_time('imag', 1 / 50)
+    pl.load(np.stack([np.array(base.psik)] * B))
+    pops = torch.zeros((B, 4, 2), dtype=torch.float64, device='cuda')
+    pl.full_steps(4, pops)
+    out = pl.store().cpu().numpy()
+    for b in range(B):
+        assert rel(out[b], wants[b]['psik']) < TOL_PSI
+        np.testing.assert_allclose(pops[b].cpu().numpy(), wants[b]['pops_vals'], rtol=TOL_SCALAR)
+
+
+def test_host_buffer_entry_point():
+    from spinor_gpe_b200 import _capi
+    from spinor_gpe_b200.plan import Plan
+    ps = make_ps((256, 256))
+    want = orc.OraclePropagator(problem_of(ps), 1 / 50, 'imag').run(3)
+    pl = Plan(256, 256, 1)
+    pl.set_grid(ps.space['dr'][0], ps.space['dr'][1], ps.space['dv_r'], ps.space['dv_k'], ps.atom_num)
+    pl.set_interactions(ps.g_sc['uu'], ps.g_sc['dd'], ps.g_sc['ud'])
+    pl.set_kinetic(ps.kin_eng_spin[0], ps.kin_eng_spin[1])
+    pl.set_potential(ps.pot_eng_spin[0], ps.pot_eng_spin[1], shared=True)
+    pl.set_coupling(_capi.SGPE_COUPLING_NONE)
+    pl.set_time('imag', 1 / 50)
+    out, pops = pl.run_host(np.array(ps.psik)[None], 3)
+    assert rel(out[0].numpy(), want['psik']) < TOL_PSI
+    np.testing.assert_allclose(pops[0].numpy(), want['pops_vals'], rtol=TOL_SCALAR)
+
+
+# ------------------------------------------------------------------ properties at full size
+@pytest.mark.parametrize('n', [2048, 4096])
+def test_full_size_fft_roundtrip_and_parseval(n):
+    from spinor_gpe_b200.plan import Plan
+    g = torch.Generator(device='cuda').manual_seed(99999)
+    psi = torch.randn((1, 2, n, n), dtype=torch.float64, device='cuda', generator=g) \
+        + 1j * torch.randn((1, 2, n, n), dtype=torch.float64, device='cuda', generator=g)
+    pl = Plan(n, n, 1)
+    dx = 16.0 / n
+    dvk = (2 * np.pi / 16.0) ** 2
+    pl.set_grid(dx, dx, dx * dx, dvk, 100.0)
+    psik = pl.fft2d(psi)
+    back = pl.fft2d(psik, inverse=True)
+    assert float((back - psi).abs().max()) < 1e-12
+    n_r = pl.sumsq(psi).sum().item() * dx * dx
+    n_k = pl.sumsq(psik).sum().item() * dvk
+    assert abs(n_r / n_k - 1) < 1e-12
+    # linearity of the transform
+    a, b = psi, torch.flip(psi, dims=(-1,))
+    lhs = pl.fft2d(2.0 * a + b)
+    rhs = 2.0 * psik + pl.fft2d(b)
+    assert float((lhs - rhs).abs().max() / rhs.abs().max()) < 1e-13
+
+
+def test_full_size_propagation_properties():
+    """2048^2 complex128 (the headline mesh): real-time evolution conserves the atom number and, with the
+    interactions off, a harmonic-oscillator eigenstate only acquires a phase; imaginary time renormalises
+    to N every step; the stationary state of imaginary time is a fixed point of further steps."""
+    ps = make_ps((2048, 2048), atom_num=1e2)
+    ps.coupling_setup(wavel=790.1e-9, kin_shift=False)
+    res, prop = ps.imaginary(1 / 50, 10, 'cuda')
+    np.testing.assert_allclose(res.pops['vals'].sum(axis=1), ps.atom_num, rtol=1e-12)
+    np.testing.assert_allclose(res.pops['vals'][:, 0], res.pops['vals'][:, 1], rtol=1e-9)   # symmetric spinor
+    res_r, _ = ps.real(1 / 5000, 10, 'cuda')
+    np.testing.assert_allclose(res_r.pops['vals'].sum(axis=1), ps.atom_num, rtol=1e-12)
+
+    # non-interacting oscillator ground state exp(-(x^2+y^2)/2): |psi| invariant under real-time steps
+    ps0 = make_ps((2048, 2048), atom_num=1e2, g_sc={'uu': 0.0, 'dd': 0.0, 'ud': 0.0})
+    x, y = ps0.space['x_mesh'], ps0.space['y_mesh']
+    gauss = np.exp(-(x ** 2 + y ** 2) / 2).astype(complex)
+    from spinor_gpe_b200 import tensor_tools as tt
+    psi, _ = tt.norm([gauss, gauss.copy()], ps0.space['dv_r'], ps0.atom_num)
+    ps0.psi, ps0.psik = psi, tt.fft_2d(psi, ps0.space['dr'])
+    res0, _ = ps0.real(1 / 1000, 10, 'cuda')
+    dens0 = np.abs(psi[0]) ** 2
+    assert np.abs(res0.dens[0] - dens0).max() / dens0.max() < 1e-6      # splitting error O(dt^4)
