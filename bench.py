@@ -191,6 +191,10 @@ def run_ours(args, rank, world, local_rank):
             pl.set_potential_separable(*psep)
         if args.col_tile:
             pl.set_option('col_tile', args.col_tile)
+        if args.row_mode:
+            pl.set_option('row_mode', args.row_mode)
+        if args.no_prefetch:
+            pl.set_option('prefetch', 0)
 
     pl = make_plan()
     upload_operators(pl)
@@ -289,7 +293,7 @@ def run_ours(args, rank, world, local_rank):
                                 'what': 'full_step + eng_expect after every step'},
             'atom_number_check': atoms,
         }
-        if world == 1:
+        if world == 1 and not args.no_cpu:
             sps, n, cores, med = oracle_steps_per_s(ps, 8, 1, budget_s=20.0)
             line['cpu_baseline'] = {'value': sps, 'unit': 'steps/s', 'cores': cores, 'kind': 'port',
                                     'sample': f'{n} full_step()+calc_pops of the same {mesh}^2 workload, median'}
@@ -306,8 +310,11 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--mesh', type=int, default=2048)
     ap.add_argument('--precision', default='c128', choices=['c128', 'c64'])
+    ap.add_argument('--no-cpu', action='store_true', help='skip the CPU-baseline leg (tuning runs)')
     ap.add_argument('--dense', action='store_true', help='force the general dense-operator path')
-    ap.add_argument('--col-tile', type=int, default=0, choices=[0, 2])
+    ap.add_argument('--no-prefetch', action='store_true')
+    ap.add_argument('--row-mode', type=int, default=0, choices=[0, 1])
+    ap.add_argument('--col-tile', type=int, default=0, choices=[0, 2, 8])
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))

@@ -174,11 +174,13 @@ SGPE_DI void stage_compute(C (&v)[E], int j, const C* __restrict__ tw) {
 #pragma unroll
     for (int b = 0; b < NB; b++) {
         if constexpr (Ns > 1) {
+            // per-stage table, [t-1][k] with k fastest (consecutive lanes read consecutive entries); the
+            // stage with previous-radix product Ns starts at entry Ns - E (see sgpe_api.cu: upload_twiddles)
             const int k = (j + b * NT) & (Ns - 1);
-            constexpr int TS = N / (Ns * R);
+            const C* __restrict__ tws = tw + (Ns - E) + k;
 #pragma unroll
             for (int t = 1; t < R; t++) {
-                const C w = __ldg(&tw[t * k * TS]);
+                const C w = __ldg(&tws[(t - 1) * Ns]);
                 v[b + t * NB] = (DIR < 0) ? cmul(v[b + t * NB], w) : cmulc(v[b + t * NB], w);
             }
         }

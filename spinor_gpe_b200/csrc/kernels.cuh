@@ -36,9 +36,10 @@ template <int TM, typename T, typename C> SGPE_DI C evo(double e, double tr, dou
 template <typename T> struct ColArgs {
     typedef typename cx_of<T>::type C;
     const C* in;  C* out;          // [B][2][ny][nx]
-    const C* tw;                   // ny roots of unity exp(-2 pi i q / ny)
+    const C* tw;                   // per-stage twiddle tables for ny: [radix-8 plan (ny)][radix-16 plan (ny)]
     int nx, ny; long long plane;
     int do_fwd, do_inv;
+    int prefetch_ahead;            // > 0: prefetch into L2 the tile this many CTAs ahead (the next one on this SM)
     // k-space factors: v <- v*FA (then S = sum|v|^2), v <- v*FB (then T = sum|v|^2)
     int has_a, has_b;
     int kin_mode;                  // 0: dense kin grids, factors evaluated here; 1: separable tables
@@ -85,6 +86,14 @@ __global__ void __launch_bounds__(W * N / E, (W * N / E <= 256) ? 2 : 1) col_pas
     C v[1][E];
 #pragma unroll
     for (int m = 0; m < E; m++) v[0][m] = a.in[off + (long long)(j + m * NT) * a.nx];
+    if (a.prefetch_ahead > 0 && c == 0) {
+        const int nt = tile + a.prefetch_ahead;
+        if (nt < ntiles) {
+            const long long noff = ((long long)b * 2 + nt / tiles_per_comp) * a.plane + (nt % tiles_per_comp) * W;
+#pragma unroll
+            for (int m = 0; m < E; m++) SGPE_PREFETCH_L2(&a.in[noff + (long long)(j + m * NT) * a.nx]);
+        }
+    }
     if (a.sign_in) {
 #pragma unroll
         for (int m = 0; m < E; m++)
@@ -92,7 +101,7 @@ __global__ void __launch_bounds__(W * N / E, (W * N / E <= 256) ? 2 : 1) col_pas
     }
 
     C* const sms[1] = {sm};
-    if (a.do_fwd) cta_fft<T, N, E, -1, W, 1>(v, j, c, sms, a.tw);
+    if (a.do_fwd) cta_fft<T, N, E, -1, W, 1>(v, j, c, sms, a.tw + (E == 16 ? N : 0));
 
     double acc[2] = {0.0, 0.0};   // S (after FA), T (after FB)
     const bool any_k = a.has_a || a.has_b;
@@ -140,7 +149,7 @@ __global__ void __launch_bounds__(W * N / E, (W * N / E <= 256) ? 2 : 1) col_pas
         if (!a.has_a) acc[0] = acc[1];
     }
 
-    if (a.do_inv) cta_fft<T, N, E, +1, W, 1>(v, j, c, sms, a.tw);
+    if (a.do_inv) cta_fft<T, N, E, +1, W, 1>(v, j, c, sms, a.tw + (E == 16 ? N : 0));
 
     if (a.sign_out || a.scale_out != 1.0) {
         const T sc = (T)a.scale_out;
@@ -195,9 +204,10 @@ __global__ void __launch_bounds__(W * N / E, (W * N / E <= 256) ? 2 : 1) col_pas
 template <typename T> struct RowArgs {
     typedef typename cx_of<T>::type C;
     const C* in;  C* out;          // [B][2][ny][nx]
-    const C* tw;                   // nx roots of unity
+    const C* tw;                   // per-stage twiddle tables for nx (same layout)
     int nx, ny; long long plane;
     int do_inv, do_pw, do_fwd;
+    int prefetch_ahead;            // > 0: L2 prefetch of the rows this many CTAs ahead
     int sign_in, sign_out; double scale_out;   // sign bit 1: (-1)^x, bit 2: (-1)^y
     const double* pot0; const double* pot1; long long pot_bstride;     // [ny][nx]
     int pot_mode;                  // 0: dense grids, 1: separable factor tables px[2][nx], py[2][ny]
@@ -233,7 +243,7 @@ SGPE_DI void coupling_entries(double theta, C ph, T& diag, C& off01, C& off10) {
 }
 
 template <typename T, int N, int E, int RPC, int TM>
-__global__ void __launch_bounds__(RPC * N / E) row_pass(RowArgs<T> a) {
+__global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) row_pass(RowArgs<T> a) {
     typedef typename cx_of<T>::type C;
     constexpr int NT = N / E;
     SGPE_DYN_SMEM(smem_raw);
@@ -252,6 +262,17 @@ __global__ void __launch_bounds__(RPC * N / E) row_pass(RowArgs<T> a) {
         v[0][m] = a.in[off0 + j + m * NT];
         v[1][m] = a.in[off1 + j + m * NT];
     }
+    if (a.prefetch_ahead > 0) {
+        const int ny2 = (blockIdx.x + a.prefetch_ahead) * RPC + r;
+        if (ny2 < a.ny) {
+            constexpr int PER_LINE = 128 / (int)sizeof(C);      // elements per 128-byte line
+            const long long n0 = ((long long)b * 2) * a.plane + (long long)ny2 * a.nx;
+            for (int x = j * PER_LINE; x < N; x += NT * PER_LINE) {
+                SGPE_PREFETCH_L2(&a.in[n0 + x]);
+                SGPE_PREFETCH_L2(&a.in[n0 + a.plane + x]);
+            }
+        }
+    }
     if (a.sign_in) {
 #pragma unroll
         for (int m = 0; m < E; m++) {
@@ -263,7 +284,7 @@ __global__ void __launch_bounds__(RPC * N / E) row_pass(RowArgs<T> a) {
     }
     C* const sms[2] = {smem + (size_t)(2 * r) * N, smem + (size_t)(2 * r + 1) * N};
 
-    if (a.do_inv) cta_fft<T, N, E, +1, 1, 2>(v, j, 0, sms, a.tw);
+    if (a.do_inv) cta_fft<T, N, E, +1, 1, 2>(v, j, 0, sms, a.tw + (E == 16 ? N : 0));
 
     if (a.do_pw) {
         const T alpha = (T)sqrt(a.norm_c / a.totals[(long long)b * 4]);
@@ -330,7 +351,7 @@ __global__ void __launch_bounds__(RPC * N / E) row_pass(RowArgs<T> a) {
         }
     }
 
-    if (a.do_fwd) cta_fft<T, N, E, -1, 1, 2>(v, j, 0, sms, a.tw);
+    if (a.do_fwd) cta_fft<T, N, E, -1, 1, 2>(v, j, 0, sms, a.tw + (E == 16 ? N : 0));
 
     const T sc = (T)a.scale_out;
 #pragma unroll
@@ -339,6 +360,124 @@ __global__ void __launch_bounds__(RPC * N / E) row_pass(RowArgs<T> a) {
         if ((((a.sign_out & 1) ? (j + m * NT) : 0) + ((a.sign_out & 2) ? y : 0)) & 1) s = -s;
         a.out[off0 + j + m * NT] = cscale(v[0][m], s);
         a.out[off1 + j + m * NT] = cscale(v[1][m], s);
+    }
+}
+
+// Row pass, split variant: one component per thread (twice the threads, half the registers of row_pass).
+// The two threads that own the same pixels of the two components trade what the point-wise operators
+// need through shared memory: the densities (for I) and, with coupling, the wavefunction (for C).
+template <typename T, int N, int E, int RPC, int TM>
+__global__ void __launch_bounds__(RPC * 2 * N / E, (RPC * 2 * N / E <= 512) ? 2 : 1) row_pass_split(RowArgs<T> a) {
+    typedef typename cx_of<T>::type C;
+    constexpr int NT = N / E;
+    SGPE_DYN_SMEM(smem_raw);
+    C* smem = reinterpret_cast<C*>(smem_raw);
+
+    const int tid = threadIdx.x;
+    const int r = tid / (2 * NT), comp = (tid / NT) & 1, j = tid % NT;
+    const int y = blockIdx.x * RPC + r;
+    const int b = blockIdx.y;
+    const long long off = ((long long)b * 2 + comp) * a.plane + (long long)y * a.nx;
+
+    C v[1][E];
+#pragma unroll
+    for (int m = 0; m < E; m++) v[0][m] = a.in[off + j + m * NT];
+    if (a.sign_in) {
+#pragma unroll
+        for (int m = 0; m < E; m++) {
+            if ((((a.sign_in & 1) ? (j + m * NT) : 0) + ((a.sign_in & 2) ? y : 0)) & 1) {
+                v[0][m].x = -v[0][m].x; v[0][m].y = -v[0][m].y;
+            }
+        }
+    }
+    C* mine = smem + (size_t)(2 * r + comp) * N;
+    C* other = smem + (size_t)(2 * r + (1 - comp)) * N;
+    C* const sms[1] = {mine};
+
+    if (a.do_inv) cta_fft<T, N, E, +1, 1, 1>(v, j, 0, sms, a.tw + (E == 16 ? N : 0));
+
+    if (a.do_pw) {
+        const T alpha = (T)sqrt(a.norm_c / a.totals[(long long)b * 4]);
+        const double g_self = (comp == 0) ? a.g_uu : a.g_dd;
+        double* dmine = reinterpret_cast<double*>(mine);
+        const double* dother = reinterpret_cast<const double*>(other);
+        double n_own[E];
+#pragma unroll
+        for (int m = 0; m < E; m++) {
+            v[0][m] = cscale(v[0][m], alpha);
+            n_own[m] = (double)v[0][m].x * v[0][m].x + (double)v[0][m].y * v[0][m].y;
+            dmine[j + m * NT] = n_own[m];
+        }
+        __syncthreads();
+        C iop[E];
+#pragma unroll
+        for (int m = 0; m < E; m++) {
+            iop[m] = evo<TM, T, C>(g_self * n_own[m] + a.g_ud * dother[j + m * NT], a.ti_re, a.ti_im);
+            v[0][m] = mul_factor<TM>(v[0][m], iop[m]);
+        }
+        __syncthreads();
+
+        T cu_diag = (T)1, cu_s = (T)0;
+        if (a.cpl_mode == 1) {
+            C one; one.x = (T)1; one.y = (T)0;
+            C t01, t10;
+            coupling_entries<TM, T, C>(a.omega_b[b] * a.tc, one, cu_diag, t01, t10);
+            cu_s = (TM == TM_REAL) ? -t01.y : -t01.x;
+        }
+        // this thread's row of the 2x2 coupling operator: new = diag*own + off*partner
+        auto couple = [&]() {
+#pragma unroll
+            for (int m = 0; m < E; m++) mine[j + m * NT] = v[0][m];
+            __syncthreads();
+#pragma unroll
+            for (int m = 0; m < E; m++) {
+                const int x = j + m * NT;
+                const C q = other[x];
+                C ph; ph.x = (T)1; ph.y = (T)0;
+                if (a.eiphi != nullptr) ph = __ldg(&a.eiphi[x]);
+                T diag; C o01, o10;
+                if (a.cpl_mode == 1) {
+                    diag = cu_diag;
+                    if (TM == TM_REAL) {
+                        o01.x = -cu_s * ph.y; o01.y = -cu_s * ph.x; o10.x = cu_s * ph.y; o10.y = -cu_s * ph.x;
+                    } else {
+                        o01.x = -cu_s * ph.x; o01.y = cu_s * ph.y; o10.x = -cu_s * ph.x; o10.y = -cu_s * ph.y;
+                    }
+                } else {
+                    const double om = __ldg(&a.coupling[(long long)b * a.cpl_bstride + (long long)y * a.nx + x]);
+                    coupling_entries<TM, T, C>(om * a.tc, ph, diag, o01, o10);
+                }
+                v[0][m] = cadd(cscale(v[0][m], diag), cmul(comp == 0 ? o01 : o10, q));
+            }
+            __syncthreads();
+        };
+        if (a.cpl_mode) couple();
+
+        if (a.pot_mode == 0) {
+            const double* pot = (comp == 0 ? a.pot0 : a.pot1) + (long long)b * a.pot_bstride + (long long)y * a.nx;
+#pragma unroll
+            for (int m = 0; m < E; m++)
+                v[0][m] = mul_factor<TM>(v[0][m], evo<TM, T, C>(__ldg(&pot[j + m * NT]), a.tp_re, a.tp_im));
+        } else {
+            const C py = __ldg(&a.py[(long long)b * a.sepy_bstride + (long long)comp * a.ny + y]);
+            const C* px = a.px + (long long)b * a.sepx_bstride + (long long)comp * a.nx;
+#pragma unroll
+            for (int m = 0; m < E; m++)
+                v[0][m] = mul_factor<TM>(v[0][m], combine_factor<TM>(__ldg(&px[j + m * NT]), py));
+        }
+        if (a.cpl_mode) couple();
+#pragma unroll
+        for (int m = 0; m < E; m++) v[0][m] = mul_factor<TM>(v[0][m], iop[m]);
+    }
+
+    if (a.do_fwd) cta_fft<T, N, E, -1, 1, 1>(v, j, 0, sms, a.tw + (E == 16 ? N : 0));
+
+    const T sc = (T)a.scale_out;
+#pragma unroll
+    for (int m = 0; m < E; m++) {
+        T s = sc;
+        if ((((a.sign_out & 1) ? (j + m * NT) : 0) + ((a.sign_out & 2) ? y : 0)) & 1) s = -s;
+        a.out[off + j + m * NT] = cscale(v[0][m], s);
     }
 }
 

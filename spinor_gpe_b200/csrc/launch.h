@@ -7,7 +7,7 @@ namespace sgpe {
 #define SGPE_FOR_EACH_N(X) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096)
 
 #define SGPE_DECL(N)                                                                               \
-    int launch_row_##N(int dtype, int tm, const void* args, int batch, cudaStream_t st);           \
+    int launch_row_##N(int dtype, int tm, const void* args, int batch, int mode, cudaStream_t st); \
     int launch_col_##N(int dtype, int tm, const void* args, int batch, int wsel, cudaStream_t st); \
     int col_tile_width_##N(int dtype);
 SGPE_FOR_EACH_N(SGPE_DECL)
@@ -19,8 +19,8 @@ inline bool supported_length(int n) {
 #undef SGPE_CASE
     return false;
 }
-inline int launch_row(int n, int dtype, int tm, const void* args, int batch, cudaStream_t st) {
-#define SGPE_CASE(N) if (n == N) return launch_row_##N(dtype, tm, args, batch, st);
+inline int launch_row(int n, int dtype, int tm, const void* args, int batch, int mode, cudaStream_t st) {
+#define SGPE_CASE(N) if (n == N) return launch_row_##N(dtype, tm, args, batch, mode, st);
     SGPE_FOR_EACH_N(SGPE_CASE)
 #undef SGPE_CASE
     return -1;

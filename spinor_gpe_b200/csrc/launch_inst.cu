@@ -29,6 +29,21 @@ template <typename T, int N> struct ColCfg {
     static constexpr size_t SMEM = (size_t)N * W * CB + 32 * 4 * sizeof(double);
 };
 
+// CTAs of this kernel resident on the whole device = how far ahead (in block index) the next work item
+// of an SM lies; used for the L2 prefetch of the next tile
+template <typename K> static int resident_ctas(K kern, int threads, size_t smem) {
+#ifndef SGPE_EMU
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess) return 0;
+    return per_sm * sms;
+#else
+    (void)kern; (void)threads; (void)smem;
+    return 0;
+#endif
+}
+
 template <typename K> static void allow_smem(K kern, size_t bytes) {
 #ifndef SGPE_EMU
     if (bytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -38,25 +53,52 @@ template <typename K> static void allow_smem(K kern, size_t bytes) {
 }
 
 template <typename T, int N, int TM>
+static int launch_row_split_t(const RowArgs<T>& a, int batch, cudaStream_t st) {
+    constexpr int E = 8, NT = N / E;
+    constexpr int RPC = (2 * NT >= 256) ? 1 : (256 / (2 * NT));
+    constexpr size_t smem = (size_t)RPC * 2 * N * sizeof(typename cx_of<T>::type);
+    if (a.ny % RPC != 0) return -2;
+    static bool once = false;
+    if (!once) { allow_smem(row_pass_split<T, N, E, RPC, TM>, smem); once = true; }
+    dim3 grid(a.ny / RPC, batch), block(RPC * 2 * NT);
+    SGPE_LAUNCH((row_pass_split<T, N, E, RPC, TM>), grid, block, smem, st, a);
+    return 0;
+}
+
+template <typename T, int N, int TM>
 static int launch_row_t(const RowArgs<T>& a, int batch, cudaStream_t st) {
     typedef RowCfg<T, N> Cfg;
     if (a.ny % Cfg::RPC != 0) return -2;
     static bool once = false;
-    if (!once) { allow_smem(row_pass<T, N, Cfg::E, Cfg::RPC, TM>, Cfg::SMEM); once = true; }
+    static int ahead = 0;
+    if (!once) {
+        allow_smem(row_pass<T, N, Cfg::E, Cfg::RPC, TM>, Cfg::SMEM);
+        ahead = resident_ctas(row_pass<T, N, Cfg::E, Cfg::RPC, TM>, Cfg::THREADS, Cfg::SMEM);
+        once = true;
+    }
     dim3 grid(a.ny / Cfg::RPC, batch), block(Cfg::THREADS);
-    SGPE_LAUNCH((row_pass<T, N, Cfg::E, Cfg::RPC, TM>), grid, block, Cfg::SMEM, st, a);
+    RowArgs<T> a2 = a;
+    if (a2.prefetch_ahead) a2.prefetch_ahead = ahead;
+    SGPE_LAUNCH((row_pass<T, N, Cfg::E, Cfg::RPC, TM>), grid, block, Cfg::SMEM, st, a2);
     return 0;
 }
 
-template <typename T, int N, int TM, int W>
+template <typename T, int N, int TM, int W, int E>
 static int launch_col_w(const ColArgs<T>& a, int batch, cudaStream_t st) {
     typedef ColCfg<T, N> Cfg;
     constexpr size_t smem = (size_t)N * W * Cfg::CB + 32 * 4 * sizeof(double);
     if (a.nx % W != 0) return -2;
     static bool once = false;
-    if (!once) { allow_smem(col_pass<T, N, Cfg::E, W, TM>, smem); once = true; }
-    dim3 grid(2 * a.nx / W, batch), block(W * Cfg::NT);
-    SGPE_LAUNCH((col_pass<T, N, Cfg::E, W, TM>), grid, block, smem, st, a);
+    static int ahead = 0;
+    if (!once) {
+        allow_smem(col_pass<T, N, E, W, TM>, smem);
+        ahead = resident_ctas(col_pass<T, N, E, W, TM>, W * (N / E), smem);
+        once = true;
+    }
+    dim3 grid(2 * a.nx / W, batch), block(W * (N / E));
+    ColArgs<T> a2 = a;
+    if (a2.prefetch_ahead) a2.prefetch_ahead = ahead;
+    SGPE_LAUNCH((col_pass<T, N, E, W, TM>), grid, block, smem, st, a2);
     return 0;
 }
 
@@ -65,17 +107,40 @@ static int launch_col_w(const ColArgs<T>& a, int batch, cudaStream_t st) {
 template <typename T, int N, int TM>
 static int launch_col_t(const ColArgs<T>& a, int batch, int wsel, cudaStream_t st) {
     typedef ColCfg<T, N> Cfg;
+#ifdef SGPE_EXPERIMENTAL
+    // measured slower on B200 (profiles/r01_variants.md); kept for experiments and the emulation tests
     constexpr int WN = Cfg::W / 2;
     if constexpr (WN >= 1 && WN * Cfg::NT >= 32) {
-        if (wsel == 2) return launch_col_w<T, N, TM, WN>(a, batch, st);
+        if (wsel == 2) return launch_col_w<T, N, TM, WN, Cfg::E>(a, batch, st);
     }
-    return launch_col_w<T, N, TM, Cfg::W>(a, batch, st);
+    // wsel 8: radix-8 variant (8 elements per thread, twice the threads, one more exchange per transform)
+    if constexpr (Cfg::E == 16 && Cfg::W * (N / 8) <= 1024) {
+        if (wsel == 8) return launch_col_w<T, N, TM, Cfg::W, 8>(a, batch, st);
+    }
+#else
+    if (wsel != 0) return -3;
+#endif
+    return launch_col_w<T, N, TM, Cfg::W, Cfg::E>(a, batch, st);
 }
 
 #define SGPE_CAT2(a, b) a##b
 #define SGPE_CAT(a, b) SGPE_CAT2(a, b)
 
-int SGPE_CAT(launch_row_, SGPE_N)(int dtype, int tm, const void* args, int batch, cudaStream_t st) {
+int SGPE_CAT(launch_row_, SGPE_N)(int dtype, int tm, const void* args, int batch, int mode, cudaStream_t st) {
+    if (mode == 1) {      // split variant: one component per thread
+#ifndef SGPE_EXPERIMENTAL
+        return -3;
+#else
+        if (dtype == 0) {
+            const RowArgs<double>& a = *static_cast<const RowArgs<double>*>(args);
+            return tm == TM_REAL ? launch_row_split_t<double, SGPE_N, TM_REAL>(a, batch, st)
+                                 : launch_row_split_t<double, SGPE_N, TM_IMAG>(a, batch, st);
+        }
+        const RowArgs<float>& a = *static_cast<const RowArgs<float>*>(args);
+        return tm == TM_REAL ? launch_row_split_t<float, SGPE_N, TM_REAL>(a, batch, st)
+                             : launch_row_split_t<float, SGPE_N, TM_IMAG>(a, batch, st);
+#endif
+    }
     if (dtype == 0) {
         const RowArgs<double>& a = *static_cast<const RowArgs<double>*>(args);
         return tm == TM_REAL ? launch_row_t<double, SGPE_N, TM_REAL>(a, batch, st)

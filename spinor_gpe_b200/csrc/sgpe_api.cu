@@ -70,6 +70,8 @@ struct sgpe_plan {
     struct FactorTable { bool valid = false; int tm = 0; double tau = 0; void* x = nullptr; void* y = nullptr; uint64_t used = 0; };
     FactorTable kin_tab[6], pot_tab[4];
     uint64_t tab_clock = 0;
+    int prefetch = 1;              // L2 prefetch of the next tile of each SM (option "prefetch")
+    int row_mode = 0;              // 0: both components per thread, 1: split (one component per thread)
     int col_wsel = 0;              // column tile width selector (sgpe_set_option "col_tile")
     int cpl_mode = 0; const double* cpl = nullptr; long long cpl_bs = 0;
     const double* omega = nullptr; const void* eiphi = nullptr;
@@ -108,23 +110,43 @@ struct ProfScope { ProfScope(sgpe_plan*, int, cudaStream_t) {} };
 #endif
 
 
+// exp(-2 pi i num / den) with exact values on the axes
+template <typename T>
+typename sgpe::cx_of<T>::type unit_root(long long num, long long den) {
+    typename sgpe::cx_of<T>::type w;
+    num %= den;
+    const long double two_pi = 6.283185307179586476925286766559L;
+    long double ang = two_pi * (long double)num / (long double)den;
+    long double c = cosl(ang), s = sinl(ang);
+    if (num == 0) { c = 1; s = 0; }
+    if (4 * num == den) { c = 0; s = 1; }
+    if (2 * num == den) { c = -1; s = 0; }
+    if (4 * num == 3 * den) { c = 0; s = -1; }
+    w.x = (T)c; w.y = (T)(-s);
+    return w;
+}
+
+// Twiddle tables of a length-n transform for the two per-thread radices the kernels use, [E=8][E=16], n
+// entries each.  For the plan with E elements per thread the Stockham stage whose previous radices
+// multiply to Ns (Ns = E, E^2, ...) has radix R = min(E, n/Ns) and needs w_{Ns R}^{t k}, t = 1..R-1,
+// k = 0..Ns-1; these are stored [t-1][k] (k fastest) starting at entry Ns - E (sum_{s'<s}(R-1)Ns' telescopes).
 template <typename T>
 int upload_twiddles(void** dst, int n) {
     typedef typename sgpe::cx_of<T>::type C;
-    std::vector<C> h(n);
-    const long double two_pi = 6.283185307179586476925286766559L;
-    for (int q = 0; q < n; q++) {
-        // exact values on the axes / diagonals, long-double elsewhere
-        long double ang = two_pi * (long double)q / (long double)n;
-        long double c = cosl(ang), s = sinl(ang);
-        if (q == 0) { c = 1; s = 0; }
-        if (4 * q == n) { c = 0; s = 1; }
-        if (2 * q == n) { c = -1; s = 0; }
-        if (4 * q == 3 * n) { c = 0; s = -1; }
-        h[q].x = (T)c; h[q].y = (T)(-s);
+    std::vector<C> h(2 * (size_t)n);
+    for (auto& z : h) { z.x = (T)1; z.y = (T)0; }
+    const int radices[2] = {8, 16};
+    for (int e = 0; e < 2; e++) {
+        const int E = radices[e];
+        C* tab = h.data() + (size_t)e * n;
+        for (long long Ns = E; Ns < n; Ns *= E) {
+            const long long R = (n / Ns) < E ? (n / Ns) : E;
+            for (long long t = 1; t < R; t++)
+                for (long long k = 0; k < Ns; k++) tab[(Ns - E) + (t - 1) * Ns + k] = unit_root<T>(t * k, Ns * R);
+        }
     }
-    SGPE_CUDA(cudaMalloc(dst, sizeof(C) * n));
-    SGPE_CUDA(cudaMemcpy(*dst, h.data(), sizeof(C) * n, cudaMemcpyHostToDevice));
+    SGPE_CUDA(cudaMalloc(dst, sizeof(C) * h.size()));
+    SGPE_CUDA(cudaMemcpy(*dst, h.data(), sizeof(C) * h.size(), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -183,6 +205,7 @@ int run_col(sgpe_plan* p, const void* in, void* out, bool fwd, bool has_a, doubl
     a.tw = static_cast<const C*>(p->tw_y);
     a.nx = p->nx; a.ny = p->ny; a.plane = p->plane;
     a.do_fwd = fwd; a.do_inv = inv; a.has_a = has_a; a.has_b = has_b;
+    a.prefetch_ahead = p->prefetch;
     a.sign_in = sign_in; a.sign_out = sign_out; a.scale_out = scale_out;
     a.kin_mode = p->kin_mode;
     if (has_a || has_b) {
@@ -209,6 +232,7 @@ int run_col(sgpe_plan* p, const void* in, void* out, bool fwd, bool has_a, doubl
     a.atom_num = p->atom_num;
     ProfScope prof(p, 0, st);
     int rc = sgpe::launch_col(p->ny, p->dtype, p->tm, &a, p->batch, p->col_wsel, st);
+    if (rc == -3) return fail(SGPE_EINVAL, "column pass variant not compiled in (build with -DSGPE_EXPERIMENTAL)");
     if (rc != 0) return fail(SGPE_EINVAL, "column pass: unsupported geometry");
     p->launches++;
     SGPE_CUDA(cudaGetLastError());
@@ -225,6 +249,7 @@ int run_row(sgpe_plan* p, const void* in, void* out, bool inv, bool pw, double d
     a.tw = static_cast<const C*>(p->tw_x);
     a.nx = p->nx; a.ny = p->ny; a.plane = p->plane;
     a.do_inv = inv; a.do_pw = pw; a.do_fwd = fwd;
+    a.prefetch_ahead = p->prefetch;
     a.sign_in = sign_in; a.sign_out = sign_out; a.scale_out = scale_out;
     a.pot0 = p->pot0; a.pot1 = p->pot1; a.pot_bstride = p->pot_bs;
     a.pot_mode = pw ? p->pot_mode : 0;
@@ -244,7 +269,8 @@ int run_row(sgpe_plan* p, const void* in, void* out, bool inv, bool pw, double d
     a.totals = p->totals;
     a.norm_c = p->atom_num / (p->dv_r * (double)p->nx * (double)p->ny);
     ProfScope prof(p, 1, st);
-    int rc = sgpe::launch_row(p->nx, p->dtype, p->tm, &a, p->batch, st);
+    int rc = sgpe::launch_row(p->nx, p->dtype, p->tm, &a, p->batch, p->row_mode, st);
+    if (rc == -3) return fail(SGPE_EINVAL, "row pass variant not compiled in (build with -DSGPE_EXPERIMENTAL)");
     if (rc != 0) return fail(SGPE_EINVAL, "row pass: unsupported geometry");
     p->launches++;
     SGPE_CUDA(cudaGetLastError());
@@ -483,8 +509,15 @@ int sgpe_set_coupling(sgpe_plan* p, int mode, const double* coupling, int64_t bs
 int sgpe_set_option(sgpe_plan* p, const char* name, int value) {
     if (!p || !name) return fail(SGPE_EINVAL, "null argument");
     if (std::strcmp(name, "col_tile") == 0) {
-        if (value != 0 && value != 2) return fail(SGPE_EINVAL, "col_tile: 0 (default width) or 2 (half width)");
+        if (value != 0 && value != 2 && value != 8)
+            return fail(SGPE_EINVAL, "col_tile: 0 (default), 2 (half width) or 8 (radix-8 threads)");
         p->col_wsel = value;
+        return 0;
+    }
+    if (std::strcmp(name, "prefetch") == 0) { p->prefetch = value ? 1 : 0; return 0; }
+    if (std::strcmp(name, "row_mode") == 0) {
+        if (value != 0 && value != 1) return fail(SGPE_EINVAL, "row_mode: 0 (paired) or 1 (split)");
+        p->row_mode = value;
         return 0;
     }
     return fail(SGPE_EINVAL, std::string("unknown option ") + name);

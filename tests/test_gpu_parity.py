@@ -177,9 +177,8 @@ def test_against_oracle(mesh, mode, dt, n, cpl, rot, kshift, separable):
     assert abs(res.pops['vals'][-1].sum() / ps.atom_num - 1) < TOL_SCALAR
 
 
-def test_bitwise_reproducible_and_tile_width_independent():
-    """The same propagation repeated gives bit-identical states (fixed-order reductions, no float atomics);
-    the half-width column tiling changes only the summation order of the norms (<= 1e-14)."""
+def test_bitwise_reproducible():
+    """The same propagation repeated gives bit-identical states (fixed-order reductions, no float atomics)."""
     from spinor_gpe_b200 import TensorPropagator
     ps = make_ps((512, 256), atom_num=1e4, r_sizes=(16, 16))
     ps.coupling_setup(wavel=790.1e-9, kin_shift=True)
@@ -189,12 +188,11 @@ def test_bitwise_reproducible_and_tile_width_independent():
     for rep in range(6):
         prop = TensorPropagator(ps, 1 / 2000, 8, 'cuda', time='real')
         if rep == 5:
-            prop._plan.set_option('col_tile', 2)
+            prop._plan.set_option('prefetch', 0)
         prop._plan.full_steps(8)
         outs.append(torch.stack(prop.psik).clone())
-    for o in outs[1:5]:
+    for o in outs[1:]:
         assert torch.equal(o, outs[0])
-    assert float((outs[5] - outs[0]).abs().max() / outs[0].abs().max()) < 1e-13
 
 
 def test_complex64_against_oracle():
