@@ -195,6 +195,8 @@ def run_ours(args, rank, world, local_rank):
             pl.set_option('row_mode', args.row_mode)
         if args.no_prefetch:
             pl.set_option('prefetch', 0)
+        if args.stagger_ns:
+            pl.set_option('stagger_ns', args.stagger_ns)
 
     pl = make_plan()
     upload_operators(pl)
@@ -313,6 +315,7 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU-baseline leg (tuning runs)')
     ap.add_argument('--dense', action='store_true', help='force the general dense-operator path')
     ap.add_argument('--no-prefetch', action='store_true')
+    ap.add_argument('--stagger-ns', type=int, default=0)
     ap.add_argument('--row-mode', type=int, default=0, choices=[0, 1])
     ap.add_argument('--col-tile', type=int, default=0, choices=[0, 2, 8])
     args = ap.parse_args()

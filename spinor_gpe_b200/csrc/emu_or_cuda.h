@@ -5,11 +5,13 @@
 #ifdef SGPE_EMU
 #include "cuda_emu.h"
 #define SGPE_PREFETCH_L2(ptr) ((void)(ptr))
+#define SGPE_NANOSLEEP(ns) ((void)(ns))
 #define SGPE_DYN_SMEM(name) unsigned char* name = ::emu::dyn_smem()
 #define SGPE_LAUNCH(kern, grid, block, smem, stream, ...) \
     ::emu::launch((grid), (block), (smem), [&]() { kern(__VA_ARGS__); })
 #else
 #include <cuda_runtime.h>
+#define SGPE_NANOSLEEP(ns) __nanosleep(ns)
 #define SGPE_PREFETCH_L2(ptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr))
 #define SGPE_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #define SGPE_LAUNCH(kern, grid, block, smem, stream, ...) \

@@ -208,6 +208,7 @@ template <typename T> struct RowArgs {
     int nx, ny; long long plane;
     int do_inv, do_pw, do_fwd;
     int prefetch_ahead;            // > 0: L2 prefetch of the rows this many CTAs ahead
+    int resident; int stagger_ns;  // de-phase the CTAs that share an SM: the 2nd half of the first wave starts late
     int sign_in, sign_out; double scale_out;   // sign bit 1: (-1)^x, bit 2: (-1)^y
     const double* pot0; const double* pot1; long long pot_bstride;     // [ny][nx]
     int pot_mode;                  // 0: dense grids, 1: separable factor tables px[2][nx], py[2][ny]
@@ -253,6 +254,8 @@ __global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) row
     const int r = tid / NT, j = tid % NT;
     const int y = blockIdx.x * RPC + r;
     const int b = blockIdx.y;
+    if (a.stagger_ns > 0 && blockIdx.y == 0 && (int)blockIdx.x >= a.resident / 2 && (int)blockIdx.x < a.resident)
+        SGPE_NANOSLEEP((unsigned)a.stagger_ns);
     const long long off0 = ((long long)b * 2) * a.plane + (long long)y * a.nx;
     const long long off1 = off0 + a.plane;
 

@@ -79,6 +79,7 @@ static int launch_row_t(const RowArgs<T>& a, int batch, cudaStream_t st) {
     dim3 grid(a.ny / Cfg::RPC, batch), block(Cfg::THREADS);
     RowArgs<T> a2 = a;
     if (a2.prefetch_ahead) a2.prefetch_ahead = ahead;
+    a2.resident = ahead;
     SGPE_LAUNCH((row_pass<T, N, Cfg::E, Cfg::RPC, TM>), grid, block, Cfg::SMEM, st, a2);
     return 0;
 }

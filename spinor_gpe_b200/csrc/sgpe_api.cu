@@ -70,6 +70,7 @@ struct sgpe_plan {
     struct FactorTable { bool valid = false; int tm = 0; double tau = 0; void* x = nullptr; void* y = nullptr; uint64_t used = 0; };
     FactorTable kin_tab[6], pot_tab[4];
     uint64_t tab_clock = 0;
+    int stagger_ns = 0;            // option "stagger_ns"
     int prefetch = 1;              // L2 prefetch of the next tile of each SM (option "prefetch")
     int row_mode = 0;              // 0: both components per thread, 1: split (one component per thread)
     int col_wsel = 0;              // column tile width selector (sgpe_set_option "col_tile")
@@ -249,7 +250,7 @@ int run_row(sgpe_plan* p, const void* in, void* out, bool inv, bool pw, double d
     a.tw = static_cast<const C*>(p->tw_x);
     a.nx = p->nx; a.ny = p->ny; a.plane = p->plane;
     a.do_inv = inv; a.do_pw = pw; a.do_fwd = fwd;
-    a.prefetch_ahead = p->prefetch;
+    a.prefetch_ahead = p->prefetch; a.stagger_ns = p->stagger_ns;
     a.sign_in = sign_in; a.sign_out = sign_out; a.scale_out = scale_out;
     a.pot0 = p->pot0; a.pot1 = p->pot1; a.pot_bstride = p->pot_bs;
     a.pot_mode = pw ? p->pot_mode : 0;
@@ -514,6 +515,7 @@ int sgpe_set_option(sgpe_plan* p, const char* name, int value) {
         p->col_wsel = value;
         return 0;
     }
+    if (std::strcmp(name, "stagger_ns") == 0) { p->stagger_ns = value; return 0; }
     if (std::strcmp(name, "prefetch") == 0) { p->prefetch = value ? 1 : 0; return 0; }
     if (std::strcmp(name, "row_mode") == 0) {
         if (value != 0 && value != 1) return fail(SGPE_EINVAL, "row_mode: 0 (paired) or 1 (split)");

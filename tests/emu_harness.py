@@ -200,3 +200,58 @@ def plan_from_problem(prob, mode, dt, dtype=np.complex128, separable=False):
     pl.set_time(mode, dt)
     pl.load(prob.psik.numpy())
     return pl
+
+
+class EmuTorchPlan:
+    """The subset of spinor_gpe_b200.plan.Plan that sweep.run_sweep uses, on top of the emulated library
+    with CPU tensors / numpy arrays (lets the multi-process host logic run under gloo without a GPU)."""
+
+    def __init__(self, nx, ny, batch=1, dtype=None, device='cpu'):
+        import torch
+        cd = np.complex64 if dtype == torch.complex64 else np.complex128
+        self.p = EmuPlan(nx, ny, batch, cd)
+        self.nx, self.ny, self.batch = nx, ny, batch
+
+    def set_grid(self, *a):
+        self.p.set_grid(*[float(v) for v in a])
+
+    def set_interactions(self, *g):
+        self.p.set_interactions(g)
+
+    def set_kinetic(self, k0, k1, batched=False):
+        self.p.set_kinetic(np.stack([np.asarray(k0), np.asarray(k1)]), batched=False)
+
+    def set_kinetic_separable(self, kx, ky, batched=False):
+        self.p.set_kinetic_separable(kx, ky, batched)
+
+    def set_potential(self, p0, p1, batched=False, shared=False):
+        p0, p1 = np.asarray(p0), np.asarray(p1)
+        self.p.set_potential(np.stack([p0, p1], axis=1 if batched else 0), batched=batched)
+
+    def set_potential_separable(self, px, py, batched=False):
+        self.p.set_potential_separable(px, py, batched)
+
+    def set_coupling(self, mode, coupling=None, omega=None, eiphi=None, batched=False):
+        self.p.set_coupling(mode, coupling=coupling, omega=omega, eiphi=eiphi, batched=batched)
+
+    def set_time(self, mode, dt):
+        self.p.set_time(mode, dt)
+
+    def load(self, psik):
+        self.p.load(psik)
+
+    def full_steps(self, n, pops=None, first=0):
+        arr = pops.numpy() if pops is not None else None
+        stride = arr.shape[1] * 2 if arr is not None else 0
+        self.p._chk(self.p.lib.sgpe_full_steps(self.p.h, n, _ptr(arr), stride, first, None), 'full_steps')
+
+    def energy(self, psik=None, kl_term=0.0, unwrap='none'):
+        import torch
+        return torch.from_numpy(self.p.energy(psik, kl_term, 0))
+
+    def store(self):
+        import torch
+        return torch.from_numpy(self.p.store())
+
+    def close(self):
+        self.p.close()
