@@ -118,6 +118,28 @@ int sgpe_normalise(sgpe_plan* p, const void* in_dev, void* out_dev, double vol, 
 int sgpe_energy(sgpe_plan* p, const void* psik_dev, int unwrap_mode, double kl_term, double* out_dev,
                 sgpe_stream st);
 
+/* ---- Slab-decomposed (multi-GPU) transforms: local building blocks.  The grid is split by rows over P
+ * ranks; the caller owns the buffers and the collectives (all-to-all transpose, all-reduce of the norm
+ * sums) — spinor_gpe_b200/slab.py does it with torch.distributed over NCCL.  The reference has no
+ * counterpart (single device only, benchmarks/benchmark_prop.py:86-88 stops at out-of-memory).
+ *  sgpe_pass_rows   : row_pass on a local [2][ny_local][nx] buffer of a plan(nx, ny_local): iFFT_x, norm with
+ *                     the GLOBAL sum totals_dev[0] and global point count, I C P C I, FFT_x
+ *                     (tensor_propagator.py:243-269).
+ *  sgpe_pass_klines : the k-space junction on a transposed local buffer [2][nlines][len] of a
+ *                     plan(nx = len, ny = nlines): [FFT] FA sums FB sums [iFFT] along the contiguous lines
+ *                     (tensor_propagator.py:270-271 and :242 of the next sub-step); the plan's kinetic operator
+ *                     is given line-major (dense [nlines][len], or separable kin_x <-> position, kin_y <-> line);
+ *                     sums_dev[3] receives the local T, S0, S1.
+ *  sgpe_slab_pack   : [2][lines][P*chunk] -> [P][2][lines][chunk]    (send buffer of the all-to-all)
+ *  sgpe_slab_unpack : [P][2][h][w] -> [2][w][P*h], transposing every block (receive side). */
+int sgpe_pass_rows(sgpe_plan* p, void* buf_dev, double dt_sub, const double* totals_dev, double global_points,
+                   sgpe_stream st);
+int sgpe_pass_klines(sgpe_plan* p, void* buf_dev, int do_fwd, int has_a, double tau_a, int has_b, double tau_b,
+                     int do_inv, double* sums_dev, sgpe_stream st);
+int sgpe_slab_pack(sgpe_plan* p, const void* in_dev, void* out_dev, int lines, int nranks, int chunk, sgpe_stream st);
+int sgpe_slab_unpack(sgpe_plan* p, const void* in_dev, void* out_dev, int nranks, int block_h, int block_w,
+                     sgpe_stream st);
+
 /* The same path with HOST buffers (pageable or pinned): H2D of the state, n full steps, D2H of the
  * final normalised state and the populations [batch][n][2]; synchronises the stream before returning.
  * Equivalent of PSpinor.imaginary()/real() minus file output (pspinor.py:912-925). */

@@ -30,6 +30,11 @@ PROTOTYPES = {
     'sgpe_sumsq': (C.c_int, [c_plan, c_dptr, c_dptr, c_stream]),
     'sgpe_normalise': (C.c_int, [c_plan, c_dptr, c_dptr, C.c_double, c_stream]),
     'sgpe_energy': (C.c_int, [c_plan, c_dptr, C.c_int, C.c_double, c_dptr, c_stream]),
+    'sgpe_pass_rows': (C.c_int, [c_plan, c_dptr, C.c_double, c_dptr, C.c_double, c_stream]),
+    'sgpe_pass_klines': (C.c_int, [c_plan, c_dptr, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int, c_dptr,
+                                   c_stream]),
+    'sgpe_slab_pack': (C.c_int, [c_plan, c_dptr, c_dptr, C.c_int, C.c_int, C.c_int, c_stream]),
+    'sgpe_slab_unpack': (C.c_int, [c_plan, c_dptr, c_dptr, C.c_int, C.c_int, C.c_int, c_stream]),
     'sgpe_run_host': (C.c_int, [c_plan, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, c_stream]),
     'sgpe_step_accounting': (C.c_int, [c_plan, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     'sgpe_profile_begin': (C.c_int, [c_plan]),

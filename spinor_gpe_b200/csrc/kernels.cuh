@@ -484,6 +484,155 @@ __global__ void __launch_bounds__(RPC * 2 * N / E, (RPC * 2 * N / E <= 512) ? 2 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Slab (distributed) mode.  The grid is split by rows over P ranks; a 2-D transform is x-lines locally,
+// an all-to-all transpose, y-lines locally.  In the transposed layout the k-space junction
+// (FFT_y, K_a, sums, K_b, sums, iFFT_y) runs on CONTIGUOUS lines: kline_pass is the column pass of the
+// single-GPU path re-expressed on rows (both components of one line per CTA, like row_pass).
+// Array seen by this kernel: [2][nlines][N]; `nx` of the args = N (line length), `ny` = nlines.
+template <typename T> struct KLineArgs {
+    typedef typename cx_of<T>::type C;
+    const C* in; C* out; const C* tw;
+    int nx, ny; long long plane;
+    int do_fwd, do_inv, has_a, has_b;
+    int kin_mode;                                    // 0 dense (grids given line-major), 1 separable
+    const double* kin0; const double* kin1;          // dense: [nlines][N]
+    double ka_re, ka_im, kb_re, kb_im;
+    const C* la; const C* pa; const C* lb; const C* pb;   // separable: per-line [2][nlines], per-position [2][N]
+    double* partials; unsigned* counter; double* sums;    // sums: [3] = T, S0, S1 of the LOCAL slab
+};
+
+template <typename T, int N, int E, int RPC, int TM>
+__global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) kline_pass(KLineArgs<T> a) {
+    typedef typename cx_of<T>::type C;
+    constexpr int NT = N / E;
+    SGPE_DYN_SMEM(smem_raw);
+    C* smem = reinterpret_cast<C*>(smem_raw);
+    double* red = reinterpret_cast<double*>(smem_raw + sizeof(C) * (size_t)RPC * 2 * N);
+
+    const int tid = threadIdx.x;
+    const int r = tid / NT, j = tid % NT;
+    const int line = blockIdx.x * RPC + r;
+    const long long off0 = (long long)line * a.nx, off1 = off0 + a.plane;
+
+    C v[2][E];
+#pragma unroll
+    for (int m = 0; m < E; m++) {
+        v[0][m] = a.in[off0 + j + m * NT];
+        v[1][m] = a.in[off1 + j + m * NT];
+    }
+    C* const sms[2] = {smem + (size_t)(2 * r) * N, smem + (size_t)(2 * r + 1) * N};
+    if (a.do_fwd) cta_fft<T, N, E, -1, 1, 2>(v, j, 0, sms, a.tw + (E == 16 ? N : 0));
+
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};      // S0, T0, S1, T1
+    if (a.has_a || a.has_b) {
+#pragma unroll
+        for (int comp = 0; comp < 2; comp++) {
+            C la, lb;
+            la.x = (T)1; la.y = (T)0; lb = la;
+            if (a.kin_mode == 1) {
+                if (a.has_a) la = __ldg(&a.la[(long long)comp * a.ny + line]);
+                if (a.has_b) lb = __ldg(&a.lb[(long long)comp * a.ny + line]);
+            }
+            const double* kin = (comp == 0 ? a.kin0 : a.kin1);
+#pragma unroll
+            for (int m = 0; m < E; m++) {
+                const int pos = j + m * NT;
+                C x = v[comp][m];
+                if (a.has_a) {
+                    const C f = (a.kin_mode == 0) ? evo<TM, T, C>(__ldg(&kin[off0 + pos]), a.ka_re, a.ka_im)
+                                                  : combine_factor<TM>(la, __ldg(&a.pa[(long long)comp * a.nx + pos]));
+                    x = mul_factor<TM>(x, f);
+                    acc[2 * comp] += (double)x.x * x.x + (double)x.y * x.y;
+                }
+                if (a.has_b) {
+                    const C f = (a.kin_mode == 0) ? evo<TM, T, C>(__ldg(&kin[off0 + pos]), a.kb_re, a.kb_im)
+                                                  : combine_factor<TM>(lb, __ldg(&a.pb[(long long)comp * a.nx + pos]));
+                    x = mul_factor<TM>(x, f);
+                    acc[2 * comp + 1] += (double)x.x * x.x + (double)x.y * x.y;
+                }
+                v[comp][m] = x;
+            }
+        }
+        if (!a.has_b) { acc[1] = acc[0]; acc[3] = acc[2]; }
+        if (!a.has_a) { acc[0] = acc[1]; acc[2] = acc[3]; }
+    }
+    if (a.do_inv) cta_fft<T, N, E, +1, 1, 2>(v, j, 0, sms, a.tw + (E == 16 ? N : 0));
+#pragma unroll
+    for (int m = 0; m < E; m++) {
+        a.out[off0 + j + m * NT] = v[0][m];
+        a.out[off1 + j + m * NT] = v[1][m];
+    }
+    if (a.has_a || a.has_b) {
+        const int nblk = gridDim.x;
+        cta_reduce<4>(acc, red);
+        if (tid == 0) {
+            double* p = a.partials + (long long)blockIdx.x * 4;
+            p[0] = acc[0]; p[1] = acc[1]; p[2] = acc[2]; p[3] = acc[3];
+            __threadfence();
+            red[0] = (atomicAdd(&a.counter[0], 1u) == (unsigned)(nblk - 1)) ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        const bool last = red[0] != 0.0;
+        __syncthreads();
+        if (last) {
+            __threadfence();
+            double t4[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int t = tid; t < nblk; t += blockDim.x) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) t4[q] += __ldcg(&a.partials[4LL * t + q]);
+            }
+            cta_reduce<4>(t4, red);
+            if (tid == 0) {
+                a.sums[0] = t4[1] + t4[3]; a.sums[1] = t4[0]; a.sums[2] = t4[2];
+                a.counter[0] = 0u;
+            }
+        }
+    }
+}
+
+// pack for the all-to-all: in [2][A][P*Bw] -> out [P][2][A][Bw]   (chunk q of every line goes to rank q)
+template <typename T> struct PackArgs {
+    typedef typename cx_of<T>::type C;
+    const C* in; C* out; int A, P, Bw;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) slab_pack(PackArgs<T> a) {
+    typedef typename cx_of<T>::type C;
+    const long long per_line = (long long)a.P * a.Bw;
+    const long long total = 2LL * a.A * per_line;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long w = i % a.Bw, q = (i / a.Bw) % a.P, l = (i / per_line) % a.A, c = i / (per_line * a.A);
+        a.out[((q * 2 + c) * a.A + l) * a.Bw + w] = a.in[i];
+    }
+}
+// unpack + transpose after the all-to-all: in [P][2][Bh][Bw] -> out [2][Bw][P*Bh], out[c][w][p*Bh+h] = in[p][c][h][w]
+template <typename T> struct UnpackArgs {
+    typedef typename cx_of<T>::type C;
+    const C* in; C* out; int P, Bh, Bw;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) slab_unpack_transpose(UnpackArgs<T> a) {
+    typedef typename cx_of<T>::type C;
+    SGPE_DYN_SMEM(smem_raw);
+    C* tile = reinterpret_cast<C*>(smem_raw);            // 32 x 33
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const int tiles_w = a.Bw / 32, tiles_h = a.Bh / 32;
+    const long long ntiles = (long long)a.P * 2 * tiles_h * tiles_w;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int tw_ = (int)(t % tiles_w), th = (int)((t / tiles_w) % tiles_h);
+        const int c = (int)((t / ((long long)tiles_w * tiles_h)) % 2), p = (int)(t / ((long long)tiles_w * tiles_h * 2));
+        const C* src = a.in + (((long long)p * 2 + c) * a.Bh + th * 32) * a.Bw + tw_ * 32;
+#pragma unroll
+        for (int k = 0; k < 4; k++) tile[(ty + 8 * k) * 33 + tx] = src[(long long)(ty + 8 * k) * a.Bw + tx];
+        __syncthreads();
+        C* dst = a.out + ((long long)c * a.Bw + tw_ * 32) * ((long long)a.P * a.Bh) + (long long)p * a.Bh + th * 32;
+#pragma unroll
+        for (int k = 0; k < 4; k++) dst[(long long)(ty + 8 * k) * ((long long)a.P * a.Bh) + tx] = tile[tx * 33 + ty + 8 * k];
+        __syncthreads();
+    }
+}
+
 // factor table: out[i] = exp(-i * e[i] * tau)   (separable operators: 1-D energy vectors -> 1-D factor tables)
 template <typename T> struct ExpTableArgs {
     typedef typename cx_of<T>::type C;

@@ -124,6 +124,18 @@ static int launch_col_t(const ColArgs<T>& a, int batch, int wsel, cudaStream_t s
     return launch_col_w<T, N, TM, Cfg::W, Cfg::E>(a, batch, st);
 }
 
+template <typename T, int N, int TM>
+static int launch_kline_t(const KLineArgs<T>& a, cudaStream_t st) {
+    typedef RowCfg<T, N> Cfg;
+    constexpr size_t smem = Cfg::SMEM + 32 * 4 * sizeof(double);
+    if (a.ny % Cfg::RPC != 0) return -2;
+    static bool once = false;
+    if (!once) { allow_smem(kline_pass<T, N, Cfg::E, Cfg::RPC, TM>, smem); once = true; }
+    dim3 grid(a.ny / Cfg::RPC), block(Cfg::THREADS);
+    SGPE_LAUNCH((kline_pass<T, N, Cfg::E, Cfg::RPC, TM>), grid, block, smem, st, a);
+    return 0;
+}
+
 #define SGPE_CAT2(a, b) a##b
 #define SGPE_CAT(a, b) SGPE_CAT2(a, b)
 
@@ -161,6 +173,15 @@ int SGPE_CAT(launch_col_, SGPE_N)(int dtype, int tm, const void* args, int batch
     const ColArgs<float>& a = *static_cast<const ColArgs<float>*>(args);
     return tm == TM_REAL ? launch_col_t<float, SGPE_N, TM_REAL>(a, batch, wsel, st)
                          : launch_col_t<float, SGPE_N, TM_IMAG>(a, batch, wsel, st);
+}
+
+int SGPE_CAT(launch_kline_, SGPE_N)(int dtype, int tm, const void* args, cudaStream_t st) {
+    if (dtype == 0) {
+        const KLineArgs<double>& a = *static_cast<const KLineArgs<double>*>(args);
+        return tm == TM_REAL ? launch_kline_t<double, SGPE_N, TM_REAL>(a, st) : launch_kline_t<double, SGPE_N, TM_IMAG>(a, st);
+    }
+    const KLineArgs<float>& a = *static_cast<const KLineArgs<float>*>(args);
+    return tm == TM_REAL ? launch_kline_t<float, SGPE_N, TM_REAL>(a, st) : launch_kline_t<float, SGPE_N, TM_IMAG>(a, st);
 }
 
 int SGPE_CAT(col_tile_width_, SGPE_N)(int dtype) {

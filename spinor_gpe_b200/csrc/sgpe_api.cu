@@ -242,7 +242,8 @@ int run_col(sgpe_plan* p, const void* in, void* out, bool fwd, bool has_a, doubl
 
 template <typename T>
 int run_row(sgpe_plan* p, const void* in, void* out, bool inv, bool pw, double dt_sub, bool fwd, int sign_in,
-            int sign_out, double scale_out, cudaStream_t st) {
+            int sign_out, double scale_out, cudaStream_t st, const double* totals_override = nullptr,
+            double norm_points = 0.0) {
     typedef typename sgpe::cx_of<T>::type C;
     RowArgs<T> a;
     memset(&a, 0, sizeof(a));
@@ -267,8 +268,8 @@ int run_row(sgpe_plan* p, const void* in, void* out, bool inv, bool pw, double d
     time_arg(p->tm, dt_sub / 2, &a.ti_re, &a.ti_im);        // evolution_op(t_step / 2, int_eng), :249
     time_arg(p->tm, dt_sub, &a.tp_re, &a.tp_im);            // evolution_op(dt, pot_eng_spin), :140, 146
     a.tc = dt_sub / 4;                                      // coupling_op: Omega * dt_sub / 4, :142-149
-    a.totals = p->totals;
-    a.norm_c = p->atom_num / (p->dv_r * (double)p->nx * (double)p->ny);
+    a.totals = totals_override ? totals_override : p->totals;
+    a.norm_c = p->atom_num / (p->dv_r * (norm_points > 0 ? norm_points : (double)p->nx * (double)p->ny));
     ProfScope prof(p, 1, st);
     int rc = sgpe::launch_row(p->nx, p->dtype, p->tm, &a, p->batch, p->row_mode, st);
     if (rc == -3) return fail(SGPE_EINVAL, "row pass variant not compiled in (build with -DSGPE_EXPERIMENTAL)");
@@ -395,6 +396,65 @@ int run_energy(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, d
     return 0;
 }
 
+template <typename T>
+static int run_klines(sgpe_plan* p, void* buf, bool fwd, bool has_a, double tau_a, bool has_b, double tau_b, bool inv,
+                      double* sums, cudaStream_t st) {
+    typedef typename sgpe::cx_of<T>::type C;
+    sgpe::KLineArgs<T> a;
+    memset(&a, 0, sizeof(a));
+    a.in = static_cast<const C*>(buf); a.out = static_cast<C*>(buf);
+    a.tw = static_cast<const C*>(p->tw_x);
+    a.nx = p->nx; a.ny = p->ny; a.plane = p->plane;
+    a.do_fwd = fwd; a.do_inv = inv; a.has_a = has_a; a.has_b = has_b;
+    a.kin_mode = p->kin_mode;
+    if (has_a || has_b) {
+        if (p->kin_mode == 0) {
+            a.kin0 = p->kin0; a.kin1 = p->kin1;
+            time_arg(p->tm, tau_a, &a.ka_re, &a.ka_im);
+            time_arg(p->tm, tau_b, &a.kb_re, &a.kb_im);
+        } else {
+            sgpe_plan::FactorTable* t = nullptr;
+            int rc;
+            if (has_a) {
+                if ((rc = factor_table<T>(p, p->kin_tab, 6, p->kin_x, 0, p->kin_y, 0, tau_a, st, &t))) return rc;
+                a.pa = static_cast<const C*>(t->x); a.la = static_cast<const C*>(t->y);
+            }
+            if (has_b) {
+                if ((rc = factor_table<T>(p, p->kin_tab, 6, p->kin_x, 0, p->kin_y, 0, tau_b, st, &t))) return rc;
+                a.pb = static_cast<const C*>(t->x); a.lb = static_cast<const C*>(t->y);
+            }
+        }
+    }
+    a.partials = p->partials; a.counter = p->counter; a.sums = sums;
+    ProfScope prof(p, 0, st);
+    int rc = sgpe::launch_kline(p->nx, p->dtype, p->tm, &a, st);
+    if (rc != 0) return fail(SGPE_EINVAL, "line pass: unsupported geometry");
+    p->launches++;
+    SGPE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+static int run_pack(sgpe_plan* p, const void* in, void* out, int A, int P, int Bw, cudaStream_t st) {
+    typedef typename sgpe::cx_of<T>::type C;
+    sgpe::PackArgs<T> a;
+    a.in = static_cast<const C*>(in); a.out = static_cast<C*>(out); a.A = A; a.P = P; a.Bw = Bw;
+    SGPE_LAUNCH((sgpe::slab_pack<T>), dim3(148 * 8), dim3(256), 0, st, a);
+    p->launches++;
+    SGPE_CUDA(cudaGetLastError());
+    return 0;
+}
+template <typename T>
+static int run_unpack(sgpe_plan* p, const void* in, void* out, int P, int Bh, int Bw, cudaStream_t st) {
+    typedef typename sgpe::cx_of<T>::type C;
+    sgpe::UnpackArgs<T> a;
+    a.in = static_cast<const C*>(in); a.out = static_cast<C*>(out); a.P = P; a.Bh = Bh; a.Bw = Bw;
+    SGPE_LAUNCH((sgpe::slab_unpack_transpose<T>), dim3(148 * 8), dim3(256), 33 * 32 * sizeof(C), st, a);
+    p->launches++;
+    SGPE_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -421,7 +481,7 @@ int sgpe_plan_create(sgpe_plan** out, int nx, int ny, int batch, int dtype, int 
     p->nx = nx; p->ny = ny; p->batch = batch; p->dtype = dtype; p->device = device;
     p->csize = dtype == SGPE_C128 ? 16 : 8;
     p->plane = (long long)nx * ny;
-    p->max_tiles = 2 * nx;                       // covers every column tile width
+    p->max_tiles = 2 * (nx > ny ? nx : ny);      // covers every column tile width and the line passes
     if (p->max_tiles < 1024) p->max_tiles = 1024;
     int rc = 0;
     do {
@@ -664,6 +724,40 @@ int sgpe_energy(sgpe_plan* p, const void* psik, int unwrap_mode, double kl_term,
     }
     if ((rc = sgpe_fft2d(p, psik, p->scratch, 1, st))) return rc;
     return SGPE_BY_DTYPE(p, run_energy, p, p->scratch, unwrap_mode, kl_term, out, (cudaStream_t)st);
+}
+
+// ---- slab (distributed) mode building blocks: the caller (spinor_gpe_b200/slab.py) owns the buffers and the
+// collectives (torch.distributed all_to_all / all_reduce over NCCL); these are the local passes.
+int sgpe_pass_rows(sgpe_plan* p, void* buf, double dt_sub, const double* totals_dev, double global_points,
+                   sgpe_stream st) {
+    if (!p || !buf || !totals_dev) return fail(SGPE_EINVAL, "null argument");
+    if (!(p->grid_set && p->g_set && p->pot_set && p->time_set)) return fail(SGPE_ESTATE, "plan not configured");
+    DeviceGuard guard(p->device);
+    return SGPE_BY_DTYPE(p, run_row, p, buf, buf, true, true, dt_sub, true, 0, 0, 1.0, (cudaStream_t)st, totals_dev,
+                         global_points);
+}
+
+int sgpe_pass_klines(sgpe_plan* p, void* buf, int do_fwd, int has_a, double tau_a, int has_b, double tau_b, int do_inv,
+                     double* sums_dev, sgpe_stream st) {
+    if (!p || !buf) return fail(SGPE_EINVAL, "null argument");
+    if ((has_a || has_b) && (!p->kin_set || !p->time_set || !sums_dev)) return fail(SGPE_ESTATE, "kinetic operator / time / sums missing");
+    if (p->batch != 1) return fail(SGPE_EINVAL, "line passes are for batch == 1 plans");
+    DeviceGuard guard(p->device);
+    return SGPE_BY_DTYPE(p, run_klines, p, buf, do_fwd != 0, has_a != 0, tau_a, has_b != 0, tau_b, do_inv != 0,
+                         sums_dev, (cudaStream_t)st);
+}
+
+int sgpe_slab_pack(sgpe_plan* p, const void* in, void* out, int lines, int nranks, int chunk, sgpe_stream st) {
+    if (!p || !in || !out || in == out) return fail(SGPE_EINVAL, "bad argument");
+    DeviceGuard guard(p->device);
+    return SGPE_BY_DTYPE(p, run_pack, p, in, out, lines, nranks, chunk, (cudaStream_t)st);
+}
+
+int sgpe_slab_unpack(sgpe_plan* p, const void* in, void* out, int nranks, int block_h, int block_w, sgpe_stream st) {
+    if (!p || !in || !out || in == out) return fail(SGPE_EINVAL, "bad argument");
+    if (block_h % 32 || block_w % 32) return fail(SGPE_EINVAL, "transpose blocks must be multiples of 32");
+    DeviceGuard guard(p->device);
+    return SGPE_BY_DTYPE(p, run_unpack, p, in, out, nranks, block_h, block_w, (cudaStream_t)st);
 }
 
 int sgpe_run_host(sgpe_plan* p, const void* psik_in, void* psik_out, int n_steps, double* pops_host, sgpe_stream st) {

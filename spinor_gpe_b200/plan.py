@@ -21,21 +21,26 @@ def _dp(t):
 class Plan:
     """One propagator plan on one GPU for ``batch`` independent trajectories of an (ny, nx) mesh."""
 
-    def __init__(self, nx, ny, batch=1, dtype=torch.complex128, device='cuda'):
-        require_cuda()
-        self.lib = lib()
+    def __init__(self, nx, ny, batch=1, dtype=torch.complex128, device='cuda', _lib=None):
+        # ``_lib`` is a test hook: tests/emu_harness.py passes the emulated build of the same sources so that
+        # host-side logic (sharding, slab orchestration) can run on CPU tensors; the product never sets it.
         self.device = torch.device(device)
-        if self.device.type != 'cuda':
-            raise ValueError("spinor_gpe_b200 plans live on CUDA devices only (no CPU fallback)")
-        if self.device.index is None:
-            self.device = torch.device('cuda', torch.cuda.current_device())
+        if _lib is None:
+            require_cuda()
+            self.lib = lib()
+            if self.device.type != 'cuda':
+                raise ValueError("spinor_gpe_b200 plans live on CUDA devices only (no CPU fallback)")
+            if self.device.index is None:
+                self.device = torch.device('cuda', torch.cuda.current_device())
+        else:
+            self.lib = _lib
         self.nx, self.ny, self.batch = int(nx), int(ny), int(batch)
         self.cdtype = dtype
         self.rdtype = torch.float64
         code = _capi.SGPE_C128 if dtype == torch.complex128 else _capi.SGPE_C64
         self.h = ctypes.c_void_p()
         self._chk(self.lib.sgpe_plan_create(ctypes.byref(self.h), self.nx, self.ny, self.batch, code,
-                                            self.device.index), 'sgpe_plan_create')
+                                            self.device.index or 0), 'sgpe_plan_create')
         self.keep = {}
 
     # ------------------------------------------------------------------ plumbing
@@ -73,6 +78,8 @@ class Plan:
 
     @property
     def stream(self):
+        if self.device.type != 'cuda':
+            return None
         return _stream_ptr(self.device)
 
     # ------------------------------------------------------------------ problem definition
@@ -198,6 +205,23 @@ class Plan:
         mode = {'none': 0, 'local': 1}[unwrap]
         self._chk(self.lib.sgpe_energy(self.h, _dp(t), mode, float(kl_term), _dp(out), self.stream), 'sgpe_energy')
         return out
+
+    # ------------------------------------------------------------------ slab-mode local passes
+    def pass_rows(self, buf, dt_sub, totals, global_points):
+        self._chk(self.lib.sgpe_pass_rows(self.h, _dp(buf), float(dt_sub), _dp(totals), float(global_points),
+                                          self.stream), 'sgpe_pass_rows')
+
+    def pass_klines(self, buf, do_fwd, has_a, tau_a, has_b, tau_b, do_inv, sums):
+        self._chk(self.lib.sgpe_pass_klines(self.h, _dp(buf), int(do_fwd), int(has_a), float(tau_a), int(has_b),
+                                            float(tau_b), int(do_inv), _dp(sums), self.stream), 'sgpe_pass_klines')
+
+    def slab_pack(self, src, dst, lines, nranks, chunk):
+        self._chk(self.lib.sgpe_slab_pack(self.h, _dp(src), _dp(dst), int(lines), int(nranks), int(chunk),
+                                          self.stream), 'sgpe_slab_pack')
+
+    def slab_unpack(self, src, dst, nranks, block_h, block_w):
+        self._chk(self.lib.sgpe_slab_unpack(self.h, _dp(src), _dp(dst), int(nranks), int(block_h), int(block_w),
+                                            self.stream), 'sgpe_slab_unpack')
 
     def accounting(self):
         a, b, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_int()

@@ -314,3 +314,56 @@ def test_full_size_propagation_properties():
     res0, _ = ps0.real(1 / 1000, 10, 'cuda')
     dens0 = np.abs(psi[0]) ** 2
     assert np.abs(res0.dens[0] - dens0).max() / dens0.max() < 1e-6      # splitting error O(dt^4)
+
+
+def test_run_sweep_on_gpu():
+    """sweep.run_sweep (single process): batched trajectories == one-by-one oracle runs."""
+    from spinor_gpe_b200.sweep import detuning_coupling_grid, run_sweep
+    base = make_ps((128, 128), atom_num=1e4, r_sizes=(16, 16), g_sc={'uu': 1, 'dd': 0.995, 'ud': 0.995})
+    base.coupling_setup(wavel=804e-9, kin_shift=True)
+    base.shift_momentum(scale=0.6, frac=(0.5, 0.5))
+    trajs = detuning_coupling_grid(base, [0.5 * base.EL_recoil, 5 * base.EL_recoil], [-12.0, 12.0])
+    out = run_sweep(base, trajs, 1 / 50, 4, time='imag', device='cuda', batch=3, keep_states=True)
+    for i, tr in enumerate(trajs):
+        prob = orc.Problem(base.psik, base.kin_eng_spin, tr.pot, np.full_like(base.pot_eng, tr.omega),
+                           base.space['dr'], base.space['dv_r'], base.space['dv_k'],
+                           [base.g_sc['uu'], base.g_sc['dd'], base.g_sc['ud']], base.atom_num, x=base.space['x'],
+                           kL=base.kL_recoil, is_coupling=True, rot_coupling=True)
+        want = orc.OraclePropagator(prob, 1 / 50, 'imag').run(4)
+        assert rel(out['psik'][i], want['psik']) < TOL_PSI
+        np.testing.assert_allclose(out['pops'][i], want['pops_vals'], rtol=TOL_SCALAR)
+
+
+def _slab_worker(rank, world, port, outdir):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        from spinor_gpe_b200.slab import SlabPropagator
+        ps = make_ps((512, 256), atom_num=1e4, r_sizes=(16, 16))
+        ps.coupling_setup(wavel=790.1e-9, kin_shift=True)
+        ps.coupling_uniform(1.5 * ps.EL_recoil)
+        ps.rot_coupling = False
+        want = orc.OraclePropagator(problem_of(ps), 1 / 2000, 'real').run(4)
+        sp = SlabPropagator(ps, 1 / 2000, time='real', device=f'cuda:{rank}')
+        pops = torch.zeros((4, 2), dtype=torch.float64, device=f'cuda:{rank}')
+        sp.full_steps(4, pops)
+        got = sp.gather_psik().cpu().numpy()
+        assert rel(got, want['psik']) < TOL_PSI
+        np.testing.assert_allclose(pops.cpu().numpy(), want['pops_vals'], rtol=TOL_SCALAR)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_two_gpus():
+    """Slab-decomposed propagation over 2 GPUs with the NCCL all-to-all (skipped on a 1-GPU box)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mp.spawn(_slab_worker, args=(2, port, tempfile.mkdtemp(prefix='sgpe_slab_')), nprocs=2, join=True)
