@@ -12,10 +12,20 @@ RTOL = 1e-13
 
 def split_separable(grids, rtol=RTOL):
     """(2, Ny, Nx) -> (gx (2, Nx), gy (2, Ny)) with grids == gx[:, None, :] + gy[:, :, None] to within
-    ``rtol`` of the largest entry, or None when the grids are not separable."""
+    ``rtol`` of the largest entry, or None when the grids are not separable.
+
+    The split is anchored at the row where the y-dependence is smallest, so that gy >= 0 with min(gy) = 0 and
+    gx carries the rest: the factor tables exp(-gx tau), exp(-gy tau) then stay as well scaled as the
+    operator itself (anchoring at a corner would make one table overflow in imaginary time on fine meshes,
+    where k_max^2 tau / 2 exceeds 709)."""
     g = np.asarray(grids, dtype=np.float64)
-    gx = g[:, 0, :].copy()
-    gy = g[:, :, 0] - g[:, 0, 0][:, None]
+    gx = np.empty((g.shape[0], g.shape[2]))
+    gy = np.empty((g.shape[0], g.shape[1]))
+    for c in range(g.shape[0]):
+        col = g[c, :, 0]
+        i0 = int(np.argmin(col))
+        gy[c] = col - col[i0]
+        gx[c] = g[c, i0, :]
     err = np.abs(g - (gx[:, None, :] + gy[:, :, None])).max()
     if err <= rtol * max(float(np.abs(g).max()), 1e-300):
         return gx, gy

@@ -147,3 +147,26 @@ def test_emulated_batch_of_two():
         assert rel(out[b], want[b]['psik']) < 1e-12
         np.testing.assert_allclose(pops[b], want[b]['pops_vals'], rtol=1e-12)
     pl.close()
+
+
+def test_emulated_fine_mesh_factor_tables():
+    """Separable factor tables on a mesh fine enough that exp(k_max^2 tau / 2) overflows a double."""
+    import tempfile
+    from spinor_gpe_b200 import PSpinor
+    w0 = 2 * np.pi * 50
+    ps = PSpinor(os.path.join(tempfile.mkdtemp(prefix='sgpe_t_'), 'run') + os.sep, atom_num=1e3,
+                 omeg={'x': w0, 'y': w0, 'z': 40 * w0}, g_sc={'uu': 1, 'dd': 1, 'ud': 1.04}, r_sizes=(0.25, 2),
+                 mesh_points=(1024, 32))
+    ps.coupling_setup(wavel=790.1e-9, kin_shift=False)
+    prob = orc.Problem(ps.psik, ps.kin_eng_spin, ps.pot_eng_spin, ps.coupling, ps.space['dr'], ps.space['dv_r'],
+                       ps.space['dv_k'], [ps.g_sc['uu'], ps.g_sc['dd'], ps.g_sc['ud']], ps.atom_num,
+                       is_coupling=False)
+    assert (np.pi / ps.space['dr'][0]) ** 2 / 2 * (1 / 50) / 4 > 709
+    want = orc.OraclePropagator(prob, 1 / 50, 'imag').run(2)
+    pl = plan_from_problem(prob, 'imag', 1 / 50, separable=True)
+    assert pl.sep_used == (True, True)
+    pl.full_steps(2)
+    out = pl.store()[0]
+    assert np.isfinite(out).all()
+    assert rel(out, want['psik']) < 1e-12
+    pl.close()

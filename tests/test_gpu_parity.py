@@ -367,3 +367,24 @@ def test_slab_two_gpus():
         s.bind(('127.0.0.1', 0))
         port = s.getsockname()[1]
     mp.spawn(_slab_worker, args=(2, port, tempfile.mkdtemp(prefix='sgpe_slab_')), nprocs=2, join=True)
+
+
+def test_fine_mesh_imaginary_time_factor_tables():
+    """k_max^2 dt / 4 >> 709 (exp overflow range): the separable factor tables must stay finite and agree with
+    the dense path and the oracle (regression: anchoring the split at a grid corner overflowed at 4096 points)."""
+    ps = make_ps((4096, 64), atom_num=1e3, r_sizes=(2, 2))
+    ps.coupling_setup(wavel=790.1e-9, kin_shift=False)
+    want = orc.OraclePropagator(problem_of(ps), 1 / 50, 'imag').run(2)
+    for sep in (True, False):
+        res, prop = ps_copy_run(ps, sep)
+        assert np.isfinite(np.array(res.psik)).all()
+        assert rel(np.array(res.psik), want['psik']) < TOL_PSI
+        np.testing.assert_allclose(res.pops['vals'], want['pops_vals'], rtol=TOL_SCALAR)
+
+
+def ps_copy_run(ps, separable):
+    import copy
+    q = copy.copy(ps)
+    q.psik = [p.copy() for p in ps.psik]
+    q.psi = [p.copy() for p in ps.psi]
+    return q.imaginary(1 / 50, 2, 'cuda', separable=separable)
