@@ -157,6 +157,8 @@ int sgpe_step_accounting(const sgpe_plan* p, uint64_t* algorithmic_bytes, uint64
  * launch counts per kind (used by bench.py for the roofline of the dominant kernel). */
 int sgpe_profile_begin(sgpe_plan* p);
 int sgpe_profile_end(sgpe_plan* p, double* ms_col, uint64_t* n_col, double* ms_row, uint64_t* n_row);
+/* Dev tool: when buf_dev != NULL every row-pass CTA writes 8 uint64 (globaltimer at 6 phase boundaries, -, SM id). */
+int sgpe_debug_timeline(sgpe_plan* p, unsigned long long* buf_dev);
 /* Number of kernels this plan has launched since creation. */
 int sgpe_launch_count(const sgpe_plan* p, uint64_t* launches);
 

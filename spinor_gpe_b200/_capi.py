@@ -40,6 +40,7 @@ PROTOTYPES = {
     'sgpe_profile_begin': (C.c_int, [c_plan]),
     'sgpe_profile_end': (C.c_int, [c_plan, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double),
                                    C.POINTER(C.c_uint64)]),
+    'sgpe_debug_timeline': (C.c_int, [c_plan, c_dptr]),
     'sgpe_launch_count': (C.c_int, [c_plan, C.POINTER(C.c_uint64)]),
 }
 

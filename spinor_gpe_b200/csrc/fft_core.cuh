@@ -231,9 +231,39 @@ SGPE_DI void cta_fft_from(C (&v)[L][E], int j, int c, C* const (&sm)[L], const C
     }
 }
 
+// Two lines per thread: software-pipelined exchange.  Line A's shared-memory read latency is covered by
+// line B's stores and vice versa, and each barrier serves one line's write->read and the other line's
+// read->write hazard, so the barrier count is unchanged (2 per stage) while the post-barrier bubble shrinks.
+// Precondition of a round: A's stage-Ns outputs are stored (not yet visible), B's are still in registers.
+template <typename T, int N, int E, int DIR, int W, int Ns, typename C>
+SGPE_DI void cta_fft2_round(C (&v)[2][E], int j, int c, C* const (&sm)[2], const C* __restrict__ tw) {
+    constexpr int R = (N / Ns) < E ? (N / Ns) : E;
+    constexpr int Ns2 = Ns * R;
+    constexpr int R2 = (N / Ns2) < E ? (N / Ns2) : E;
+    constexpr bool more = (Ns2 * R2 < N);
+    __syncthreads();
+    stage_load<T, N, E, W>(v[0], j, c, sm[0]);
+    stage_store<T, N, E, W, Ns>(v[1], j, c, sm[1]);
+    stage_compute<T, N, E, DIR, Ns2>(v[0], j, tw);
+    __syncthreads();
+    stage_load<T, N, E, W>(v[1], j, c, sm[1]);
+    if constexpr (more) stage_store<T, N, E, W, Ns2>(v[0], j, c, sm[0]);
+    stage_compute<T, N, E, DIR, Ns2>(v[1], j, tw);
+    if constexpr (more) cta_fft2_round<T, N, E, DIR, W, Ns2>(v, j, c, sm, tw);
+}
+
 template <typename T, int N, int E, int DIR, int W, int L, typename C>
 SGPE_DI void cta_fft(C (&v)[L][E], int j, int c, C* const (&sm)[L], const C* __restrict__ tw) {
-    cta_fft_from<T, N, E, DIR, W, L, 1>(v, j, c, sm, tw);
+    if constexpr (L == 2 && E < N) {
+        // (a following cta_fft of the same two lines may start right away: it touches line A's image, whose
+        // readers are past the last barrier, before its own first barrier, and line B's only after it)
+        stage_compute<T, N, E, DIR, 1>(v[0], j, tw);
+        stage_store<T, N, E, W, 1>(v[0], j, c, sm[0]);
+        stage_compute<T, N, E, DIR, 1>(v[1], j, tw);
+        cta_fft2_round<T, N, E, DIR, W, 1>(v, j, c, sm, tw);
+    } else {
+        cta_fft_from<T, N, E, DIR, W, L, 1>(v, j, c, sm, tw);
+    }
 }
 
 // ---- deterministic CTA reduction of NV doubles (warp shuffle, then shared memory in warp order)

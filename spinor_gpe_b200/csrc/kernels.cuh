@@ -65,7 +65,9 @@ template <int TM, typename C> SGPE_DI C combine_factor(C f, C g) {
     C r; r.x = f.x * g.x; r.y = 0; return r;
 }
 
-template <typename T, int N, int E, int W, int TM>
+// FAST = 1: the steady-state junction (forward + factors + inverse, separable tables, no sign / scale) with the
+// other branches compiled out.
+template <typename T, int N, int E, int W, int TM, int FAST>
 __global__ void __launch_bounds__(W * N / E, (W * N / E <= 256) ? 2 : 1) col_pass(ColArgs<T> a) {
     typedef typename cx_of<T>::type C;
     constexpr int NT = N / E;
@@ -81,11 +83,14 @@ __global__ void __launch_bounds__(W * N / E, (W * N / E <= 256) ? 2 : 1) col_pas
     const int comp = tile / tiles_per_comp;
     const int col = (tile % tiles_per_comp) * W + c;
     const int b = blockIdx.y;
+    const bool do_fwd = FAST ? true : (a.do_fwd != 0), do_inv = FAST ? true : (a.do_inv != 0);
+    const int kin_mode = FAST ? 1 : a.kin_mode;
+    const int sign_in = FAST ? 0 : a.sign_in, sign_out = FAST ? 0 : a.sign_out;
     const long long off = ((long long)b * 2 + comp) * a.plane + col;
 
     C v[1][E];
 #pragma unroll
-    for (int m = 0; m < E; m++) v[0][m] = a.in[off + (long long)(j + m * NT) * a.nx];
+    for (int m = 0; m < E; m++) v[0][m] = SGPE_LD_STREAM(&a.in[off + (long long)(j + m * NT) * a.nx]);
     if (a.prefetch_ahead > 0 && c == 0) {
         const int nt = tile + a.prefetch_ahead;
         if (nt < ntiles) {
@@ -94,19 +99,19 @@ __global__ void __launch_bounds__(W * N / E, (W * N / E <= 256) ? 2 : 1) col_pas
             for (int m = 0; m < E; m++) SGPE_PREFETCH_L2(&a.in[noff + (long long)(j + m * NT) * a.nx]);
         }
     }
-    if (a.sign_in) {
+    if (sign_in) {
 #pragma unroll
         for (int m = 0; m < E; m++)
             if ((j + m * NT) & 1) { v[0][m].x = -v[0][m].x; v[0][m].y = -v[0][m].y; }
     }
 
     C* const sms[1] = {sm};
-    if (a.do_fwd) cta_fft<T, N, E, -1, W, 1>(v, j, c, sms, a.tw + (E == 16 ? N : 0));
+    if (do_fwd) cta_fft<T, N, E, -1, W, 1>(v, j, c, sms, a.tw + (E == 16 ? N : 0));
 
     double acc[2] = {0.0, 0.0};   // S (after FA), T (after FB)
     const bool any_k = a.has_a || a.has_b;
     if (any_k) {
-        if (a.kin_mode == 0) {
+        if (kin_mode == 0) {
             const double* kin = (comp == 0 ? a.kin0 : a.kin1) + (long long)b * a.kin_bstride + col;
             double e[E];
 #pragma unroll
@@ -149,18 +154,18 @@ __global__ void __launch_bounds__(W * N / E, (W * N / E <= 256) ? 2 : 1) col_pas
         if (!a.has_a) acc[0] = acc[1];
     }
 
-    if (a.do_inv) cta_fft<T, N, E, +1, W, 1>(v, j, c, sms, a.tw + (E == 16 ? N : 0));
+    if (do_inv) cta_fft<T, N, E, +1, W, 1>(v, j, c, sms, a.tw + (E == 16 ? N : 0));
 
-    if (a.sign_out || a.scale_out != 1.0) {
+    if (!FAST && (sign_out || a.scale_out != 1.0)) {
         const T sc = (T)a.scale_out;
 #pragma unroll
         for (int m = 0; m < E; m++) {
-            const T s = (a.sign_out && ((j + m * NT) & 1)) ? -sc : sc;
+            const T s = (sign_out && ((j + m * NT) & 1)) ? -sc : sc;
             v[0][m] = cscale(v[0][m], s);
         }
     }
 #pragma unroll
-    for (int m = 0; m < E; m++) a.out[off + (long long)(j + m * NT) * a.nx] = v[0][m];
+    for (int m = 0; m < E; m++) SGPE_ST_STREAM(&a.out[off + (long long)(j + m * NT) * a.nx], v[0][m]);
 
     if (any_k) {
         cta_reduce<2>(acc, red);
@@ -208,7 +213,9 @@ template <typename T> struct RowArgs {
     int nx, ny; long long plane;
     int do_inv, do_pw, do_fwd;
     int prefetch_ahead;            // > 0: L2 prefetch of the rows this many CTAs ahead
-    int resident; int stagger_ns;  // de-phase the CTAs that share an SM: the 2nd half of the first wave starts late
+    int resident; int stagger_ns;  // de-phase the CTAs that share an SM: the 2nd arrival on each SM starts late
+    unsigned* sm_slots;            // [>= #SMs] arrival counters, zeroed before the launch
+    unsigned long long* dbg;       // dev tool: per-CTA phase timestamps [nCTA][8] (null in production)
     int sign_in, sign_out; double scale_out;   // sign bit 1: (-1)^x, bit 2: (-1)^y
     const double* pot0; const double* pot1; long long pot_bstride;     // [ny][nx]
     int pot_mode;                  // 0: dense grids, 1: separable factor tables px[2][nx], py[2][ny]
@@ -243,7 +250,10 @@ SGPE_DI void coupling_entries(double theta, C ph, T& diag, C& off01, C& off10) {
     }
 }
 
-template <typename T, int N, int E, int RPC, int TM>
+// FAST = 1 is the specialisation for the common full pass (inverse + point-wise + forward, no coupling,
+// separable potential, no sign / scale): same code with the other branches compiled out, which roughly halves
+// the instruction footprint (the generic kernel does not fit the instruction cache: ncu stall_no_inst).
+template <typename T, int N, int E, int RPC, int TM, int FAST>
 __global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) row_pass(RowArgs<T> a) {
     typedef typename cx_of<T>::type C;
     constexpr int NT = N / E;
@@ -254,16 +264,37 @@ __global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) row
     const int r = tid / NT, j = tid % NT;
     const int y = blockIdx.x * RPC + r;
     const int b = blockIdx.y;
-    if (a.stagger_ns > 0 && blockIdx.y == 0 && (int)blockIdx.x >= a.resident / 2 && (int)blockIdx.x < a.resident)
-        SGPE_NANOSLEEP((unsigned)a.stagger_ns);
+    const int cpl_mode = FAST ? 0 : a.cpl_mode, pot_mode = FAST ? 1 : a.pot_mode;
+    const int sign_in = FAST ? 0 : a.sign_in, sign_out = FAST ? 0 : a.sign_out;
+    const bool do_inv = FAST ? true : (a.do_inv != 0), do_pw = FAST ? true : (a.do_pw != 0);
+    const bool do_fwd = FAST ? true : (a.do_fwd != 0);
+    // everything the point-wise phase needs from memory is pulled into L1 before the transforms start
+    // (prefetches cost no registers; holding the values across the FFT made the kernel spill)
+    if (do_pw) {
+        SGPE_PREFETCH_L1(&a.totals[(long long)b * 4]);
+        if (pot_mode == 1) {
+            const long long oy = (long long)b * a.sepy_bstride + y;
+            SGPE_PREFETCH_L1(&a.py[oy]);
+            SGPE_PREFETCH_L1(&a.py[oy + a.ny]);
+        }
+    }
+    if (!FAST && a.stagger_ns > 0) {
+        // co-resident CTAs launched together run in lock-step (same phase -> they fight for the same unit);
+        // delaying the second arrival on every SM by ~half a CTA lifetime interleaves their phases for good
+        if (tid == 0 && (atomicAdd(&a.sm_slots[SGPE_SMID()], 1u) == 1u)) SGPE_NANOSLEEP((unsigned)a.stagger_ns);
+        __syncthreads();
+    }
     const long long off0 = ((long long)b * 2) * a.plane + (long long)y * a.nx;
     const long long off1 = off0 + a.plane;
+#define SGPE_MARK(k) do { if (!FAST && a.dbg != nullptr && tid == 0) a.dbg[(long long)blockIdx.x * 8 + (k)] = SGPE_GLOBALTIMER(); } while (0)
+    if (!FAST && a.dbg != nullptr && tid == 0) a.dbg[(long long)blockIdx.x * 8 + 7] = SGPE_SMID();
+    SGPE_MARK(0);
 
     C v[2][E];
 #pragma unroll
     for (int m = 0; m < E; m++) {
-        v[0][m] = a.in[off0 + j + m * NT];
-        v[1][m] = a.in[off1 + j + m * NT];
+        v[0][m] = SGPE_LD_STREAM(&a.in[off0 + j + m * NT]);
+        v[1][m] = SGPE_LD_STREAM(&a.in[off1 + j + m * NT]);
     }
     if (a.prefetch_ahead > 0) {
         const int ny2 = (blockIdx.x + a.prefetch_ahead) * RPC + r;
@@ -276,36 +307,38 @@ __global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) row
             }
         }
     }
-    if (a.sign_in) {
+    if (sign_in) {
 #pragma unroll
         for (int m = 0; m < E; m++) {
-            if ((((a.sign_in & 1) ? (j + m * NT) : 0) + ((a.sign_in & 2) ? y : 0)) & 1) {
+            if ((((sign_in & 1) ? (j + m * NT) : 0) + ((sign_in & 2) ? y : 0)) & 1) {
                 v[0][m].x = -v[0][m].x; v[0][m].y = -v[0][m].y;
                 v[1][m].x = -v[1][m].x; v[1][m].y = -v[1][m].y;
             }
         }
     }
     C* const sms[2] = {smem + (size_t)(2 * r) * N, smem + (size_t)(2 * r + 1) * N};
+    if (!FAST && a.dbg != nullptr) { if (v[0][0].x == (T)1.2345e300 || v[1][E - 1].y == (T)1.2345e300) a.dbg[6] = 1; SGPE_MARK(1); }
 
-    if (a.do_inv) cta_fft<T, N, E, +1, 1, 2>(v, j, 0, sms, a.tw + (E == 16 ? N : 0));
+    if (do_inv) cta_fft<T, N, E, +1, 1, 2>(v, j, 0, sms, a.tw + (E == 16 ? N : 0));
+    SGPE_MARK(2);
 
-    if (a.do_pw) {
+    if (do_pw) {
         const T alpha = (T)sqrt(a.norm_c / a.totals[(long long)b * 4]);
+        C py0, py1;
+        py0.x = (T)1; py0.y = (T)0; py1 = py0;
+        if (pot_mode == 1) {
+            const long long oy = (long long)b * a.sepy_bstride + y;
+            py0 = __ldg(&a.py[oy]);
+            py1 = __ldg(&a.py[oy + a.ny]);
+        }
         const long long prow = (long long)b * a.pot_bstride + (long long)y * a.nx;
         const bool same_pot = (a.pot0 == a.pot1);
         T cu_diag = (T)1, cu_s = (T)0;          // uniform coupling: cos/sin (cosh/sinh) once per thread
-        if (a.cpl_mode == 1) {
+        if (cpl_mode == 1) {
             C one; one.x = (T)1; one.y = (T)0;
             C t01, t10;
             coupling_entries<TM, T, C>(a.omega_b[b] * a.tc, one, cu_diag, t01, t10);
             cu_s = (TM == TM_REAL) ? -t01.y : -t01.x;       // sin(theta) resp. sinh(theta)
-        }
-        C py0, py1;
-        py0.x = (T)1; py0.y = (T)0; py1 = py0;
-        if (a.pot_mode == 1) {
-            const long long oy = (long long)b * a.sepy_bstride + y;
-            py0 = __ldg(&a.py[oy]);
-            py1 = __ldg(&a.py[oy + a.ny]);
         }
 #pragma unroll
         for (int m = 0; m < E; m++) {
@@ -317,10 +350,10 @@ __global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) row
             const C i1 = evo<TM, T, C>(a.g_dd * n1 + a.g_ud * n0, a.ti_re, a.ti_im);
             p = mul_factor<TM>(p, i0); q = mul_factor<TM>(q, i1);
             T diag = (T)1; C o01, o10;
-            if (a.cpl_mode) {
+            if (cpl_mode) {
                 C ph; ph.x = (T)1; ph.y = (T)0;
                 if (a.eiphi != nullptr) ph = __ldg(&a.eiphi[x]);
-                if (a.cpl_mode == 1) {
+                if (cpl_mode == 1) {
                     diag = cu_diag;
                     if (TM == TM_REAL) {
                         o01.x = -cu_s * ph.y; o01.y = -cu_s * ph.x; o10.x = cu_s * ph.y; o10.y = -cu_s * ph.x;
@@ -336,7 +369,7 @@ __global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) row
                 p = p2; q = q2;
             }
             C f0, f1;
-            if (a.pot_mode == 0) {
+            if (pot_mode == 0) {
                 f0 = evo<TM, T, C>(__ldg(&a.pot0[prow + x]), a.tp_re, a.tp_im);
                 f1 = same_pot ? f0 : evo<TM, T, C>(__ldg(&a.pot1[prow + x]), a.tp_re, a.tp_im);
             } else {
@@ -345,7 +378,7 @@ __global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) row
                 f1 = combine_factor<TM>(__ldg(&a.px[ox + a.nx]), py1);
             }
             p = mul_factor<TM>(p, f0); q = mul_factor<TM>(q, f1);
-            if (a.cpl_mode) {
+            if (cpl_mode) {
                 const C p2 = cadd(cscale(p, diag), cmul(o01, q));
                 const C q2 = cadd(cmul(o10, p), cscale(q, diag));
                 p = p2; q = q2;
@@ -354,16 +387,20 @@ __global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) row
         }
     }
 
-    if (a.do_fwd) cta_fft<T, N, E, -1, 1, 2>(v, j, 0, sms, a.tw + (E == 16 ? N : 0));
+    SGPE_MARK(3);
+    if (do_fwd) cta_fft<T, N, E, -1, 1, 2>(v, j, 0, sms, a.tw + (E == 16 ? N : 0));
+    SGPE_MARK(4);
 
-    const T sc = (T)a.scale_out;
+    const T sc = FAST ? (T)1 : (T)a.scale_out;
 #pragma unroll
     for (int m = 0; m < E; m++) {
         T s = sc;
-        if ((((a.sign_out & 1) ? (j + m * NT) : 0) + ((a.sign_out & 2) ? y : 0)) & 1) s = -s;
-        a.out[off0 + j + m * NT] = cscale(v[0][m], s);
-        a.out[off1 + j + m * NT] = cscale(v[1][m], s);
+        if ((((sign_out & 1) ? (j + m * NT) : 0) + ((sign_out & 2) ? y : 0)) & 1) s = -s;
+        SGPE_ST_STREAM(&a.out[off0 + j + m * NT], cscale(v[0][m], s));
+        SGPE_ST_STREAM(&a.out[off1 + j + m * NT], cscale(v[1][m], s));
     }
+    SGPE_MARK(5);
+#undef SGPE_MARK
 }
 
 // Row pass, split variant: one component per thread (twice the threads, half the registers of row_pass).

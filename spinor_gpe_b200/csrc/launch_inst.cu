@@ -72,15 +72,22 @@ static int launch_row_t(const RowArgs<T>& a, int batch, cudaStream_t st) {
     static bool once = false;
     static int ahead = 0;
     if (!once) {
-        allow_smem(row_pass<T, N, Cfg::E, Cfg::RPC, TM>, Cfg::SMEM);
-        ahead = resident_ctas(row_pass<T, N, Cfg::E, Cfg::RPC, TM>, Cfg::THREADS, Cfg::SMEM);
+        allow_smem(row_pass<T, N, Cfg::E, Cfg::RPC, TM, 0>, Cfg::SMEM);
+        allow_smem(row_pass<T, N, Cfg::E, Cfg::RPC, TM, 1>, Cfg::SMEM);
+        ahead = resident_ctas(row_pass<T, N, Cfg::E, Cfg::RPC, TM, 1>, Cfg::THREADS, Cfg::SMEM);
         once = true;
     }
     dim3 grid(a.ny / Cfg::RPC, batch), block(Cfg::THREADS);
     RowArgs<T> a2 = a;
     if (a2.prefetch_ahead) a2.prefetch_ahead = ahead;
     a2.resident = ahead;
-    SGPE_LAUNCH((row_pass<T, N, Cfg::E, Cfg::RPC, TM>), grid, block, Cfg::SMEM, st, a2);
+    const bool fast = a.do_inv && a.do_pw && a.do_fwd && a.cpl_mode == 0 && a.pot_mode == 1 && !a.sign_in &&
+                      !a.sign_out && a.scale_out == 1.0 && a.stagger_ns == 0 && a.dbg == nullptr;
+    if (fast) {
+        SGPE_LAUNCH((row_pass<T, N, Cfg::E, Cfg::RPC, TM, 1>), grid, block, Cfg::SMEM, st, a2);
+    } else {
+        SGPE_LAUNCH((row_pass<T, N, Cfg::E, Cfg::RPC, TM, 0>), grid, block, Cfg::SMEM, st, a2);
+    }
     return 0;
 }
 
@@ -92,14 +99,20 @@ static int launch_col_w(const ColArgs<T>& a, int batch, cudaStream_t st) {
     static bool once = false;
     static int ahead = 0;
     if (!once) {
-        allow_smem(col_pass<T, N, E, W, TM>, smem);
-        ahead = resident_ctas(col_pass<T, N, E, W, TM>, W * (N / E), smem);
+        allow_smem(col_pass<T, N, E, W, TM, 0>, smem);
+        allow_smem(col_pass<T, N, E, W, TM, 1>, smem);
+        ahead = resident_ctas(col_pass<T, N, E, W, TM, 1>, W * (N / E), smem);
         once = true;
     }
     dim3 grid(2 * a.nx / W, batch), block(W * (N / E));
     ColArgs<T> a2 = a;
     if (a2.prefetch_ahead) a2.prefetch_ahead = ahead;
-    SGPE_LAUNCH((col_pass<T, N, E, W, TM>), grid, block, smem, st, a2);
+    const bool fast = a.do_fwd && a.do_inv && a.kin_mode == 1 && !a.sign_in && !a.sign_out && a.scale_out == 1.0;
+    if (fast) {
+        SGPE_LAUNCH((col_pass<T, N, E, W, TM, 1>), grid, block, smem, st, a2);
+    } else {
+        SGPE_LAUNCH((col_pass<T, N, E, W, TM, 0>), grid, block, smem, st, a2);
+    }
     return 0;
 }
 

@@ -70,6 +70,8 @@ struct sgpe_plan {
     struct FactorTable { bool valid = false; int tm = 0; double tau = 0; void* x = nullptr; void* y = nullptr; uint64_t used = 0; };
     FactorTable kin_tab[6], pot_tab[4];
     uint64_t tab_clock = 0;
+    unsigned* sm_slots = nullptr;
+    unsigned long long* dbg = nullptr;   // dev tool (sgpe_debug_timeline)
     int stagger_ns = 0;            // option "stagger_ns"
     int prefetch = 1;              // L2 prefetch of the next tile of each SM (option "prefetch")
     int row_mode = 0;              // 0: both components per thread, 1: split (one component per thread)
@@ -251,7 +253,12 @@ int run_row(sgpe_plan* p, const void* in, void* out, bool inv, bool pw, double d
     a.tw = static_cast<const C*>(p->tw_x);
     a.nx = p->nx; a.ny = p->ny; a.plane = p->plane;
     a.do_inv = inv; a.do_pw = pw; a.do_fwd = fwd;
-    a.prefetch_ahead = p->prefetch; a.stagger_ns = p->stagger_ns;
+    a.prefetch_ahead = p->prefetch; a.stagger_ns = p->stagger_ns; a.dbg = pw ? p->dbg : nullptr;
+    if (p->stagger_ns > 0) {
+        if (!p->sm_slots) SGPE_CUDA(cudaMalloc((void**)&p->sm_slots, 1024 * sizeof(unsigned)));
+        SGPE_CUDA(cudaMemsetAsync(p->sm_slots, 0, 1024 * sizeof(unsigned), st));
+        a.sm_slots = p->sm_slots;
+    }
     a.sign_in = sign_in; a.sign_out = sign_out; a.scale_out = scale_out;
     a.pot0 = p->pot0; a.pot1 = p->pot1; a.pot_bstride = p->pot_bs;
     a.pot_mode = pw ? p->pot_mode : 0;
@@ -511,7 +518,7 @@ int sgpe_plan_destroy(sgpe_plan* p) {
     DeviceGuard guard(p->device);
     cudaFree(p->state); cudaFree(p->tw_x); cudaFree(p->tw_y); cudaFree(p->partials);
     cudaFree(p->counter); cudaFree(p->totals); cudaFree(p->totals_aux); cudaFree(p->pops_buf);
-    cudaFree(p->scratch); cudaFree(p->maxdens);
+    cudaFree(p->scratch); cudaFree(p->maxdens); cudaFree(p->sm_slots);
     for (auto& t : p->kin_tab) { cudaFree(t.x); cudaFree(t.y); }
     for (auto& t : p->pot_tab) { cudaFree(t.x); cudaFree(t.y); }
     delete p;
@@ -828,6 +835,12 @@ int sgpe_profile_end(sgpe_plan* p, double* ms_col, uint64_t* n_col, double* ms_r
     if (n_col) *n_col = cnt[0];
     if (ms_row) *ms_row = ms[1];
     if (n_row) *n_row = cnt[1];
+    return 0;
+}
+
+int sgpe_debug_timeline(sgpe_plan* p, unsigned long long* buf_dev) {
+    if (!p) return fail(SGPE_EINVAL, "null plan");
+    p->dbg = buf_dev;
     return 0;
 }
 

@@ -154,6 +154,11 @@ inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v
 inline void sincos(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }
 inline void sincosf(float x, float* s, float* c) { *s = std::sin(x); *c = std::cos(x); }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+inline int __double2loint(double x) { unsigned long long u; memcpy(&u, &x, 8); return (int)(unsigned)(u & 0xffffffffull); }
+inline int __double2hiint(double x) { unsigned long long u; memcpy(&u, &x, 8); return (int)(unsigned)(u >> 32); }
+inline double __hiloint2double(int hi, int lo) {
+    unsigned long long u = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo; double x; memcpy(&x, &u, 8); return x;
+}
 
 // runtime shims
 inline cudaError_t cudaMalloc(void** p, size_t n) { *p = aligned_alloc(256, (n + 255) / 256 * 256); return *p ? 0 : 2; }
