@@ -33,6 +33,13 @@ template <int TM, typename T, typename C> SGPE_DI C evo(double e, double tr, dou
     return r;
 }
 
+// conjugate E values in place (the inverse transform runs the forward code between two conjugations, so that
+// each pass contains ONE copy of the FFT code, executed by a two-iteration loop: instruction-cache footprint)
+template <int E, typename C> SGPE_DI void conj_all(C (&v)[E]) {
+#pragma unroll
+    for (int m = 0; m < E; m++) v[m].y = -v[m].y;
+}
+
 template <typename T> struct ColArgs {
     typedef typename cx_of<T>::type C;
     const C* in;  C* out;          // [B][2][ny][nx]
@@ -106,10 +113,11 @@ __global__ void __launch_bounds__(W * N / E, (W * N / E <= 256) ? 2 : 1) col_pas
     }
 
     C* const sms[1] = {sm};
+    // (the two-iteration-loop trick of row_pass was measured slower here: 16 elements per thread, more spills)
     if (do_fwd) cta_fft<T, N, E, -1, W, 1>(v, j, c, sms, a.tw + (E == 16 ? N : 0));
-
     double acc[2] = {0.0, 0.0};   // S (after FA), T (after FB)
     const bool any_k = a.has_a || a.has_b;
+
     if (any_k) {
         if (kin_mode == 0) {
             const double* kin = (comp == 0 ? a.kin0 : a.kin1) + (long long)b * a.kin_bstride + col;
@@ -319,7 +327,14 @@ __global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) row
     C* const sms[2] = {smem + (size_t)(2 * r) * N, smem + (size_t)(2 * r + 1) * N};
     if (!FAST && a.dbg != nullptr) { if (v[0][0].x == (T)1.2345e300 || v[1][E - 1].y == (T)1.2345e300) a.dbg[6] = 1; SGPE_MARK(1); }
 
-    if (do_inv) cta_fft<T, N, E, +1, 1, 2>(v, j, 0, sms, a.tw + (E == 16 ? N : 0));
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+    if (pass == 0 ? do_inv : do_fwd) {
+        if (pass == 0) { conj_all(v[0]); conj_all(v[1]); }
+        cta_fft<T, N, E, -1, 1, 2>(v, j, 0, sms, a.tw + (E == 16 ? N : 0));
+        if (pass == 0) { conj_all(v[0]); conj_all(v[1]); }
+    }
+    if (pass == 1) break;
     SGPE_MARK(2);
 
     if (do_pw) {
@@ -388,7 +403,7 @@ __global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) row
     }
 
     SGPE_MARK(3);
-    if (do_fwd) cta_fft<T, N, E, -1, 1, 2>(v, j, 0, sms, a.tw + (E == 16 ? N : 0));
+    }   // pass loop
     SGPE_MARK(4);
 
     const T sc = FAST ? (T)1 : (T)a.scale_out;
@@ -559,9 +574,15 @@ __global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) kli
         v[1][m] = a.in[off1 + j + m * NT];
     }
     C* const sms[2] = {smem + (size_t)(2 * r) * N, smem + (size_t)(2 * r + 1) * N};
-    if (a.do_fwd) cta_fft<T, N, E, -1, 1, 2>(v, j, 0, sms, a.tw + (E == 16 ? N : 0));
-
     double acc[4] = {0.0, 0.0, 0.0, 0.0};      // S0, T0, S1, T1
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+    if (pass == 0 ? a.do_fwd : a.do_inv) {
+        if (pass == 1) { conj_all(v[0]); conj_all(v[1]); }
+        cta_fft<T, N, E, -1, 1, 2>(v, j, 0, sms, a.tw + (E == 16 ? N : 0));
+        if (pass == 1) { conj_all(v[0]); conj_all(v[1]); }
+    }
+    if (pass == 1) break;
     if (a.has_a || a.has_b) {
 #pragma unroll
         for (int comp = 0; comp < 2; comp++) {
@@ -594,7 +615,7 @@ __global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) kli
         if (!a.has_b) { acc[1] = acc[0]; acc[3] = acc[2]; }
         if (!a.has_a) { acc[0] = acc[1]; acc[2] = acc[3]; }
     }
-    if (a.do_inv) cta_fft<T, N, E, +1, 1, 2>(v, j, 0, sms, a.tw + (E == 16 ? N : 0));
+    }   // pass loop
 #pragma unroll
     for (int m = 0; m < E; m++) {
         a.out[off0 + j + m * NT] = v[0][m];
