@@ -28,6 +28,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 W0 = 2 * np.pi * 50
+MODE = 'imag'                       # --mode real switches the whole run to real-time propagation
+DT = {'imag': 1 / 50, 'real': 1 / 5000}
 
 
 def build_problem(mesh, g_ud=1.04, tag='bench'):
@@ -106,7 +108,7 @@ def oracle_steps_per_s(ps, max_steps, warmup, budget_s=40.0):
                        ps.space['dv_r'], ps.space['dv_k'], [ps.g_sc['uu'], ps.g_sc['dd'], ps.g_sc['ud']],
                        ps.atom_num, x=ps.space['x'], kL=ps.kL_recoil, is_coupling=ps.is_coupling,
                        rot_coupling=ps.rot_coupling)
-    o = orc.OraclePropagator(prob, 1 / 50, 'imag')
+    o = orc.OraclePropagator(prob, DT[MODE], MODE)
     t0 = time.perf_counter()
     o.full_step()
     t_first = time.perf_counter() - t0
@@ -141,7 +143,8 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, where):
-    return {'workload': f'imaginary-time ground state {args.mesh}x{args.mesh} {args.precision}, benchmark_prop.py '
+    kind = 'imaginary-time ground state' if MODE == 'imag' else 'real-time propagation (dt=1/5000)'
+    return {'workload': f'{kind} {args.mesh}x{args.mesh} {args.precision}, benchmark_prop.py '
                         'parameters (atom_num=1e2, g=(1,1,1.04), r_sizes=(8,8), coupling_setup(kin_shift=False), '
                         'dt=1/50), per-step renormalisation + populations (BASELINE configs[2])',
             'mesh': [args.mesh, args.mesh], 'trajectories_per_gpu': 1, 'where': where,
@@ -172,7 +175,7 @@ def run_ours(args, rank, world, local_rank):
         pl = Plan(mesh, mesh, 1, cdtype, dev)
         pl.set_grid(ps.space['dr'][0], ps.space['dr'][1], ps.space['dv_r'], ps.space['dv_k'], ps.atom_num)
         pl.set_interactions(ps.g_sc['uu'], ps.g_sc['dd'], ps.g_sc['ud'])
-        pl.set_time('imag', 1 / 50)
+        pl.set_time(MODE, DT[MODE])
         pl.set_coupling(_capi.SGPE_COUPLING_NONE)        # Omega == 0: C is exactly the identity
         return pl
 
@@ -318,7 +321,10 @@ def main():
     ap.add_argument('--stagger-ns', type=int, default=0)
     ap.add_argument('--row-mode', type=int, default=0, choices=[0, 1])
     ap.add_argument('--col-tile', type=int, default=0, choices=[0, 2, 8])
+    ap.add_argument('--mode', default='imag', choices=['imag', 'real'])
     args = ap.parse_args()
+    global MODE
+    MODE = args.mode
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
