@@ -132,6 +132,16 @@ int sgpe_energy(sgpe_plan* p, const void* psik_dev, int unwrap_mode, double kl_t
  *                     sums_dev[3] receives the local T, S0, S1.
  *  sgpe_slab_pack   : [2][lines][P*chunk] -> [P][2][lines][chunk]    (send buffer of the all-to-all)
  *  sgpe_slab_unpack : [P][2][h][w] -> [2][w][P*h], transposing every block (receive side). */
+/* Line plans for the slab mode: `nlines` contiguous lines of `len` points, both components, caller-owned
+ * buffers ([2][nlines][len]).  n1 == 1: len in [32, 4096].  n1 > 1: four-step split len = n1 * n2 for lines a
+ * CTA cannot hold (16384 = 128 x 128): sgpe_pass_klines then transforms the contiguous sub-lines of n2 points
+ * (its operator tables are indexed by the position n1-digit * n2 + n2-digit, i.e. k-space is kept in the
+ * digit-transposed order  position k1*n2 + k2  <->  frequency k1 + n1*k2), and sgpe_pass_mid does the strided
+ * half over n1 with the four-step twiddles and, optionally, the real-space operators fused in:
+ *   [* conj w] [iFFT over k1] [norm, I C P C I] [FFT over n1] [* w]. */
+int sgpe_plan_create_lines(sgpe_plan** out, int len, int nlines, int n1, int dtype, int device);
+int sgpe_pass_mid(sgpe_plan* p, void* buf_dev, int pre_tw, int do_inv, int do_pw, double dt_sub, int do_fwd,
+                  int post_tw, const double* totals_dev, double global_points, sgpe_stream st);
 int sgpe_pass_rows(sgpe_plan* p, void* buf_dev, double dt_sub, const double* totals_dev, double global_points,
                    sgpe_stream st);
 int sgpe_pass_klines(sgpe_plan* p, void* buf_dev, int do_fwd, int has_a, double tau_a, int has_b, double tau_b,

@@ -23,12 +23,23 @@ enum { TM_REAL = 0, TM_IMAG = 1 };
 // exp(-i * e * tau), tau = (tr, ti):  real time tau = (dt, 0);  imaginary time tau = (0, -dt)
 template <int TM, typename T, typename C> SGPE_DI C evo(double e, double tr, double ti) {
     C r;
-    if (TM == TM_REAL) {
-        double s, c;
-        sincos(e * tr, &s, &c);
-        r.x = (T)c; r.y = (T)(-s);
+    if constexpr (sizeof(T) == 4) {
+        // complex64 plans: the argument is formed in double, the transcendental runs on the FP32 pipe
+        if (TM == TM_REAL) {
+            float s, c;
+            sincosf((float)(e * tr), &s, &c);
+            r.x = c; r.y = -s;
+        } else {
+            r.x = expf((float)(e * ti)); r.y = 0.f;
+        }
     } else {
-        r.x = (T)exp(e * ti); r.y = (T)0;
+        if (TM == TM_REAL) {
+            double s, c;
+            sincos(e * tr, &s, &c);
+            r.x = (T)c; r.y = (T)(-s);
+        } else {
+            r.x = (T)exp(e * ti); r.y = (T)0;
+        }
     }
     return r;
 }
@@ -550,7 +561,9 @@ template <typename T> struct KLineArgs {
     int kin_mode;                                    // 0 dense (grids given line-major), 1 separable
     const double* kin0; const double* kin1;          // dense: [nlines][N]
     double ka_re, ka_im, kb_re, kb_im;
-    const C* la; const C* pa; const C* lb; const C* pb;   // separable: per-line [2][nlines], per-position [2][N]
+    const C* la; const C* pa; const C* lb; const C* pb;   // separable: per-line [2][nlines/group], per-position [2][group*N]
+    int group;                                       // sub-lines per long line (1 normally): line table index =
+                                                     // line/group, position table index = (line%group)*N + pos
     double* partials; unsigned* counter; double* sums;    // sums: [3] = T, S0, S1 of the LOCAL slab
 };
 
@@ -588,9 +601,11 @@ __global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) kli
         for (int comp = 0; comp < 2; comp++) {
             C la, lb;
             la.x = (T)1; la.y = (T)0; lb = la;
+            const int lgrp = line / a.group;
+            const long long pbase = (long long)comp * a.group * a.nx + (long long)(line % a.group) * a.nx;
             if (a.kin_mode == 1) {
-                if (a.has_a) la = __ldg(&a.la[(long long)comp * a.ny + line]);
-                if (a.has_b) lb = __ldg(&a.lb[(long long)comp * a.ny + line]);
+                if (a.has_a) la = __ldg(&a.la[(long long)comp * (a.ny / a.group) + lgrp]);
+                if (a.has_b) lb = __ldg(&a.lb[(long long)comp * (a.ny / a.group) + lgrp]);
             }
             const double* kin = (comp == 0 ? a.kin0 : a.kin1);
 #pragma unroll
@@ -599,13 +614,13 @@ __global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) kli
                 C x = v[comp][m];
                 if (a.has_a) {
                     const C f = (a.kin_mode == 0) ? evo<TM, T, C>(__ldg(&kin[off0 + pos]), a.ka_re, a.ka_im)
-                                                  : combine_factor<TM>(la, __ldg(&a.pa[(long long)comp * a.nx + pos]));
+                                                  : combine_factor<TM>(la, __ldg(&a.pa[pbase + pos]));
                     x = mul_factor<TM>(x, f);
                     acc[2 * comp] += (double)x.x * x.x + (double)x.y * x.y;
                 }
                 if (a.has_b) {
                     const C f = (a.kin_mode == 0) ? evo<TM, T, C>(__ldg(&kin[off0 + pos]), a.kb_re, a.kb_im)
-                                                  : combine_factor<TM>(lb, __ldg(&a.pb[(long long)comp * a.nx + pos]));
+                                                  : combine_factor<TM>(lb, __ldg(&a.pb[pbase + pos]));
                     x = mul_factor<TM>(x, f);
                     acc[2 * comp + 1] += (double)x.x * x.x + (double)x.y * x.y;
                 }
@@ -646,6 +661,131 @@ __global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) kli
                 a.counter[0] = 0u;
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Lines longer than one CTA can hold (> 4096 points): four-step transform.  A line of N = N1*N2 points is the
+// matrix A[n1][n2] (n = n1*N2 + n2).  forward:  FFT over n1 (stride N2)  ->  * w_N^(k1 n2)  ->  FFT over n2
+// (contiguous), result X[k1 + N1 k2] left at position k1*N2 + k2 ("digit-transposed" order, which the
+// propagator never needs to undo: operator tables are permuted instead).  inverse: the mirror image.
+// mid_pass is the STRIDED half with the real-space operators fused in, for both components of one line:
+//     [* conj w] -> [iFFT over k1] -> [normalise, I C P C I at x = n1*N2 + n2] -> [FFT over n1] -> [* w]
+// i.e. for long lines the row pass becomes  contiguous-iFFT | mid_pass | contiguous-FFT  (kline_pass does the
+// contiguous halves), and the k-space junction  mid_pass(fwd) | kline_pass(FFT K iFFT) | mid_pass(inv).
+// Array: [2][nlines][N1][N2].  One CTA = W adjacent n2 of one line; thread (c, j) holds n1 = j + m*N1/E.
+template <typename T> struct MidArgs {
+    typedef typename cx_of<T>::type C;
+    RowArgs<T> r;                  // operators / flags of the row pass (r.nx = N1*N2, r.ny = nlines, r.tw = N1 tables)
+    int n2;                        // contiguous dimension of the matrix view
+    int pre_tw, post_tw;           // multiply by conj(w_N^(k1 n2)) before the inverse / by w_N^(k1 n2) after the forward
+    const C* tw4;                  // [N1][N2] four-step twiddles exp(-2 pi i k1 n2 / N)
+};
+
+template <typename T, int N1, int E, int W, int TM>
+__global__ void __launch_bounds__(W * N1 / E) mid_pass(MidArgs<T> ma) {
+    typedef typename cx_of<T>::type C;
+    const RowArgs<T>& a = ma.r;
+    constexpr int NT = N1 / E;
+    SGPE_DYN_SMEM(smem_raw);
+    C* smem = reinterpret_cast<C*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int c = tid % W, j = tid / W;
+    const int n2 = blockIdx.x * W + c;
+    const int y = blockIdx.y;                       // line (local row)
+    const int b = 0;
+    const long long line0 = (long long)y * a.nx + n2, line1 = line0 + a.plane;
+
+    C v[2][E];
+#pragma unroll
+    for (int m = 0; m < E; m++) {
+        const long long o = (long long)(j + m * NT) * ma.n2;
+        v[0][m] = SGPE_LD_STREAM(&a.in[line0 + o]);
+        v[1][m] = SGPE_LD_STREAM(&a.in[line1 + o]);
+    }
+    if (ma.pre_tw) {
+#pragma unroll
+        for (int m = 0; m < E; m++) {
+            const C w = __ldg(&ma.tw4[(long long)(j + m * NT) * ma.n2 + n2]);
+            v[0][m] = cmulc(v[0][m], w); v[1][m] = cmulc(v[1][m], w);
+        }
+    }
+    C* const sms[2] = {smem, smem + (size_t)N1 * W};
+    if (a.do_inv) cta_fft<T, N1, E, +1, W, 2>(v, j, c, sms, a.tw + (E == 16 ? N1 : 0));
+
+    if (a.do_pw) {
+        const int cpl_mode = a.cpl_mode, pot_mode = a.pot_mode;
+        const T alpha = (T)sqrt(a.norm_c / a.totals[0]);
+        C py0, py1;
+        py0.x = (T)1; py0.y = (T)0; py1 = py0;
+        if (pot_mode == 1) { py0 = __ldg(&a.py[y]); py1 = __ldg(&a.py[y + a.ny]); }
+        const long long prow = (long long)y * a.nx;
+        const bool same_pot = (a.pot0 == a.pot1);
+        T cu_diag = (T)1, cu_s = (T)0;
+        if (cpl_mode == 1) {
+            C one; one.x = (T)1; one.y = (T)0;
+            C t01, t10;
+            coupling_entries<TM, T, C>(a.omega_b[b] * a.tc, one, cu_diag, t01, t10);
+            cu_s = (TM == TM_REAL) ? -t01.y : -t01.x;
+        }
+#pragma unroll
+        for (int m = 0; m < E; m++) {
+            const int x = (j + m * NT) * ma.n2 + n2;           // natural position along the long line
+            C p = cscale(v[0][m], alpha), q = cscale(v[1][m], alpha);
+            const double d0 = (double)p.x * p.x + (double)p.y * p.y;
+            const double d1 = (double)q.x * q.x + (double)q.y * q.y;
+            const C i0 = evo<TM, T, C>(a.g_uu * d0 + a.g_ud * d1, a.ti_re, a.ti_im);
+            const C i1 = evo<TM, T, C>(a.g_dd * d1 + a.g_ud * d0, a.ti_re, a.ti_im);
+            p = mul_factor<TM>(p, i0); q = mul_factor<TM>(q, i1);
+            T diag = (T)1; C o01, o10;
+            if (cpl_mode) {
+                C ph; ph.x = (T)1; ph.y = (T)0;
+                if (a.eiphi != nullptr) ph = __ldg(&a.eiphi[x]);
+                if (cpl_mode == 1) {
+                    diag = cu_diag;
+                    if (TM == TM_REAL) {
+                        o01.x = -cu_s * ph.y; o01.y = -cu_s * ph.x; o10.x = cu_s * ph.y; o10.y = -cu_s * ph.x;
+                    } else {
+                        o01.x = -cu_s * ph.x; o01.y = cu_s * ph.y; o10.x = -cu_s * ph.x; o10.y = -cu_s * ph.y;
+                    }
+                } else {
+                    coupling_entries<TM, T, C>(__ldg(&a.coupling[prow + x]) * a.tc, ph, diag, o01, o10);
+                }
+                const C p2 = cadd(cscale(p, diag), cmul(o01, q));
+                const C q2 = cadd(cmul(o10, p), cscale(q, diag));
+                p = p2; q = q2;
+            }
+            C f0, f1;
+            if (pot_mode == 0) {
+                f0 = evo<TM, T, C>(__ldg(&a.pot0[prow + x]), a.tp_re, a.tp_im);
+                f1 = same_pot ? f0 : evo<TM, T, C>(__ldg(&a.pot1[prow + x]), a.tp_re, a.tp_im);
+            } else {
+                f0 = combine_factor<TM>(__ldg(&a.px[x]), py0);
+                f1 = combine_factor<TM>(__ldg(&a.px[x + a.nx]), py1);
+            }
+            p = mul_factor<TM>(p, f0); q = mul_factor<TM>(q, f1);
+            if (cpl_mode) {
+                const C p2 = cadd(cscale(p, diag), cmul(o01, q));
+                const C q2 = cadd(cmul(o10, p), cscale(q, diag));
+                p = p2; q = q2;
+            }
+            v[0][m] = mul_factor<TM>(p, i0); v[1][m] = mul_factor<TM>(q, i1);
+        }
+    }
+
+    if (a.do_fwd) cta_fft<T, N1, E, -1, W, 2>(v, j, c, sms, a.tw + (E == 16 ? N1 : 0));
+    if (ma.post_tw) {
+#pragma unroll
+        for (int m = 0; m < E; m++) {
+            const C w = __ldg(&ma.tw4[(long long)(j + m * NT) * ma.n2 + n2]);
+            v[0][m] = cmul(v[0][m], w); v[1][m] = cmul(v[1][m], w);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < E; m++) {
+        const long long o = (long long)(j + m * NT) * ma.n2;
+        SGPE_ST_STREAM(&a.out[line0 + o], v[0][m]);
+        SGPE_ST_STREAM(&a.out[line1 + o], v[1][m]);
     }
 }
 
@@ -700,7 +840,12 @@ template <typename T>
 __global__ void __launch_bounds__(256) exp_table(ExpTableArgs<T> a) {
     typedef typename cx_of<T>::type C;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x)
-        a.out[i] = (a.tm == TM_REAL) ? evo<TM_REAL, T, C>(a.e[i], a.tr, a.ti) : evo<TM_IMAG, T, C>(a.e[i], a.tr, a.ti);
+    {   // one-off tables: always evaluated in double, rounded once to the plan's precision
+        const double2 w = (a.tm == TM_REAL) ? evo<TM_REAL, double, double2>(a.e[i], a.tr, a.ti)
+                                            : evo<TM_IMAG, double, double2>(a.e[i], a.tr, a.ti);
+        C o; o.x = (T)w.x; o.y = (T)w.y;
+        a.out[i] = o;
+    }
 }
 
 // out = in * sqrt(N / (dv * (S0 + S1)))  — the trailing ttools.norm of single_step

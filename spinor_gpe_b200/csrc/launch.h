@@ -10,6 +10,7 @@ namespace sgpe {
     int launch_row_##N(int dtype, int tm, const void* args, int batch, int mode, cudaStream_t st); \
     int launch_col_##N(int dtype, int tm, const void* args, int batch, int wsel, cudaStream_t st); \
     int launch_kline_##N(int dtype, int tm, const void* args, cudaStream_t st);                    \
+    int launch_mid_##N(int dtype, int tm, const void* args, cudaStream_t st);                      \
     int col_tile_width_##N(int dtype);
 SGPE_FOR_EACH_N(SGPE_DECL)
 #undef SGPE_DECL
@@ -34,6 +35,12 @@ inline int launch_col(int n, int dtype, int tm, const void* args, int batch, int
 }
 inline int launch_kline(int n, int dtype, int tm, const void* args, cudaStream_t st) {
 #define SGPE_CASE(N) if (n == N) return launch_kline_##N(dtype, tm, args, st);
+    SGPE_FOR_EACH_N(SGPE_CASE)
+#undef SGPE_CASE
+    return -1;
+}
+inline int launch_mid(int n, int dtype, int tm, const void* args, cudaStream_t st) {
+#define SGPE_CASE(N) if (n == N) return launch_mid_##N(dtype, tm, args, st);
     SGPE_FOR_EACH_N(SGPE_CASE)
 #undef SGPE_CASE
     return -1;

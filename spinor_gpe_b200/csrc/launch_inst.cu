@@ -149,6 +149,27 @@ static int launch_kline_t(const KLineArgs<T>& a, cudaStream_t st) {
     return 0;
 }
 
+// strided half of the four-step transform (only lengths that fit: 2 * N1 * W elements of shared memory)
+template <typename T, int N, int TM>
+static int launch_mid_t(const MidArgs<T>& a, int n2_tiles_unused, cudaStream_t st) {
+    (void)n2_tiles_unused;
+    if constexpr (N <= 1024) {
+        constexpr int E = 8, NT = N / E;
+        constexpr int CB = (int)sizeof(typename cx_of<T>::type);
+        constexpr int W0 = (NT <= 16) ? (128 / NT) : 4;
+        constexpr int W = (CB == 8 && W0 < 8) ? 8 : W0;          // complex64: keep 64-byte segments
+        constexpr size_t smem = (size_t)2 * N * W * CB;
+        if (a.n2 % W != 0) return -2;
+        static bool once = false;
+        if (!once) { allow_smem(mid_pass<T, N, E, W, TM>, smem); once = true; }
+        dim3 grid(a.n2 / W, a.r.ny), block(W * NT);
+        SGPE_LAUNCH((mid_pass<T, N, E, W, TM>), grid, block, smem, st, a);
+        return 0;
+    } else {
+        return -2;
+    }
+}
+
 #define SGPE_CAT2(a, b) a##b
 #define SGPE_CAT(a, b) SGPE_CAT2(a, b)
 
@@ -195,6 +216,15 @@ int SGPE_CAT(launch_kline_, SGPE_N)(int dtype, int tm, const void* args, cudaStr
     }
     const KLineArgs<float>& a = *static_cast<const KLineArgs<float>*>(args);
     return tm == TM_REAL ? launch_kline_t<float, SGPE_N, TM_REAL>(a, st) : launch_kline_t<float, SGPE_N, TM_IMAG>(a, st);
+}
+
+int SGPE_CAT(launch_mid_, SGPE_N)(int dtype, int tm, const void* args, cudaStream_t st) {
+    if (dtype == 0) {
+        const MidArgs<double>& a = *static_cast<const MidArgs<double>*>(args);
+        return tm == TM_REAL ? launch_mid_t<double, SGPE_N, TM_REAL>(a, 0, st) : launch_mid_t<double, SGPE_N, TM_IMAG>(a, 0, st);
+    }
+    const MidArgs<float>& a = *static_cast<const MidArgs<float>*>(args);
+    return tm == TM_REAL ? launch_mid_t<float, SGPE_N, TM_REAL>(a, 0, st) : launch_mid_t<float, SGPE_N, TM_IMAG>(a, 0, st);
 }
 
 int SGPE_CAT(col_tile_width_, SGPE_N)(int dtype) {

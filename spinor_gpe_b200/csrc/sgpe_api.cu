@@ -75,6 +75,8 @@ struct sgpe_plan {
     int stagger_ns = 0;            // option "stagger_ns"
     int prefetch = 1;              // L2 prefetch of the next tile of each SM (option "prefetch")
     int row_mode = 0;              // 0: both components per thread, 1: split (one component per thread)
+    // long lines (four-step): nx = n1 * n2 with the strided part n1 (1 = ordinary plan)
+    int n1 = 1, n2 = 0; void* tw_mid = nullptr; void* tw4 = nullptr;
     int col_wsel = 0;              // column tile width selector (sgpe_set_option "col_tile")
     int cpl_mode = 0; const double* cpl = nullptr; long long cpl_bs = 0;
     const double* omega = nullptr; const void* eiphi = nullptr;
@@ -411,9 +413,12 @@ static int run_klines(sgpe_plan* p, void* buf, bool fwd, bool has_a, double tau_
     memset(&a, 0, sizeof(a));
     a.in = static_cast<const C*>(buf); a.out = static_cast<C*>(buf);
     a.tw = static_cast<const C*>(p->tw_x);
-    a.nx = p->nx; a.ny = p->ny; a.plane = p->plane;
+    const int len = (p->n1 > 1) ? p->n2 : p->nx;           // contiguous transform length (sub-lines of a long line)
+    a.nx = len; a.ny = p->ny * p->n1; a.plane = p->plane; a.group = p->n1;
     a.do_fwd = fwd; a.do_inv = inv; a.has_a = has_a; a.has_b = has_b;
     a.kin_mode = p->kin_mode;
+    if (p->n1 > 1 && p->kin_mode == 0 && (has_a || has_b))
+        return fail(SGPE_EINVAL, "long lines need the separable kinetic operator");
     if (has_a || has_b) {
         if (p->kin_mode == 0) {
             a.kin0 = p->kin0; a.kin1 = p->kin1;
@@ -434,10 +439,57 @@ static int run_klines(sgpe_plan* p, void* buf, bool fwd, bool has_a, double tau_
     }
     a.partials = p->partials; a.counter = p->counter; a.sums = sums;
     ProfScope prof(p, 0, st);
-    int rc = sgpe::launch_kline(p->nx, p->dtype, p->tm, &a, st);
+    int rc = sgpe::launch_kline(len, p->dtype, p->tm, &a, st);
     if (rc != 0) return fail(SGPE_EINVAL, "line pass: unsupported geometry");
     p->launches++;
     SGPE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+static int run_mid(sgpe_plan* p, void* buf, bool pre_tw, bool inv, bool pw, double dt_sub, bool fwd, bool post_tw,
+                   const double* totals, double global_points, cudaStream_t st) {
+    typedef typename sgpe::cx_of<T>::type C;
+    sgpe::MidArgs<T> m;
+    memset(&m, 0, sizeof(m));
+    sgpe::RowArgs<T>& a = m.r;
+    a.in = static_cast<const C*>(buf); a.out = static_cast<C*>(buf);
+    a.tw = static_cast<const C*>(p->tw_mid);
+    a.nx = p->nx; a.ny = p->ny; a.plane = p->plane;
+    a.do_inv = inv; a.do_pw = pw; a.do_fwd = fwd; a.scale_out = 1.0;
+    a.pot0 = p->pot0; a.pot1 = p->pot1; a.pot_bstride = 0;
+    a.pot_mode = pw ? p->pot_mode : 0;
+    if (pw && p->pot_mode == 1) {
+        sgpe_plan::FactorTable* t = nullptr;
+        int rc0 = factor_table<T>(p, p->pot_tab, 4, p->pot_x, 0, p->pot_y, 0, dt_sub, st, &t);
+        if (rc0) return rc0;
+        a.px = static_cast<const C*>(t->x); a.py = static_cast<const C*>(t->y);
+    }
+    a.cpl_mode = p->cpl_mode; a.coupling = p->cpl; a.omega_b = p->omega;
+    a.eiphi = static_cast<const C*>(p->eiphi);
+    a.g_uu = p->g_uu; a.g_dd = p->g_dd; a.g_ud = p->g_ud;
+    time_arg(p->tm, dt_sub / 2, &a.ti_re, &a.ti_im);
+    time_arg(p->tm, dt_sub, &a.tp_re, &a.tp_im);
+    a.tc = dt_sub / 4;
+    a.totals = totals;
+    a.norm_c = p->atom_num / (p->dv_r * global_points);
+    m.n2 = p->n2; m.pre_tw = pre_tw; m.post_tw = post_tw; m.tw4 = static_cast<const C*>(p->tw4);
+    ProfScope prof(p, 1, st);
+    int rc = sgpe::launch_mid(p->n1, p->dtype, p->tm, &m, st);
+    if (rc != 0) return fail(SGPE_EINVAL, "strided pass: unsupported geometry");
+    p->launches++;
+    SGPE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+static int upload_tw4(sgpe_plan* p) {
+    typedef typename sgpe::cx_of<T>::type C;
+    std::vector<C> h((size_t)p->n1 * p->n2);
+    for (long long k1 = 0; k1 < p->n1; k1++)
+        for (long long q = 0; q < p->n2; q++) h[k1 * p->n2 + q] = unit_root<T>(k1 * q, (long long)p->n1 * p->n2);
+    SGPE_CUDA(cudaMalloc(&p->tw4, sizeof(C) * h.size()));
+    SGPE_CUDA(cudaMemcpy(p->tw4, h.data(), sizeof(C) * h.size(), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -518,7 +570,7 @@ int sgpe_plan_destroy(sgpe_plan* p) {
     DeviceGuard guard(p->device);
     cudaFree(p->state); cudaFree(p->tw_x); cudaFree(p->tw_y); cudaFree(p->partials);
     cudaFree(p->counter); cudaFree(p->totals); cudaFree(p->totals_aux); cudaFree(p->pops_buf);
-    cudaFree(p->scratch); cudaFree(p->maxdens); cudaFree(p->sm_slots);
+    cudaFree(p->scratch); cudaFree(p->maxdens); cudaFree(p->sm_slots); cudaFree(p->tw_mid); cudaFree(p->tw4);
     for (auto& t : p->kin_tab) { cudaFree(t.x); cudaFree(t.y); }
     for (auto& t : p->pot_tab) { cudaFree(t.x); cudaFree(t.y); }
     delete p;
@@ -742,6 +794,62 @@ int sgpe_pass_rows(sgpe_plan* p, void* buf, double dt_sub, const double* totals_
     DeviceGuard guard(p->device);
     return SGPE_BY_DTYPE(p, run_row, p, buf, buf, true, true, dt_sub, true, 0, 0, 1.0, (cudaStream_t)st, totals_dev,
                          global_points);
+}
+
+int sgpe_plan_create_lines(sgpe_plan** out, int len, int nlines, int n1, int dtype, int device) {
+    if (!out) return fail(SGPE_EINVAL, "null output pointer");
+    *out = nullptr;
+    if (n1 < 1 || len % n1 != 0) return fail(SGPE_EINVAL, "n1 must divide the line length");
+    const int n2 = len / n1;
+    if (n1 == 1) {
+        if (!sgpe::supported_length(len)) return fail(SGPE_EINVAL, "line length must be a power of two in [32, 4096]");
+    } else if (!sgpe::supported_length(n1) || n1 > 1024 || !sgpe::supported_length(n2)) {
+        return fail(SGPE_EINVAL, "four-step split: n1 in [32, 1024], n2 = len / n1 in [32, 4096], powers of two");
+    }
+    if (nlines < 1) return fail(SGPE_EINVAL, "nlines must be >= 1");
+    if (dtype != SGPE_C128 && dtype != SGPE_C64) return fail(SGPE_EINVAL, "dtype must be 0 (c128) or 1 (c64)");
+    DeviceGuard guard(device);
+    sgpe_plan* p = new sgpe_plan();
+    p->nx = len; p->ny = nlines; p->batch = 1; p->dtype = dtype; p->device = device;
+    p->csize = dtype == SGPE_C128 ? 16 : 8;
+    p->plane = (long long)len * nlines;
+    p->n1 = n1; p->n2 = n2;
+    p->max_tiles = 2 * (nlines * n1 > len ? nlines * n1 : len);
+    if (p->max_tiles < 1024) p->max_tiles = 1024;
+    int rc = 0;
+    do {
+        if (cudaMalloc((void**)&p->partials, sizeof(double) * 2 * (size_t)p->max_tiles) != cudaSuccess) { rc = SGPE_ENOMEM; break; }
+        if (cudaMalloc((void**)&p->counter, sizeof(unsigned)) != cudaSuccess) { rc = SGPE_ENOMEM; break; }
+        if (cudaMalloc((void**)&p->totals, sizeof(double) * 4) != cudaSuccess) { rc = SGPE_ENOMEM; break; }
+        if (cudaMalloc((void**)&p->totals_aux, sizeof(double) * 4) != cudaSuccess) { rc = SGPE_ENOMEM; break; }
+        cudaMemset(p->counter, 0, sizeof(unsigned));
+        const int cont = n1 == 1 ? len : n2;
+        rc = dtype == SGPE_C128 ? upload_twiddles<double>(&p->tw_x, cont) : upload_twiddles<float>(&p->tw_x, cont);
+        if (rc) break;
+        if (n1 > 1) {
+            rc = dtype == SGPE_C128 ? upload_twiddles<double>(&p->tw_mid, n1) : upload_twiddles<float>(&p->tw_mid, n1);
+            if (rc) break;
+            rc = dtype == SGPE_C128 ? upload_tw4<double>(p) : upload_tw4<float>(p);
+        }
+    } while (0);
+    if (rc) {
+        if (rc == SGPE_ENOMEM) fail(rc, "device allocation failed");
+        sgpe_plan_destroy(p);
+        return rc;
+    }
+    *out = p;
+    return 0;
+}
+
+int sgpe_pass_mid(sgpe_plan* p, void* buf, int pre_tw, int do_inv, int do_pw, double dt_sub, int do_fwd, int post_tw,
+                  const double* totals_dev, double global_points, sgpe_stream st) {
+    if (!p || !buf) return fail(SGPE_EINVAL, "null argument");
+    if (p->n1 <= 1) return fail(SGPE_ESTATE, "not a four-step (long line) plan");
+    if (do_pw && (!totals_dev || !(p->grid_set && p->g_set && p->pot_set && p->time_set)))
+        return fail(SGPE_ESTATE, "plan not configured for the point-wise operators");
+    DeviceGuard guard(p->device);
+    return SGPE_BY_DTYPE(p, run_mid, p, buf, pre_tw != 0, do_inv != 0, do_pw != 0, dt_sub, do_fwd != 0, post_tw != 0,
+                         totals_dev, global_points > 0 ? global_points : 1.0, (cudaStream_t)st);
 }
 
 int sgpe_pass_klines(sgpe_plan* p, void* buf, int do_fwd, int has_a, double tau_a, int has_b, double tau_b, int do_inv,

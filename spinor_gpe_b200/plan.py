@@ -21,7 +21,7 @@ def _dp(t):
 class Plan:
     """One propagator plan on one GPU for ``batch`` independent trajectories of an (ny, nx) mesh."""
 
-    def __init__(self, nx, ny, batch=1, dtype=torch.complex128, device='cuda', _lib=None):
+    def __init__(self, nx, ny, batch=1, dtype=torch.complex128, device='cuda', _lib=None, lines_n1=None):
         # ``_lib`` is a test hook: tests/emu_harness.py passes the emulated build of the same sources so that
         # host-side logic (sharding, slab orchestration) can run on CPU tensors; the product never sets it.
         self.device = torch.device(device)
@@ -39,8 +39,13 @@ class Plan:
         self.rdtype = torch.float64
         code = _capi.SGPE_C128 if dtype == torch.complex128 else _capi.SGPE_C64
         self.h = ctypes.c_void_p()
-        self._chk(self.lib.sgpe_plan_create(ctypes.byref(self.h), self.nx, self.ny, self.batch, code,
-                                            self.device.index or 0), 'sgpe_plan_create')
+        if lines_n1 is None:
+            self._chk(self.lib.sgpe_plan_create(ctypes.byref(self.h), self.nx, self.ny, self.batch, code,
+                                                self.device.index or 0), 'sgpe_plan_create')
+        else:
+            # line plan of the slab mode: ny lines of nx points, caller-owned buffers, optional four-step split
+            self._chk(self.lib.sgpe_plan_create_lines(ctypes.byref(self.h), self.nx, self.ny, int(lines_n1), code,
+                                                      self.device.index or 0), 'sgpe_plan_create_lines')
         self.keep = {}
 
     # ------------------------------------------------------------------ plumbing
@@ -214,6 +219,11 @@ class Plan:
     def pass_klines(self, buf, do_fwd, has_a, tau_a, has_b, tau_b, do_inv, sums):
         self._chk(self.lib.sgpe_pass_klines(self.h, _dp(buf), int(do_fwd), int(has_a), float(tau_a), int(has_b),
                                             float(tau_b), int(do_inv), _dp(sums), self.stream), 'sgpe_pass_klines')
+
+    def pass_mid(self, buf, pre_tw, do_inv, do_pw, dt_sub, do_fwd, post_tw, totals, global_points):
+        self._chk(self.lib.sgpe_pass_mid(self.h, _dp(buf), int(pre_tw), int(do_inv), int(do_pw), float(dt_sub),
+                                         int(do_fwd), int(post_tw), _dp(totals), float(global_points), self.stream),
+                  'sgpe_pass_mid')
 
     def slab_pack(self, src, dst, lines, nranks, chunk):
         self._chk(self.lib.sgpe_slab_pack(self.h, _dp(src), _dp(dst), int(lines), int(nranks), int(chunk),

@@ -10,12 +10,15 @@ Rank r of P owns the rows y in [r Ny/P, (r+1) Ny/P).  A split sub-step is
 
 i.e. two all-to-alls per sub-step and k-space kept in the transposed layout, so a 2-D transform costs one
 exchange.  The local passes are the hand-written kernels behind ``sgpe_pass_rows / sgpe_pass_klines /
-sgpe_slab_pack / sgpe_slab_unpack``; ``torch.distributed`` (NCCL over NVLink) carries the collectives.
-Line lengths are limited to 4096 points this round, so this path is exercised on grids that
-would also fit one GPU and is checked against the single-GPU propagator.
-"""
-import math
+sgpe_pass_mid / sgpe_slab_pack / sgpe_slab_unpack``; ``torch.distributed`` (NCCL over NVLink) carries the
+collectives.
 
+Lines longer than 4096 points (16384^2 of config 5) use the four-step split N = n1 * n2 inside each line:
+contiguous sub-transforms (``pass_klines``) + a strided pass with the twiddles and the real-space operators
+fused in (``pass_mid``): three local passes per direction instead of one.  k-space then lives in the
+digit-transposed order (position k1*n2 + k2 <-> frequency k1 + n1*k2) along the split axes; the operator
+tables are permuted once on the host and the state is permuted back only when it is gathered.
+"""
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -24,21 +27,104 @@ from . import _capi
 from ._separable import split_separable
 
 MAGIC_GAMMA = 1 / (2 + 2 ** (1 / 3))
+MAX_LINE = 4096
+
+
+def four_step_split(n, forced=None):
+    """n1 of the split n = n1 * n2 (1 = the line fits one CTA)."""
+    if forced:
+        return int(forced)
+    if n <= MAX_LINE:
+        return 1
+    n1 = 32
+    while n // n1 > MAX_LINE or n1 * n1 < n:
+        n1 *= 2
+    return n1
+
+
+def digit_order(n, n1):
+    """nat[p]: natural index held at position p of the digit-transposed order (identity when n1 == 1)."""
+    if n1 == 1:
+        return np.arange(n)
+    n2 = n // n1
+    p = np.arange(n)
+    return (p // n2) + n1 * (p % n2)
+
+
+class SeparableProblem:
+    """A problem given by 1-D vectors only (no (Ny, Nx) host arrays) for grids too large to set up with
+    ``PSpinor`` on the host: harmonic trap (+ optional linear detuning along y), free / Raman-shifted
+    dispersion, uniform coupling; Thomas-Fermi initial state evaluated per rank on the device.  The scalar
+    set-up (a_x, rescaled g_sc, chemical potential, recoil units) comes from a tiny ``PSpinor``, so it is the
+    reference's arithmetic (pspinor.py:283-313, 469-501)."""
+
+    def __init__(self, mesh_points, r_sizes, atom_num=1e4, omeg=None, g_sc=None, pop_frac=(0.5, 0.5),
+                 coupling=None, wavel=790.1e-9, kin_shift=False, rot_coupling=True, detuning_slope=0.0):
+        import tempfile, os
+        from .pspinor import PSpinor
+        tiny = PSpinor(os.path.join(tempfile.mkdtemp(prefix='sgpe_sep_'), 'p') + os.sep, omeg=omeg, g_sc=g_sc,
+                       mesh_points=(32, 32), r_sizes=r_sizes, atom_num=atom_num, pop_frac=pop_frac)
+        self.atom_num, self.g_sc, self.chem_pot, self.pop_frac = atom_num, tiny.g_sc, tiny.chem_pot, pop_frac
+        self.omeg = tiny.omeg
+        nx, ny = int(mesh_points[0]), int(mesh_points[1])
+        self.nx, self.ny = nx, ny
+        rs = np.array(r_sizes, dtype=np.float64)
+        dr = 2 * rs / np.array([nx, ny])
+        self.space = {'dr': dr, 'dk': np.pi / rs, 'dv_r': float(np.prod(dr)), 'dv_k': float(np.prod(np.pi / rs)),
+                      'x': np.linspace(-rs[0], rs[0], nx, endpoint=False),
+                      'y': np.linspace(-rs[1], rs[1], ny, endpoint=False)}
+        ks = np.pi / dr
+        kx = np.linspace(-ks[0], ks[0], nx, endpoint=False)
+        ky = np.linspace(-ks[1], ks[1], ny, endpoint=False)
+        self.is_coupling = coupling is not None
+        self.rot_coupling = rot_coupling
+        self.kL_recoil, self.EL_recoil = 1.0, 1.0
+        shift = 0.0
+        if self.is_coupling:
+            tiny.coupling_setup(wavel=wavel, kin_shift=kin_shift)
+            self.kL_recoil, self.EL_recoil = tiny.kL_recoil, tiny.EL_recoil
+            shift = kx * self.kL_recoil if kin_shift else 0.0
+        gx = np.stack([kx ** 2 / 2 + shift, kx ** 2 / 2 - shift])
+        gx = gx - gx.min(axis=1, keepdims=True)                    # kin_eng_spin - min (pspinor.py:501)
+        self.kin_x, self.kin_y = gx, np.stack([ky ** 2 / 2, ky ** 2 / 2])
+        y_trap = self.omeg['y'] / self.omeg['x']
+        x, y = self.space['x'], self.space['y']
+        det = detuning_slope * y
+        self.pot_x = np.stack([x ** 2 / 2, x ** 2 / 2])
+        self.pot_y = np.stack([(y_trap * y) ** 2 / 2 + det / 2, (y_trap * y) ** 2 / 2 - det / 2])
+        self.omega = float(coupling) if self.is_coupling else 0.0
+
+    def tf_rows(self, y_rows, device, dtype):
+        """Thomas-Fermi amplitudes (pspinor.py:265-271) on the rows ``y_rows``: (2, len(y_rows), nx) tensor."""
+        x = torch.as_tensor(self.space['x'], device=device)
+        y = torch.as_tensor(np.asarray(y_rows), device=device)
+        y_trap = self.omeg['y'] / self.omeg['x']
+        v = (x[None, :] ** 2 + (y_trap * y[:, None]) ** 2) / 2
+        prof = torch.sqrt(torch.clamp(self.chem_pot - v, min=0.0))
+        g_bare = [self.g_sc['uu'], self.g_sc['dd']]
+        comps = [prof * float(np.sqrt(p / abs(g))) for p, g in zip(self.pop_frac, g_bare)]
+        return torch.stack(comps).to(dtype)
 
 
 class SlabPropagator:
     """Distributed TensorPropagator for one trajectory.  Every rank passes the same (global) ``PSpinor``; each
-    keeps only its slab on the device."""
+    keeps only its slab on the device.  ``split_x`` / ``split_y`` force a four-step split (tests)."""
 
-    def __init__(self, spin, t_step, time='imag', device='cuda', group=None, precision='c128', plan_kwargs=None):
+    def __init__(self, spin, t_step, time='imag', device='cuda', group=None, precision='c128', plan_kwargs=None,
+                 split_x=None, split_y=None):
         from .plan import Plan
         assert dist.is_initialized(), "SlabPropagator needs an initialised torch.distributed process group"
         self.group = group
         self.rank, self.P = dist.get_rank(group), dist.get_world_size(group)
         self.dev = torch.device(device)
         self.cdtype = torch.complex128 if precision == 'c128' else torch.complex64
-        psik = np.array([np.asarray(p) for p in spin.psik])
-        _, self.ny, self.nx = psik.shape
+        sep_only = isinstance(spin, SeparableProblem)
+        if sep_only:
+            self.nx, self.ny = spin.nx, spin.ny
+            psik = None
+        else:
+            psik = np.array([np.asarray(p) for p in spin.psik])
+            _, self.ny, self.nx = psik.shape
         P, r = self.P, self.rank
         assert self.nx % (32 * P) == 0 and self.ny % (32 * P) == 0, "mesh must split into multiples of 32 per rank"
         self.nxl, self.nyl = self.nx // P, self.ny // P
@@ -46,52 +132,95 @@ class SlabPropagator:
         self.dt_out, self.dt_in = self.dt * MAGIC_GAMMA, self.dt * (1 - 2 * MAGIC_GAMMA)
         self.atom_num = float(spin.atom_num)
         self.dv_k = float(spin.space['dv_k'])
+        self.n1x, self.n1y = four_step_split(self.nx, split_x), four_step_split(self.ny, split_y)
+        self.nat_x, self.nat_y = digit_order(self.nx, self.n1x), digit_order(self.ny, self.n1y)
         kw = dict(plan_kwargs or {})
         ys, xs = slice(r * self.nyl, (r + 1) * self.nyl), slice(r * self.nxl, (r + 1) * self.nxl)
+        self._ys = ys
 
-        # ---- row plan: local rows, full x
-        self.rp = rp = Plan(self.nx, self.nyl, 1, self.cdtype, self.dev, **kw)
+        # ---- row plan: local rows (natural y), full x
+        self.rp = rp = Plan(self.nx, self.nyl, 1, self.cdtype, self.dev, lines_n1=self.n1x, **kw)
         dr = spin.space['dr']
         rp.set_grid(dr[0], dr[1], spin.space['dv_r'], spin.space['dv_k'], spin.atom_num)
         rp.set_interactions(spin.g_sc['uu'], spin.g_sc['dd'], spin.g_sc['ud'])
-        pot = np.array([np.asarray(v) for v in spin.pot_eng_spin])
-        rp.set_potential(np.ascontiguousarray(pot[0, ys]), np.ascontiguousarray(pot[1, ys]))
-        psep = split_separable(pot)
-        if psep is not None:
-            rp.set_potential_separable(psep[0], np.ascontiguousarray(psep[1][:, ys]))
-        cpl = np.asarray(spin.coupling, dtype=np.float64)
         eiphi = None
         if spin.is_coupling and not spin.rot_coupling:
             eiphi = np.exp(1j * 2 * spin.kL_recoil * np.asarray(spin.space['x']))
-        if not spin.is_coupling or not np.any(cpl):
-            rp.set_coupling(_capi.SGPE_COUPLING_NONE)
-        elif np.all(cpl == cpl.flat[0]):
-            rp.set_coupling(_capi.SGPE_COUPLING_UNIFORM, omega=np.array([cpl.flat[0]]), eiphi=eiphi)
+        if sep_only:
+            rp.set_potential_separable(spin.pot_x, np.ascontiguousarray(spin.pot_y[:, ys]))
+            if spin.is_coupling and spin.omega != 0.0:
+                rp.set_coupling(_capi.SGPE_COUPLING_UNIFORM, omega=np.array([spin.omega]), eiphi=eiphi)
+            else:
+                rp.set_coupling(_capi.SGPE_COUPLING_NONE)
         else:
-            rp.set_coupling(_capi.SGPE_COUPLING_DENSE, coupling=np.ascontiguousarray(cpl[ys]), eiphi=eiphi)
+            pot = np.array([np.asarray(v) for v in spin.pot_eng_spin])
+            rp.set_potential(np.ascontiguousarray(pot[0, ys]), np.ascontiguousarray(pot[1, ys]))
+            psep = split_separable(pot)
+            if psep is not None:
+                rp.set_potential_separable(psep[0], np.ascontiguousarray(psep[1][:, ys]))
+            cpl = np.asarray(spin.coupling, dtype=np.float64)
+            if not spin.is_coupling or not np.any(cpl):
+                rp.set_coupling(_capi.SGPE_COUPLING_NONE)
+            elif np.all(cpl == cpl.flat[0]):
+                rp.set_coupling(_capi.SGPE_COUPLING_UNIFORM, omega=np.array([cpl.flat[0]]), eiphi=eiphi)
+            else:
+                rp.set_coupling(_capi.SGPE_COUPLING_DENSE, coupling=np.ascontiguousarray(cpl[ys]), eiphi=eiphi)
         rp.set_time(time, self.dt)
 
-        # ---- transposed plan: lines = local k_x, positions = k_y
-        self.tp = tp = Plan(self.ny, self.nxl, 1, self.cdtype, self.dev, **kw)
+        # ---- transposed plan: lines = local k_x positions, positions along the line = k_y positions
+        self.tp = tp = Plan(self.ny, self.nxl, 1, self.cdtype, self.dev, lines_n1=self.n1y, **kw)
         tp.set_grid(dr[0], dr[1], spin.space['dv_r'], spin.space['dv_k'], spin.atom_num)
-        kin = np.array([np.asarray(k) for k in spin.kin_eng_spin])
-        kin_t = np.ascontiguousarray(kin[:, :, xs].transpose(0, 2, 1))          # (2, nxl, ny)
-        tp.set_kinetic(kin_t[0], kin_t[1])
-        ksep = split_separable(kin)
+        if sep_only:
+            ksep = (spin.kin_x[:, self.nat_x], spin.kin_y[:, self.nat_y])
+        else:
+            kin = np.array([np.asarray(k) for k in spin.kin_eng_spin])
+            kin = kin[:, self.nat_y][:, :, self.nat_x]             # k-space grids in the stored (position) order
+            ksep = split_separable(kin)
         if ksep is not None:      # kin[ky][kx] = gx[kx] + gy[ky]:  position table <- gy, line table <- local gx
-            tp.set_kinetic_separable(ksep[1], np.ascontiguousarray(ksep[0][:, xs]))
+            tp.set_kinetic_separable(np.ascontiguousarray(ksep[1]), np.ascontiguousarray(ksep[0][:, xs]))
+        else:
+            if self.n1y > 1:
+                raise NotImplementedError("four-step lines need a separable kinetic energy grid")
+            kin_t = np.ascontiguousarray(kin[:, :, xs].transpose(0, 2, 1))      # (2, nxl, ny)
+            tp.set_kinetic(kin_t[0], kin_t[1])
         tp.set_time(time, self.dt)
 
         n_local = 2 * self.nxl * self.ny
         mk = lambda: torch.empty(n_local, dtype=self.cdtype, device=self.dev)      # noqa: E731
         self.tbuf, self.rbuf, self.send, self.recv = mk(), mk(), mk(), mk()
         self.sums = torch.zeros(4, dtype=torch.float64, device=self.dev)
-        local = np.ascontiguousarray(psik[:, :, xs].transpose(0, 2, 1))          # (2, nxl, ny) transposed slab
-        self.tbuf.copy_(torch.as_tensor(local).reshape(-1).to(self.cdtype))
         self.mid = False
         self.pending_dt = 0.0
         self.scale_pending = False
         self.a2a_bytes = 0
+        self.points = float(self.nx) * float(self.ny)
+        if sep_only:
+            self.set_real_space(spin.tf_rows(spin.space['y'][ys], self.dev, self.cdtype))
+        else:
+            stored = psik[:, self.nat_y][:, :, self.nat_x]
+            local = np.ascontiguousarray(stored[:, :, xs].transpose(0, 2, 1))     # (2, nxl, ny) transposed slab
+            self.tbuf.copy_(torch.as_tensor(local).reshape(-1).to(self.cdtype))
+
+    def set_real_space(self, psi_rows):
+        """Load a REAL-space state given by this rank's rows, (2, Ny/P, Nx) on the device: the distributed forward
+        transform (x-lines, transpose, y-lines) leaves it in the stored k-space layout.  The overall scale is
+        irrelevant (the first sub-step renormalises to the atom number)."""
+        ny0 = self._ys.start
+        sign = 1.0 - 2.0 * ((torch.arange(self.nx, device=self.dev)[None, :]
+                             + torch.arange(ny0, ny0 + self.nyl, device=self.dev)[:, None]) % 2)
+        self.rbuf.view(2, self.nyl, self.nx).copy_(psi_rows * sign.to(psi_rows.real.dtype))    # the fftshift sign
+        if self.n1x == 1:
+            self.rp.pass_klines(self.rbuf, True, False, 0.0, False, 0.0, False, None)
+        else:
+            self.rp.pass_mid(self.rbuf, False, False, False, 0.0, True, True, None, 0.0)
+            self.rp.pass_klines(self.rbuf, True, False, 0.0, False, 0.0, False, None)
+        self._to_lines()
+        if self.n1y == 1:
+            self.tp.pass_klines(self.tbuf, True, False, 0.0, False, 0.0, False, None)
+        else:
+            self.tp.pass_mid(self.tbuf, False, False, False, 0.0, True, True, None, 0.0)
+            self.tp.pass_klines(self.tbuf, True, False, 0.0, False, 0.0, False, None)
+        self.mid, self.scale_pending = False, False
 
     # ------------------------------------------------------------------ collectives
     def _all_to_all(self):
@@ -112,27 +241,48 @@ class SlabPropagator:
     def _reduce_sums(self):
         dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=self.group)
 
+    # ------------------------------------------------------------------ local passes (one or three per direction)
+    def _k_junction(self, do_fwd, has_a, tau_a, has_b, tau_b, do_inv):
+        tp = self.tp
+        if self.n1y == 1:
+            tp.pass_klines(self.tbuf, do_fwd, has_a, tau_a, has_b, tau_b, do_inv, self.sums)
+            return
+        if do_fwd:        # strided forward over y1, then the four-step twiddle
+            tp.pass_mid(self.tbuf, False, False, False, 0.0, True, True, None, 0.0)
+        tp.pass_klines(self.tbuf, do_fwd, has_a, tau_a, has_b, tau_b, do_inv, self.sums)
+        if do_inv:        # conjugate twiddle, strided inverse over k1
+            tp.pass_mid(self.tbuf, True, True, False, 0.0, False, False, None, 0.0)
+
+    def _row_pass(self, dt_sub):
+        rp = self.rp
+        if self.n1x == 1:
+            rp.pass_rows(self.rbuf, dt_sub, self.sums, self.points)
+            return
+        rp.pass_klines(self.rbuf, False, False, 0.0, False, 0.0, True, None)       # contiguous inverse over k2
+        rp.pass_mid(self.rbuf, True, True, True, dt_sub, True, True, self.sums, self.points)
+        rp.pass_klines(self.rbuf, True, False, 0.0, False, 0.0, False, None)       # contiguous forward over n2
+
     # ------------------------------------------------------------------ stepping
     def single_step(self, dt_sub, pops_out=None):
         imag = (self.time == 'imag')
         if not self.mid:
-            self.tp.pass_klines(self.tbuf, False, False, 0.0, True, dt_sub / 2, True, self.sums)
+            self._k_junction(False, False, 0.0, True, dt_sub / 2, True)
         elif pops_out is not None and imag:
-            self.tp.pass_klines(self.tbuf, True, True, self.pending_dt / 2, True, dt_sub / 2, True, self.sums)
+            self._k_junction(True, True, self.pending_dt / 2, True, dt_sub / 2, True)
         else:
-            self.tp.pass_klines(self.tbuf, True, False, 0.0, True, (self.pending_dt + dt_sub) / 2, True, self.sums)
+            self._k_junction(True, False, 0.0, True, (self.pending_dt + dt_sub) / 2, True)
         self._reduce_sums()
         if pops_out is not None and self.mid:
             pops_out.copy_(self.atom_num * self.sums[1:3] / (self.sums[1] + self.sums[2]))
         self._to_rows()
-        self.rp.pass_rows(self.rbuf, dt_sub, self.sums, float(self.nx) * float(self.ny))
+        self._row_pass(dt_sub)
         self._to_lines()
         self.mid, self.pending_dt, self.scale_pending = True, dt_sub, False
 
     def close_junction(self, pops_out=None):
         if not self.mid:
             return
-        self.tp.pass_klines(self.tbuf, True, True, self.pending_dt / 2, False, 0.0, False, self.sums)
+        self._k_junction(True, True, self.pending_dt / 2, False, 0.0, False)
         self._reduce_sums()
         if pops_out is not None:
             pops_out.copy_(self.atom_num * self.sums[1:3] / (self.sums[1] + self.sums[2]))
@@ -150,7 +300,8 @@ class SlabPropagator:
             self.close_junction(pending)
 
     def local_psik(self):
-        """Normalised k-space state of this rank in the transposed layout, (2, Nx/P, Ny)."""
+        """Normalised k-space state of this rank in the transposed (and, for split axes, digit-transposed)
+        layout, (2, Nx/P, Ny)."""
         self.close_junction()
         out = self.tbuf.view(2, self.nxl, self.ny)
         if self.scale_pending:
@@ -159,9 +310,12 @@ class SlabPropagator:
         return out
 
     def gather_psik(self):
-        """Full (2, Ny, Nx) k-space state on every rank (tests / small grids only)."""
+        """Full (2, Ny, Nx) k-space state in the reference's order on every rank (tests / small grids only)."""
         loc = torch.view_as_real(self.local_psik().contiguous())
         parts = [torch.empty_like(loc) for _ in range(self.P)]
         dist.all_gather(parts, loc, group=self.group)
-        full = torch.cat([torch.view_as_complex(p) for p in parts], dim=1)       # (2, Nx, Ny)
-        return full.transpose(1, 2).contiguous()
+        full = torch.cat([torch.view_as_complex(p) for p in parts], dim=1)       # (2, Nx, Ny), stored order
+        full = full.transpose(1, 2).contiguous()
+        inv_x = torch.as_tensor(np.argsort(self.nat_x), device=full.device)
+        inv_y = torch.as_tensor(np.argsort(self.nat_y), device=full.device)
+        return full.index_select(2, inv_x).index_select(1, inv_y).contiguous()

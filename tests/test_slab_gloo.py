@@ -18,7 +18,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, outdir, mode):
+def _worker(rank, world, port, outdir, mode, splits=(None, None), mesh=(128, 64)):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -30,7 +30,7 @@ def _worker(rank, world, port, outdir, mode):
         w0 = 2 * np.pi * 50
         ps = PSpinor(os.path.join(outdir, f'rank{rank}') + os.sep, overwrite=True, atom_num=1e4,
                      omeg={'x': w0, 'y': 1.5 * w0, 'z': 40 * w0}, g_sc={'uu': 1, 'dd': 0.98, 'ud': 1.02},
-                     r_sizes=(16, 12), mesh_points=(128, 64))
+                     r_sizes=(16, 12), mesh_points=mesh)
         ps.coupling_setup(wavel=790.1e-9, kin_shift=True)
         ps.shift_momentum(scale=0.7, frac=(0.3, 0.7))
         ps.coupling_uniform(1.5 * ps.EL_recoil)
@@ -41,7 +41,8 @@ def _worker(rank, world, port, outdir, mode):
                            ps.space['dv_r'], ps.space['dv_k'], [ps.g_sc['uu'], ps.g_sc['dd'], ps.g_sc['ud']],
                            ps.atom_num, x=ps.space['x'], kL=ps.kL_recoil, is_coupling=True, rot_coupling=False)
         want = orc.OraclePropagator(prob, dt, mode).run(n)
-        sp = SlabPropagator(ps, dt, time=mode, device='cpu', plan_kwargs={'_lib': emu_lib()})
+        sp = SlabPropagator(ps, dt, time=mode, device='cpu', plan_kwargs={'_lib': emu_lib()},
+                            split_x=splits[0], split_y=splits[1])
         pops = torch.zeros((n, 2), dtype=torch.float64)
         sp.full_steps(n, pops)
         got = sp.gather_psik().numpy()
@@ -58,3 +59,48 @@ def test_slab_two_gloo_ranks(mode):
     from tests.emu_harness import emu_lib
     emu_lib()
     mp.spawn(_worker, args=(2, _free_port(), tempfile.mkdtemp(prefix='sgpe_slab_'), mode), nprocs=2, join=True)
+
+
+@pytest.mark.parametrize('splits,mesh', [((32, None), (1024, 64)), ((None, 32), (64, 1024))])
+def test_slab_four_step_lines(splits, mesh):
+    """The long-line machinery (four-step split, digit-transposed k order, strided pass with fused operators)
+    forced on a small grid: 1024 = 32 x 32 along x or along y must still match the oracle."""
+    from tests.emu_harness import emu_lib
+    emu_lib()
+    mp.spawn(_worker, args=(2, _free_port(), tempfile.mkdtemp(prefix='sgpe_slab_'), 'real', splits, mesh), nprocs=2,
+             join=True)
+
+
+def _worker_sep(rank, world, port, outdir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from spinor_gpe_b200 import PSpinor
+        from spinor_gpe_b200.slab import SeparableProblem, SlabPropagator
+        from tests.emu_harness import emu_lib
+        w0 = 2 * np.pi * 50
+        kw = dict(atom_num=1e4, omeg={'x': w0, 'y': 1.5 * w0, 'z': 40 * w0}, g_sc={'uu': 1, 'dd': 0.98, 'ud': 1.02},
+                  r_sizes=(16, 12), pop_frac=(0.5, 0.5))
+        ps = PSpinor(os.path.join(outdir, f'rank{rank}') + os.sep, overwrite=True, mesh_points=(128, 64), **kw)
+        ps.coupling_setup(wavel=790.1e-9, kin_shift=True)
+        ps.coupling_uniform(1.5 * ps.EL_recoil)
+        ps.detuning_grad(-3.0)
+        sep = SeparableProblem((128, 64), coupling=1.5 * ps.EL_recoil, kin_shift=True, detuning_slope=-3.0, **kw)
+        outs = []
+        for prob in (ps, sep):
+            sp = SlabPropagator(prob, 1 / 50, time='imag', device='cpu', plan_kwargs={'_lib': emu_lib()})
+            sp.full_steps(2)
+            outs.append(sp.gather_psik().numpy())
+        err = np.linalg.norm(outs[1] - outs[0]) / np.linalg.norm(outs[0])
+        assert err < 1e-11, err
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_separable_problem_matches_pspinor():
+    """The host-light problem description (1-D vectors, Thomas-Fermi state generated per rank and transformed by
+    the distributed FFT) reproduces the PSpinor-based set-up."""
+    from tests.emu_harness import emu_lib
+    emu_lib()
+    mp.spawn(_worker_sep, args=(2, _free_port(), tempfile.mkdtemp(prefix='sgpe_slab_')), nprocs=2, join=True)

@@ -1,0 +1,98 @@
+"""Slab-mode validation + benchmark under torch.distributed.run (one rank per GPU).
+
+    python -m torch.distributed.run --nproc-per-node P tools/slab_bench.py check      # parity of the four-step path
+    python -m torch.distributed.run --nproc-per-node P tools/slab_bench.py bench MESH [steps]
+
+check: 2048^2 with forced 32x64 / 64x32 splits and the natural path vs the single-GPU propagator (rank 0).
+bench: BASELINE config 5 style — real-time propagation with uniform Raman coupling on a MESH^2 grid
+       (16384 on 8 GPUs), set up from 1-D vectors only; prints steps/s, all-to-all bytes and the NVLink / HBM
+       roofline fractions (algorithmic 768 B/pt/step; NVLink 770 GB/s per direction measured on this pool)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from spinor_gpe_b200.slab import SeparableProblem, SlabPropagator  # noqa: E402
+
+W0 = 2 * np.pi * 50
+
+
+def check(rank, world, dev):
+    from spinor_gpe_b200 import TensorPropagator
+    mesh = 2048
+    ps = bench.build_problem(mesh, tag=f'slab{rank}')
+    ps.coupling_uniform(0.5 * ps.EL_recoil)
+    ps.rot_coupling = False
+    ref = None
+    for mode, dt in (('real', 1 / 5000), ('imag', 1 / 50)):
+        n = 2
+        if rank == 0:
+            prop = TensorPropagator(ps, dt, n, dev, time=mode)
+            prop._plan.full_steps(n)
+            ref = torch.stack(prop.psik)
+        for splits in ((None, None), (32, None), (None, 64), (64, 32)):
+            sp = SlabPropagator(ps, dt, time=mode, device=dev, split_x=splits[0], split_y=splits[1])
+            pops = torch.zeros((n, 2), dtype=torch.float64, device=dev)
+            sp.full_steps(n, pops)
+            full = sp.gather_psik()
+            if rank == 0:
+                err = float(torch.linalg.norm(full - ref) / torch.linalg.norm(ref))
+                print(f'check {mesh}^2 {mode} splits={splits} ranks={world}: rel-L2 vs single GPU {err:.2e} '
+                      f'atoms {float(pops[-1].sum()):.10g}', flush=True)
+                assert err < 1e-10
+            del sp
+
+
+def run_bench(rank, world, dev, mesh, steps):
+    g_sc = {'uu': 1, 'dd': 1, 'ud': 1.04}
+    prob = SeparableProblem((mesh, mesh), r_sizes=(64, 64), atom_num=1e6, omeg={'x': W0, 'y': W0, 'z': 40 * W0},
+                            g_sc=g_sc, pop_frac=(0.5, 0.5), coupling=1.0, kin_shift=True, rot_coupling=False)
+    sp = SlabPropagator(prob, 1 / 5000, time='real', device=dev)
+    pops = torch.zeros((steps, 2), dtype=torch.float64, device=dev)
+    sp.full_steps(2)
+    dist.barrier(); torch.cuda.synchronize()
+    sp.a2a_bytes = 0
+    l0 = sp.rp.launch_count() + sp.tp.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sp.full_steps(steps, pops)
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    if rank == 0:
+        sent = sp.a2a_bytes / steps
+        nvl = sent / (ms * 1e-3) / 1e9
+        hbm = 768.0 * mesh * mesh / world / (ms * 1e-3) / 1e9
+        print(json.dumps({
+            'slab_bench': True, 'mesh': mesh, 'ranks': world, 'mode': 'real', 'dtype': 'c128',
+            'four_step': [sp.n1x, sp.n1y], 'steps': steps, 'ms_per_step': ms, 'steps_per_s': 1e3 / ms,
+            'kernel_launches_per_step': (sp.rp.launch_count() + sp.tp.launch_count() - l0) / steps,
+            'a2a_bytes_sent_per_rank_per_step': sent, 'nvlink_GBps_per_rank': nvl, 'nvlink_frac_of_770': nvl / 770.0,
+            'hbm_algorithmic_GBps_per_rank': hbm, 'hbm_frac': hbm / bench.hbm_peak()[0],
+            'atoms_first_last': [float(pops[0].sum()), float(pops[-1].sum())],
+            'pops_last': pops[-1].tolist()}), flush=True)
+
+
+def main():
+    rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist.init_process_group('nccl', device_id=dev)
+    what = sys.argv[1] if len(sys.argv) > 1 else 'check'
+    if what == 'check':
+        check(rank, world, dev)
+    else:
+        run_bench(rank, world, dev, int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 10)
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
