@@ -81,6 +81,47 @@ def run_bench(rank, world, dev, mesh, steps):
             'pops_last': pops[-1].tolist()}), flush=True)
 
 
+def breakdown(rank, world, dev, mesh):
+    """Time the phases of one sub-step with CUDA events (rank 0 prints; max over ranks not taken: indicative)."""
+    prob = SeparableProblem((mesh, mesh), r_sizes=(64, 64), atom_num=1e6, omeg={'x': W0, 'y': W0, 'z': 40 * W0},
+                            g_sc={'uu': 1, 'dd': 1, 'ud': 1.04}, pop_frac=(0.5, 0.5), coupling=1.0, kin_shift=True,
+                            rot_coupling=False)
+    sp = SlabPropagator(prob, 1 / 5000, time='real', device=dev)
+    sp.full_steps(2)
+    sp.single_step(sp.dt_out)
+    dist.barrier(); torch.cuda.synchronize()
+    names, evs = [], []
+
+    def mark(name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        names.append(name); evs.append(e)
+
+    dt = sp.dt_in
+    mark('start')
+    sp._k_junction(True, False, 0.0, True, (sp.pending_dt + dt) / 2, True); mark('k-junction (local passes)')
+    sp._reduce_sums(); mark('all-reduce sums')
+    sp.tp.slab_pack(sp.tbuf, sp.send, sp.nxl, sp.P, sp.nyl); mark('pack')
+    sp._all_to_all(); mark('all-to-all')
+    sp.rp.slab_unpack(sp.recv, sp.rbuf, sp.P, sp.nxl, sp.nyl); mark('unpack+transpose')
+    sp._row_pass(dt); mark('row passes (local)')
+    sp.rp.slab_pack(sp.rbuf, sp.send, sp.nyl, sp.P, sp.nxl); mark('pack')
+    sp._all_to_all(); mark('all-to-all')
+    sp.tp.slab_unpack(sp.recv, sp.tbuf, sp.P, sp.nyl, sp.nxl); mark('unpack+transpose')
+    torch.cuda.synchronize()
+    if rank == 0:
+        per = sp.send.numel() * sp.send.element_size()
+        for i in range(1, len(evs)):
+            ms = evs[i - 1].elapsed_time(evs[i])
+            extra = ''
+            if names[i] == 'all-to-all':
+                extra = f'  ({per * (world - 1) / world / ms * 1e-6:.0f} GB/s sent per rank)'
+            elif 'pack' in names[i]:
+                extra = f'  ({2 * per / ms * 1e-6:.0f} GB/s r+w)'
+            print(f'  {names[i]:28s} {ms:7.3f} ms{extra}', flush=True)
+        print(f'  sub-step total               {evs[0].elapsed_time(evs[-1]):7.3f} ms', flush=True)
+
+
 def main():
     rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
     torch.cuda.set_device(local)
@@ -89,6 +130,8 @@ def main():
     what = sys.argv[1] if len(sys.argv) > 1 else 'check'
     if what == 'check':
         check(rank, world, dev)
+    elif what == 'breakdown':
+        breakdown(rank, world, dev, int(sys.argv[2]))
     else:
         run_bench(rank, world, dev, int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 10)
     dist.destroy_process_group()
