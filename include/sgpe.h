@@ -141,14 +141,44 @@ int sgpe_energy(sgpe_plan* p, const void* psik_dev, int unwrap_mode, double kl_t
  *   [* conj w] [iFFT over k1] [norm, I C P C I] [FFT over n1] [* w]. */
 int sgpe_plan_create_lines(sgpe_plan** out, int len, int nlines, int n1, int dtype, int device);
 int sgpe_pass_mid(sgpe_plan* p, void* buf_dev, int pre_tw, int do_inv, int do_pw, double dt_sub, int do_fwd,
-                  int post_tw, const double* totals_dev, double global_points, sgpe_stream st);
+                  int post_tw, const double* totals_dev, double global_points, int inner, int scatter,
+                  sgpe_stream st);
 int sgpe_pass_rows(sgpe_plan* p, void* buf_dev, double dt_sub, const double* totals_dev, double global_points,
-                   sgpe_stream st);
+                   int scatter, sgpe_stream st);
 int sgpe_pass_klines(sgpe_plan* p, void* buf_dev, int do_fwd, int has_a, double tau_a, int has_b, double tau_b,
-                     int do_inv, double* sums_dev, sgpe_stream st);
+                     int do_inv, double* sums_dev, int scatter, sgpe_stream st);
 int sgpe_slab_pack(sgpe_plan* p, const void* in_dev, void* out_dev, int lines, int nranks, int chunk, sgpe_stream st);
 int sgpe_slab_unpack(sgpe_plan* p, const void* in_dev, void* out_dev, int nranks, int block_h, int block_w,
                      sgpe_stream st);
+
+/* ---- Fused exchange (compute + collective in ONE kernel over peer memory).  Instead of pack -> NCCL all-to-all ->
+ * unpack, the last pass of each direction stores every element directly into the buffer of the rank that needs it
+ * next (buffers of the other GPUs of the node mapped with CUDA IPC; the stores travel over NVLink / NVSwitch while
+ * the CTA's neighbours are still transforming), so the transfer overlaps the math tile by tile and four HBM passes
+ * per sub-step disappear.  Everything stays ROW-MAJOR (no transposes):
+ *     row slab of rank r : [2][Ny/P][Nx]     k slab of rank q : [2][Ny][Nx/P]
+ *  sgpe_slab_set_peers : destination map of a plan's scatter stores.  peer_bufs[q] = rank q's destination buffer as
+ *                        seen from this device.  mode 1 (row direction -> k slabs): seg = Nx/P, drow = Nx/P,
+ *                        dplane = Ny*Nx/P, base = this rank's first global row.  mode 2 (k direction -> row slabs):
+ *                        seg = Ny/P, drow = Nx, dplane = (Ny/P)*Nx, base = this rank's first global column.
+ *  scatter != 0 on a pass = "store through the map" (the input is still read from buf_dev).  Ordering between ranks is
+ *                        the caller's: a collective (the all-reduce of the norm sums, or a barrier) after the storing
+ *                        kernel orders it before the consumers on every rank.
+ *  sgpe_pass_kcols     : the k-space junction on a k slab [2][len][nlines] of a line plan(len, nlines[, n1]): W adjacent
+ *                        columns per CTA, [FFT] K_a sums K_b sums [iFFT] down the columns (with n1 > 1: over the n2
+ *                        sub-lines of every n1 group, the strided halves being sgpe_pass_mid(inner = nlines)).
+ *  sgpe_pass_mid(inner = nlines > 1) : the strided four-step half on the k slab viewed as [2][n1][n2][nlines].
+ *  sgpe_ipc_*          : cudaMalloc'ed exchange buffers exported to / imported from the other processes of the node
+ *                        (cudaIpcGetMemHandle / cudaIpcOpenMemHandle with lazy peer access). */
+#define SGPE_IPC_HANDLE_BYTES 64
+int sgpe_slab_set_peers(sgpe_plan* p, void* const* peer_bufs, int nranks, int mode, int seg, int drow, int64_t dplane,
+                        int base);
+int sgpe_pass_kcols(sgpe_plan* p, void* buf_dev, int do_fwd, int has_a, double tau_a, int has_b, double tau_b,
+                    int do_inv, double* sums_dev, int scatter, sgpe_stream st);
+int sgpe_ipc_alloc(int device, uint64_t bytes, void** dev_ptr, unsigned char handle[SGPE_IPC_HANDLE_BYTES]);
+int sgpe_ipc_open(int device, const unsigned char handle[SGPE_IPC_HANDLE_BYTES], void** dev_ptr);
+int sgpe_ipc_close(void* dev_ptr);
+int sgpe_ipc_free(void* dev_ptr);
 
 /* The same path with HOST buffers (pageable or pinned): H2D of the state, n full steps, D2H of the
  * final normalised state and the populations [batch][n][2]; synchronises the stream before returning.

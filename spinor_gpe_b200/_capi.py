@@ -32,10 +32,18 @@ PROTOTYPES = {
     'sgpe_energy': (C.c_int, [c_plan, c_dptr, C.c_int, C.c_double, c_dptr, c_stream]),
     'sgpe_plan_create_lines': (C.c_int, [C.POINTER(c_plan), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     'sgpe_pass_mid': (C.c_int, [c_plan, c_dptr, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, c_dptr, C.c_double,
-                                c_stream]),
-    'sgpe_pass_rows': (C.c_int, [c_plan, c_dptr, C.c_double, c_dptr, C.c_double, c_stream]),
+                                C.c_int, C.c_int, c_stream]),
+    'sgpe_pass_rows': (C.c_int, [c_plan, c_dptr, C.c_double, c_dptr, C.c_double, C.c_int, c_stream]),
     'sgpe_pass_klines': (C.c_int, [c_plan, c_dptr, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int, c_dptr,
-                                   c_stream]),
+                                   C.c_int, c_stream]),
+    'sgpe_pass_kcols': (C.c_int, [c_plan, c_dptr, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int, c_dptr,
+                                  C.c_int, c_stream]),
+    'sgpe_slab_set_peers': (C.c_int, [c_plan, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
+                                      C.c_int]),
+    'sgpe_ipc_alloc': (C.c_int, [C.c_int, C.c_uint64, C.POINTER(C.c_void_p), C.c_char_p]),
+    'sgpe_ipc_open': (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
+    'sgpe_ipc_close': (C.c_int, [C.c_void_p]),
+    'sgpe_ipc_free': (C.c_int, [C.c_void_p]),
     'sgpe_slab_pack': (C.c_int, [c_plan, c_dptr, c_dptr, C.c_int, C.c_int, C.c_int, c_stream]),
     'sgpe_slab_unpack': (C.c_int, [c_plan, c_dptr, c_dptr, C.c_int, C.c_int, C.c_int, c_stream]),
     'sgpe_run_host': (C.c_int, [c_plan, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, c_stream]),

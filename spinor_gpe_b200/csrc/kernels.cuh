@@ -51,6 +51,33 @@ template <int E, typename C> SGPE_DI void conj_all(C (&v)[E]) {
     for (int m = 0; m < E; m++) v[m].y = -v[m].y;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused exchange of the slab (multi-GPU) mode.  Instead of "store locally, pack, NCCL all-to-all, unpack", the
+// LAST pass of each direction stores every element straight into the buffer of the rank that owns it in the
+// next direction (peer device memory mapped through CUDA IPC, NVLink / NVSwitch): the transfer overlaps the
+// transforms tile by tile and the pack / unpack passes disappear.  All arrays stay row-major:
+//   row slab of rank r : [2][Ny/P][Nx]   (rows  Y in [r Ny/P, (r+1) Ny/P))
+//   k slab   of rank q : [2][Ny][Nx/P]   (columns X in [q Nx/P, (q+1) Nx/P))
+// mode 1 (written by the row direction): element (Y_local, X) -> rank X / seg, k slab;
+// mode 2 (written by the k direction)  : element (Y, X_local) -> rank Y / seg, row slab.
+#define SGPE_MAX_PEERS 16
+template <typename C> struct Scatter {
+    C* peer[SGPE_MAX_PEERS];
+    int mode;              // 0: off (plain store to `out`)
+    int seg;               // mode 1: Nx/P columns per rank;  mode 2: Ny/P rows per rank
+    int drow;              // row length of the destination arrays (mode 1: Nx/P, mode 2: Nx)
+    int base;              // mode 1: first global row of this rank;  mode 2: first global column of this rank
+    long long dplane;      // component stride of the destination arrays
+};
+template <typename C> SGPE_DI C* scatter_ptr(const Scatter<C>& s, int comp, int Y, int X) {
+    if (s.mode == 1) {
+        const int q = X / s.seg;
+        return s.peer[q] + (long long)comp * s.dplane + (long long)(Y + s.base) * s.drow + (X - q * s.seg);
+    }
+    const int q = Y / s.seg;
+    return s.peer[q] + (long long)comp * s.dplane + (long long)(Y - q * s.seg) * s.drow + (X + s.base);
+}
+
 template <typename T> struct ColArgs {
     typedef typename cx_of<T>::type C;
     const C* in;  C* out;          // [B][2][ny][nx]
@@ -249,6 +276,7 @@ template <typename T> struct RowArgs {
     double tc;                     // coupling angle per unit Omega (|dt_sub| / 4)
     const double* totals;          // [B][4], T at [0]
     double norm_c;                 // N_atoms / (dv_r * nx * ny)
+    Scatter<C> sc;                 // slab mode: fused exchange on the store (non-FAST kernels only)
 };
 
 // 2x2 coupling operator (reference tensor_tools.py:586-590) for theta = Omega*tc and exp(i phi) = ph
@@ -418,12 +446,20 @@ __global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) row
     SGPE_MARK(4);
 
     const T sc = FAST ? (T)1 : (T)a.scale_out;
+    if (!FAST && a.sc.mode) {       // fused exchange: each run of `seg` columns goes to the rank that owns it
+#pragma unroll
+        for (int m = 0; m < E; m++) {
+            SGPE_ST_STREAM(scatter_ptr(a.sc, 0, y, j + m * NT), v[0][m]);
+            SGPE_ST_STREAM(scatter_ptr(a.sc, 1, y, j + m * NT), v[1][m]);
+        }
+    } else {
 #pragma unroll
     for (int m = 0; m < E; m++) {
         T s = sc;
         if ((((sign_out & 1) ? (j + m * NT) : 0) + ((sign_out & 2) ? y : 0)) & 1) s = -s;
         SGPE_ST_STREAM(&a.out[off0 + j + m * NT], cscale(v[0][m], s));
         SGPE_ST_STREAM(&a.out[off1 + j + m * NT], cscale(v[1][m], s));
+    }
     }
     SGPE_MARK(5);
 #undef SGPE_MARK
@@ -565,6 +601,7 @@ template <typename T> struct KLineArgs {
     int group;                                       // sub-lines per long line (1 normally): line table index =
                                                      // line/group, position table index = (line%group)*N + pos
     double* partials; unsigned* counter; double* sums;    // sums: [3] = T, S0, S1 of the LOCAL slab
+    Scatter<C> sc;                                   // fused exchange on the store (mode 1: row direction)
 };
 
 template <typename T, int N, int E, int RPC, int TM>
@@ -631,10 +668,19 @@ __global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) kli
         if (!a.has_a) { acc[0] = acc[1]; acc[2] = acc[3]; }
     }
     }   // pass loop
+    if (a.sc.mode) {      // long line = line / group (local row), position along it = (line % group) * N + pos
+        const int Y = line / a.group, X0 = (line % a.group) * a.nx + j;
+#pragma unroll
+        for (int m = 0; m < E; m++) {
+            SGPE_ST_STREAM(scatter_ptr(a.sc, 0, Y, X0 + m * NT), v[0][m]);
+            SGPE_ST_STREAM(scatter_ptr(a.sc, 1, Y, X0 + m * NT), v[1][m]);
+        }
+    } else {
 #pragma unroll
     for (int m = 0; m < E; m++) {
         a.out[off0 + j + m * NT] = v[0][m];
         a.out[off1 + j + m * NT] = v[1][m];
+    }
     }
     if (a.has_a || a.has_b) {
         const int nblk = gridDim.x;
@@ -680,6 +726,8 @@ template <typename T> struct MidArgs {
     int n2;                        // contiguous dimension of the matrix view
     int pre_tw, post_tw;           // multiply by conj(w_N^(k1 n2)) before the inverse / by w_N^(k1 n2) after the forward
     const C* tw4;                  // [N1][N2] four-step twiddles exp(-2 pi i k1 n2 / N)
+    int inner;                     // 1: array [2][nlines][N1][N2].  > 1: k slab [2][N1][N2][inner] (row-major slab, the
+                                   // lines run down the columns): r.ny = 1, n2 = N2 * inner, twiddle column = n2 / inner
 };
 
 template <typename T, int N1, int E, int W, int TM>
@@ -703,10 +751,11 @@ __global__ void __launch_bounds__(W * N1 / E) mid_pass(MidArgs<T> ma) {
         v[0][m] = SGPE_LD_STREAM(&a.in[line0 + o]);
         v[1][m] = SGPE_LD_STREAM(&a.in[line1 + o]);
     }
+    const int tw_col = n2 / ma.inner, tw_row = ma.n2 / ma.inner;     // inner == 1: (n2, N2)
     if (ma.pre_tw) {
 #pragma unroll
         for (int m = 0; m < E; m++) {
-            const C w = __ldg(&ma.tw4[(long long)(j + m * NT) * ma.n2 + n2]);
+            const C w = __ldg(&ma.tw4[(long long)(j + m * NT) * tw_row + tw_col]);
             v[0][m] = cmulc(v[0][m], w); v[1][m] = cmulc(v[1][m], w);
         }
     }
@@ -777,15 +826,135 @@ __global__ void __launch_bounds__(W * N1 / E) mid_pass(MidArgs<T> ma) {
     if (ma.post_tw) {
 #pragma unroll
         for (int m = 0; m < E; m++) {
-            const C w = __ldg(&ma.tw4[(long long)(j + m * NT) * ma.n2 + n2]);
+            const C w = __ldg(&ma.tw4[(long long)(j + m * NT) * tw_row + tw_col]);
             v[0][m] = cmul(v[0][m], w); v[1][m] = cmul(v[1][m], w);
         }
     }
+    if (a.sc.mode) {      // k slab -> row slabs: natural row Y = n1 * N2 + n2-digit, local column n2 % inner
+        const int X = n2 - tw_col * ma.inner;
+#pragma unroll
+        for (int m = 0; m < E; m++) {
+            const int Y = (j + m * NT) * tw_row + tw_col;
+            SGPE_ST_STREAM(scatter_ptr(a.sc, 0, Y, X), v[0][m]);
+            SGPE_ST_STREAM(scatter_ptr(a.sc, 1, Y, X), v[1][m]);
+        }
+    } else {
 #pragma unroll
     for (int m = 0; m < E; m++) {
         const long long o = (long long)(j + m * NT) * ma.n2;
         SGPE_ST_STREAM(&a.out[line0 + o], v[0][m]);
         SGPE_ST_STREAM(&a.out[line1 + o], v[1][m]);
+    }
+    }
+}
+
+// k-space junction of the slab mode on the ROW-MAJOR k slab [2][G][N][inner] (the fused-exchange layout): for W
+// adjacent columns of one component and one group g (G = n1 of a four-step split, 1 otherwise):
+//   [FFT over N, stride inner] -> K_a -> sums -> K_b -> sums -> [iFFT]     (col_pass of the single-GPU path with a
+// group index, slab-wide sums and the scatter store).  Kinetic operator: separable tables pa/pb [2][G*N] (position
+// along the line) x la/lb [2][inner] (column), or dense grids [G*N][inner] evaluated here.
+template <typename T> struct KColArgs {
+    typedef typename cx_of<T>::type C;
+    const C* in; C* out; const C* tw;
+    int inner, groups; long long plane;               // plane = G * N * inner
+    int do_fwd, do_inv, has_a, has_b, kin_mode;
+    const double* kin0; const double* kin1;
+    double ka_re, ka_im, kb_re, kb_im;
+    const C* la; const C* pa; const C* lb; const C* pb;
+    double* partials; unsigned* counter; double* sums;
+    Scatter<C> sc;                                    // mode 2 (k direction -> row slabs)
+};
+
+template <typename T, int N, int E, int W, int TM>
+__global__ void __launch_bounds__(W * N / E) kcol_pass(KColArgs<T> a) {
+    typedef typename cx_of<T>::type C;
+    constexpr int NT = N / E;
+    SGPE_DYN_SMEM(smem_raw);
+    C* sm = reinterpret_cast<C*>(smem_raw);
+    double* red = reinterpret_cast<double*>(smem_raw + sizeof(C) * (size_t)N * W);
+    const int tid = threadIdx.x;
+    const int c = tid % W, j = tid / W;
+    const int col = blockIdx.x * W + c;
+    const int g = blockIdx.y, comp = blockIdx.z;
+    const long long off = (long long)comp * a.plane + (long long)g * N * a.inner + col;
+
+    C v[1][E];
+#pragma unroll
+    for (int m = 0; m < E; m++) v[0][m] = SGPE_LD_STREAM(&a.in[off + (long long)(j + m * NT) * a.inner]);
+    C* const sms[1] = {sm};
+    if (a.do_fwd) cta_fft<T, N, E, -1, W, 1>(v, j, c, sms, a.tw + (E == 16 ? N : 0));
+    double acc[2] = {0.0, 0.0};       // S (after K_a), T (after K_b) of this component
+    const bool any_k = a.has_a || a.has_b;
+    if (any_k) {
+        C la, lb;
+        la.x = (T)1; la.y = (T)0; lb = la;
+        if (a.kin_mode == 1) {
+            if (a.has_a) la = __ldg(&a.la[(long long)comp * a.inner + col]);
+            if (a.has_b) lb = __ldg(&a.lb[(long long)comp * a.inner + col]);
+        }
+        const double* kin = (comp == 0 ? a.kin0 : a.kin1);
+        const long long pbase = (long long)comp * a.groups * N + (long long)g * N;
+#pragma unroll
+        for (int m = 0; m < E; m++) {
+            const int pos = j + m * NT;
+            C x = v[0][m];
+            if (a.has_a) {
+                const C f = (a.kin_mode == 0)
+                    ? evo<TM, T, C>(__ldg(&kin[((long long)g * N + pos) * a.inner + col]), a.ka_re, a.ka_im)
+                    : combine_factor<TM>(la, __ldg(&a.pa[pbase + pos]));
+                x = mul_factor<TM>(x, f);
+                acc[0] += (double)x.x * x.x + (double)x.y * x.y;
+            }
+            if (a.has_b) {
+                const C f = (a.kin_mode == 0)
+                    ? evo<TM, T, C>(__ldg(&kin[((long long)g * N + pos) * a.inner + col]), a.kb_re, a.kb_im)
+                    : combine_factor<TM>(lb, __ldg(&a.pb[pbase + pos]));
+                x = mul_factor<TM>(x, f);
+                acc[1] += (double)x.x * x.x + (double)x.y * x.y;
+            }
+            v[0][m] = x;
+        }
+        if (!a.has_b) acc[1] = acc[0];
+        if (!a.has_a) acc[0] = acc[1];
+    }
+    if (a.do_inv) cta_fft<T, N, E, +1, W, 1>(v, j, c, sms, a.tw + (E == 16 ? N : 0));
+
+    if (a.sc.mode) {          // only without a group split: the line index is the natural row
+#pragma unroll
+        for (int m = 0; m < E; m++) SGPE_ST_STREAM(scatter_ptr(a.sc, comp, j + m * NT, col), v[0][m]);
+    } else {
+#pragma unroll
+        for (int m = 0; m < E; m++) SGPE_ST_STREAM(&a.out[off + (long long)(j + m * NT) * a.inner], v[0][m]);
+    }
+
+    if (any_k) {
+        const int nblk = gridDim.x * gridDim.y * gridDim.z;
+        const int blk = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;     // component-major
+        cta_reduce<2>(acc, red);
+        if (tid == 0) {
+            double* p = a.partials + 2LL * blk;
+            p[0] = acc[0]; p[1] = acc[1];
+            __threadfence();
+            red[0] = (atomicAdd(&a.counter[0], 1u) == (unsigned)(nblk - 1)) ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        const bool last = red[0] != 0.0;
+        __syncthreads();
+        if (last) {       // fixed-order fold: bit-reproducible
+            __threadfence();
+            double t4[4] = {0.0, 0.0, 0.0, 0.0};     // S0, T0, S1, T1
+            const int half = nblk / 2;
+            for (int t = tid; t < nblk; t += blockDim.x) {
+                const int cp = (t >= half) ? 2 : 0;
+                t4[cp + 0] += __ldcg(&a.partials[2LL * t]);
+                t4[cp + 1] += __ldcg(&a.partials[2LL * t + 1]);
+            }
+            cta_reduce<4>(t4, red);
+            if (tid == 0) {
+                a.sums[0] = t4[1] + t4[3]; a.sums[1] = t4[0]; a.sums[2] = t4[2];
+                a.counter[0] = 0u;
+            }
+        }
     }
 }
 

@@ -11,6 +11,8 @@ namespace sgpe {
     int launch_col_##N(int dtype, int tm, const void* args, int batch, int wsel, cudaStream_t st); \
     int launch_kline_##N(int dtype, int tm, const void* args, cudaStream_t st);                    \
     int launch_mid_##N(int dtype, int tm, const void* args, cudaStream_t st);                      \
+    int launch_kcol_##N(int dtype, int tm, const void* args, cudaStream_t st);                     \
+    int kcol_tile_width_##N(int dtype);                                                            \
     int col_tile_width_##N(int dtype);
 SGPE_FOR_EACH_N(SGPE_DECL)
 #undef SGPE_DECL
@@ -41,6 +43,18 @@ inline int launch_kline(int n, int dtype, int tm, const void* args, cudaStream_t
 }
 inline int launch_mid(int n, int dtype, int tm, const void* args, cudaStream_t st) {
 #define SGPE_CASE(N) if (n == N) return launch_mid_##N(dtype, tm, args, st);
+    SGPE_FOR_EACH_N(SGPE_CASE)
+#undef SGPE_CASE
+    return -1;
+}
+inline int launch_kcol(int n, int dtype, int tm, const void* args, cudaStream_t st) {
+#define SGPE_CASE(N) if (n == N) return launch_kcol_##N(dtype, tm, args, st);
+    SGPE_FOR_EACH_N(SGPE_CASE)
+#undef SGPE_CASE
+    return -1;
+}
+inline int kcol_tile_width(int n, int dtype) {
+#define SGPE_CASE(N) if (n == N) return kcol_tile_width_##N(dtype);
     SGPE_FOR_EACH_N(SGPE_CASE)
 #undef SGPE_CASE
     return -1;

@@ -82,7 +82,7 @@ static int launch_row_t(const RowArgs<T>& a, int batch, cudaStream_t st) {
     if (a2.prefetch_ahead) a2.prefetch_ahead = ahead;
     a2.resident = ahead;
     const bool fast = a.do_inv && a.do_pw && a.do_fwd && a.cpl_mode == 0 && a.pot_mode == 1 && !a.sign_in &&
-                      !a.sign_out && a.scale_out == 1.0 && a.stagger_ns == 0 && a.dbg == nullptr;
+                      !a.sign_out && a.scale_out == 1.0 && a.stagger_ns == 0 && a.dbg == nullptr && a.sc.mode == 0;
     if (fast) {
         SGPE_LAUNCH((row_pass<T, N, Cfg::E, Cfg::RPC, TM, 1>), grid, block, Cfg::SMEM, st, a2);
     } else {
@@ -146,6 +146,26 @@ static int launch_kline_t(const KLineArgs<T>& a, cudaStream_t st) {
     if (!once) { allow_smem(kline_pass<T, N, Cfg::E, Cfg::RPC, TM>, smem); once = true; }
     dim3 grid(a.ny / Cfg::RPC), block(Cfg::THREADS);
     SGPE_LAUNCH((kline_pass<T, N, Cfg::E, Cfg::RPC, TM>), grid, block, smem, st, a);
+    return 0;
+}
+
+// k-space junction on the row-major k slab (fused-exchange layout): W adjacent columns of one component
+template <typename T, int N> struct KColCfg {
+    static constexpr int CB = (int)sizeof(typename cx_of<T>::type);
+    static constexpr int E = ColCfg<T, N>::E;
+    static constexpr int NT = N / E;
+    static constexpr int WT = (256 / NT > 32) ? 32 : (256 / NT);       // aim at 256 threads, tiles <= 32 columns
+    static constexpr int W = (ColCfg<T, N>::W > WT) ? ColCfg<T, N>::W : WT;
+    static constexpr size_t SMEM = (size_t)N * W * CB + 32 * 4 * sizeof(double);
+};
+template <typename T, int N, int TM>
+static int launch_kcol_t(const KColArgs<T>& a, cudaStream_t st) {
+    typedef KColCfg<T, N> Cfg;
+    if (a.inner % Cfg::W != 0) return -2;
+    static bool once = false;
+    if (!once) { allow_smem(kcol_pass<T, N, Cfg::E, Cfg::W, TM>, Cfg::SMEM); once = true; }
+    dim3 grid(a.inner / Cfg::W, a.groups, 2), block(Cfg::W * Cfg::NT);
+    SGPE_LAUNCH((kcol_pass<T, N, Cfg::E, Cfg::W, TM>), grid, block, Cfg::SMEM, st, a);
     return 0;
 }
 
@@ -216,6 +236,18 @@ int SGPE_CAT(launch_kline_, SGPE_N)(int dtype, int tm, const void* args, cudaStr
     }
     const KLineArgs<float>& a = *static_cast<const KLineArgs<float>*>(args);
     return tm == TM_REAL ? launch_kline_t<float, SGPE_N, TM_REAL>(a, st) : launch_kline_t<float, SGPE_N, TM_IMAG>(a, st);
+}
+
+int SGPE_CAT(launch_kcol_, SGPE_N)(int dtype, int tm, const void* args, cudaStream_t st) {
+    if (dtype == 0) {
+        const KColArgs<double>& a = *static_cast<const KColArgs<double>*>(args);
+        return tm == TM_REAL ? launch_kcol_t<double, SGPE_N, TM_REAL>(a, st) : launch_kcol_t<double, SGPE_N, TM_IMAG>(a, st);
+    }
+    const KColArgs<float>& a = *static_cast<const KColArgs<float>*>(args);
+    return tm == TM_REAL ? launch_kcol_t<float, SGPE_N, TM_REAL>(a, st) : launch_kcol_t<float, SGPE_N, TM_IMAG>(a, st);
+}
+int SGPE_CAT(kcol_tile_width_, SGPE_N)(int dtype) {
+    return dtype == 0 ? KColCfg<double, SGPE_N>::W : KColCfg<float, SGPE_N>::W;
 }
 
 int SGPE_CAT(launch_mid_, SGPE_N)(int dtype, int tm, const void* args, cudaStream_t st) {

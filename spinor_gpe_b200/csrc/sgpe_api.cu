@@ -78,6 +78,8 @@ struct sgpe_plan {
     // long lines (four-step): nx = n1 * n2 with the strided part n1 (1 = ordinary plan)
     int n1 = 1, n2 = 0; void* tw_mid = nullptr; void* tw4 = nullptr;
     int col_wsel = 0;              // column tile width selector (sgpe_set_option "col_tile")
+    // fused exchange of the slab mode (sgpe_slab_set_peers): where the scatter stores of this plan's passes go
+    struct Peers { void* ptr[SGPE_MAX_PEERS]; int n = 0, mode = 0, seg = 0, drow = 0, base = 0; long long dplane = 0; } peers;
     int cpl_mode = 0; const double* cpl = nullptr; long long cpl_bs = 0;
     const double* omega = nullptr; const void* eiphi = nullptr;
     int tm = SGPE_TIME_IMAG; double dt = 0, dt_out = 0, dt_in = 0;
@@ -114,6 +116,15 @@ struct ProfScope {
 struct ProfScope { ProfScope(sgpe_plan*, int, cudaStream_t) {} };
 #endif
 
+
+template <typename C>
+void fill_scatter(const sgpe_plan* p, bool on, sgpe::Scatter<C>* sc) {
+    memset(sc, 0, sizeof(*sc));
+    if (!on) return;
+    for (int i = 0; i < p->peers.n; i++) sc->peer[i] = static_cast<C*>(p->peers.ptr[i]);
+    sc->mode = p->peers.mode; sc->seg = p->peers.seg; sc->drow = p->peers.drow; sc->base = p->peers.base;
+    sc->dplane = p->peers.dplane;
+}
 
 // exp(-2 pi i num / den) with exact values on the axes
 template <typename T>
@@ -247,7 +258,7 @@ int run_col(sgpe_plan* p, const void* in, void* out, bool fwd, bool has_a, doubl
 template <typename T>
 int run_row(sgpe_plan* p, const void* in, void* out, bool inv, bool pw, double dt_sub, bool fwd, int sign_in,
             int sign_out, double scale_out, cudaStream_t st, const double* totals_override = nullptr,
-            double norm_points = 0.0) {
+            double norm_points = 0.0, bool scatter = false) {
     typedef typename sgpe::cx_of<T>::type C;
     RowArgs<T> a;
     memset(&a, 0, sizeof(a));
@@ -279,6 +290,7 @@ int run_row(sgpe_plan* p, const void* in, void* out, bool inv, bool pw, double d
     a.tc = dt_sub / 4;                                      // coupling_op: Omega * dt_sub / 4, :142-149
     a.totals = totals_override ? totals_override : p->totals;
     a.norm_c = p->atom_num / (p->dv_r * (norm_points > 0 ? norm_points : (double)p->nx * (double)p->ny));
+    fill_scatter(p, scatter, &a.sc);
     ProfScope prof(p, 1, st);
     int rc = sgpe::launch_row(p->nx, p->dtype, p->tm, &a, p->batch, p->row_mode, st);
     if (rc == -3) return fail(SGPE_EINVAL, "row pass variant not compiled in (build with -DSGPE_EXPERIMENTAL)");
@@ -407,7 +419,7 @@ int run_energy(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, d
 
 template <typename T>
 static int run_klines(sgpe_plan* p, void* buf, bool fwd, bool has_a, double tau_a, bool has_b, double tau_b, bool inv,
-                      double* sums, cudaStream_t st) {
+                      double* sums, bool scatter, cudaStream_t st) {
     typedef typename sgpe::cx_of<T>::type C;
     sgpe::KLineArgs<T> a;
     memset(&a, 0, sizeof(a));
@@ -438,6 +450,7 @@ static int run_klines(sgpe_plan* p, void* buf, bool fwd, bool has_a, double tau_
         }
     }
     a.partials = p->partials; a.counter = p->counter; a.sums = sums;
+    fill_scatter(p, scatter, &a.sc);
     ProfScope prof(p, 0, st);
     int rc = sgpe::launch_kline(len, p->dtype, p->tm, &a, st);
     if (rc != 0) return fail(SGPE_EINVAL, "line pass: unsupported geometry");
@@ -448,7 +461,7 @@ static int run_klines(sgpe_plan* p, void* buf, bool fwd, bool has_a, double tau_
 
 template <typename T>
 static int run_mid(sgpe_plan* p, void* buf, bool pre_tw, bool inv, bool pw, double dt_sub, bool fwd, bool post_tw,
-                   const double* totals, double global_points, cudaStream_t st) {
+                   const double* totals, double global_points, int inner, bool scatter, cudaStream_t st) {
     typedef typename sgpe::cx_of<T>::type C;
     sgpe::MidArgs<T> m;
     memset(&m, 0, sizeof(m));
@@ -474,9 +487,62 @@ static int run_mid(sgpe_plan* p, void* buf, bool pre_tw, bool inv, bool pw, doub
     a.totals = totals;
     a.norm_c = p->atom_num / (p->dv_r * global_points);
     m.n2 = p->n2; m.pre_tw = pre_tw; m.post_tw = post_tw; m.tw4 = static_cast<const C*>(p->tw4);
+    m.inner = 1;
+    if (inner > 1) {      // row-major k slab [2][n1][n2][inner]: one "line" whose contiguous dimension is n2 * inner
+        if (pw) return fail(SGPE_EINVAL, "the point-wise operators are not available on the column-slab layout");
+        if (inner != p->ny) return fail(SGPE_EINVAL, "inner must equal the number of lines of the plan");
+        m.inner = inner; m.n2 = p->n2 * inner;
+        a.ny = 1; a.nx = p->nx * inner;
+    }
+    fill_scatter(p, scatter, &a.sc);
     ProfScope prof(p, 1, st);
     int rc = sgpe::launch_mid(p->n1, p->dtype, p->tm, &m, st);
     if (rc != 0) return fail(SGPE_EINVAL, "strided pass: unsupported geometry");
+    p->launches++;
+    SGPE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// k-space junction on the row-major k slab [2][len][nlines] of a line plan (len = p->nx points down the columns,
+// nlines = p->ny adjacent columns): the fused-exchange counterpart of run_klines.
+template <typename T>
+static int run_kcols(sgpe_plan* p, void* buf, bool fwd, bool has_a, double tau_a, bool has_b, double tau_b, bool inv,
+                     double* sums, bool scatter, cudaStream_t st) {
+    typedef typename sgpe::cx_of<T>::type C;
+    sgpe::KColArgs<T> a;
+    memset(&a, 0, sizeof(a));
+    a.in = static_cast<const C*>(buf); a.out = static_cast<C*>(buf);
+    a.tw = static_cast<const C*>(p->tw_x);
+    const int len = (p->n1 > 1) ? p->n2 : p->nx;
+    a.inner = p->ny; a.groups = p->n1; a.plane = p->plane;
+    a.do_fwd = fwd; a.do_inv = inv; a.has_a = has_a; a.has_b = has_b;
+    a.kin_mode = p->kin_mode;
+    if (scatter && p->n1 > 1) return fail(SGPE_EINVAL, "with a four-step split the strided pass stores the exchange");
+    if (p->n1 > 1 && p->kin_mode == 0 && (has_a || has_b))
+        return fail(SGPE_EINVAL, "long lines need the separable kinetic operator");
+    if (has_a || has_b) {
+        if (p->kin_mode == 0) {
+            a.kin0 = p->kin0; a.kin1 = p->kin1;
+            time_arg(p->tm, tau_a, &a.ka_re, &a.ka_im);
+            time_arg(p->tm, tau_b, &a.kb_re, &a.kb_im);
+        } else {
+            sgpe_plan::FactorTable* t = nullptr;
+            int rc;
+            if (has_a) {
+                if ((rc = factor_table<T>(p, p->kin_tab, 6, p->kin_x, 0, p->kin_y, 0, tau_a, st, &t))) return rc;
+                a.pa = static_cast<const C*>(t->x); a.la = static_cast<const C*>(t->y);
+            }
+            if (has_b) {
+                if ((rc = factor_table<T>(p, p->kin_tab, 6, p->kin_x, 0, p->kin_y, 0, tau_b, st, &t))) return rc;
+                a.pb = static_cast<const C*>(t->x); a.lb = static_cast<const C*>(t->y);
+            }
+        }
+    }
+    a.partials = p->partials; a.counter = p->counter; a.sums = sums;
+    fill_scatter(p, scatter, &a.sc);
+    ProfScope prof(p, 0, st);
+    int rc = sgpe::launch_kcol(len, p->dtype, p->tm, &a, st);
+    if (rc != 0) return fail(SGPE_EINVAL, "column-slab pass: unsupported geometry");
     p->launches++;
     SGPE_CUDA(cudaGetLastError());
     return 0;
@@ -787,13 +853,106 @@ int sgpe_energy(sgpe_plan* p, const void* psik, int unwrap_mode, double kl_term,
 
 // ---- slab (distributed) mode building blocks: the caller (spinor_gpe_b200/slab.py) owns the buffers and the
 // collectives (torch.distributed all_to_all / all_reduce over NCCL); these are the local passes.
+static int scatter_ready(const sgpe_plan* p, int scatter, int mode) {
+    if (!scatter) return 0;
+    if (p->peers.n < 1) return fail(SGPE_ESTATE, "scatter store requested before sgpe_slab_set_peers");
+    if (p->peers.mode != mode) return fail(SGPE_EINVAL, "this pass cannot store through the plan's exchange map");
+    return 0;
+}
+
 int sgpe_pass_rows(sgpe_plan* p, void* buf, double dt_sub, const double* totals_dev, double global_points,
-                   sgpe_stream st) {
+                   int scatter, sgpe_stream st) {
     if (!p || !buf || !totals_dev) return fail(SGPE_EINVAL, "null argument");
     if (!(p->grid_set && p->g_set && p->pot_set && p->time_set)) return fail(SGPE_ESTATE, "plan not configured");
+    int rc = scatter_ready(p, scatter, 1);
+    if (rc) return rc;
     DeviceGuard guard(p->device);
     return SGPE_BY_DTYPE(p, run_row, p, buf, buf, true, true, dt_sub, true, 0, 0, 1.0, (cudaStream_t)st, totals_dev,
-                         global_points);
+                         global_points, scatter != 0);
+}
+
+int sgpe_slab_set_peers(sgpe_plan* p, void* const* peer_bufs, int nranks, int mode, int seg, int drow, int64_t dplane,
+                        int base) {
+    if (!p || !peer_bufs) return fail(SGPE_EINVAL, "null argument");
+    if (nranks < 1 || nranks > SGPE_MAX_PEERS) return fail(SGPE_EINVAL, "1..16 ranks");
+    if (mode != 1 && mode != 2) return fail(SGPE_EINVAL, "mode must be 1 (split along x) or 2 (split along y)");
+    if (seg < 1 || drow < 1 || dplane < 1 || base < 0) return fail(SGPE_EINVAL, "bad exchange geometry");
+    for (int i = 0; i < nranks; i++) {
+        if (!peer_bufs[i]) return fail(SGPE_EINVAL, "null peer buffer");
+        p->peers.ptr[i] = peer_bufs[i];
+    }
+    p->peers.n = nranks; p->peers.mode = mode; p->peers.seg = seg; p->peers.drow = drow; p->peers.dplane = dplane;
+    p->peers.base = base;
+    return 0;
+}
+
+int sgpe_pass_kcols(sgpe_plan* p, void* buf, int do_fwd, int has_a, double tau_a, int has_b, double tau_b, int do_inv,
+                    double* sums_dev, int scatter, sgpe_stream st) {
+    if (!p || !buf) return fail(SGPE_EINVAL, "null argument");
+    if ((has_a || has_b) && (!p->kin_set || !p->time_set || !sums_dev)) return fail(SGPE_ESTATE, "kinetic operator / time / sums missing");
+    if (p->batch != 1) return fail(SGPE_EINVAL, "line passes are for batch == 1 plans");
+    int rc = scatter_ready(p, scatter, 2);
+    if (rc) return rc;
+    DeviceGuard guard(p->device);
+    return SGPE_BY_DTYPE(p, run_kcols, p, buf, do_fwd != 0, has_a != 0, tau_a, has_b != 0, tau_b, do_inv != 0,
+                         sums_dev, scatter != 0, (cudaStream_t)st);
+}
+
+// ---- exchange buffers visible to the other ranks of the node (one process per GPU): cudaMalloc + CUDA IPC.
+int sgpe_ipc_alloc(int device, uint64_t bytes, void** dev_ptr, unsigned char handle[SGPE_IPC_HANDLE_BYTES]) {
+    if (!dev_ptr || !handle || bytes == 0) return fail(SGPE_EINVAL, "bad argument");
+    *dev_ptr = nullptr;
+    memset(handle, 0, SGPE_IPC_HANDLE_BYTES);
+#ifndef SGPE_EMU
+    static_assert(sizeof(cudaIpcMemHandle_t) <= SGPE_IPC_HANDLE_BYTES, "handle size");
+    DeviceGuard guard(device);
+    if (cudaMalloc(dev_ptr, bytes) != cudaSuccess) { cudaGetLastError(); return fail(SGPE_ENOMEM, "device allocation failed"); }
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *dev_ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*dev_ptr); *dev_ptr = nullptr;
+        return fail(SGPE_ECUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+    }
+    memcpy(handle, &h, sizeof(h));
+#else
+    (void)device;
+    *dev_ptr = malloc(bytes);
+    if (!*dev_ptr) return fail(SGPE_ENOMEM, "allocation failed");
+    memcpy(handle, dev_ptr, sizeof(void*));          // emulation: only meaningful inside one process
+#endif
+    return 0;
+}
+
+int sgpe_ipc_open(int device, const unsigned char handle[SGPE_IPC_HANDLE_BYTES], void** dev_ptr) {
+    if (!dev_ptr || !handle) return fail(SGPE_EINVAL, "bad argument");
+#ifndef SGPE_EMU
+    DeviceGuard guard(device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    SGPE_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+#else
+    (void)device;
+    memcpy(dev_ptr, handle, sizeof(void*));
+#endif
+    return 0;
+}
+
+int sgpe_ipc_close(void* dev_ptr) {
+#ifndef SGPE_EMU
+    if (dev_ptr) SGPE_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+#else
+    (void)dev_ptr;
+#endif
+    return 0;
+}
+
+int sgpe_ipc_free(void* dev_ptr) {
+#ifndef SGPE_EMU
+    if (dev_ptr) SGPE_CUDA(cudaFree(dev_ptr));
+#else
+    free(dev_ptr);
+#endif
+    return 0;
 }
 
 int sgpe_plan_create_lines(sgpe_plan** out, int len, int nlines, int n1, int dtype, int device) {
@@ -842,24 +1001,29 @@ int sgpe_plan_create_lines(sgpe_plan** out, int len, int nlines, int n1, int dty
 }
 
 int sgpe_pass_mid(sgpe_plan* p, void* buf, int pre_tw, int do_inv, int do_pw, double dt_sub, int do_fwd, int post_tw,
-                  const double* totals_dev, double global_points, sgpe_stream st) {
+                  const double* totals_dev, double global_points, int inner, int scatter, sgpe_stream st) {
     if (!p || !buf) return fail(SGPE_EINVAL, "null argument");
     if (p->n1 <= 1) return fail(SGPE_ESTATE, "not a four-step (long line) plan");
     if (do_pw && (!totals_dev || !(p->grid_set && p->g_set && p->pot_set && p->time_set)))
         return fail(SGPE_ESTATE, "plan not configured for the point-wise operators");
+    int rcs = scatter_ready(p, scatter, 2);
+    if (rcs) return rcs;
+    if (scatter && inner <= 1) return fail(SGPE_EINVAL, "the strided pass stores the exchange only on the column-slab layout");
     DeviceGuard guard(p->device);
     return SGPE_BY_DTYPE(p, run_mid, p, buf, pre_tw != 0, do_inv != 0, do_pw != 0, dt_sub, do_fwd != 0, post_tw != 0,
-                         totals_dev, global_points > 0 ? global_points : 1.0, (cudaStream_t)st);
+                         totals_dev, global_points > 0 ? global_points : 1.0, inner, scatter != 0, (cudaStream_t)st);
 }
 
 int sgpe_pass_klines(sgpe_plan* p, void* buf, int do_fwd, int has_a, double tau_a, int has_b, double tau_b, int do_inv,
-                     double* sums_dev, sgpe_stream st) {
+                     double* sums_dev, int scatter, sgpe_stream st) {
     if (!p || !buf) return fail(SGPE_EINVAL, "null argument");
     if ((has_a || has_b) && (!p->kin_set || !p->time_set || !sums_dev)) return fail(SGPE_ESTATE, "kinetic operator / time / sums missing");
     if (p->batch != 1) return fail(SGPE_EINVAL, "line passes are for batch == 1 plans");
+    int rcs = scatter_ready(p, scatter, 1);
+    if (rcs) return rcs;
     DeviceGuard guard(p->device);
     return SGPE_BY_DTYPE(p, run_klines, p, buf, do_fwd != 0, has_a != 0, tau_a, has_b != 0, tau_b, do_inv != 0,
-                         sums_dev, (cudaStream_t)st);
+                         sums_dev, scatter != 0, (cudaStream_t)st);
 }
 
 int sgpe_slab_pack(sgpe_plan* p, const void* in, void* out, int lines, int nranks, int chunk, sgpe_stream st) {

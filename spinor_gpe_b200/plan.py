@@ -212,18 +212,31 @@ class Plan:
         return out
 
     # ------------------------------------------------------------------ slab-mode local passes
-    def pass_rows(self, buf, dt_sub, totals, global_points):
+    def pass_rows(self, buf, dt_sub, totals, global_points, scatter=False):
         self._chk(self.lib.sgpe_pass_rows(self.h, _dp(buf), float(dt_sub), _dp(totals), float(global_points),
-                                          self.stream), 'sgpe_pass_rows')
+                                          int(scatter), self.stream), 'sgpe_pass_rows')
 
-    def pass_klines(self, buf, do_fwd, has_a, tau_a, has_b, tau_b, do_inv, sums):
+    def pass_klines(self, buf, do_fwd, has_a, tau_a, has_b, tau_b, do_inv, sums, scatter=False):
         self._chk(self.lib.sgpe_pass_klines(self.h, _dp(buf), int(do_fwd), int(has_a), float(tau_a), int(has_b),
-                                            float(tau_b), int(do_inv), _dp(sums), self.stream), 'sgpe_pass_klines')
+                                            float(tau_b), int(do_inv), _dp(sums), int(scatter), self.stream),
+                  'sgpe_pass_klines')
 
-    def pass_mid(self, buf, pre_tw, do_inv, do_pw, dt_sub, do_fwd, post_tw, totals, global_points):
+    def pass_kcols(self, buf, do_fwd, has_a, tau_a, has_b, tau_b, do_inv, sums, scatter=False):
+        self._chk(self.lib.sgpe_pass_kcols(self.h, _dp(buf), int(do_fwd), int(has_a), float(tau_a), int(has_b),
+                                           float(tau_b), int(do_inv), _dp(sums), int(scatter), self.stream),
+                  'sgpe_pass_kcols')
+
+    def pass_mid(self, buf, pre_tw, do_inv, do_pw, dt_sub, do_fwd, post_tw, totals, global_points, inner=1,
+                 scatter=False):
         self._chk(self.lib.sgpe_pass_mid(self.h, _dp(buf), int(pre_tw), int(do_inv), int(do_pw), float(dt_sub),
-                                         int(do_fwd), int(post_tw), _dp(totals), float(global_points), self.stream),
-                  'sgpe_pass_mid')
+                                         int(do_fwd), int(post_tw), _dp(totals), float(global_points), int(inner),
+                                         int(scatter), self.stream), 'sgpe_pass_mid')
+
+    def set_peers(self, peer_ptrs, mode, seg, drow, dplane, base):
+        """Destination map of the fused exchange: peer_ptrs[q] = integer address of rank q's buffer."""
+        arr = (ctypes.c_void_p * len(peer_ptrs))(*[ctypes.c_void_p(int(v)) for v in peer_ptrs])
+        self._chk(self.lib.sgpe_slab_set_peers(self.h, arr, len(peer_ptrs), int(mode), int(seg), int(drow),
+                                               int(dplane), int(base)), 'sgpe_slab_set_peers')
 
     def slab_pack(self, src, dst, lines, nranks, chunk):
         self._chk(self.lib.sgpe_slab_pack(self.h, _dp(src), _dp(dst), int(lines), int(nranks), int(chunk),

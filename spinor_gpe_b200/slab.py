@@ -13,6 +13,12 @@ exchange.  The local passes are the hand-written kernels behind ``sgpe_pass_rows
 sgpe_pass_mid / sgpe_slab_pack / sgpe_slab_unpack``; ``torch.distributed`` (NCCL over NVLink) carries the
 collectives.
 
+``exchange='p2p'`` is the fused variant: every array stays row-major (k slab = [2][Ny][Nx/P], the y-lines run down
+the columns: ``sgpe_pass_kcols``), and the LAST kernel of each direction stores its output straight into the
+buffers of the ranks that need it next, through peer memory mapped with CUDA IPC (NVLink / NVSwitch) — compute
+and collective in one kernel, no pack / all-to-all / unpack passes.  The all-reduce of the norm sums (after the
+k-junction) and a one-word all-reduce (after the row passes) order the stores before their consumers.
+
 Lines longer than 4096 points (16384^2 of config 5) use the four-step split N = n1 * n2 inside each line:
 contiguous sub-transforms (``pass_klines``) + a strided pass with the twiddles and the real-space operators
 fused in (``pass_mid``): three local passes per direction instead of one.  k-space then lives in the
@@ -111,12 +117,15 @@ class SlabPropagator:
     keeps only its slab on the device.  ``split_x`` / ``split_y`` force a four-step split (tests)."""
 
     def __init__(self, spin, t_step, time='imag', device='cuda', group=None, precision='c128', plan_kwargs=None,
-                 split_x=None, split_y=None):
+                 split_x=None, split_y=None, exchange='nccl', exchange_buffers=None):
         from .plan import Plan
         assert dist.is_initialized(), "SlabPropagator needs an initialised torch.distributed process group"
         self.group = group
         self.rank, self.P = dist.get_rank(group), dist.get_world_size(group)
         self.dev = torch.device(device)
+        assert exchange in ('nccl', 'p2p')
+        self.p2p = (exchange == 'p2p')
+        self._ipc = []            # (lib, own pointers, opened pointers) to release
         self.cdtype = torch.complex128 if precision == 'c128' else torch.complex64
         sep_only = isinstance(spin, SeparableProblem)
         if sep_only:
@@ -181,14 +190,21 @@ class SlabPropagator:
         else:
             if self.n1y > 1:
                 raise NotImplementedError("four-step lines need a separable kinetic energy grid")
-            kin_t = np.ascontiguousarray(kin[:, :, xs].transpose(0, 2, 1))      # (2, nxl, ny)
-            tp.set_kinetic(kin_t[0], kin_t[1])
+            if self.p2p:
+                kin_l = np.ascontiguousarray(kin[:, :, xs])                      # (2, ny, nxl) row-major k slab
+            else:
+                kin_l = np.ascontiguousarray(kin[:, :, xs].transpose(0, 2, 1))   # (2, nxl, ny)
+            tp.set_kinetic(kin_l[0], kin_l[1])
         tp.set_time(time, self.dt)
 
         n_local = 2 * self.nxl * self.ny
         mk = lambda: torch.empty(n_local, dtype=self.cdtype, device=self.dev)      # noqa: E731
-        self.tbuf, self.rbuf, self.send, self.recv = mk(), mk(), mk(), mk()
+        if self.p2p:
+            self._setup_exchange(n_local, exchange_buffers)
+        else:
+            self.tbuf, self.rbuf, self.send, self.recv = mk(), mk(), mk(), mk()
         self.sums = torch.zeros(4, dtype=torch.float64, device=self.dev)
+        self._flag = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self.mid = False
         self.pending_dt = 0.0
         self.scale_pending = False
@@ -198,8 +214,75 @@ class SlabPropagator:
             self.set_real_space(spin.tf_rows(spin.space['y'][ys], self.dev, self.cdtype))
         else:
             stored = psik[:, self.nat_y][:, :, self.nat_x]
-            local = np.ascontiguousarray(stored[:, :, xs].transpose(0, 2, 1))     # (2, nxl, ny) transposed slab
+            if self.p2p:
+                local = np.ascontiguousarray(stored[:, :, xs])                    # (2, ny, nxl) row-major k slab
+            else:
+                local = np.ascontiguousarray(stored[:, :, xs].transpose(0, 2, 1))     # (2, nxl, ny) transposed slab
             self.tbuf.copy_(torch.as_tensor(local).reshape(-1).to(self.cdtype))
+            if self.p2p:
+                self._barrier()       # nobody stores into a peer that is still setting up
+
+    # ------------------------------------------------------------------ fused exchange: buffers in peer memory
+    def _setup_exchange(self, n_local, given):
+        """k slab (``tbuf``, [2][Ny][Nx/P]) and row slab (``rbuf``, [2][Ny/P][Nx]) of every rank, addressable from
+        this device.  Product path: cudaMalloc + CUDA IPC handles exchanged over the process group.  ``given`` (tests
+        on CPU with the emulated kernels): {'k': [tensor per rank], 'r': [...]} in memory shared by the processes."""
+        import ctypes
+        P, r = self.P, self.rank
+        if given is not None:
+            self.tbuf, self.rbuf = given['k'][r].view(-1), given['r'][r].view(-1)
+            assert self.tbuf.numel() == n_local and self.rbuf.numel() == n_local and self.tbuf.dtype == self.cdtype
+            kptrs = [t.data_ptr() for t in given['k']]
+            rptrs = [t.data_ptr() for t in given['r']]
+            self._keep_given = given
+        else:
+            assert self.dev.type == 'cuda', "the fused exchange needs CUDA devices (or shared test buffers)"
+            lib = self.rp.lib
+            dev_index = self.dev.index if self.dev.index is not None else torch.cuda.current_device()
+            nbytes = n_local * (16 if self.cdtype == torch.complex128 else 8)
+            own, handles = [], []
+            for _ in range(2):
+                ptr, h = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+                _capi.check(lib, lib.sgpe_ipc_alloc(dev_index, nbytes, ctypes.byref(ptr), h), 'sgpe_ipc_alloc')
+                own.append(ptr.value)
+                handles.append(bytes(h.raw))
+            everyone = [None] * P
+            dist.all_gather_object(everyone, handles, group=self.group)
+            kptrs, rptrs, opened = [], [], []
+            for q in range(P):
+                if q == r:
+                    kptrs.append(own[0]); rptrs.append(own[1])
+                    continue
+                for which, dst in ((0, kptrs), (1, rptrs)):
+                    ptr = ctypes.c_void_p()
+                    _capi.check(lib, lib.sgpe_ipc_open(dev_index, everyone[q][which], ctypes.byref(ptr)), 'sgpe_ipc_open')
+                    dst.append(ptr.value); opened.append(ptr.value)
+            self._ipc.append((lib, own, opened))
+
+            class _DevMem:            # raw device memory -> torch tensor (no copy)
+                def __init__(self, ptr, n):
+                    self.__cuda_array_interface__ = {'shape': (n,), 'typestr': '|u1', 'data': (ptr, False), 'version': 2}
+            wrap = lambda ptr: torch.as_tensor(_DevMem(ptr, nbytes), device=self.dev).view(self.cdtype)   # noqa: E731
+            self.tbuf, self.rbuf = wrap(own[0]), wrap(own[1])
+        # row direction -> k slabs (split along x);  k direction -> row slabs (split along y)
+        self.rp.set_peers(kptrs, 1, self.nxl, self.nxl, self.ny * self.nxl, r * self.nyl)
+        self.tp.set_peers(rptrs, 2, self.nyl, self.nx, self.nyl * self.nx, r * self.nxl)
+
+    def close(self):
+        """Unmap / free the exchange buffers (all ranks must have stopped stepping)."""
+        for lib, own, opened in self._ipc:
+            self.tbuf = self.rbuf = None
+            for ptr in opened:
+                lib.sgpe_ipc_close(ptr)
+            for ptr in own:
+                lib.sgpe_ipc_free(ptr)
+        self._ipc = []
+
+    def _barrier(self):
+        dist.all_reduce(self._flag, op=dist.ReduceOp.SUM, group=self.group)
+
+    def _count_exchange(self):
+        self.a2a_bytes += self.tbuf.numel() * self.tbuf.element_size() * (self.P - 1) // self.P
 
     def set_real_space(self, psi_rows):
         """Load a REAL-space state given by this rank's rows, (2, Ny/P, Nx) on the device: the distributed forward
@@ -208,17 +291,23 @@ class SlabPropagator:
         ny0 = self._ys.start
         sign = 1.0 - 2.0 * ((torch.arange(self.nx, device=self.dev)[None, :]
                              + torch.arange(ny0, ny0 + self.nyl, device=self.dev)[:, None]) % 2)
+        if self.p2p:
+            self._barrier()           # the peers are done with whatever they were reading
         self.rbuf.view(2, self.nyl, self.nx).copy_(psi_rows * sign.to(psi_rows.real.dtype))    # the fftshift sign
-        if self.n1x == 1:
-            self.rp.pass_klines(self.rbuf, True, False, 0.0, False, 0.0, False, None)
-        else:
+        if self.n1x > 1:
             self.rp.pass_mid(self.rbuf, False, False, False, 0.0, True, True, None, 0.0)
-            self.rp.pass_klines(self.rbuf, True, False, 0.0, False, 0.0, False, None)
-        self._to_lines()
-        if self.n1y == 1:
-            self.tp.pass_klines(self.tbuf, True, False, 0.0, False, 0.0, False, None)
+        self.rp.pass_klines(self.rbuf, True, False, 0.0, False, 0.0, False, None, scatter=self.p2p)
+        if self.p2p:
+            self._count_exchange()
+            self._barrier()
+            if self.n1y > 1:
+                self.tp.pass_mid(self.tbuf, False, False, False, 0.0, True, True, None, 0.0, inner=self.nxl)
+            self.tp.pass_kcols(self.tbuf, True, False, 0.0, False, 0.0, False, None)
+            self._barrier()
         else:
-            self.tp.pass_mid(self.tbuf, False, False, False, 0.0, True, True, None, 0.0)
+            self._to_lines()
+            if self.n1y > 1:
+                self.tp.pass_mid(self.tbuf, False, False, False, 0.0, True, True, None, 0.0)
             self.tp.pass_klines(self.tbuf, True, False, 0.0, False, 0.0, False, None)
         self.mid, self.scale_pending = False, False
 
@@ -244,6 +333,18 @@ class SlabPropagator:
     # ------------------------------------------------------------------ local passes (one or three per direction)
     def _k_junction(self, do_fwd, has_a, tau_a, has_b, tau_b, do_inv):
         tp = self.tp
+        if self.p2p:          # row-major k slab; the kernel that finishes the inverse stores into the peers' row slabs
+            if self.n1y == 1:
+                tp.pass_kcols(self.tbuf, do_fwd, has_a, tau_a, has_b, tau_b, do_inv, self.sums, scatter=do_inv)
+            else:
+                if do_fwd:
+                    tp.pass_mid(self.tbuf, False, False, False, 0.0, True, True, None, 0.0, inner=self.nxl)
+                tp.pass_kcols(self.tbuf, do_fwd, has_a, tau_a, has_b, tau_b, do_inv, self.sums)
+                if do_inv:
+                    tp.pass_mid(self.tbuf, True, True, False, 0.0, False, False, None, 0.0, inner=self.nxl, scatter=True)
+            if do_inv:
+                self._count_exchange()
+            return
         if self.n1y == 1:
             tp.pass_klines(self.tbuf, do_fwd, has_a, tau_a, has_b, tau_b, do_inv, self.sums)
             return
@@ -256,11 +357,13 @@ class SlabPropagator:
     def _row_pass(self, dt_sub):
         rp = self.rp
         if self.n1x == 1:
-            rp.pass_rows(self.rbuf, dt_sub, self.sums, self.points)
-            return
-        rp.pass_klines(self.rbuf, False, False, 0.0, False, 0.0, True, None)       # contiguous inverse over k2
-        rp.pass_mid(self.rbuf, True, True, True, dt_sub, True, True, self.sums, self.points)
-        rp.pass_klines(self.rbuf, True, False, 0.0, False, 0.0, False, None)       # contiguous forward over n2
+            rp.pass_rows(self.rbuf, dt_sub, self.sums, self.points, scatter=self.p2p)
+        else:
+            rp.pass_klines(self.rbuf, False, False, 0.0, False, 0.0, True, None)       # contiguous inverse over k2
+            rp.pass_mid(self.rbuf, True, True, True, dt_sub, True, True, self.sums, self.points)
+            rp.pass_klines(self.rbuf, True, False, 0.0, False, 0.0, False, None, scatter=self.p2p)   # forward over n2
+        if self.p2p:
+            self._count_exchange()
 
     # ------------------------------------------------------------------ stepping
     def single_step(self, dt_sub, pops_out=None):
@@ -274,9 +377,13 @@ class SlabPropagator:
         self._reduce_sums()
         if pops_out is not None and self.mid:
             pops_out.copy_(self.atom_num * self.sums[1:3] / (self.sums[1] + self.sums[2]))
-        self._to_rows()
-        self._row_pass(dt_sub)
-        self._to_lines()
+        if self.p2p:          # the all-reduce above ordered the peers' stores into rbuf before this point
+            self._row_pass(dt_sub)
+            self._barrier()
+        else:
+            self._to_rows()
+            self._row_pass(dt_sub)
+            self._to_lines()
         self.mid, self.pending_dt, self.scale_pending = True, dt_sub, False
 
     def close_junction(self, pops_out=None):
@@ -303,7 +410,10 @@ class SlabPropagator:
         """Normalised k-space state of this rank in the transposed (and, for split axes, digit-transposed)
         layout, (2, Nx/P, Ny)."""
         self.close_junction()
-        out = self.tbuf.view(2, self.nxl, self.ny)
+        if self.p2p:
+            out = self.tbuf.view(2, self.ny, self.nxl).transpose(1, 2)
+        else:
+            out = self.tbuf.view(2, self.nxl, self.ny)
         if self.scale_pending:
             scale = torch.sqrt(self.atom_num / (self.dv_k * (self.sums[1] + self.sums[2])))
             out = out * scale.to(out.real.dtype)

@@ -18,7 +18,15 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, outdir, mode, splits=(None, None), mesh=(128, 64)):
+def _shared_exchange_buffers(world, mesh):
+    """Exchange buffers of the fused ('p2p') variant for the CPU test: one k slab and one row slab per rank in shared
+    memory, so that every process can store into every rank's buffers like the GPUs do through CUDA IPC."""
+    n_local = 2 * mesh[0] * mesh[1] // world
+    mk = lambda: [torch.zeros(n_local, dtype=torch.complex128).share_memory_() for _ in range(world)]   # noqa: E731
+    return {'k': mk(), 'r': mk()}
+
+
+def _worker(rank, world, port, outdir, mode, splits=(None, None), mesh=(128, 64), given=None):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -42,7 +50,8 @@ def _worker(rank, world, port, outdir, mode, splits=(None, None), mesh=(128, 64)
                            ps.atom_num, x=ps.space['x'], kL=ps.kL_recoil, is_coupling=True, rot_coupling=False)
         want = orc.OraclePropagator(prob, dt, mode).run(n)
         sp = SlabPropagator(ps, dt, time=mode, device='cpu', plan_kwargs={'_lib': emu_lib()},
-                            split_x=splits[0], split_y=splits[1])
+                            split_x=splits[0], split_y=splits[1], exchange='p2p' if given else 'nccl',
+                            exchange_buffers=given)
         pops = torch.zeros((n, 2), dtype=torch.float64)
         sp.full_steps(n, pops)
         got = sp.gather_psik().numpy()
@@ -71,7 +80,19 @@ def test_slab_four_step_lines(splits, mesh):
              join=True)
 
 
-def _worker_sep(rank, world, port, outdir):
+@pytest.mark.parametrize('mode,splits,mesh', [('imag', (None, None), (128, 64)), ('real', (None, None), (128, 64)),
+                                               ('real', (32, None), (1024, 64)), ('imag', (None, 32), (64, 1024))])
+def test_slab_fused_exchange(mode, splits, mesh):
+    """exchange='p2p': row-major k slab, column-wise k junction (kcol_pass / strided mid_pass) and the scatter stores
+    of the last pass of each direction into the other rank's buffers, against the single-domain oracle."""
+    from tests.emu_harness import emu_lib
+    emu_lib()
+    given = _shared_exchange_buffers(2, mesh)
+    mp.spawn(_worker, args=(2, _free_port(), tempfile.mkdtemp(prefix='sgpe_slab_'), mode, splits, mesh, given),
+             nprocs=2, join=True)
+
+
+def _worker_sep(rank, world, port, outdir, given=None):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -89,7 +110,8 @@ def _worker_sep(rank, world, port, outdir):
         sep = SeparableProblem((128, 64), coupling=1.5 * ps.EL_recoil, kin_shift=True, detuning_slope=-3.0, **kw)
         outs = []
         for prob in (ps, sep):
-            sp = SlabPropagator(prob, 1 / 50, time='imag', device='cpu', plan_kwargs={'_lib': emu_lib()})
+            sp = SlabPropagator(prob, 1 / 50, time='imag', device='cpu', plan_kwargs={'_lib': emu_lib()},
+                                exchange='p2p' if given else 'nccl', exchange_buffers=given)
             sp.full_steps(2)
             outs.append(sp.gather_psik().numpy())
         err = np.linalg.norm(outs[1] - outs[0]) / np.linalg.norm(outs[0])
@@ -104,3 +126,11 @@ def test_slab_separable_problem_matches_pspinor():
     from tests.emu_harness import emu_lib
     emu_lib()
     mp.spawn(_worker_sep, args=(2, _free_port(), tempfile.mkdtemp(prefix='sgpe_slab_')), nprocs=2, join=True)
+
+
+def test_slab_fused_exchange_real_space_setup():
+    """The distributed forward transform of set_real_space through the scatter stores."""
+    from tests.emu_harness import emu_lib
+    emu_lib()
+    given = _shared_exchange_buffers(2, (128, 64))
+    mp.spawn(_worker_sep, args=(2, _free_port(), tempfile.mkdtemp(prefix='sgpe_slab_'), given), nprocs=2, join=True)
