@@ -21,6 +21,7 @@ import bench  # noqa: E402
 from spinor_gpe_b200.slab import SeparableProblem, SlabPropagator  # noqa: E402
 
 W0 = 2 * np.pi * 50
+EXCHANGE = 'nccl'          # --exchange=p2p: fused scatter stores into peer memory instead of pack / all-to-all / unpack
 
 
 def check(rank, world, dev):
@@ -37,15 +38,16 @@ def check(rank, world, dev):
             prop._plan.full_steps(n)
             ref = torch.stack(prop.psik)
         for splits in ((None, None), (32, None), (None, 64), (64, 32)):
-            sp = SlabPropagator(ps, dt, time=mode, device=dev, split_x=splits[0], split_y=splits[1])
+            sp = SlabPropagator(ps, dt, time=mode, device=dev, split_x=splits[0], split_y=splits[1], exchange=EXCHANGE)
             pops = torch.zeros((n, 2), dtype=torch.float64, device=dev)
             sp.full_steps(n, pops)
             full = sp.gather_psik()
             if rank == 0:
                 err = float(torch.linalg.norm(full - ref) / torch.linalg.norm(ref))
-                print(f'check {mesh}^2 {mode} splits={splits} ranks={world}: rel-L2 vs single GPU {err:.2e} '
+                print(f'check {mesh}^2 {mode} splits={splits} ranks={world} exchange={EXCHANGE}: rel-L2 vs single GPU {err:.2e} '
                       f'atoms {float(pops[-1].sum()):.10g}', flush=True)
                 assert err < 1e-10
+            sp.close()
             del sp
 
 
@@ -53,7 +55,7 @@ def run_bench(rank, world, dev, mesh, steps):
     g_sc = {'uu': 1, 'dd': 1, 'ud': 1.04}
     prob = SeparableProblem((mesh, mesh), r_sizes=(64, 64), atom_num=1e6, omeg={'x': W0, 'y': W0, 'z': 40 * W0},
                             g_sc=g_sc, pop_frac=(0.5, 0.5), coupling=1.0, kin_shift=True, rot_coupling=False)
-    sp = SlabPropagator(prob, 1 / 5000, time='real', device=dev)
+    sp = SlabPropagator(prob, 1 / 5000, time='real', device=dev, exchange=EXCHANGE)
     pops = torch.zeros((steps, 2), dtype=torch.float64, device=dev)
     sp.full_steps(2)
     dist.barrier(); torch.cuda.synchronize()
@@ -72,7 +74,7 @@ def run_bench(rank, world, dev, mesh, steps):
         nvl = sent / (ms * 1e-3) / 1e9
         hbm = 768.0 * mesh * mesh / world / (ms * 1e-3) / 1e9
         print(json.dumps({
-            'slab_bench': True, 'mesh': mesh, 'ranks': world, 'mode': 'real', 'dtype': 'c128',
+            'slab_bench': True, 'mesh': mesh, 'ranks': world, 'mode': 'real', 'dtype': 'c128', 'exchange': EXCHANGE,
             'four_step': [sp.n1x, sp.n1y], 'steps': steps, 'ms_per_step': ms, 'steps_per_s': 1e3 / ms,
             'kernel_launches_per_step': (sp.rp.launch_count() + sp.tp.launch_count() - l0) / steps,
             'a2a_bytes_sent_per_rank_per_step': sent, 'nvlink_GBps_per_rank': nvl, 'nvlink_frac_of_770': nvl / 770.0,
@@ -86,7 +88,7 @@ def breakdown(rank, world, dev, mesh):
     prob = SeparableProblem((mesh, mesh), r_sizes=(64, 64), atom_num=1e6, omeg={'x': W0, 'y': W0, 'z': 40 * W0},
                             g_sc={'uu': 1, 'dd': 1, 'ud': 1.04}, pop_frac=(0.5, 0.5), coupling=1.0, kin_shift=True,
                             rot_coupling=False)
-    sp = SlabPropagator(prob, 1 / 5000, time='real', device=dev)
+    sp = SlabPropagator(prob, 1 / 5000, time='real', device=dev, exchange=EXCHANGE)
     sp.full_steps(2)
     sp.single_step(sp.dt_out)
     dist.barrier(); torch.cuda.synchronize()
@@ -98,6 +100,19 @@ def breakdown(rank, world, dev, mesh):
         names.append(name); evs.append(e)
 
     dt = sp.dt_in
+    if EXCHANGE == 'p2p':
+        for rep in range(2):
+            mark('start')
+            sp._k_junction(True, False, 0.0, True, (sp.pending_dt + dt) / 2, True); mark('k-junction + scatter to row slabs')
+            sp._reduce_sums(); mark('all-reduce sums (orders the stores)')
+            sp._row_pass(dt); mark('row passes + scatter to k slabs')
+            sp._barrier(); mark('barrier')
+        torch.cuda.synchronize()
+        if rank == 0:
+            for i in range(6, len(evs)):
+                print(f'  {names[i]:40s} {evs[i - 1].elapsed_time(evs[i]):7.3f} ms', flush=True)
+            print(f'  sub-step total                           {evs[5].elapsed_time(evs[-1]):7.3f} ms', flush=True)
+        return
     mark('start')
     sp._k_junction(True, False, 0.0, True, (sp.pending_dt + dt) / 2, True); mark('k-junction (local passes)')
     sp._reduce_sums(); mark('all-reduce sums')
@@ -127,6 +142,11 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     dist.init_process_group('nccl', device_id=dev)
+    global EXCHANGE
+    for a in list(sys.argv):
+        if a.startswith('--exchange='):
+            EXCHANGE = a.split('=', 1)[1]
+            sys.argv.remove(a)
     what = sys.argv[1] if len(sys.argv) > 1 else 'check'
     if what == 'check':
         check(rank, world, dev)
