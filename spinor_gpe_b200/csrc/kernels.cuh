@@ -20,6 +20,33 @@ namespace sgpe {
 
 enum { TM_REAL = 0, TM_IMAG = 1 };
 
+// exp(x) for the imaginary-time factors evaluated per grid point (the non-linear term; dense operator grids).
+// Same scheme as the library routine — x = k ln2 + r, |r| <= ln2/2, degree-11 minimax polynomial (3e-18), 2^k
+// through the exponent field — without its out-of-range branches: k is clamped to +-1000, so results that would
+// underflow / overflow a double come out as ~1e-301 / ~1e+301 instead of 0 / inf (|x| > 690 never occurs for a
+// propagator factor).  Max error 1 ulp against exp() (tests/test_fast_exp.py); roughly half the instructions.
+SGPE_DI double sgpe_exp(double x) {
+    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);          // 1.5 * 2^52: low word = round(x/ln2)
+    int k = (int)(unsigned)(__double_as_longlong(t) & 0xffffffffLL);
+    const double kf = t - 6755399441055744.0;
+    double r = fma(kf, -6.93147180369123816490e-01, x);
+    r = fma(kf, -1.90821492927058770002e-10, r);
+    double p = 2.5110049204818658e-08;
+    p = fma(p, r, 2.763265472252779e-07);
+    p = fma(p, r, 2.755724088722987e-06);
+    p = fma(p, r, 2.4801485441561313e-05);
+    p = fma(p, r, 0.00019841269890076403);
+    p = fma(p, r, 0.0013888888952352863);
+    p = fma(p, r, 0.008333333333319589);
+    p = fma(p, r, 0.04166666666648795);
+    p = fma(p, r, 0.1666666666666668);
+    p = fma(p, r, 0.5000000000000019);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    k = k < -1000 ? -1000 : (k > 1000 ? 1000 : k);
+    return __longlong_as_double(__double_as_longlong(p) + ((long long)k << 52));
+}
+
 // exp(-i * e * tau), tau = (tr, ti):  real time tau = (dt, 0);  imaginary time tau = (0, -dt)
 template <int TM, typename T, typename C> SGPE_DI C evo(double e, double tr, double ti) {
     C r;
@@ -38,7 +65,7 @@ template <int TM, typename T, typename C> SGPE_DI C evo(double e, double tr, dou
             sincos(e * tr, &s, &c);
             r.x = (T)c; r.y = (T)(-s);
         } else {
-            r.x = (T)exp(e * ti); r.y = (T)0;
+            r.x = (T)sgpe_exp(e * ti); r.y = (T)0;
         }
     }
     return r;
@@ -200,6 +227,20 @@ __global__ void __launch_bounds__(W * N / E, (W * N / E <= 256) ? 2 : 1) col_pas
         if (!a.has_a) acc[0] = acc[1];
     }
 
+    // The tile's partial sums are published BEFORE the inverse transform: the barriers of the reduction and the
+    // round trip of the ticket to L2 then hide behind the transform, and the CTA retires right after its stores
+    // (with one CTA per SM the epilogue is dead time for the whole SM).
+    unsigned ticket = 0u;
+    if (any_k) {
+        cta_reduce<2>(acc, red);
+        if (tid == 0) {
+            double* p = a.partials + ((long long)b * ntiles + tile) * 2;
+            p[0] = acc[0]; p[1] = acc[1];
+            __threadfence();
+            ticket = atomicAdd(&a.counter[b], 1u);
+        }
+    }
+
     if (do_inv) cta_fft<T, N, E, +1, W, 1>(v, j, c, sms, a.tw + (E == 16 ? N : 0));
 
     if (!FAST && (sign_out || a.scale_out != 1.0)) {
@@ -214,17 +255,9 @@ __global__ void __launch_bounds__(W * N / E, (W * N / E <= 256) ? 2 : 1) col_pas
     for (int m = 0; m < E; m++) SGPE_ST_STREAM(&a.out[off + (long long)(j + m * NT) * a.nx], v[0][m]);
 
     if (any_k) {
-        cta_reduce<2>(acc, red);
-        if (tid == 0) {
-            double* p = a.partials + ((long long)b * ntiles + tile) * 2;
-            p[0] = acc[0]; p[1] = acc[1];
-            __threadfence();
-            const unsigned ticket = atomicAdd(&a.counter[b], 1u);
-            red[0] = (ticket == (unsigned)(ntiles - 1)) ? 1.0 : 0.0;
-        }
+        if (tid == 0) red[0] = (ticket == (unsigned)(ntiles - 1)) ? 1.0 : 0.0;
         __syncthreads();
-        const bool last = red[0] != 0.0;
-        __syncthreads();
+        const bool last = red[0] != 0.0;      // (the fold's first write to `red` comes after a barrier of its own)
         if (last) {       // the last tile of this trajectory folds the partials in a fixed order
             __threadfence();
             double t4[4] = {0.0, 0.0, 0.0, 0.0};     // S0, T0, S1, T1
@@ -300,8 +333,16 @@ SGPE_DI void coupling_entries(double theta, C ph, T& diag, C& off01, C& off10) {
 // FAST = 1 is the specialisation for the common full pass (inverse + point-wise + forward, no coupling,
 // separable potential, no sign / scale): same code with the other branches compiled out, which roughly halves
 // the instruction footprint (the generic kernel does not fit the instruction cache: ncu stall_no_inst).
+// resident CTAs asked of the compiler: complex128 -> 128 registers per thread (64 hold the two components' data),
+// complex64 -> 64 registers per thread (twice the CTAs per SM: the FP32 passes are latency-, not register-bound)
+#ifndef SGPE_F32_THREADS_PER_SM
+#define SGPE_F32_THREADS_PER_SM 1024
+#endif
+template <typename T> constexpr int row_min_blocks(int threads) {
+    return sizeof(T) == 8 ? (threads <= 256 ? 2 : 1) : (threads <= SGPE_F32_THREADS_PER_SM ? SGPE_F32_THREADS_PER_SM / threads : 1);
+}
 template <typename T, int N, int E, int RPC, int TM, int FAST>
-__global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) row_pass(RowArgs<T> a) {
+__global__ void __launch_bounds__(RPC * N / E, row_min_blocks<T>(RPC * N / E)) row_pass(RowArgs<T> a) {
     typedef typename cx_of<T>::type C;
     constexpr int NT = N / E;
     SGPE_DYN_SMEM(smem_raw);
@@ -1174,48 +1215,59 @@ SGPE_DI double sgpe_grad3_wrapped(double fm, double f0, double fp, int i, int n,
     return (sgpe_wrap_pi(fp - f0) + sgpe_wrap_pi(f0 - fm)) * (0.5 * inv_h);
 }
 
+// Each CTA walks 32 x 8 pixel tiles.  sqrt(n) and the masked phase are evaluated ONCE per pixel of the tile plus its
+// one-pixel halo (340 points for 256 outputs) into shared memory and the stencils read them from there: the
+// square roots and arctangents were 5x redundant when every pixel evaluated its own neighbours (FP64-bound).
 template <typename T>
 __global__ void __launch_bounds__(256) energy_pass(EnergyArgs<T> a) {
     typedef typename cx_of<T>::type C;
+    constexpr int TX = 32, TY = 8, HX = TX + 2, HY = TY + 2;
     SGPE_DYN_SMEM(smem_raw);
-    double* red = reinterpret_cast<double*>(smem_raw);
+    double* red = reinterpret_cast<double*>(smem_raw);                 // [32 * 4]
+    double* s_r = red + 32 * 4;                                        // [HY][HX] sqrt(n)
+    double* s_ph = s_r + HX * HY;                                      // [HY][HX] masked phase
     const int b = blockIdx.y, nblk = gridDim.x, tid = threadIdx.x;
-    const int tx = tid & 31, ty = tid >> 5;                 // 32 x 8 pixel tiles
-    const int tiles_x = a.nx / 32, tiles_y = a.ny / 8;
+    const int tx = tid & 31, ty = tid >> 5;
+    const int tiles_x = a.nx / TX, tiles_y = a.ny / TY;
     const long long ntiles = (long long)tiles_x * tiles_y;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (long long t = blockIdx.x; t < ntiles; t += nblk) {
-        const int i = (int)(t / tiles_x) * 8 + ty;          // axis 0 (y)
-        const int j = (int)(t % tiles_x) * 32 + tx;         // axis 1 (x)
-        const int im = i > 0 ? i - 1 : 0, ip = i < a.ny - 1 ? i + 1 : a.ny - 1;
-        const int jm = j > 0 ? j - 1 : 0, jp = j < a.nx - 1 ? j + 1 : a.nx - 1;
+        const int i0 = (int)(t / tiles_x) * TY, j0 = (int)(t % tiles_x) * TX;
+        const int i = i0 + ty;          // axis 0 (y)
+        const int j = j0 + tx;          // axis 1 (x)
         double kin = 0.0, dens[2];
         C ctr[2];
         for (int comp = 0; comp < 2; comp++) {
             const C* p = a.psi + ((long long)b * 2 + comp) * a.plane;
             const double thr = a.maxdens[2 * b + comp] * 1e-6;
-            const C z[5] = {p[(long long)i * a.nx + j], p[(long long)im * a.nx + j], p[(long long)ip * a.nx + j],
-                            p[(long long)i * a.nx + jm], p[(long long)i * a.nx + jp]};
-            double n[5], r[5], ph[5];
-#pragma unroll
-            for (int q = 0; q < 5; q++) {
-                n[q] = (double)z[q].x * z[q].x + (double)z[q].y * z[q].y;
-                r[q] = sqrt(n[q]);
-                ph[q] = (n[q] < thr) ? 0.0 : atan2((double)z[q].y, (double)z[q].x);
+            for (int q = tid; q < HX * HY; q += 256) {
+                const int ly = q / HX, lx = q - ly * HX;
+                int gi = i0 + ly - 1, gj = j0 + lx - 1;                 // clamped: the edge stencils never use them
+                gi = gi < 0 ? 0 : (gi > a.ny - 1 ? a.ny - 1 : gi);
+                gj = gj < 0 ? 0 : (gj > a.nx - 1 ? a.nx - 1 : gj);
+                const C z = p[(long long)gi * a.nx + gj];
+                const double n = (double)z.x * z.x + (double)z.y * z.y;
+                s_r[q] = sqrt(n);
+                s_ph[q] = (n < thr) ? 0.0 : atan2((double)z.y, (double)z.x);
             }
-            const double r0 = sgpe_grad3(r[1], r[0], r[2], i, a.ny, a.inv_h0);
-            const double r1 = sgpe_grad3(r[3], r[0], r[4], j, a.nx, a.inv_h1);
+            __syncthreads();
+            const int c0 = (ty + 1) * HX + (tx + 1);
+            const C z0 = p[(long long)i * a.nx + j];
+            const double n0 = (double)z0.x * z0.x + (double)z0.y * z0.y;
+            const double r0 = sgpe_grad3(s_r[c0 - HX], s_r[c0], s_r[c0 + HX], i, a.ny, a.inv_h0);
+            const double r1 = sgpe_grad3(s_r[c0 - 1], s_r[c0], s_r[c0 + 1], j, a.nx, a.inv_h1);
             double g0, g1;
             if (a.unwrap_mode == 0) {
-                g0 = sgpe_grad3(ph[1], ph[0], ph[2], i, a.ny, a.inv_h0);
-                g1 = sgpe_grad3(ph[3], ph[0], ph[4], j, a.nx, a.inv_h1);
+                g0 = sgpe_grad3(s_ph[c0 - HX], s_ph[c0], s_ph[c0 + HX], i, a.ny, a.inv_h0);
+                g1 = sgpe_grad3(s_ph[c0 - 1], s_ph[c0], s_ph[c0 + 1], j, a.nx, a.inv_h1);
             } else {
-                g0 = sgpe_grad3_wrapped(ph[1], ph[0], ph[2], i, a.ny, a.inv_h0);
-                g1 = sgpe_grad3_wrapped(ph[3], ph[0], ph[4], j, a.nx, a.inv_h1);
+                g0 = sgpe_grad3_wrapped(s_ph[c0 - HX], s_ph[c0], s_ph[c0 + HX], i, a.ny, a.inv_h0);
+                g1 = sgpe_grad3_wrapped(s_ph[c0 - 1], s_ph[c0], s_ph[c0 + 1], j, a.nx, a.inv_h1);
             }
-            kin += (r0 * r0 + r1 * r1) + n[0] * (g0 * g0 + g1 * g1) + n[0] * g0 * a.kl2;
-            dens[comp] = n[0];
-            ctr[comp] = z[0];
+            kin += (r0 * r0 + r1 * r1) + n0 * (g0 * g0 + g1 * g1) + n0 * g0 * a.kl2;
+            dens[comp] = n0;
+            ctr[comp] = z0;
+            __syncthreads();
         }
         kin *= 0.5;
         const long long pix = (long long)i * a.nx + j;

@@ -152,7 +152,7 @@ static int launch_kline_t(const KLineArgs<T>& a, cudaStream_t st) {
 // k-space junction on the row-major k slab (fused-exchange layout): W adjacent columns of one component
 template <typename T, int N> struct KColCfg {
     static constexpr int CB = (int)sizeof(typename cx_of<T>::type);
-    static constexpr int E = ColCfg<T, N>::E;
+    static constexpr int E = (N >= 128) ? 16 : 8;                      // 128 = 16 x 8: one exchange per transform
     static constexpr int NT = N / E;
     static constexpr int WT = (256 / NT > 32) ? 32 : (256 / NT);       // aim at 256 threads, tiles <= 32 columns
     static constexpr int W = (ColCfg<T, N>::W > WT) ? ColCfg<T, N>::W : WT;

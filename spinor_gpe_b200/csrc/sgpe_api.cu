@@ -409,9 +409,10 @@ int run_energy(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, d
     a.unwrap_mode = unwrap_mode;
     a.maxdens = p->maxdens; a.partials = p->partials; a.counter = p->counter; a.out = out;
     long long tiles = (long long)(p->nx / 32) * (p->ny / 8);
-    blocks = tiles < 512 ? tiles : 512;
+    blocks = tiles < 888 ? tiles : 888;                     // six 256-thread CTAs per SM x 148 SMs
+    if (blocks > p->max_tiles / 2) blocks = p->max_tiles / 2;   // four partial sums per CTA in `partials`
     dim3 grid((unsigned)blocks, p->batch), block(256);
-    SGPE_LAUNCH((sgpe::energy_pass<T>), grid, block, 32 * 4 * sizeof(double), st, a);
+    SGPE_LAUNCH((sgpe::energy_pass<T>), grid, block, (32 * 4 + 2 * 34 * 10) * sizeof(double), st, a);
     p->launches++;
     SGPE_CUDA(cudaGetLastError());
     return 0;

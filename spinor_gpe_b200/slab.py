@@ -117,13 +117,16 @@ class SlabPropagator:
     keeps only its slab on the device.  ``split_x`` / ``split_y`` force a four-step split (tests)."""
 
     def __init__(self, spin, t_step, time='imag', device='cuda', group=None, precision='c128', plan_kwargs=None,
-                 split_x=None, split_y=None, exchange='nccl', exchange_buffers=None):
+                 split_x=None, split_y=None, exchange='auto', exchange_buffers=None):
         from .plan import Plan
         assert dist.is_initialized(), "SlabPropagator needs an initialised torch.distributed process group"
         self.group = group
         self.rank, self.P = dist.get_rank(group), dist.get_world_size(group)
         self.dev = torch.device(device)
-        assert exchange in ('nccl', 'p2p')
+        assert exchange in ('auto', 'nccl', 'p2p')
+        if exchange == 'auto':    # one node, one process per GPU: the fused exchange through peer memory
+            exchange = 'p2p' if (self.dev.type == 'cuda' or exchange_buffers is not None) else 'nccl'
+        self.exchange = exchange
         self.p2p = (exchange == 'p2p')
         self._ipc = []            # (lib, own pointers, opened pointers) to release
         self.cdtype = torch.complex128 if precision == 'c128' else torch.complex64

@@ -149,6 +149,8 @@ inline void __syncthreads() { ::emu::syncthreads(); }
 inline void __threadfence() {}
 inline double __shfl_xor_sync(unsigned, double v, int m) { return ::emu::shfl_xor(v, m); }
 template <typename T> inline T __ldg(const T* p) { return *p; }
+inline long long __double_as_longlong(double x) { long long r; std::memcpy(&r, &x, 8); return r; }
+inline double __longlong_as_double(long long x) { double r; std::memcpy(&r, &x, 8); return r; }
 template <typename T> inline T __ldcg(const T* p) { return *p; }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 inline void sincos(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }

@@ -21,7 +21,7 @@ import bench  # noqa: E402
 from spinor_gpe_b200.slab import SeparableProblem, SlabPropagator  # noqa: E402
 
 W0 = 2 * np.pi * 50
-EXCHANGE = 'nccl'          # --exchange=p2p: fused scatter stores into peer memory instead of pack / all-to-all / unpack
+EXCHANGE = 'p2p'           # --exchange=nccl: pack / NCCL all-to-all / unpack instead of the fused scatter stores
 
 
 def check(rank, world, dev):
@@ -37,7 +37,7 @@ def check(rank, world, dev):
             prop = TensorPropagator(ps, dt, n, dev, time=mode)
             prop._plan.full_steps(n)
             ref = torch.stack(prop.psik)
-        for splits in ((None, None), (32, None), (None, 64), (64, 32)):
+        for splits in ((None, None), (32, None), (None, 64), (64, 32), (16, 16)):
             sp = SlabPropagator(ps, dt, time=mode, device=dev, split_x=splits[0], split_y=splits[1], exchange=EXCHANGE)
             pops = torch.zeros((n, 2), dtype=torch.float64, device=dev)
             sp.full_steps(n, pops)
