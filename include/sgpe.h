@@ -169,8 +169,16 @@ int sgpe_slab_unpack(sgpe_plan* p, const void* in_dev, void* out_dev, int nranks
  *                        sub-lines of every n1 group, the strided halves being sgpe_pass_mid(inner = nlines)).
  *  sgpe_pass_mid(inner = nlines > 1) : the strided four-step half on the k slab viewed as [2][n1][n2][nlines].
  *  sgpe_ipc_*          : cudaMalloc'ed exchange buffers exported to / imported from the other processes of the node
- *                        (cudaIpcGetMemHandle / cudaIpcOpenMemHandle with lazy peer access). */
+ *                        (cudaIpcGetMemHandle / cudaIpcOpenMemHandle with lazy peer access).
+ *  sgpe_slab_window    : chunked pipelining of the exchange.  The line passes that follow work on the lines
+ *                        [first, first + count) of the plan only (rows of a row slab, columns of a k slab), with
+ *                        reduction slot `chunk` (0..15; sums of a chunk go to the sums pointer of that call) and,
+ *                        for the passes that walk their window with persistent CTAs (sgpe_pass_klines,
+ *                        sgpe_pass_mid on the column slab), at most max_ctas CTAs (0: one CTA per block).  A
+ *                        scatter pass capped to a few CTAs per SM on a second stream sends chunk c over NVLink
+ *                        while the local passes of chunk c + 1 run beside it.  count == 0 clears the window. */
 #define SGPE_IPC_HANDLE_BYTES 64
+int sgpe_slab_window(sgpe_plan* p, int first, int count, int chunk, int max_ctas);
 int sgpe_slab_set_peers(sgpe_plan* p, void* const* peer_bufs, int nranks, int mode, int seg, int drow, int64_t dplane,
                         int base);
 int sgpe_pass_kcols(sgpe_plan* p, void* buf_dev, int do_fwd, int has_a, double tau_a, int has_b, double tau_b,

@@ -40,6 +40,7 @@ PROTOTYPES = {
                                   C.c_int, c_stream]),
     'sgpe_slab_set_peers': (C.c_int, [c_plan, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
                                       C.c_int]),
+    'sgpe_slab_window': (C.c_int, [c_plan, C.c_int, C.c_int, C.c_int, C.c_int]),
     'sgpe_ipc_alloc': (C.c_int, [C.c_int, C.c_uint64, C.POINTER(C.c_void_p), C.c_char_p]),
     'sgpe_ipc_open': (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
     'sgpe_ipc_close': (C.c_int, [C.c_void_p]),

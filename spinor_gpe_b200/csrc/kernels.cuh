@@ -336,7 +336,7 @@ SGPE_DI void coupling_entries(double theta, C ph, T& diag, C& off01, C& off10) {
 // resident CTAs asked of the compiler: complex128 -> 128 registers per thread (64 hold the two components' data),
 // complex64 -> 64 registers per thread (twice the CTAs per SM: the FP32 passes are latency-, not register-bound)
 #ifndef SGPE_F32_THREADS_PER_SM
-#define SGPE_F32_THREADS_PER_SM 1024
+#define SGPE_F32_THREADS_PER_SM 768
 #endif
 template <typename T> constexpr int row_min_blocks(int threads) {
     return sizeof(T) == 8 ? (threads <= 256 ? 2 : 1) : (threads <= SGPE_F32_THREADS_PER_SM ? SGPE_F32_THREADS_PER_SM / threads : 1);
@@ -643,6 +643,11 @@ template <typename T> struct KLineArgs {
                                                      // line/group, position table index = (line%group)*N + pos
     double* partials; unsigned* counter; double* sums;    // sums: [3] = T, S0, S1 of the LOCAL slab
     Scatter<C> sc;                                   // fused exchange on the store (mode 1: row direction)
+    // window of the slab handled by this launch (chunked pipelining of the exchange, sgpe_slab_window): the lines
+    // [line0, line0 + nblk * RPC); the grid may be smaller than nblk (persistent CTAs walking the window), which is
+    // how a scatter launch leaves most of every SM to the passes of the next chunk running beside it
+    int line0, nblk;
+    int wlines, max_ctas;                            // host side: lines in the window, cap on the grid (0 = none)
 };
 
 template <typename T, int N, int E, int RPC, int TM>
@@ -655,7 +660,10 @@ __global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) kli
 
     const int tid = threadIdx.x;
     const int r = tid / NT, j = tid % NT;
-    const int line = blockIdx.x * RPC + r;
+    C* const sms[2] = {smem + (size_t)(2 * r) * N, smem + (size_t)(2 * r + 1) * N};
+#pragma unroll 1
+    for (int vb = blockIdx.x; vb < a.nblk; vb += gridDim.x) {
+    const int line = a.line0 + vb * RPC + r;
     const long long off0 = (long long)line * a.nx, off1 = off0 + a.plane;
 
     C v[2][E];
@@ -664,7 +672,6 @@ __global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) kli
         v[0][m] = a.in[off0 + j + m * NT];
         v[1][m] = a.in[off1 + j + m * NT];
     }
-    C* const sms[2] = {smem + (size_t)(2 * r) * N, smem + (size_t)(2 * r + 1) * N};
     double acc[4] = {0.0, 0.0, 0.0, 0.0};      // S0, T0, S1, T1
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
@@ -724,10 +731,10 @@ __global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) kli
     }
     }
     if (a.has_a || a.has_b) {
-        const int nblk = gridDim.x;
+        const int nblk = a.nblk;
         cta_reduce<4>(acc, red);
         if (tid == 0) {
-            double* p = a.partials + (long long)blockIdx.x * 4;
+            double* p = a.partials + (long long)vb * 4;
             p[0] = acc[0]; p[1] = acc[1]; p[2] = acc[2]; p[3] = acc[3];
             __threadfence();
             red[0] = (atomicAdd(&a.counter[0], 1u) == (unsigned)(nblk - 1)) ? 1.0 : 0.0;
@@ -749,6 +756,8 @@ __global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) kli
             }
         }
     }
+    __syncthreads();      // the next window block reuses the exchange images
+    }   // window loop
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -769,6 +778,11 @@ template <typename T> struct MidArgs {
     const C* tw4;                  // [N1][N2] four-step twiddles exp(-2 pi i k1 n2 / N)
     int inner;                     // 1: array [2][nlines][N1][N2].  > 1: k slab [2][N1][N2][inner] (row-major slab, the
                                    // lines run down the columns): r.ny = 1, n2 = N2 * inner, twiddle column = n2 / inner
+    // window of the slab handled by this launch (sgpe_slab_window).  inner == 1: lines y0 .. y0 + gridDim.y.
+    // inner > 1: columns [x0, x0 + wtiles * W) of every n2 digit: virtual block vb -> digit vb / wtiles, tile
+    // vb % wtiles; nvb virtual blocks walked by gridDim.x (possibly fewer, persistent) CTAs.
+    int y0, x0, wtiles, wstride, nvb;
+    int wcount, max_ctas;                            // host side: lines / columns in the window, cap on the grid
 };
 
 template <typename T, int N1, int E, int W, int TM>
@@ -780,8 +794,11 @@ __global__ void __launch_bounds__(W * N1 / E) mid_pass(MidArgs<T> ma) {
     C* smem = reinterpret_cast<C*>(smem_raw);
     const int tid = threadIdx.x;
     const int c = tid % W, j = tid / W;
-    const int n2 = blockIdx.x * W + c;
-    const int y = blockIdx.y;                       // line (local row)
+    C* const sms[2] = {smem, smem + (size_t)N1 * W};
+#pragma unroll 1
+    for (int vb = blockIdx.x; vb < ma.nvb; vb += gridDim.x) {
+    const int n2 = (vb / ma.wtiles) * ma.wstride + ma.x0 + (vb % ma.wtiles) * W + c;
+    const int y = ma.y0 + blockIdx.y;               // line (local row)
     const int b = 0;
     const long long line0 = (long long)y * a.nx + n2, line1 = line0 + a.plane;
 
@@ -800,7 +817,6 @@ __global__ void __launch_bounds__(W * N1 / E) mid_pass(MidArgs<T> ma) {
             v[0][m] = cmulc(v[0][m], w); v[1][m] = cmulc(v[1][m], w);
         }
     }
-    C* const sms[2] = {smem, smem + (size_t)N1 * W};
     if (a.do_inv) cta_fft<T, N1, E, +1, W, 2>(v, j, c, sms, a.tw + (E == 16 ? N1 : 0));
 
     if (a.do_pw) {
@@ -887,6 +903,8 @@ __global__ void __launch_bounds__(W * N1 / E) mid_pass(MidArgs<T> ma) {
         SGPE_ST_STREAM(&a.out[line1 + o], v[1][m]);
     }
     }
+    __syncthreads();      // the next window block reuses the exchange images
+    }   // window loop
 }
 
 // k-space junction of the slab mode on the ROW-MAJOR k slab [2][G][N][inner] (the fused-exchange layout): for W
@@ -904,6 +922,8 @@ template <typename T> struct KColArgs {
     const C* la; const C* pa; const C* lb; const C* pb;
     double* partials; unsigned* counter; double* sums;
     Scatter<C> sc;                                    // mode 2 (k direction -> row slabs)
+    int x0;                                           // first column of the window (gridDim.x * W columns)
+    int wcount;                                       // host side: columns in the window
 };
 
 template <typename T, int N, int E, int W, int TM>
@@ -915,7 +935,7 @@ __global__ void __launch_bounds__(W * N / E) kcol_pass(KColArgs<T> a) {
     double* red = reinterpret_cast<double*>(smem_raw + sizeof(C) * (size_t)N * W);
     const int tid = threadIdx.x;
     const int c = tid % W, j = tid / W;
-    const int col = blockIdx.x * W + c;
+    const int col = a.x0 + blockIdx.x * W + c;
     const int g = blockIdx.y, comp = blockIdx.z;
     const long long off = (long long)comp * a.plane + (long long)g * N * a.inner + col;
 

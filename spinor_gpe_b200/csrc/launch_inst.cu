@@ -141,11 +141,14 @@ template <typename T, int N, int TM>
 static int launch_kline_t(const KLineArgs<T>& a, cudaStream_t st) {
     typedef RowCfg<T, N> Cfg;
     constexpr size_t smem = Cfg::SMEM + 32 * 4 * sizeof(double);
-    if (a.ny % Cfg::RPC != 0) return -2;
+    if (a.ny % Cfg::RPC != 0 || a.wlines % Cfg::RPC != 0 || a.line0 % Cfg::RPC != 0) return -2;
     static bool once = false;
     if (!once) { allow_smem(kline_pass<T, N, Cfg::E, Cfg::RPC, TM>, smem); once = true; }
-    dim3 grid(a.ny / Cfg::RPC), block(Cfg::THREADS);
-    SGPE_LAUNCH((kline_pass<T, N, Cfg::E, Cfg::RPC, TM>), grid, block, smem, st, a);
+    KLineArgs<T> a2 = a;
+    a2.nblk = a.wlines / Cfg::RPC;
+    const int ctas = (a.max_ctas > 0 && a.max_ctas < a2.nblk) ? a.max_ctas : a2.nblk;
+    dim3 grid(ctas), block(Cfg::THREADS);
+    SGPE_LAUNCH((kline_pass<T, N, Cfg::E, Cfg::RPC, TM>), grid, block, smem, st, a2);
     return 0;
 }
 
@@ -161,10 +164,10 @@ template <typename T, int N> struct KColCfg {
 template <typename T, int N, int TM>
 static int launch_kcol_t(const KColArgs<T>& a, cudaStream_t st) {
     typedef KColCfg<T, N> Cfg;
-    if (a.inner % Cfg::W != 0) return -2;
+    if (a.inner % Cfg::W != 0 || a.wcount % Cfg::W != 0 || a.x0 % Cfg::W != 0) return -2;
     static bool once = false;
     if (!once) { allow_smem(kcol_pass<T, N, Cfg::E, Cfg::W, TM>, Cfg::SMEM); once = true; }
-    dim3 grid(a.inner / Cfg::W, a.groups, 2), block(Cfg::W * Cfg::NT);
+    dim3 grid(a.wcount / Cfg::W, a.groups, 2), block(Cfg::W * Cfg::NT);
     SGPE_LAUNCH((kcol_pass<T, N, Cfg::E, Cfg::W, TM>), grid, block, Cfg::SMEM, st, a);
     return 0;
 }
@@ -182,8 +185,17 @@ static int launch_mid_t(const MidArgs<T>& a, int n2_tiles_unused, cudaStream_t s
         if (a.n2 % W != 0) return -2;
         static bool once = false;
         if (!once) { allow_smem(mid_pass<T, N, E, W, TM>, smem); once = true; }
-        dim3 grid(a.n2 / W, a.r.ny), block(W * NT);
-        SGPE_LAUNCH((mid_pass<T, N, E, W, TM>), grid, block, smem, st, a);
+        MidArgs<T> a2 = a;
+        dim3 grid(1, 1), block(W * NT);
+        if (a.inner == 1) {       // lines y0 .. y0 + wcount, every line fully
+            a2.x0 = 0; a2.wtiles = a.n2 / W; a2.wstride = 0; a2.nvb = a.n2 / W;
+            grid.x = a2.nvb; grid.y = a.wcount;
+        } else {                  // columns [x0, x0 + wcount) of every n2 digit of the column slab
+            if (a.wcount % W != 0 || a.x0 % W != 0) return -2;
+            a2.y0 = 0; a2.wtiles = a.wcount / W; a2.wstride = a.inner; a2.nvb = (a.n2 / a.inner) * a2.wtiles;
+            grid.x = (a.max_ctas > 0 && a.max_ctas < a2.nvb) ? a.max_ctas : a2.nvb;
+        }
+        SGPE_LAUNCH((mid_pass<T, N, E, W, TM>), grid, block, smem, st, a2);
         return 0;
     } else {
         return -2;

@@ -42,6 +42,7 @@ struct DeviceGuard {
 
 }  // namespace
 
+#define SGPE_MAX_CHUNKS 16
 struct sgpe_plan {
     int nx = 0, ny = 0, batch = 0, dtype = 0, device = 0;
     size_t csize = 16;
@@ -79,6 +80,9 @@ struct sgpe_plan {
     int n1 = 1, n2 = 0; void* tw_mid = nullptr; void* tw4 = nullptr;
     int col_wsel = 0;              // column tile width selector (sgpe_set_option "col_tile")
     // fused exchange of the slab mode (sgpe_slab_set_peers): where the scatter stores of this plan's passes go
+    // window of the slab the next line passes work on (sgpe_slab_window): lines [first, first + count), reduction
+    // slot `chunk`, cap on the grid of persistent launches; count == 0: the whole slab
+    struct Window { int first = 0, count = 0, chunk = 0, max_ctas = 0; } win;
     struct Peers { void* ptr[SGPE_MAX_PEERS]; int n = 0, mode = 0, seg = 0, drow = 0, base = 0; long long dplane = 0; } peers;
     int cpl_mode = 0; const double* cpl = nullptr; long long cpl_bs = 0;
     const double* omega = nullptr; const void* eiphi = nullptr;
@@ -450,7 +454,9 @@ static int run_klines(sgpe_plan* p, void* buf, bool fwd, bool has_a, double tau_
             }
         }
     }
-    a.partials = p->partials; a.counter = p->counter; a.sums = sums;
+    const int wfirst = p->win.count ? p->win.first : 0, wcount = p->win.count ? p->win.count : p->ny;
+    a.line0 = wfirst * p->n1; a.wlines = wcount * p->n1; a.max_ctas = p->win.max_ctas;
+    a.partials = p->partials + 4LL * p->win.chunk * a.wlines; a.counter = p->counter + p->win.chunk; a.sums = sums;
     fill_scatter(p, scatter, &a.sc);
     ProfScope prof(p, 0, st);
     int rc = sgpe::launch_kline(len, p->dtype, p->tm, &a, st);
@@ -489,6 +495,11 @@ static int run_mid(sgpe_plan* p, void* buf, bool pre_tw, bool inv, bool pw, doub
     a.norm_c = p->atom_num / (p->dv_r * global_points);
     m.n2 = p->n2; m.pre_tw = pre_tw; m.post_tw = post_tw; m.tw4 = static_cast<const C*>(p->tw4);
     m.inner = 1;
+    m.y0 = m.x0 = 0; m.wcount = p->ny; m.max_ctas = p->win.max_ctas;
+    if (p->win.count) {
+        m.wcount = p->win.count;
+        if (inner > 1) m.x0 = p->win.first; else m.y0 = p->win.first;
+    }
     if (inner > 1) {      // row-major k slab [2][n1][n2][inner]: one "line" whose contiguous dimension is n2 * inner
         if (pw) return fail(SGPE_EINVAL, "the point-wise operators are not available on the column-slab layout");
         if (inner != p->ny) return fail(SGPE_EINVAL, "inner must equal the number of lines of the plan");
@@ -539,7 +550,9 @@ static int run_kcols(sgpe_plan* p, void* buf, bool fwd, bool has_a, double tau_a
             }
         }
     }
-    a.partials = p->partials; a.counter = p->counter; a.sums = sums;
+    a.x0 = p->win.count ? p->win.first : 0; a.wcount = p->win.count ? p->win.count : p->ny;
+    a.partials = p->partials + 4LL * p->win.chunk * a.wcount * a.groups; a.counter = p->counter + p->win.chunk;
+    a.sums = sums;
     fill_scatter(p, scatter, &a.sc);
     ProfScope prof(p, 0, st);
     int rc = sgpe::launch_kcol(len, p->dtype, p->tm, &a, st);
@@ -887,6 +900,17 @@ int sgpe_slab_set_peers(sgpe_plan* p, void* const* peer_bufs, int nranks, int mo
     return 0;
 }
 
+int sgpe_slab_window(sgpe_plan* p, int first, int count, int chunk, int max_ctas) {
+    if (!p) return fail(SGPE_EINVAL, "null plan");
+    if (count == 0) { p->win = sgpe_plan::Window(); return 0; }
+    if (first < 0 || count < 0 || first + count > p->ny) return fail(SGPE_EINVAL, "window outside the slab");
+    if (chunk < 0 || chunk >= SGPE_MAX_CHUNKS) return fail(SGPE_EINVAL, "reduction slot out of range");
+    if ((long long)(chunk + 1) * count > p->ny) return fail(SGPE_EINVAL, "reduction slots assume equal windows: (chunk + 1) * count <= lines");
+    if (max_ctas < 0) return fail(SGPE_EINVAL, "negative grid cap");
+    p->win.first = first; p->win.count = count; p->win.chunk = chunk; p->win.max_ctas = max_ctas;
+    return 0;
+}
+
 int sgpe_pass_kcols(sgpe_plan* p, void* buf, int do_fwd, int has_a, double tau_a, int has_b, double tau_b, int do_inv,
                     double* sums_dev, int scatter, sgpe_stream st) {
     if (!p || !buf) return fail(SGPE_EINVAL, "null argument");
@@ -979,10 +1003,10 @@ int sgpe_plan_create_lines(sgpe_plan** out, int len, int nlines, int n1, int dty
     int rc = 0;
     do {
         if (cudaMalloc((void**)&p->partials, sizeof(double) * 2 * (size_t)p->max_tiles) != cudaSuccess) { rc = SGPE_ENOMEM; break; }
-        if (cudaMalloc((void**)&p->counter, sizeof(unsigned)) != cudaSuccess) { rc = SGPE_ENOMEM; break; }
+        if (cudaMalloc((void**)&p->counter, sizeof(unsigned) * SGPE_MAX_CHUNKS) != cudaSuccess) { rc = SGPE_ENOMEM; break; }
         if (cudaMalloc((void**)&p->totals, sizeof(double) * 4) != cudaSuccess) { rc = SGPE_ENOMEM; break; }
         if (cudaMalloc((void**)&p->totals_aux, sizeof(double) * 4) != cudaSuccess) { rc = SGPE_ENOMEM; break; }
-        cudaMemset(p->counter, 0, sizeof(unsigned));
+        cudaMemset(p->counter, 0, sizeof(unsigned) * SGPE_MAX_CHUNKS);
         const int cont = n1 == 1 ? len : n2;
         rc = dtype == SGPE_C128 ? upload_twiddles<double>(&p->tw_x, cont) : upload_twiddles<float>(&p->tw_x, cont);
         if (rc) break;

@@ -232,6 +232,11 @@ class Plan:
                                          int(do_fwd), int(post_tw), _dp(totals), float(global_points), int(inner),
                                          int(scatter), self.stream), 'sgpe_pass_mid')
 
+    def window(self, first=0, count=0, chunk=0, max_ctas=0):
+        """Restrict the following line passes to the lines [first, first + count) (count == 0: whole slab)."""
+        self._chk(self.lib.sgpe_slab_window(self.h, int(first), int(count), int(chunk), int(max_ctas)),
+                  'sgpe_slab_window')
+
     def set_peers(self, peer_ptrs, mode, seg, drow, dplane, base):
         """Destination map of the fused exchange: peer_ptrs[q] = integer address of rank q's buffer."""
         arr = (ctypes.c_void_p * len(peer_ptrs))(*[ctypes.c_void_p(int(v)) for v in peer_ptrs])

@@ -117,7 +117,7 @@ class SlabPropagator:
     keeps only its slab on the device.  ``split_x`` / ``split_y`` force a four-step split (tests)."""
 
     def __init__(self, spin, t_step, time='imag', device='cuda', group=None, precision='c128', plan_kwargs=None,
-                 split_x=None, split_y=None, exchange='auto', exchange_buffers=None):
+                 split_x=None, split_y=None, exchange='auto', exchange_buffers=None, chunks=None, scatter_ctas=None):
         from .plan import Plan
         assert dist.is_initialized(), "SlabPropagator needs an initialised torch.distributed process group"
         self.group = group
@@ -208,6 +208,19 @@ class SlabPropagator:
             self.tbuf, self.rbuf, self.send, self.recv = mk(), mk(), mk(), mk()
         self.sums = torch.zeros(4, dtype=torch.float64, device=self.dev)
         self._flag = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        # Chunked pipelining of the fused exchange (four-step lines only: three local passes per direction, the last
+        # one NVLink-bound).  The slab is cut into `chunks` windows; the scatter pass of window c runs on a second
+        # stream with a few persistent CTAs per SM while the first two passes of window c + 1 run beside it.
+        if chunks is None:
+            chunks = 4 if (self.p2p and self.dev.type == 'cuda') else 1
+        self.chunks_x = chunks if (self.p2p and self.n1x > 1 and self.nyl % chunks == 0) else 1
+        self.chunks_y = chunks if (self.p2p and self.n1y > 1 and self.nxl % (chunks * 32) == 0) else 1
+        if scatter_ctas is None:
+            scatter_ctas = 2 * torch.cuda.get_device_properties(self.dev).multi_processor_count \
+                if self.dev.type == 'cuda' else 3
+        self.scatter_ctas = int(scatter_ctas)
+        self._side = torch.cuda.Stream(self.dev) if self.dev.type == 'cuda' else None
+        self._chunk_sums = torch.zeros((max(self.chunks_y, 1), 4), dtype=torch.float64, device=self.dev)
         self.mid = False
         self.pending_dt = 0.0
         self.scale_pending = False
@@ -333,9 +346,39 @@ class SlabPropagator:
     def _reduce_sums(self):
         dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=self.group)
 
+    # ------------------------------------------------------------------ second stream of the chunked exchange
+    def _fork(self):
+        """The side stream waits for everything enqueued on the current stream so far."""
+        if self._side is not None:
+            self._side.wait_stream(torch.cuda.current_stream(self.dev))
+
+    def _join(self):
+        if self._side is not None:
+            torch.cuda.current_stream(self.dev).wait_stream(self._side)
+
+    def _on_side(self):
+        import contextlib
+        return torch.cuda.stream(self._side) if self._side is not None else contextlib.nullcontext()
+
     # ------------------------------------------------------------------ local passes (one or three per direction)
     def _k_junction(self, do_fwd, has_a, tau_a, has_b, tau_b, do_inv):
         tp = self.tp
+        if self.p2p and self.chunks_y > 1 and do_inv:
+            cw = self.nxl // self.chunks_y
+            for c in range(self.chunks_y):
+                tp.window(c * cw, cw, c, 0)
+                if do_fwd:
+                    tp.pass_mid(self.tbuf, False, False, False, 0.0, True, True, None, 0.0, inner=self.nxl)
+                tp.pass_kcols(self.tbuf, do_fwd, has_a, tau_a, has_b, tau_b, do_inv, self._chunk_sums[c])
+                self._fork()
+                with self._on_side():      # NVLink-bound: a few persistent CTAs per SM, beside the next window's passes
+                    tp.window(c * cw, cw, c, self.scatter_ctas)
+                    tp.pass_mid(self.tbuf, True, True, False, 0.0, False, False, None, 0.0, inner=self.nxl, scatter=True)
+            tp.window()
+            self._join()
+            self.sums.copy_(self._chunk_sums.sum(0))
+            self._count_exchange()
+            return
         if self.p2p:          # row-major k slab; the kernel that finishes the inverse stores into the peers' row slabs
             if self.n1y == 1:
                 tp.pass_kcols(self.tbuf, do_fwd, has_a, tau_a, has_b, tau_b, do_inv, self.sums, scatter=do_inv)
@@ -359,7 +402,19 @@ class SlabPropagator:
 
     def _row_pass(self, dt_sub):
         rp = self.rp
-        if self.n1x == 1:
+        if self.p2p and self.chunks_x > 1:
+            rw = self.nyl // self.chunks_x
+            for c in range(self.chunks_x):
+                rp.window(c * rw, rw, c, 0)
+                rp.pass_klines(self.rbuf, False, False, 0.0, False, 0.0, True, None)
+                rp.pass_mid(self.rbuf, True, True, True, dt_sub, True, True, self.sums, self.points)
+                self._fork()
+                with self._on_side():
+                    rp.window(c * rw, rw, c, self.scatter_ctas)
+                    rp.pass_klines(self.rbuf, True, False, 0.0, False, 0.0, False, None, scatter=True)
+            rp.window()
+            self._join()
+        elif self.n1x == 1:
             rp.pass_rows(self.rbuf, dt_sub, self.sums, self.points, scatter=self.p2p)
         else:
             rp.pass_klines(self.rbuf, False, False, 0.0, False, 0.0, True, None)       # contiguous inverse over k2

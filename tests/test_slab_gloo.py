@@ -26,7 +26,7 @@ def _shared_exchange_buffers(world, mesh):
     return {'k': mk(), 'r': mk()}
 
 
-def _worker(rank, world, port, outdir, mode, splits=(None, None), mesh=(128, 64), given=None):
+def _worker(rank, world, port, outdir, mode, splits=(None, None), mesh=(128, 64), given=None, chunks=None):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -51,7 +51,9 @@ def _worker(rank, world, port, outdir, mode, splits=(None, None), mesh=(128, 64)
         want = orc.OraclePropagator(prob, dt, mode).run(n)
         sp = SlabPropagator(ps, dt, time=mode, device='cpu', plan_kwargs={'_lib': emu_lib()},
                             split_x=splits[0], split_y=splits[1], exchange='p2p' if given else 'nccl',
-                            exchange_buffers=given)
+                            exchange_buffers=given, chunks=chunks)
+        if chunks:
+            assert max(sp.chunks_x, sp.chunks_y) == chunks
         pops = torch.zeros((n, 2), dtype=torch.float64)
         sp.full_steps(n, pops)
         got = sp.gather_psik().numpy()
@@ -89,6 +91,17 @@ def test_slab_fused_exchange(mode, splits, mesh):
     emu_lib()
     given = _shared_exchange_buffers(2, mesh)
     mp.spawn(_worker, args=(2, _free_port(), tempfile.mkdtemp(prefix='sgpe_slab_'), mode, splits, mesh, given),
+             nprocs=2, join=True)
+
+
+@pytest.mark.parametrize('mode,splits,mesh', [('real', (32, None), (1024, 64)), ('imag', (None, 32), (128, 1024))])
+def test_slab_fused_exchange_chunked(mode, splits, mesh):
+    """The chunked pipeline of the fused exchange (sgpe_slab_window): windows of the slab, per-chunk reduction slots,
+    persistent scatter launches (3 CTAs walking each window in the emulation)."""
+    from tests.emu_harness import emu_lib
+    emu_lib()
+    given = _shared_exchange_buffers(2, mesh)
+    mp.spawn(_worker, args=(2, _free_port(), tempfile.mkdtemp(prefix='sgpe_slab_'), mode, splits, mesh, given, 2),
              nprocs=2, join=True)
 
 

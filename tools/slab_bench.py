@@ -21,6 +21,8 @@ import bench  # noqa: E402
 from spinor_gpe_b200.slab import SeparableProblem, SlabPropagator  # noqa: E402
 
 W0 = 2 * np.pi * 50
+CHUNKS = None              # --chunks=N: windows of the chunked exchange pipeline (default: SlabPropagator's choice)
+CTAS = None                # --ctas=N: persistent CTAs of a scatter launch
 EXCHANGE = 'p2p'           # --exchange=nccl: pack / NCCL all-to-all / unpack instead of the fused scatter stores
 
 
@@ -38,7 +40,7 @@ def check(rank, world, dev):
             prop._plan.full_steps(n)
             ref = torch.stack(prop.psik)
         for splits in ((None, None), (32, None), (None, 64), (64, 32), (16, 16)):
-            sp = SlabPropagator(ps, dt, time=mode, device=dev, split_x=splits[0], split_y=splits[1], exchange=EXCHANGE)
+            sp = SlabPropagator(ps, dt, time=mode, device=dev, split_x=splits[0], split_y=splits[1], exchange=EXCHANGE, chunks=CHUNKS, scatter_ctas=CTAS)
             pops = torch.zeros((n, 2), dtype=torch.float64, device=dev)
             sp.full_steps(n, pops)
             full = sp.gather_psik()
@@ -55,7 +57,7 @@ def run_bench(rank, world, dev, mesh, steps):
     g_sc = {'uu': 1, 'dd': 1, 'ud': 1.04}
     prob = SeparableProblem((mesh, mesh), r_sizes=(64, 64), atom_num=1e6, omeg={'x': W0, 'y': W0, 'z': 40 * W0},
                             g_sc=g_sc, pop_frac=(0.5, 0.5), coupling=1.0, kin_shift=True, rot_coupling=False)
-    sp = SlabPropagator(prob, 1 / 5000, time='real', device=dev, exchange=EXCHANGE)
+    sp = SlabPropagator(prob, 1 / 5000, time='real', device=dev, exchange=EXCHANGE, chunks=CHUNKS, scatter_ctas=CTAS)
     pops = torch.zeros((steps, 2), dtype=torch.float64, device=dev)
     sp.full_steps(2)
     dist.barrier(); torch.cuda.synchronize()
@@ -75,7 +77,7 @@ def run_bench(rank, world, dev, mesh, steps):
         hbm = 768.0 * mesh * mesh / world / (ms * 1e-3) / 1e9
         print(json.dumps({
             'slab_bench': True, 'mesh': mesh, 'ranks': world, 'mode': 'real', 'dtype': 'c128', 'exchange': EXCHANGE,
-            'four_step': [sp.n1x, sp.n1y], 'steps': steps, 'ms_per_step': ms, 'steps_per_s': 1e3 / ms,
+            'four_step': [sp.n1x, sp.n1y], 'chunks': [sp.chunks_x, sp.chunks_y], 'scatter_ctas': sp.scatter_ctas, 'steps': steps, 'ms_per_step': ms, 'steps_per_s': 1e3 / ms,
             'kernel_launches_per_step': (sp.rp.launch_count() + sp.tp.launch_count() - l0) / steps,
             'a2a_bytes_sent_per_rank_per_step': sent, 'nvlink_GBps_per_rank': nvl, 'nvlink_frac_of_770': nvl / 770.0,
             'hbm_algorithmic_GBps_per_rank': hbm, 'hbm_frac': hbm / bench.hbm_peak()[0],
@@ -88,7 +90,7 @@ def breakdown(rank, world, dev, mesh):
     prob = SeparableProblem((mesh, mesh), r_sizes=(64, 64), atom_num=1e6, omeg={'x': W0, 'y': W0, 'z': 40 * W0},
                             g_sc={'uu': 1, 'dd': 1, 'ud': 1.04}, pop_frac=(0.5, 0.5), coupling=1.0, kin_shift=True,
                             rot_coupling=False)
-    sp = SlabPropagator(prob, 1 / 5000, time='real', device=dev, exchange=EXCHANGE)
+    sp = SlabPropagator(prob, 1 / 5000, time='real', device=dev, exchange=EXCHANGE, chunks=CHUNKS, scatter_ctas=CTAS)
     sp.full_steps(2)
     sp.single_step(sp.dt_out)
     dist.barrier(); torch.cuda.synchronize()
@@ -142,10 +144,16 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     dist.init_process_group('nccl', device_id=dev)
-    global EXCHANGE
+    global EXCHANGE, CHUNKS, CTAS
     for a in list(sys.argv):
         if a.startswith('--exchange='):
             EXCHANGE = a.split('=', 1)[1]
+            sys.argv.remove(a)
+        elif a.startswith('--chunks='):
+            CHUNKS = int(a.split('=', 1)[1])
+            sys.argv.remove(a)
+        elif a.startswith('--ctas='):
+            CTAS = int(a.split('=', 1)[1])
             sys.argv.remove(a)
     what = sys.argv[1] if len(sys.argv) > 1 else 'check'
     if what == 'check':
