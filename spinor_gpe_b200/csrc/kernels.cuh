@@ -22,9 +22,10 @@ enum { TM_REAL = 0, TM_IMAG = 1 };
 
 // exp(x) for the imaginary-time factors evaluated per grid point (the non-linear term; dense operator grids).
 // Same scheme as the library routine — x = k ln2 + r, |r| <= ln2/2, degree-11 minimax polynomial (3e-18), 2^k
-// through the exponent field — without its out-of-range branches: k is clamped to +-1000, so results that would
-// underflow / overflow a double come out as ~1e-301 / ~1e+301 instead of 0 / inf (|x| > 690 never occurs for a
-// propagator factor).  Max error 1 ulp against exp() (tests/test_fast_exp.py); roughly half the instructions.
+// through the exponent field — without its out-of-range branches: k is clamped to [-1021, 1022], so every result
+// that is a normal double is computed as usual and those that would be subnormal / overflow come out as ~1e-308 /
+// ~1e+308 instead of (nearly) 0 / inf — a factor of that size multiplies nothing that matters.  Max error 1 ulp
+// against exp() (tests/test_fast_exp.py); roughly half the instructions.
 SGPE_DI double sgpe_exp(double x) {
     const double t = fma(x, 1.4426950408889634, 6755399441055744.0);          // 1.5 * 2^52: low word = round(x/ln2)
     int k = (int)(unsigned)(__double_as_longlong(t) & 0xffffffffLL);
@@ -43,7 +44,7 @@ SGPE_DI double sgpe_exp(double x) {
     p = fma(p, r, 0.5000000000000019);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    k = k < -1000 ? -1000 : (k > 1000 ? 1000 : k);
+    k = k < -1021 ? -1021 : (k > 1022 ? 1022 : k);
     return __longlong_as_double(__double_as_longlong(p) + ((long long)k << 52));
 }
 
@@ -786,7 +787,7 @@ template <typename T> struct MidArgs {
 };
 
 template <typename T, int N1, int E, int W, int TM>
-__global__ void __launch_bounds__(W * N1 / E) mid_pass(MidArgs<T> ma) {
+__global__ void __launch_bounds__(W * N1 / E, (W * N1 / E <= 128) ? 4 : ((W * N1 / E <= 256) ? 2 : 1)) mid_pass(MidArgs<T> ma) {
     typedef typename cx_of<T>::type C;
     const RowArgs<T>& a = ma.r;
     constexpr int NT = N1 / E;

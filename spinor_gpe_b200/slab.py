@@ -216,7 +216,7 @@ class SlabPropagator:
         self.chunks_x = chunks if (self.p2p and self.n1x > 1 and self.nyl % chunks == 0) else 1
         self.chunks_y = chunks if (self.p2p and self.n1y > 1 and self.nxl % (chunks * 32) == 0) else 1
         if scatter_ctas is None:
-            scatter_ctas = 2 * torch.cuda.get_device_properties(self.dev).multi_processor_count \
+            scatter_ctas = torch.cuda.get_device_properties(self.dev).multi_processor_count \
                 if self.dev.type == 'cuda' else 3
         self.scatter_ctas = int(scatter_ctas)
         self._side = torch.cuda.Stream(self.dev) if self.dev.type == 'cuda' else None
