@@ -114,9 +114,27 @@ int sgpe_normalise(sgpe_plan* p, const void* in_dev, void* out_dev, double vol, 
 /* TensorPropagator.eng_expect (tensor_propagator.py:273-324): [E_total, E_kin, E_pot, E_int] as raw grid
  * sums, out_dev[batch][4].  psik_dev == NULL evaluates the plan's current state.  kl_term is
  * 2*kL_recoil*is_coupling (:311).  unwrap_mode 0 leaves the wrapped phase as is (the variant pinned
- * against the reference), 1 differentiates with locally wrapped differences. */
+ * against the reference), 1 differentiates with locally wrapped differences, 2 unwraps the
+ * phase of each component the way the reference does (ttools.phase(psi, uwrap=True), tensor_propagator.py:304
+ * -> skimage.restoration.unwrap_phase, tensor_tools.py:531; see sgpe_unwrap_phase) — mode 2 synchronises st. */
 int sgpe_energy(sgpe_plan* p, const void* psik_dev, int unwrap_mode, double kl_term, double* out_dev,
                 sgpe_stream st);
+
+/* ttools.phase_comp(psi_comp, uwrap=True, dens) (tensor_tools.py:514-539): two-dimensional phase unwrapping by
+ * reliability-sorted region merging (Herraez, Burton, Lalor, Gdeisat, Appl. Opt. 41, 7437 (2002)), the algorithm
+ * behind skimage.restoration.unwrap_phase without mask and wrap-around (the reference's call, tensor_tools.py:531;
+ * scikit-image==0.16.2, requirements.txt:25 — a third-party dependency restated from the publication).
+ *   in_dev  : nplanes planes [ny][nx] (the plan's mesh); kind 0 = complex values of the plan's dtype (phase =
+ *             atan2(im, re), np.angle at :529), kind 1 = float64 wrapped angles
+ *   mask    : != 0 (kind 0 only) zeroes the result where |psi|^2 < 1e-6 * max |psi|^2 of the plane (:538)
+ *   out_dev : nplanes x [ny][nx] float64 = wrapped phase + 2 pi * integer
+ * Angles, per-pixel reliabilities, edge keys, the radix sort of the edges and the final pass run on the device; the
+ * region merging, sequential by construction, runs on the host between two copies (4 B per edge down, 4 B per pixel
+ * up), one host thread per plane.  Border pixels get the fixed reliability value 9999999 (scikit-image adds rand()),
+ * equal keys keep edge order (horizontal edges row by row, then vertical).  Synchronises st.
+ * Option "unwrap_sort" = 1 (sgpe_set_option) sorts the edges on the host instead (same order, for cross-checks). */
+int sgpe_unwrap_phase(sgpe_plan* p, const void* in_dev, int kind, int nplanes, int mask, double* out_dev,
+                      sgpe_stream st);
 
 /* ---- Slab-decomposed (multi-GPU) transforms: local building blocks.  The grid is split by rows over P
  * ranks; the caller owns the buffers and the collectives (all-to-all transpose, all-reduce of the norm

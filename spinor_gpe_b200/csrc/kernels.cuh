@@ -1213,7 +1213,9 @@ template <typename T> struct EnergyArgs {
     double g_uu, g_dd, g_ud;
     double kl2;                 // 2 * kL_recoil * is_coupling
     double inv_h0, inv_h1;      // 1/dr[0] (used along axis 0 = y!) and 1/dr[1] (axis 1 = x)
-    int unwrap_mode;            // 0: identity (wrapped phase as is), 1: local wrapped differences
+    int unwrap_mode;            // 0: identity (wrapped phase as is), 1: local wrapped differences,
+                                // 2: unwrapped field = wrapped phase + 2 pi * inc (unwrap.cuh)
+    const int* inc;             // mode 2: [B][2][ny][nx] multiples of 2 pi from the region merging
     const double* maxdens;
     double* partials; unsigned* counter; double* out;        // out [B][4]: total, kin, pot, int
 };
@@ -1260,6 +1262,7 @@ __global__ void __launch_bounds__(256) energy_pass(EnergyArgs<T> a) {
         C ctr[2];
         for (int comp = 0; comp < 2; comp++) {
             const C* p = a.psi + ((long long)b * 2 + comp) * a.plane;
+            const int* inc = a.unwrap_mode == 2 ? a.inc + ((long long)b * 2 + comp) * a.plane : nullptr;
             const double thr = a.maxdens[2 * b + comp] * 1e-6;
             for (int q = tid; q < HX * HY; q += 256) {
                 const int ly = q / HX, lx = q - ly * HX;
@@ -1269,7 +1272,12 @@ __global__ void __launch_bounds__(256) energy_pass(EnergyArgs<T> a) {
                 const C z = p[(long long)gi * a.nx + gj];
                 const double n = (double)z.x * z.x + (double)z.y * z.y;
                 s_r[q] = sqrt(n);
-                s_ph[q] = (n < thr) ? 0.0 : atan2((double)z.y, (double)z.x);
+                double ph = 0.0;
+                if (!(n < thr)) {
+                    ph = atan2((double)z.y, (double)z.x);
+                    if (inc != nullptr) ph = __dadd_rn(ph, __dmul_rn(6.283185307179586, (double)inc[(long long)gi * a.nx + gj]));
+                }
+                s_ph[q] = ph;
             }
             __syncthreads();
             const int c0 = (ty + 1) * HX + (tx + 1);
@@ -1278,7 +1286,7 @@ __global__ void __launch_bounds__(256) energy_pass(EnergyArgs<T> a) {
             const double r0 = sgpe_grad3(s_r[c0 - HX], s_r[c0], s_r[c0 + HX], i, a.ny, a.inv_h0);
             const double r1 = sgpe_grad3(s_r[c0 - 1], s_r[c0], s_r[c0 + 1], j, a.nx, a.inv_h1);
             double g0, g1;
-            if (a.unwrap_mode == 0) {
+            if (a.unwrap_mode != 1) {
                 g0 = sgpe_grad3(s_ph[c0 - HX], s_ph[c0], s_ph[c0 + HX], i, a.ny, a.inv_h0);
                 g1 = sgpe_grad3(s_ph[c0 - 1], s_ph[c0], s_ph[c0 + 1], j, a.nx, a.inv_h1);
             } else {

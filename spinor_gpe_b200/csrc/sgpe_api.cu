@@ -12,11 +12,18 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
+
+#ifndef SGPE_EMU
+#include <cub/device/device_radix_sort.cuh>
+#endif
 
 #include "../../include/sgpe.h"
 #include "kernels.cuh"
+#include "unwrap.cuh"
 #include "launch.h"
 
 namespace {
@@ -79,6 +86,8 @@ struct sgpe_plan {
     // long lines (four-step): nx = n1 * n2 with the strided part n1 (1 = ordinary plan)
     int n1 = 1, n2 = 0; void* tw_mid = nullptr; void* tw4 = nullptr;
     int col_wsel = 0;              // column tile width selector (sgpe_set_option "col_tile")
+    int unwrap_sort = 0;           // edge sort of the phase unwrapping: 0 device radix sort, 1 host (option "unwrap_sort")
+    int* unwrap_inc = nullptr;     // [B][2][ny][nx] multiples of 2 pi (sgpe_energy with unwrap_mode 2), on first use
     // fused exchange of the slab mode (sgpe_slab_set_peers): where the scatter stores of this plan's passes go
     // window of the slab the next line passes work on (sgpe_slab_window): lines [first, first + count), reduction
     // slot `chunk`, cap on the grid of persistent launches; count == 0: the whole slab
@@ -411,12 +420,180 @@ int run_energy(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, d
     a.inv_h0 = 1.0 / p->dx;        // np.gradient(f, dx, dy): dx goes with axis 0 (tensor_tools.py:342)
     a.inv_h1 = 1.0 / p->dy;
     a.unwrap_mode = unwrap_mode;
+    a.inc = p->unwrap_inc;
     a.maxdens = p->maxdens; a.partials = p->partials; a.counter = p->counter; a.out = out;
     long long tiles = (long long)(p->nx / 32) * (p->ny / 8);
     blocks = tiles < 888 ? tiles : 888;                     // six 256-thread CTAs per SM x 148 SMs
     if (blocks > p->max_tiles / 2) blocks = p->max_tiles / 2;   // four partial sums per CTA in `partials`
     dim3 grid((unsigned)blocks, p->batch), block(256);
     SGPE_LAUNCH((sgpe::energy_pass<T>), grid, block, (32 * 4 + 2 * 34 * 10) * sizeof(double), st, a);
+    p->launches++;
+    SGPE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- two-dimensional phase unwrapping (Herraez et al. 2002; skimage.restoration.unwrap_phase at the reference's
+// tensor_tools.py:531).  Device: angle, reliabilities, edge keys, radix sort, apply (unwrap.cuh).  Host: the region
+// merging below, which is sequential by construction — edge k's merge depends on the groups all earlier edges built.
+//
+// Groups are an offset-carrying union-find: pot[x] = increment(x) - increment(parent[x]); a root keeps the
+// increments of its group fixed (its own is 0) and the absorbed root receives the shift of its whole group, which is
+// what the published algorithm does by walking the smaller group's pixel list.  Who absorbs whom follows the
+// published rules (a lone second pixel joins the first pixel's group, a lone first pixel the second's, otherwise the
+// strictly larger group absorbs and a tie goes to the second pixel's group), so the integer field — global offset
+// included — equals that of the list-based formulation (oracle/unwrap_herraez.c) for the same edge order.
+struct UnwrapForest {
+    struct Node { int32_t parent, pot; };          // one cache line access per hop
+    std::vector<Node> node;
+    std::vector<int32_t> size;
+    explicit UnwrapForest(size_t n) : node(n), size(n, 1) {
+        for (size_t i = 0; i < n; i++) node[i] = {(int32_t)i, 0};
+    }
+    int32_t find(int32_t x, int32_t* offset) {
+        int32_t r = x, sum = 0;
+        while (node[r].parent != r) { sum += node[r].pot; r = node[r].parent; }
+        int32_t cur = x, s = sum;
+        while (cur != r && node[cur].parent != r) {   // path compression, offsets re-expressed against the root
+            const int32_t next = node[cur].parent, own = node[cur].pot;
+            node[cur] = {r, s};
+            s -= own; cur = next;
+        }
+        *offset = sum;
+        return r;
+    }
+};
+
+void unwrap_merge(int nx, int ny, const uint32_t* order, size_t n_edges, int32_t* inc) {
+    const size_t plane = (size_t)nx * ny;
+    const size_t n_horizontal = (size_t)ny * (nx - 1);
+    UnwrapForest f(plane);
+    for (size_t k = 0; k < n_edges; k++) {
+        const uint32_t e = order[k] >> 2;
+        const int32_t wraps = (int32_t)(order[k] & 3u) - 1;
+        int32_t p1, p2;
+        if (e < n_horizontal) { const uint32_t i = e / (uint32_t)(nx - 1), j = e - i * (uint32_t)(nx - 1); p1 = (int32_t)(i * (uint32_t)nx + j); p2 = p1 + 1; }
+        else { p1 = (int32_t)(e - n_horizontal); p2 = p1 + nx; }
+        int32_t a1, a2;
+        const int32_t r1 = f.find(p1, &a1), r2 = f.find(p2, &a2);
+        if (r1 == r2) continue;
+        const int32_t s1 = f.size[r1], s2 = f.size[r2];
+        const bool second_joins = (s2 == 1) || (s1 != 1 && s1 > s2);
+        if (second_joins) { f.node[r2] = {r1, a1 - wraps - a2}; f.size[r1] = s1 + s2; }
+        else              { f.node[r1] = {r2, a2 + wraps - a1}; f.size[r2] = s1 + s2; }
+    }
+    for (size_t i = 0; i < plane; i++) { int32_t a; f.find((int32_t)i, &a); inc[i] = a; }
+}
+
+struct UnwrapBuffers {                       // device scratch of one unwrap call
+    double* rel = nullptr; unsigned long long* keys = nullptr; unsigned long long* keys_sorted = nullptr;
+    unsigned* vals = nullptr; unsigned* vals_sorted = nullptr; void* tmp = nullptr;
+    ~UnwrapBuffers() { cudaFree(rel); cudaFree(keys); cudaFree(keys_sorted); cudaFree(vals); cudaFree(vals_sorted); cudaFree(tmp); }
+};
+
+unsigned unwrap_blocks(long long n) { long long b = (n + 255) / 256; return (unsigned)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b)); }
+
+// phi_dev: nplanes x [ny][nx] wrapped phases -> inc_dev: nplanes x [ny][nx] multiples of 2 pi.  Synchronises st.
+int unwrap_increments(sgpe_plan* p, const double* phi_dev, int nplanes, int* inc_dev, cudaStream_t st) {
+    const int nx = p->nx, ny = p->ny;
+    const size_t plane = (size_t)p->plane;
+    const size_t n_edges = (size_t)ny * (nx - 1) + (size_t)nx * (ny - 1);
+    UnwrapBuffers w;
+    if (cudaMalloc((void**)&w.rel, plane * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&w.keys, n_edges * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc((void**)&w.vals, n_edges * sizeof(unsigned)) != cudaSuccess)
+        return fail(SGPE_ENOMEM, "unwrap scratch allocation failed");
+    bool device_sort = false;
+#ifndef SGPE_EMU
+    device_sort = p->unwrap_sort == 0;
+    size_t tmp_bytes = 0;
+    if (device_sort) {
+        if (cudaMalloc((void**)&w.keys_sorted, n_edges * sizeof(unsigned long long)) != cudaSuccess ||
+            cudaMalloc((void**)&w.vals_sorted, n_edges * sizeof(unsigned)) != cudaSuccess)
+            return fail(SGPE_ENOMEM, "unwrap scratch allocation failed");
+        SGPE_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, w.keys, w.keys_sorted, w.vals, w.vals_sorted,
+                                                  (long long)n_edges, 0, 64, st));
+        if (cudaMalloc(&w.tmp, tmp_bytes ? tmp_bytes : 1) != cudaSuccess)
+            return fail(SGPE_ENOMEM, "unwrap scratch allocation failed");
+    }
+#endif
+    std::vector<std::vector<uint32_t>> order((size_t)nplanes);
+    std::vector<unsigned long long> host_keys;
+    for (int pl = 0; pl < nplanes; pl++) {
+        const double* phi = phi_dev + (size_t)pl * plane;
+        SGPE_LAUNCH((sgpe::unwrap_reliab_pass), dim3(unwrap_blocks((long long)plane)), dim3(256), 0, st, phi, nx, ny, w.rel);
+        SGPE_LAUNCH((sgpe::unwrap_edge_pass), dim3(unwrap_blocks((long long)plane)), dim3(256), 0, st, phi, w.rel, nx, ny,
+                    w.keys, w.vals);
+        p->launches += 2;
+        SGPE_CUDA(cudaGetLastError());
+        order[pl].resize(n_edges);
+        if (device_sort) {
+#ifndef SGPE_EMU
+            // least-significant-digit radix sort: stable, so equal keys stay in edge-id order
+            SGPE_CUDA(cub::DeviceRadixSort::SortPairs(w.tmp, tmp_bytes, w.keys, w.keys_sorted, w.vals, w.vals_sorted,
+                                                      (long long)n_edges, 0, 64, st));
+            p->launches++;
+            SGPE_CUDA(cudaMemcpyAsync(order[pl].data(), w.vals_sorted, n_edges * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            SGPE_CUDA(cudaStreamSynchronize(st));
+#endif
+        } else {
+            host_keys.resize(n_edges);
+            SGPE_CUDA(cudaMemcpyAsync(host_keys.data(), w.keys, n_edges * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            SGPE_CUDA(cudaMemcpyAsync(order[pl].data(), w.vals, n_edges * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            SGPE_CUDA(cudaStreamSynchronize(st));
+            std::vector<uint32_t> perm(n_edges);
+            for (size_t k = 0; k < n_edges; k++) perm[k] = (uint32_t)k;
+            const unsigned long long* hk = host_keys.data();
+            std::sort(perm.begin(), perm.end(), [hk](uint32_t a, uint32_t b) { return hk[a] != hk[b] ? hk[a] < hk[b] : a < b; });
+            std::vector<uint32_t> sorted(n_edges);
+            for (size_t k = 0; k < n_edges; k++) sorted[k] = order[pl][perm[k]];
+            order[pl].swap(sorted);
+        }
+    }
+    // region merging: the planes are independent, one host thread each (bounded by the hardware)
+    std::vector<int32_t> inc((size_t)nplanes * plane);
+    unsigned nthreads = std::thread::hardware_concurrency();
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > (unsigned)nplanes) nthreads = (unsigned)nplanes;
+    auto work = [&](unsigned t) {
+        for (int pl = (int)t; pl < nplanes; pl += (int)nthreads)
+            unwrap_merge(nx, ny, order[pl].data(), n_edges, inc.data() + (size_t)pl * plane);
+    };
+    if (nthreads == 1) work(0);
+    else {
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nthreads; t++) pool.emplace_back(work, t);
+        for (auto& th : pool) th.join();
+    }
+    SGPE_CUDA(cudaMemcpyAsync(inc_dev, inc.data(), inc.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    SGPE_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+template <typename T>
+int run_unwrap_angles(sgpe_plan* p, const void* psi, long long total, double* phi, cudaStream_t st) {
+    typedef typename sgpe::cx_of<T>::type C;
+    SGPE_LAUNCH((sgpe::unwrap_angle_pass<T>), dim3(unwrap_blocks(total)), dim3(256), 0, st, static_cast<const C*>(psi), total, phi);
+    p->launches++;
+    SGPE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+int run_unwrap_apply(sgpe_plan* p, const void* psi, const double* phi, const int* inc, int nplanes, bool mask,
+                     unsigned long long* maxbits, double* out, cudaStream_t st) {
+    typedef typename sgpe::cx_of<T>::type C;
+    const long long total = (long long)nplanes * p->plane;
+    const C* z = mask ? static_cast<const C*>(psi) : nullptr;
+    if (mask) {
+        SGPE_CUDA(cudaMemsetAsync(maxbits, 0, sizeof(unsigned long long) * nplanes, st));
+        unsigned blocks = unwrap_blocks(p->plane);
+        if (blocks > 256) blocks = 256;
+        SGPE_LAUNCH((sgpe::unwrap_maxdens_pass<T>), dim3(blocks, (unsigned)nplanes), dim3(256), 256 * sizeof(double), st, z,
+                    p->plane, maxbits);
+        p->launches++;
+    }
+    SGPE_LAUNCH((sgpe::unwrap_apply_pass<T>), dim3(unwrap_blocks(total)), dim3(256), 0, st, z, phi, inc, maxbits, p->plane,
+                total, out);
     p->launches++;
     SGPE_CUDA(cudaGetLastError());
     return 0;
@@ -650,7 +827,7 @@ int sgpe_plan_destroy(sgpe_plan* p) {
     DeviceGuard guard(p->device);
     cudaFree(p->state); cudaFree(p->tw_x); cudaFree(p->tw_y); cudaFree(p->partials);
     cudaFree(p->counter); cudaFree(p->totals); cudaFree(p->totals_aux); cudaFree(p->pops_buf);
-    cudaFree(p->scratch); cudaFree(p->maxdens); cudaFree(p->sm_slots); cudaFree(p->tw_mid); cudaFree(p->tw4);
+    cudaFree(p->scratch); cudaFree(p->maxdens); cudaFree(p->unwrap_inc); cudaFree(p->sm_slots); cudaFree(p->tw_mid); cudaFree(p->tw4);
     for (auto& t : p->kin_tab) { cudaFree(t.x); cudaFree(t.y); }
     for (auto& t : p->pot_tab) { cudaFree(t.x); cudaFree(t.y); }
     delete p;
@@ -716,6 +893,11 @@ int sgpe_set_option(sgpe_plan* p, const char* name, int value) {
     }
     if (std::strcmp(name, "stagger_ns") == 0) { p->stagger_ns = value; return 0; }
     if (std::strcmp(name, "prefetch") == 0) { p->prefetch = value ? 1 : 0; return 0; }
+    if (std::strcmp(name, "unwrap_sort") == 0) {
+        if (value != 0 && value != 1) return fail(SGPE_EINVAL, "unwrap_sort: 0 (device radix sort) or 1 (host sort)");
+        p->unwrap_sort = value;
+        return 0;
+    }
     if (std::strcmp(name, "row_mode") == 0) {
         if (value != 0 && value != 1) return fail(SGPE_EINVAL, "row_mode: 0 (paired) or 1 (split)");
         p->row_mode = value;
@@ -847,7 +1029,7 @@ int sgpe_normalise(sgpe_plan* p, const void* in, void* out, double vol, sgpe_str
 int sgpe_energy(sgpe_plan* p, const void* psik, int unwrap_mode, double kl_term, double* out, sgpe_stream st) {
     if (!p || !out) return fail(SGPE_EINVAL, "null argument");
     if (!(p->grid_set && p->g_set && p->pot_set)) return fail(SGPE_ESTATE, "set grid, interactions and potential first");
-    if (unwrap_mode != 0 && unwrap_mode != 1) return fail(SGPE_EINVAL, "unwrap_mode must be 0 or 1");
+    if (unwrap_mode < 0 || unwrap_mode > 2) return fail(SGPE_EINVAL, "unwrap_mode must be 0, 1 or 2");
     DeviceGuard guard(p->device);
     const size_t bytes = (size_t)p->batch * 2 * p->plane * p->csize;
     if (!p->scratch) {
@@ -862,7 +1044,45 @@ int sgpe_energy(sgpe_plan* p, const void* psik, int unwrap_mode, double kl_term,
         psik = p->scratch;
     }
     if ((rc = sgpe_fft2d(p, psik, p->scratch, 1, st))) return rc;
+    if (unwrap_mode == 2) {
+        // wrapped phase of the real-space state -> integer field of 2 pi multiples (synchronises the stream)
+        const long long total = (long long)p->batch * 2 * p->plane;
+        if (!p->unwrap_inc && cudaMalloc((void**)&p->unwrap_inc, sizeof(int) * total) != cudaSuccess)
+            return fail(SGPE_ENOMEM, "unwrap allocation failed");
+        double* phi = nullptr;
+        if (cudaMalloc((void**)&phi, sizeof(double) * total) != cudaSuccess) return fail(SGPE_ENOMEM, "unwrap allocation failed");
+        rc = SGPE_BY_DTYPE(p, run_unwrap_angles, p, p->scratch, total, phi, (cudaStream_t)st);
+        if (!rc) rc = unwrap_increments(p, phi, 2 * p->batch, p->unwrap_inc, (cudaStream_t)st);
+        cudaFree(phi);
+        if (rc) return rc;
+    }
     return SGPE_BY_DTYPE(p, run_energy, p, p->scratch, unwrap_mode, kl_term, out, (cudaStream_t)st);
+}
+
+int sgpe_unwrap_phase(sgpe_plan* p, const void* in, int kind, int nplanes, int mask, double* out, sgpe_stream st_) {
+    if (!p || !in || !out) return fail(SGPE_EINVAL, "null argument");
+    if (kind != 0 && kind != 1) return fail(SGPE_EINVAL, "kind must be 0 (complex field) or 1 (wrapped angles)");
+    if (nplanes < 1) return fail(SGPE_EINVAL, "nplanes must be >= 1");
+    if (mask && kind != 0) return fail(SGPE_EINVAL, "the density mask needs the complex field (kind 0)");
+    DeviceGuard guard(p->device);
+    cudaStream_t st = (cudaStream_t)st_;
+    const long long total = (long long)nplanes * p->plane;
+    struct Scratch { double* phi = nullptr; int* inc = nullptr; unsigned long long* maxbits = nullptr;
+                     ~Scratch() { cudaFree(phi); cudaFree(inc); cudaFree(maxbits); } } w;
+    if (cudaMalloc((void**)&w.inc, sizeof(int) * total) != cudaSuccess ||
+        cudaMalloc((void**)&w.maxbits, sizeof(unsigned long long) * nplanes) != cudaSuccess ||
+        (kind == 0 && cudaMalloc((void**)&w.phi, sizeof(double) * total) != cudaSuccess))
+        return fail(SGPE_ENOMEM, "unwrap allocation failed");
+    int rc;
+    const double* phi = static_cast<const double*>(in);
+    if (kind == 0) {
+        if ((rc = SGPE_BY_DTYPE(p, run_unwrap_angles, p, in, total, w.phi, st))) return rc;
+        phi = w.phi;
+    }
+    if ((rc = unwrap_increments(p, phi, nplanes, w.inc, st))) return rc;
+    if ((rc = SGPE_BY_DTYPE(p, run_unwrap_apply, p, in, phi, w.inc, nplanes, mask != 0, w.maxbits, out, st))) return rc;
+    SGPE_CUDA(cudaStreamSynchronize(st));
+    return 0;
 }
 
 // ---- slab (distributed) mode building blocks: the caller (spinor_gpe_b200/slab.py) owns the buffers and the

@@ -10,6 +10,11 @@ from . import _capi
 from ._lib import lib, require_cuda
 
 
+# TensorPropagator.eng_expect(unwrap=...): 'none' the wrapped phase as is, 'local' locally wrapped differences,
+# 'herraez' the reference's reliability-sorted unwrapping (sgpe_unwrap_phase)
+UNWRAP_MODES = {'none': 0, 'local': 1, 'herraez': 2}
+
+
 def _stream_ptr(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -207,8 +212,23 @@ class Plan:
         """[E_total, E_kin, E_pot, E_int] per trajectory, (B,4) float64 CUDA tensor."""
         t = self._state(psik) if psik is not None else None
         out = torch.zeros((self.batch, 4), dtype=torch.float64, device=self.device)
-        mode = {'none': 0, 'local': 1}[unwrap]
+        mode = UNWRAP_MODES[unwrap]
         self._chk(self.lib.sgpe_energy(self.h, _dp(t), mode, float(kl_term), _dp(out), self.stream), 'sgpe_energy')
+        return out
+
+    def unwrap_phase(self, field, mask=False):
+        """Unwrapped phase of every (ny, nx) plane of ``field`` — a complex tensor (phase = angle) or a float64
+        tensor of wrapped angles; float64 CUDA tensor of the same shape (ttools.phase(..., uwrap=True))."""
+        if not isinstance(field, torch.Tensor):
+            field = torch.as_tensor(np.asarray(field))
+        kind = 0 if field.is_complex() else 1
+        field = field.to(device=self.device, dtype=self.cdtype if kind == 0 else torch.float64).contiguous()
+        if field.shape[-2:] != (self.ny, self.nx):
+            raise ValueError(f"planes of {tuple(field.shape[-2:])}, plan has ({self.ny}, {self.nx})")
+        out = torch.empty(field.shape, dtype=torch.float64, device=self.device)
+        nplanes = field.numel() // (self.ny * self.nx)
+        self._chk(self.lib.sgpe_unwrap_phase(self.h, _dp(field), kind, nplanes, int(bool(mask)), _dp(out), self.stream),
+                  'sgpe_unwrap_phase')
         return out
 
     # ------------------------------------------------------------------ slab-mode local passes

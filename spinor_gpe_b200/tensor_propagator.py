@@ -13,8 +13,12 @@ Differences a user can observe (all documented in DESIGN.md):
 * when the kinetic / potential grids are separable (``g[y, x] = gx[x] + gy[y]``, true for everything
   ``PSpinor`` builds by default) the kernels use 1-D factor tables instead of per-point exp / sincos;
   ``separable=False`` forces the general dense path.
-* ``eng_expect`` runs on the GPU; the phase unwrapping of the reference (skimage) is replaced by
-  ``unwrap='none'`` (default, wrapped phase) or ``'local'``.
+* ``eng_expect`` runs on the GPU.  The reference unwraps the phase of each component with
+  ``skimage.restoration.unwrap_phase`` (tensor_tools.py:531); ``unwrap='herraez'`` is that algorithm
+  (``sgpe_unwrap_phase``: per-pixel work and the edge sort on the device, the sequential region merging in the
+  library's host code), ``'none'`` differentiates the wrapped phase as it is and ``'local'`` uses locally wrapped
+  differences (both stay on the device and never synchronise).  The constructor's ``unwrap`` argument
+  (default ``DEFAULT_UNWRAP``) is what ``prop_loop`` uses for ``PropResult.eng_final``.
 """
 import os
 
@@ -33,6 +37,8 @@ except ImportError:                         # pragma: no cover
     _tqdm = None
 
 MAGIC_GAMMA = 1 / (2 + 2 ** (1 / 3))        # tensor_propagator.py:101
+# phase treatment of eng_expect when the caller does not choose one (see the module docstring)
+DEFAULT_UNWRAP = 'herraez'
 
 
 def next_available_path(file_name, trial_name, ext=''):
@@ -99,8 +105,11 @@ class TensorPropagator:
 
     # pylint: disable=too-many-instance-attributes
     def __init__(self, spin, t_step, n_steps, device='cuda', time='imag', is_sampling=False, n_samples=1,
-                 precision='c128', progress=False, separable='auto'):
+                 precision='c128', progress=False, separable='auto', unwrap=None):
         dev = torch.device(device)
+        self.unwrap = DEFAULT_UNWRAP if unwrap is None else unwrap
+        if self.unwrap not in ('none', 'local', 'herraez'):
+            raise ValueError("unwrap must be 'none', 'local' or 'herraez'")
         if dev.type != 'cuda':
             raise RuntimeError(f"device={device!r}: the B200 propagator has no CPU path; pass a CUDA device")
         if dev.index is None:
@@ -311,8 +320,10 @@ class TensorPropagator:
         psi = ttools.to_numpy(psi_dev)
         return PropResult(psi, psik, energy, pops, file_name)
 
-    def eng_expect(self, psik=None, unwrap='none'):
-        """tensor_propagator.py:273-324 — [<total>, <kin>, <pot>, <int>] (raw grid sums), on the GPU."""
+    def eng_expect(self, psik=None, unwrap=None):
+        """tensor_propagator.py:273-324 — [<total>, <kin>, <pot>, <int>] (raw grid sums), on the GPU.
+        ``unwrap``: 'herraez' | 'none' | 'local' (default: the constructor's choice)."""
+        unwrap = self.unwrap if unwrap is None else unwrap
         if psik is not None:
             assert len(psik) == 2, ("Requires two spinor components to calculate "
                                     "the energy expectation value.")

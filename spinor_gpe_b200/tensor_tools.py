@@ -235,27 +235,39 @@ def conj(psi):
     return conj_comp(psi)
 
 
+def _unwrap_plan(ny, nx):
+    """A cached bare complex128 plan on the current CUDA device for the (ny, nx) mesh (raises without CUDA)."""
+    from ._lib import require_cuda
+    require_cuda()
+    key = (nx, ny, torch.complex128, torch.cuda.current_device())
+    if key not in _PLANS:
+        _PLANS[key] = Plan(nx, ny, 1, torch.complex128, torch.device('cuda', torch.cuda.current_device()))
+    return _PLANS[key]
+
+
 def _unwrap_2d(ang):
-    """The reference calls skimage.restoration.unwrap_phase (tensor_tools.py:531).  scikit-image is an
-    optional dependency here: without it the phase is returned wrapped (energy parity)."""
-    try:
-        from skimage import restoration
-    except ImportError:
-        return np.array(ang, copy=True)
-    return restoration.unwrap_phase(ang)
+    """The reference calls skimage.restoration.unwrap_phase (tensor_tools.py:531); here the same algorithm
+    (Herraez et al. 2002, reliability-sorted region merging) runs through ``sgpe_unwrap_phase``: the per-pixel work
+    and the edge sort on the GPU, the region merging in the library's host code.  NumPy in, NumPy out."""
+    ang = np.ascontiguousarray(ang, dtype=np.float64)
+    out = _unwrap_plan(*ang.shape).unwrap_phase(torch.from_numpy(ang))
+    return out.cpu().numpy()
 
 
 def phase_comp(psi_comp, uwrap=False, dens=None):
-    """tensor_tools.py:514-539."""
+    """tensor_tools.py:514-539.  Beyond the reference (which raises for tensors, :533-536), a CUDA tensor can be
+    unwrapped too; the result stays on the device."""
     if isinstance(psi_comp, np.ndarray):
         ang = np.angle(psi_comp)
         if uwrap:
             ang = _unwrap_2d(ang)
     elif isinstance(psi_comp, torch.Tensor):
         if uwrap:
-            raise NotImplementedError("Unwrapping the complex phase is not implemented for tensors "
-                                      "(reference :533-536).")
-        ang = torch.angle(psi_comp)
+            if not psi_comp.is_cuda:
+                raise RuntimeError("spinor_gpe_b200 computes on CUDA tensors only (no CPU fallback)")
+            ang = _plan_for(psi_comp.to(torch.complex128)).unwrap_phase(psi_comp.to(torch.complex128))
+        else:
+            ang = torch.angle(psi_comp)
     else:
         raise TypeError(f"`psi_comp` is of type {type(psi_comp)}")
     if dens is not None:

@@ -151,6 +151,16 @@ class EmuPlan:
         self._chk(self.lib.sgpe_normalise(self.h, _ptr(a), _ptr(out), vol, None), 'normalise')
         return out
 
+    def unwrap_phase(self, arr, mask=False):
+        """arr: (..., Ny, Nx) complex field (kind 0) or float64 wrapped angles (kind 1)."""
+        a = np.asarray(arr)
+        kind = 0 if np.iscomplexobj(a) else 1
+        a = np.ascontiguousarray(a, dtype=self.cdtype if kind == 0 else np.float64)
+        nplanes = a.size // (self.nx * self.ny)
+        out = np.empty(a.shape, dtype=np.float64)
+        self._chk(self.lib.sgpe_unwrap_phase(self.h, _ptr(a), kind, nplanes, int(mask), _ptr(out), None), 'unwrap_phase')
+        return out
+
     def energy(self, psik=None, kl_term=0.0, unwrap=0):
         a = self._state(psik) if psik is not None else None
         out = np.zeros((self.batch, 4))
