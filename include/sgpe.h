@@ -120,6 +120,13 @@ int sgpe_normalise(sgpe_plan* p, const void* in_dev, void* out_dev, double vol, 
 int sgpe_energy(sgpe_plan* p, const void* psik_dev, int unwrap_mode, double kl_term, double* out_dev,
                 sgpe_stream st);
 
+/* The same functional on a REAL-space state [batch][2][ny][nx] of the plan's dtype (eng_expect after its ifft_2d,
+ * tensor_propagator.py:301-324).  Valid on line plans too (sgpe_plan_create_lines: ny = nlines rows of nx = len points,
+ * potential / coupling / interactions set as for sgpe_pass_rows), which is how meshes beyond 4096 points per line get
+ * their energy (spinor_gpe_b200/slab.py on one device). */
+int sgpe_energy_real_space(sgpe_plan* p, const void* psi_dev, int unwrap_mode, double kl_term, double* out_dev,
+                           sgpe_stream st);
+
 /* ttools.phase_comp(psi_comp, uwrap=True, dens) (tensor_tools.py:514-539): two-dimensional phase unwrapping by
  * reliability-sorted region merging (Herraez, Burton, Lalor, Gdeisat, Appl. Opt. 41, 7437 (2002)), the algorithm
  * behind skimage.restoration.unwrap_phase without mask and wrap-around (the reference's call, tensor_tools.py:531;

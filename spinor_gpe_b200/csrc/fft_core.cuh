@@ -213,21 +213,33 @@ SGPE_DI void stage_load(C (&v)[E], int j, int c, const C* sm) {
     for (int m = 0; m < E; m++) v[m] = sm[G::swz(j + m * NT) * W + c];
 }
 
+// Who synchronises at the exchange points of a transform: the whole CTA, or one of several independent thread
+// groups of a CTA (named barrier `id` over `count` threads, whole warps).  Groups of one CTA drift out of phase, so
+// one group's butterflies overlap the other's shared-memory exchange — what two resident CTAs would give where the
+// register file only has room for one.
+struct CtaBar {
+    SGPE_DI void sync() const { __syncthreads(); }
+};
+struct GroupBar {
+    int id, count;
+    SGPE_DI void sync() const { SGPE_NAMED_BAR(id, count); }
+};
+
 // Full transform of L lines per thread (each with its own shared-memory image); all threads of the
-// CTA must call this together (it contains __syncthreads()).
-template <typename T, int N, int E, int DIR, int W, int L, int Ns, typename C>
-SGPE_DI void cta_fft_from(C (&v)[L][E], int j, int c, C* const (&sm)[L], const C* __restrict__ tw) {
+// CTA (or of the barrier group) must call this together (it contains barriers).
+template <typename T, int N, int E, int DIR, int W, int L, int Ns, typename C, typename B>
+SGPE_DI void cta_fft_from(C (&v)[L][E], int j, int c, C* const (&sm)[L], const C* __restrict__ tw, const B& bar) {
     constexpr int R = (N / Ns) < E ? (N / Ns) : E;
 #pragma unroll
     for (int l = 0; l < L; l++) stage_compute<T, N, E, DIR, Ns>(v[l], j, tw);
     if constexpr (Ns * R < N) {
 #pragma unroll
         for (int l = 0; l < L; l++) stage_store<T, N, E, W, Ns>(v[l], j, c, sm[l]);
-        __syncthreads();
+        bar.sync();
 #pragma unroll
         for (int l = 0; l < L; l++) stage_load<T, N, E, W>(v[l], j, c, sm[l]);
-        __syncthreads();
-        cta_fft_from<T, N, E, DIR, W, L, Ns * R>(v, j, c, sm, tw);
+        bar.sync();
+        cta_fft_from<T, N, E, DIR, W, L, Ns * R>(v, j, c, sm, tw, bar);
     }
 }
 
@@ -262,8 +274,13 @@ SGPE_DI void cta_fft(C (&v)[L][E], int j, int c, C* const (&sm)[L], const C* __r
         stage_compute<T, N, E, DIR, 1>(v[1], j, tw);
         cta_fft2_round<T, N, E, DIR, W, 1>(v, j, c, sm, tw);
     } else {
-        cta_fft_from<T, N, E, DIR, W, L, 1>(v, j, c, sm, tw);
+        cta_fft_from<T, N, E, DIR, W, L, 1>(v, j, c, sm, tw, CtaBar());
     }
+}
+// one line per thread, synchronising over a barrier group
+template <typename T, int N, int E, int DIR, int W, typename C, typename B>
+SGPE_DI void group_fft(C (&v)[1][E], int j, int c, C* const (&sm)[1], const C* __restrict__ tw, const B& bar) {
+    cta_fft_from<T, N, E, DIR, W, 1, 1>(v, j, c, sm, tw, bar);
 }
 
 // ---- deterministic CTA reduction of NV doubles (warp shuffle, then shared memory in warp order)
@@ -291,6 +308,33 @@ SGPE_DI void cta_reduce(double (&val)[NV], double* red /* >= 32*NV doubles of sh
         val[i] = s;       // every thread holds the CTA total
     }
     __syncthreads();
+}
+
+// the same over one barrier group of a CTA: `tid` / `nthreads` are relative to the group, `red` is the group's own
+template <int NV, typename B>
+SGPE_DI void group_reduce(double (&val)[NV], double* red, int tid, int nthreads, const B& bar) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int nwarps = (nthreads + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        double x = val[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        val[i] = x;
+    }
+    bar.sync();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) red[warp * NV + i] = val[i];
+    }
+    bar.sync();
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        double s = 0.0;
+        for (int w = 0; w < nwarps; w++) s += red[w * NV + i];
+        val[i] = s;
+    }
+    bar.sync();
 }
 
 }  // namespace sgpe

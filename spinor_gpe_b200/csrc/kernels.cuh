@@ -140,21 +140,31 @@ template <int TM, typename C> SGPE_DI C combine_factor(C f, C g) {
 
 // FAST = 1: the steady-state junction (forward + factors + inverse, separable tables, no sign / scale) with the
 // other branches compiled out.
-template <typename T, int N, int E, int W, int TM, int FAST>
-__global__ void __launch_bounds__(W * N / E, (W * N / E <= 256) ? 2 : 1) col_pass(ColArgs<T> a) {
+// G > 1: the CTA's tile of G * W adjacent columns is worked on by G independent barrier groups of W columns each
+// (own shared-memory image, own named barrier, own partial-sum slot).  Where the register file has room for one
+// CTA only (complex128 at 2048 points: 512 threads x 128 registers), the groups give the SM two instruction streams
+// that drift out of phase — one group's butterflies overlap the other's exchange — while the CTA as a whole still
+// touches G * W * sizeof(C) = 64 contiguous bytes of every row.
+template <typename T, int N, int E, int W, int TM, int FAST, int G = 1>
+__global__ void __launch_bounds__(G * W * N / E, (G * W * N / E <= 256) ? 2 : 1) col_pass(ColArgs<T> a) {
     typedef typename cx_of<T>::type C;
     constexpr int NT = N / E;
+    constexpr int TG = W * NT;                 // threads per group
     SGPE_DYN_SMEM(smem_raw);
-    C* sm = reinterpret_cast<C*>(smem_raw);
-    double* red = reinterpret_cast<double*>(smem_raw + sizeof(C) * (size_t)N * W);
+    const int g = (G == 1) ? 0 : (int)threadIdx.x / TG;
+    C* sm = reinterpret_cast<C*>(smem_raw) + (size_t)g * N * W;
+    double* red = reinterpret_cast<double*>(smem_raw + sizeof(C) * (size_t)N * W * G) + g * (32 * 4);
 
-    const int tid = threadIdx.x;
+    const int tid = (G == 1) ? (int)threadIdx.x : (int)threadIdx.x - g * TG;
     const int c = tid % W, j = tid / W;
-    const int tiles_per_comp = a.nx / W;
+    const int tiles_per_comp = a.nx / (W * G);
     const int ntiles = 2 * tiles_per_comp;
+    const int nslots = ntiles * G;             // partial-sum slots: one per group
     const int tile = blockIdx.x;
+    const int slot = tile * G + g;
     const int comp = tile / tiles_per_comp;
-    const int col = (tile % tiles_per_comp) * W + c;
+    const int col = (tile % tiles_per_comp) * (W * G) + g * W + c;
+    const GroupBar gbar = {1 + g, TG};
     const int b = blockIdx.y;
     const bool do_fwd = FAST ? true : (a.do_fwd != 0), do_inv = FAST ? true : (a.do_inv != 0);
     const int kin_mode = FAST ? 1 : a.kin_mode;
@@ -167,7 +177,7 @@ __global__ void __launch_bounds__(W * N / E, (W * N / E <= 256) ? 2 : 1) col_pas
     if (a.prefetch_ahead > 0 && c == 0) {
         const int nt = tile + a.prefetch_ahead;
         if (nt < ntiles) {
-            const long long noff = ((long long)b * 2 + nt / tiles_per_comp) * a.plane + (nt % tiles_per_comp) * W;
+            const long long noff = ((long long)b * 2 + nt / tiles_per_comp) * a.plane + (nt % tiles_per_comp) * (W * G) + g * W;
 #pragma unroll
             for (int m = 0; m < E; m++) SGPE_PREFETCH_L2(&a.in[noff + (long long)(j + m * NT) * a.nx]);
         }
@@ -180,7 +190,10 @@ __global__ void __launch_bounds__(W * N / E, (W * N / E <= 256) ? 2 : 1) col_pas
 
     C* const sms[1] = {sm};
     // (the two-iteration-loop trick of row_pass was measured slower here: 16 elements per thread, more spills)
-    if (do_fwd) cta_fft<T, N, E, -1, W, 1>(v, j, c, sms, a.tw + (E == 16 ? N : 0));
+    if (do_fwd) {
+        if constexpr (G == 1) cta_fft<T, N, E, -1, W, 1>(v, j, c, sms, a.tw + (E == 16 ? N : 0));
+        else group_fft<T, N, E, -1, W>(v, j, c, sms, a.tw + (E == 16 ? N : 0), gbar);
+    }
     double acc[2] = {0.0, 0.0};   // S (after FA), T (after FB)
     const bool any_k = a.has_a || a.has_b;
 
@@ -233,16 +246,20 @@ __global__ void __launch_bounds__(W * N / E, (W * N / E <= 256) ? 2 : 1) col_pas
     // (with one CTA per SM the epilogue is dead time for the whole SM).
     unsigned ticket = 0u;
     if (any_k) {
-        cta_reduce<2>(acc, red);
+        if constexpr (G == 1) cta_reduce<2>(acc, red);
+        else group_reduce<2>(acc, red, tid, TG, gbar);
         if (tid == 0) {
-            double* p = a.partials + ((long long)b * ntiles + tile) * 2;
+            double* p = a.partials + ((long long)b * nslots + slot) * 2;
             p[0] = acc[0]; p[1] = acc[1];
             __threadfence();
             ticket = atomicAdd(&a.counter[b], 1u);
         }
     }
 
-    if (do_inv) cta_fft<T, N, E, +1, W, 1>(v, j, c, sms, a.tw + (E == 16 ? N : 0));
+    if (do_inv) {
+        if constexpr (G == 1) cta_fft<T, N, E, +1, W, 1>(v, j, c, sms, a.tw + (E == 16 ? N : 0));
+        else group_fft<T, N, E, +1, W>(v, j, c, sms, a.tw + (E == 16 ? N : 0), gbar);
+    }
 
     if (!FAST && (sign_out || a.scale_out != 1.0)) {
         const T sc = (T)a.scale_out;
@@ -256,19 +273,20 @@ __global__ void __launch_bounds__(W * N / E, (W * N / E <= 256) ? 2 : 1) col_pas
     for (int m = 0; m < E; m++) SGPE_ST_STREAM(&a.out[off + (long long)(j + m * NT) * a.nx], v[0][m]);
 
     if (any_k) {
-        if (tid == 0) red[0] = (ticket == (unsigned)(ntiles - 1)) ? 1.0 : 0.0;
-        __syncthreads();
+        if (tid == 0) red[0] = (ticket == (unsigned)(nslots - 1)) ? 1.0 : 0.0;
+        if constexpr (G == 1) __syncthreads(); else gbar.sync();
         const bool last = red[0] != 0.0;      // (the fold's first write to `red` comes after a barrier of its own)
-        if (last) {       // the last tile of this trajectory folds the partials in a fixed order
+        if (last) {       // the last tile (group) of this trajectory folds the partials in a fixed order
             __threadfence();
             double t4[4] = {0.0, 0.0, 0.0, 0.0};     // S0, T0, S1, T1
-            const double* p = a.partials + (long long)b * ntiles * 2;
-            for (int t = tid; t < ntiles; t += blockDim.x) {
-                const int cp = (t >= tiles_per_comp) ? 2 : 0;
+            const double* p = a.partials + (long long)b * nslots * 2;
+            for (int t = tid; t < nslots; t += TG) {
+                const int cp = (t >= nslots / 2) ? 2 : 0;
                 t4[cp + 0] += __ldcg(&p[2 * t]);
                 t4[cp + 1] += __ldcg(&p[2 * t + 1]);
             }
-            cta_reduce<4>(t4, red);
+            if constexpr (G == 1) cta_reduce<4>(t4, red);
+            else group_reduce<4>(t4, red, tid, TG, gbar);
             if (tid == 0) {
                 double* tot = a.totals + (long long)b * 4;
                 tot[0] = t4[1] + t4[3];

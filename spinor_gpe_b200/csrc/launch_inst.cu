@@ -116,11 +116,42 @@ static int launch_col_w(const ColArgs<T>& a, int batch, cudaStream_t st) {
     return 0;
 }
 
+// G barrier groups of W columns each in one CTA (col_pass<..., G>): same tile, same global segments, G instruction
+// streams per SM
+template <typename T, int N, int TM, int W, int E, int G>
+static int launch_col_g(const ColArgs<T>& a, int batch, cudaStream_t st) {
+    typedef ColCfg<T, N> Cfg;
+    constexpr size_t smem = (size_t)N * W * G * Cfg::CB + (size_t)G * 32 * 4 * sizeof(double);
+    if (a.nx % (W * G) != 0) return -2;
+    static bool once = false;
+    static int ahead = 0;
+    if (!once) {
+        allow_smem(col_pass<T, N, E, W, TM, 0, G>, smem);
+        allow_smem(col_pass<T, N, E, W, TM, 1, G>, smem);
+        ahead = resident_ctas(col_pass<T, N, E, W, TM, 1, G>, G * W * (N / E), smem);
+        once = true;
+    }
+    dim3 grid(2 * a.nx / (W * G), batch), block(G * W * (N / E));
+    ColArgs<T> a2 = a;
+    if (a2.prefetch_ahead) a2.prefetch_ahead = ahead;
+    const bool fast = a.do_fwd && a.do_inv && a.kin_mode == 1 && !a.sign_in && !a.sign_out && a.scale_out == 1.0;
+    if (fast) {
+        SGPE_LAUNCH((col_pass<T, N, E, W, TM, 1, G>), grid, block, smem, st, a2);
+    } else {
+        SGPE_LAUNCH((col_pass<T, N, E, W, TM, 0, G>), grid, block, smem, st, a2);
+    }
+    return 0;
+}
+
 // wsel: 0 = default tile width (64-byte segments), 2 = narrow tiles (half the shared memory per CTA so
-// that two CTAs share an SM and their load / compute / store phases overlap)
+// that two CTAs share an SM and their load / compute / store phases overlap), 3 = default tile worked on by two
+// independent barrier groups of half the width each
 template <typename T, int N, int TM>
 static int launch_col_t(const ColArgs<T>& a, int batch, int wsel, cudaStream_t st) {
     typedef ColCfg<T, N> Cfg;
+    if constexpr (Cfg::W % 2 == 0 && (Cfg::W / 2) * Cfg::NT >= 32) {
+        if (wsel == 3) return launch_col_g<T, N, TM, Cfg::W / 2, Cfg::E, 2>(a, batch, st);
+    }
 #ifdef SGPE_EXPERIMENTAL
     // measured slower on B200 (profiles/r01_variants.md); kept for experiments and the emulation tests
     constexpr int WN = Cfg::W / 2;
@@ -132,7 +163,7 @@ static int launch_col_t(const ColArgs<T>& a, int batch, int wsel, cudaStream_t s
         if (wsel == 8) return launch_col_w<T, N, TM, Cfg::W, 8>(a, batch, st);
     }
 #else
-    if (wsel != 0) return -3;
+    if (wsel != 0 && wsel != 3) return -3;
 #endif
     return launch_col_w<T, N, TM, Cfg::W, Cfg::E>(a, batch, st);
 }

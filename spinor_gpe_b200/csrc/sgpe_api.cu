@@ -886,8 +886,8 @@ int sgpe_set_coupling(sgpe_plan* p, int mode, const double* coupling, int64_t bs
 int sgpe_set_option(sgpe_plan* p, const char* name, int value) {
     if (!p || !name) return fail(SGPE_EINVAL, "null argument");
     if (std::strcmp(name, "col_tile") == 0) {
-        if (value != 0 && value != 2 && value != 8)
-            return fail(SGPE_EINVAL, "col_tile: 0 (default), 2 (half width) or 8 (radix-8 threads)");
+        if (value != 0 && value != 2 && value != 3 && value != 8)
+            return fail(SGPE_EINVAL, "col_tile: 0 (default), 2 (half width), 3 (two barrier groups) or 8 (radix-8 threads)");
         p->col_wsel = value;
         return 0;
     }
@@ -1026,24 +1026,10 @@ int sgpe_normalise(sgpe_plan* p, const void* in, void* out, double vol, sgpe_str
     return SGPE_BY_DTYPE(p, run_scale, p, in, out, p->totals_aux, p->atom_num / vol, (cudaStream_t)st);
 }
 
-int sgpe_energy(sgpe_plan* p, const void* psik, int unwrap_mode, double kl_term, double* out, sgpe_stream st) {
-    if (!p || !out) return fail(SGPE_EINVAL, "null argument");
-    if (!(p->grid_set && p->g_set && p->pot_set)) return fail(SGPE_ESTATE, "set grid, interactions and potential first");
-    if (unwrap_mode < 0 || unwrap_mode > 2) return fail(SGPE_EINVAL, "unwrap_mode must be 0, 1 or 2");
-    DeviceGuard guard(p->device);
-    const size_t bytes = (size_t)p->batch * 2 * p->plane * p->csize;
-    if (!p->scratch) {
-        if (cudaMalloc(&p->scratch, bytes) != cudaSuccess) return fail(SGPE_ENOMEM, "scratch allocation failed");
-        if (cudaMalloc((void**)&p->maxdens, sizeof(double) * 2 * p->batch) != cudaSuccess)
-            return fail(SGPE_ENOMEM, "scratch allocation failed");
-    }
-    int rc;
-    if (psik == nullptr) {
-        if (p->phase == sgpe_plan::EMPTY) return fail(SGPE_ESTATE, "no state loaded");
-        if ((rc = sgpe_store_psik(p, p->scratch, st))) return rc;
-        psik = p->scratch;
-    }
-    if ((rc = sgpe_fft2d(p, psik, p->scratch, 1, st))) return rc;
+// the energy functional on a real-space state (the part of eng_expect after its ifft_2d, tensor_propagator.py:301-324)
+static int energy_of_real_space(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, double* out, sgpe_stream st) {
+    if (!p->maxdens && cudaMalloc((void**)&p->maxdens, sizeof(double) * 2 * p->batch) != cudaSuccess)
+        return fail(SGPE_ENOMEM, "scratch allocation failed");
     if (unwrap_mode == 2) {
         // wrapped phase of the real-space state -> integer field of 2 pi multiples (synchronises the stream)
         const long long total = (long long)p->batch * 2 * p->plane;
@@ -1051,12 +1037,38 @@ int sgpe_energy(sgpe_plan* p, const void* psik, int unwrap_mode, double kl_term,
             return fail(SGPE_ENOMEM, "unwrap allocation failed");
         double* phi = nullptr;
         if (cudaMalloc((void**)&phi, sizeof(double) * total) != cudaSuccess) return fail(SGPE_ENOMEM, "unwrap allocation failed");
-        rc = SGPE_BY_DTYPE(p, run_unwrap_angles, p, p->scratch, total, phi, (cudaStream_t)st);
+        int rc = SGPE_BY_DTYPE(p, run_unwrap_angles, p, psi, total, phi, (cudaStream_t)st);
         if (!rc) rc = unwrap_increments(p, phi, 2 * p->batch, p->unwrap_inc, (cudaStream_t)st);
         cudaFree(phi);
         if (rc) return rc;
     }
-    return SGPE_BY_DTYPE(p, run_energy, p, p->scratch, unwrap_mode, kl_term, out, (cudaStream_t)st);
+    return SGPE_BY_DTYPE(p, run_energy, p, psi, unwrap_mode, kl_term, out, (cudaStream_t)st);
+}
+
+int sgpe_energy(sgpe_plan* p, const void* psik, int unwrap_mode, double kl_term, double* out, sgpe_stream st) {
+    if (!p || !out) return fail(SGPE_EINVAL, "null argument");
+    if (!(p->grid_set && p->g_set && p->pot_set)) return fail(SGPE_ESTATE, "set grid, interactions and potential first");
+    if (unwrap_mode < 0 || unwrap_mode > 2) return fail(SGPE_EINVAL, "unwrap_mode must be 0, 1 or 2");
+    if (p->n1 != 1 || p->state == nullptr) return fail(SGPE_EINVAL, "line plans have no k-space state: use sgpe_energy_real_space");
+    DeviceGuard guard(p->device);
+    const size_t bytes = (size_t)p->batch * 2 * p->plane * p->csize;
+    if (!p->scratch && cudaMalloc(&p->scratch, bytes) != cudaSuccess) return fail(SGPE_ENOMEM, "scratch allocation failed");
+    int rc;
+    if (psik == nullptr) {
+        if (p->phase == sgpe_plan::EMPTY) return fail(SGPE_ESTATE, "no state loaded");
+        if ((rc = sgpe_store_psik(p, p->scratch, st))) return rc;
+        psik = p->scratch;
+    }
+    if ((rc = sgpe_fft2d(p, psik, p->scratch, 1, st))) return rc;
+    return energy_of_real_space(p, p->scratch, unwrap_mode, kl_term, out, st);
+}
+
+int sgpe_energy_real_space(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, double* out, sgpe_stream st) {
+    if (!p || !psi || !out) return fail(SGPE_EINVAL, "null argument");
+    if (!(p->grid_set && p->g_set && p->pot_set)) return fail(SGPE_ESTATE, "set grid, interactions and potential first");
+    if (unwrap_mode < 0 || unwrap_mode > 2) return fail(SGPE_EINVAL, "unwrap_mode must be 0, 1 or 2");
+    DeviceGuard guard(p->device);
+    return energy_of_real_space(p, psi, unwrap_mode, kl_term, out, st);
 }
 
 int sgpe_unwrap_phase(sgpe_plan* p, const void* in, int kind, int nplanes, int mask, double* out, sgpe_stream st_) {

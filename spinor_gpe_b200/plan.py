@@ -216,6 +216,16 @@ class Plan:
         self._chk(self.lib.sgpe_energy(self.h, _dp(t), mode, float(kl_term), _dp(out), self.stream), 'sgpe_energy')
         return out
 
+    def energy_real_space(self, psi, kl_term=0.0, unwrap='none'):
+        """The energy functional on a real-space state (B, 2, ny, nx) already on the device; also valid on line
+        plans (meshes beyond 4096 points per line)."""
+        if psi.dtype != self.cdtype or not psi.is_contiguous() or psi.numel() != self.batch * 2 * self.ny * self.nx:
+            raise ValueError("psi must be a contiguous (B, 2, ny, nx) tensor of the plan's dtype")
+        out = torch.zeros((self.batch, 4), dtype=torch.float64, device=self.device)
+        self._chk(self.lib.sgpe_energy_real_space(self.h, _dp(psi), UNWRAP_MODES[unwrap], float(kl_term), _dp(out),
+                                                  self.stream), 'sgpe_energy_real_space')
+        return out
+
     def unwrap_phase(self, field, mask=False):
         """Unwrapped phase of every (ny, nx) plane of ``field`` — a complex tensor (phase = angle) or a float64
         tensor of wrapped angles; float64 CUDA tensor of the same shape (ttools.phase(..., uwrap=True))."""

@@ -119,9 +119,15 @@ class SlabPropagator:
     def __init__(self, spin, t_step, time='imag', device='cuda', group=None, precision='c128', plan_kwargs=None,
                  split_x=None, split_y=None, exchange='auto', exchange_buffers=None, chunks=None, scatter_ctas=None):
         from .plan import Plan
-        assert dist.is_initialized(), "SlabPropagator needs an initialised torch.distributed process group"
-        self.group = group
-        self.rank, self.P = dist.get_rank(group), dist.get_world_size(group)
+        # group='local': ONE device, no process group — the long-line machinery (four-step lines, row-major k slab)
+        # for meshes beyond 4096 points per line on a single GPU; every collective degenerates to stream order
+        self.local = isinstance(group, str) and group == 'local'
+        if self.local:
+            self.group, self.rank, self.P = None, 0, 1
+        else:
+            assert dist.is_initialized(), "SlabPropagator needs an initialised torch.distributed process group"
+            self.group = group
+            self.rank, self.P = dist.get_rank(group), dist.get_world_size(group)
         self.dev = torch.device(device)
         assert exchange in ('auto', 'nccl', 'p2p')
         if exchange == 'auto':    # one node, one process per GPU: the fused exchange through peer memory
@@ -144,11 +150,12 @@ class SlabPropagator:
         self.dt_out, self.dt_in = self.dt * MAGIC_GAMMA, self.dt * (1 - 2 * MAGIC_GAMMA)
         self.atom_num = float(spin.atom_num)
         self.dv_k = float(spin.space['dv_k'])
+        self.dv_r = float(spin.space['dv_r'])
         self.n1x, self.n1y = four_step_split(self.nx, split_x), four_step_split(self.ny, split_y)
         self.nat_x, self.nat_y = digit_order(self.nx, self.n1x), digit_order(self.ny, self.n1y)
         kw = dict(plan_kwargs or {})
         ys, xs = slice(r * self.nyl, (r + 1) * self.nyl), slice(r * self.nxl, (r + 1) * self.nxl)
-        self._ys = ys
+        self._ys, self._xs = ys, xs
 
         # ---- row plan: local rows (natural y), full x
         self.rp = rp = Plan(self.nx, self.nyl, 1, self.cdtype, self.dev, lines_n1=self.n1x, **kw)
@@ -229,14 +236,7 @@ class SlabPropagator:
         if sep_only:
             self.set_real_space(spin.tf_rows(spin.space['y'][ys], self.dev, self.cdtype))
         else:
-            stored = psik[:, self.nat_y][:, :, self.nat_x]
-            if self.p2p:
-                local = np.ascontiguousarray(stored[:, :, xs])                    # (2, ny, nxl) row-major k slab
-            else:
-                local = np.ascontiguousarray(stored[:, :, xs].transpose(0, 2, 1))     # (2, nxl, ny) transposed slab
-            self.tbuf.copy_(torch.as_tensor(local).reshape(-1).to(self.cdtype))
-            if self.p2p:
-                self._barrier()       # nobody stores into a peer that is still setting up
+            self.load_psik(psik)
 
     # ------------------------------------------------------------------ fused exchange: buffers in peer memory
     def _setup_exchange(self, n_local, given):
@@ -263,7 +263,8 @@ class SlabPropagator:
                 own.append(ptr.value)
                 handles.append(bytes(h.raw))
             everyone = [None] * P
-            dist.all_gather_object(everyone, handles, group=self.group)
+            if P > 1:
+                dist.all_gather_object(everyone, handles, group=self.group)
             kptrs, rptrs, opened = [], [], []
             for q in range(P):
                 if q == r:
@@ -295,10 +296,34 @@ class SlabPropagator:
         self._ipc = []
 
     def _barrier(self):
-        dist.all_reduce(self._flag, op=dist.ReduceOp.SUM, group=self.group)
+        if self.P > 1:
+            dist.all_reduce(self._flag, op=dist.ReduceOp.SUM, group=self.group)
 
     def _count_exchange(self):
         self.a2a_bytes += self.tbuf.numel() * self.tbuf.element_size() * (self.P - 1) // self.P
+
+    def load_psik(self, psik):
+        """Replace the state by the k-space wavefunction ``psik`` ((2, Ny, Nx), the reference's order; NumPy array or
+        tensor, the same on every rank): each rank keeps its slab in the stored (digit-transposed) order."""
+        if isinstance(psik, torch.Tensor):
+            full = psik.reshape(2, self.ny, self.nx).to(self.dev)
+            stored = full.index_select(1, torch.as_tensor(self.nat_y, device=self.dev)) \
+                         .index_select(2, torch.as_tensor(self.nat_x, device=self.dev))
+            local = stored[:, :, self._xs] if self.p2p else stored[:, :, self._xs].transpose(1, 2)
+            local = local.contiguous().reshape(-1).to(self.cdtype)
+        else:
+            stored = np.asarray(psik).reshape(2, self.ny, self.nx)[:, self.nat_y][:, :, self.nat_x]
+            if self.p2p:
+                local = np.ascontiguousarray(stored[:, :, self._xs])                  # (2, ny, nxl) row-major k slab
+            else:
+                local = np.ascontiguousarray(stored[:, :, self._xs].transpose(0, 2, 1))   # (2, nxl, ny) transposed slab
+            local = torch.as_tensor(local).reshape(-1).to(self.cdtype)
+        if self.p2p:
+            self._barrier()           # the peers are done with whatever they were storing here
+        self.tbuf.copy_(local)
+        self.mid, self.scale_pending, self.pending_dt = False, False, 0.0
+        if self.p2p:
+            self._barrier()           # nobody stores into a peer that is still loading
 
     def set_real_space(self, psi_rows):
         """Load a REAL-space state given by this rank's rows, (2, Ny/P, Nx) on the device: the distributed forward
@@ -330,7 +355,10 @@ class SlabPropagator:
     # ------------------------------------------------------------------ collectives
     def _all_to_all(self):
         s, r = torch.view_as_real(self.send), torch.view_as_real(self.recv)
-        dist.all_to_all_single(r.view(-1), s.view(-1), group=self.group)
+        if self.P > 1:
+            dist.all_to_all_single(r.view(-1), s.view(-1), group=self.group)
+        else:
+            r.copy_(s)
         self.a2a_bytes += self.send.numel() * self.send.element_size() * (self.P - 1) // self.P
 
     def _to_rows(self):
@@ -344,7 +372,8 @@ class SlabPropagator:
         self.tp.slab_unpack(self.recv, self.tbuf, self.P, self.nyl, self.nxl)    # -> [2][nxl][P*nyl]
 
     def _reduce_sums(self):
-        dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=self.group)
+        if self.P > 1:
+            dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=self.group)
 
     # ------------------------------------------------------------------ second stream of the chunked exchange
     def _fork(self):
@@ -477,13 +506,126 @@ class SlabPropagator:
             out = out * scale.to(out.real.dtype)
         return out
 
+    def real_space_rows(self):
+        """This rank's rows of the normalised REAL-space state, (2, Ny/P, Nx) on the device — ttools.ifft_2d of the
+        current k-space state (tensor_tools.py:248-256) by the distributed inverse transform: y-lines on the k slab,
+        exchange, x-lines on the row slab.  The k-space state is left as it is (the inverse runs on a copy); the row
+        slab buffer, free between sub-steps, receives the result.  Fused-exchange layout only."""
+        if not self.p2p:
+            raise NotImplementedError("real_space_rows needs the row-major k slab (exchange='p2p')")
+        self.close_junction()
+        keep = self.tbuf.clone()
+        # norm of the state being transformed: the atom number when the lazy normalisation is pending (that is what
+        # materialising it gives), else whatever was loaded (the reference's ifft_2d does not renormalise)
+        if self.scale_pending:
+            norm_k = torch.full((1,), self.atom_num, dtype=torch.float64, device=self.dev)
+        else:
+            norm_k = (keep.real.double() ** 2 + keep.imag.double() ** 2).sum().reshape(1) * self.dv_k
+            if self.P > 1:
+                dist.all_reduce(norm_k, op=dist.ReduceOp.SUM, group=self.group)
+        tp, rp = self.tp, self.rp
+        if self.n1y == 1:
+            tp.pass_kcols(self.tbuf, False, False, 0.0, False, 0.0, True, None, scatter=True)
+        else:
+            tp.pass_kcols(self.tbuf, False, False, 0.0, False, 0.0, True, None)
+            tp.pass_mid(self.tbuf, True, True, False, 0.0, False, False, None, 0.0, inner=self.nxl, scatter=True)
+        self._count_exchange()
+        self._barrier()
+        rp.pass_klines(self.rbuf, False, False, 0.0, False, 0.0, True, None)           # inverse over x (or over k2)
+        if self.n1x > 1:
+            rp.pass_mid(self.rbuf, True, True, False, 0.0, False, False, None, 0.0)    # conj twiddle, inverse over k1
+        self.tbuf.copy_(keep)
+        del keep
+        ny0 = self._ys.start
+        sign = 1.0 - 2.0 * ((torch.arange(self.nx, device=self.dev)[None, :]
+                             + torch.arange(ny0, ny0 + self.nyl, device=self.dev)[:, None]) % 2)
+        rows = self.rbuf.view(2, self.nyl, self.nx)
+        psi = rows * sign.to(rows.real.dtype)                   # the ifftshift of the reference is this sign
+        # scale by Parseval (dv_r sum|psi|^2 = dv_k sum|psi_k|^2, the invariant of the reference's transforms),
+        # whatever factors the individual passes carry
+        tot = (psi.real.double() ** 2 + psi.imag.double() ** 2).sum().reshape(1)
+        if self.P > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)
+        psi = psi * torch.sqrt(norm_k[0] / (self.dv_r * tot[0])).to(rows.real.dtype)
+        self._barrier()
+        return psi
+
     def gather_psik(self):
         """Full (2, Ny, Nx) k-space state in the reference's order on every rank (tests / small grids only)."""
         loc = torch.view_as_real(self.local_psik().contiguous())
-        parts = [torch.empty_like(loc) for _ in range(self.P)]
-        dist.all_gather(parts, loc, group=self.group)
+        if self.P > 1:
+            parts = [torch.empty_like(loc) for _ in range(self.P)]
+            dist.all_gather(parts, loc, group=self.group)
+        else:
+            parts = [loc]
         full = torch.cat([torch.view_as_complex(p) for p in parts], dim=1)       # (2, Nx, Ny), stored order
         full = full.transpose(1, 2).contiguous()
         inv_x = torch.as_tensor(np.argsort(self.nat_x), device=full.device)
         inv_y = torch.as_tensor(np.argsort(self.nat_y), device=full.device)
         return full.index_select(2, inv_x).index_select(1, inv_y).contiguous()
+
+
+class LongLinePlan:
+    """The subset of ``plan.Plan`` that ``TensorPropagator`` drives, for ONE trajectory on ONE GPU whose mesh has more
+    than 4096 points along a line (8192^2, 16384^2 in 180 GB of HBM): a ``SlabPropagator`` with one rank and no
+    process group.  Lines are split four-step style (contiguous sub-lines + a strided pass with the twiddles and the
+    real-space operators fused in), k-space is kept in the digit-transposed order and un-permuted only when the
+    state is read.  Needs a separable kinetic energy grid (everything ``PSpinor`` builds)."""
+
+    def __init__(self, spin, t_step, time, device, precision='c128', **slab_kwargs):
+        self.sp = SlabPropagator(spin, t_step, time=time, device=device, group='local', precision=precision,
+                                 exchange='p2p', **slab_kwargs)
+        self.nx, self.ny, self.batch = self.sp.nx, self.sp.ny, 1
+        self.device = self.sp.dev
+        self.cdtype = self.sp.cdtype
+        self._kl_keep = None
+
+    def load(self, psik):
+        self.sp.load_psik(psik if isinstance(psik, torch.Tensor) else np.asarray(psik))
+
+    def store(self, out=None):
+        full = self.sp.gather_psik().reshape(1, 2, self.ny, self.nx)
+        if out is not None:
+            out.copy_(full)
+            return out
+        return full
+
+    def substeps(self):
+        return self.sp.dt_out, self.sp.dt_in
+
+    def single_step(self, dt_sub):
+        self.sp.single_step(float(dt_sub))
+
+    def full_steps(self, n, pops=None, first=0):
+        self.sp.full_steps(int(n), None if pops is None else pops[0, first:first + n])
+
+    def real_space(self):
+        """(1, 2, ny, nx) normalised real-space state (ttools.ifft_2d of the current state)."""
+        return self.sp.real_space_rows().contiguous().reshape(1, 2, self.ny, self.nx)
+
+    def energy(self, psik=None, kl_term=0.0, unwrap='none'):
+        sp = self.sp
+        saved = None
+        if psik is not None:          # evaluate another state: park the current one
+            sp.close_junction()
+            saved = (sp.tbuf.clone(), sp.scale_pending, sp.sums.clone())
+            sp.load_psik(psik)
+        psi = self.real_space()
+        out = sp.rp.energy_real_space(psi, kl_term=kl_term, unwrap=unwrap)
+        if saved is not None:
+            sp.tbuf.copy_(saved[0])
+            sp.scale_pending = saved[1]
+            sp.sums.copy_(saved[2])
+        return out
+
+    def set_option(self, name, value):
+        self.sp.rp.set_option(name, value)
+        self.sp.tp.set_option(name, value)
+
+    def launch_count(self):
+        return self.sp.rp.launch_count() + self.sp.tp.launch_count()
+
+    def close(self):
+        self.sp.close()
+        self.sp.rp.close()
+        self.sp.tp.close()

@@ -37,6 +37,7 @@ except ImportError:                         # pragma: no cover
     _tqdm = None
 
 MAGIC_GAMMA = 1 / (2 + 2 ** (1 / 3))        # tensor_propagator.py:101
+MAX_LINE = 4096                             # longest line one CTA transforms (sgpe_plan_create)
 # phase treatment of eng_expect when the caller does not choose one (see the module docstring)
 DEFAULT_UNWRAP = 'herraez'
 
@@ -105,7 +106,7 @@ class TensorPropagator:
 
     # pylint: disable=too-many-instance-attributes
     def __init__(self, spin, t_step, n_steps, device='cuda', time='imag', is_sampling=False, n_samples=1,
-                 precision='c128', progress=False, separable='auto', unwrap=None):
+                 precision='c128', progress=False, separable='auto', unwrap=None, long_lines=None):
         dev = torch.device(device)
         self.unwrap = DEFAULT_UNWRAP if unwrap is None else unwrap
         if self.unwrap not in ('none', 'local', 'herraez'):
@@ -169,11 +170,20 @@ class TensorPropagator:
         self.sample_rate = self.n_steps / n_samples         # :136
 
         # ---- the plan
-        self._plan = pl = Plan(nx, ny, 1, cdtype, dev)
-        pl.set_grid(self._dr[0], self._dr[1], self._dv_r, self._dv_k, self.atom_num)
-        pl.set_interactions(self.g_sc['uu'], self.g_sc['dd'], self.g_sc['ud'])
-        self._bind_operators(cpl_np, spin)
-        pl.set_time(time, self._dt)
+        # meshes with more than 4096 points along a line do not fit one CTA per line: they run on the long-line
+        # machinery of the slab mode (four-step lines) on this one device.  ``long_lines`` = dict of SlabPropagator
+        # keywords forces that path on a small mesh (tests: split_x / split_y).
+        self._long = long_lines is not None or max(nx, ny) > MAX_LINE
+        if self._long:
+            from .slab import LongLinePlan
+            self._plan = LongLinePlan(spin, self._dt, time, dev, precision, **(long_lines or {}))
+            self.separable = {'kin': True, 'pot': None}
+        else:
+            self._plan = pl = Plan(nx, ny, 1, cdtype, dev)
+            pl.set_grid(self._dr[0], self._dr[1], self._dv_r, self._dv_k, self.atom_num)
+            pl.set_interactions(self.g_sc['uu'], self.g_sc['dd'], self.g_sc['ud'])
+            self._bind_operators(cpl_np, spin)
+            pl.set_time(time, self._dt)
         self._psik_cache = None
         self.psik = ttools.to_tensor([psik0[0], psik0[1]], dev=dev, dtype=128)
 
@@ -315,7 +325,11 @@ class TensorPropagator:
             file_name = None
 
         psik_dev = self.psik
-        psi_dev = ttools.ifft_2d(psik_dev, self._dr)
+        if self._long:
+            rs = self._plan.real_space()[0].to(torch.complex128)
+            psi_dev = [rs[0], rs[1]]
+        else:
+            psi_dev = ttools.ifft_2d(psik_dev, self._dr)
         psik = ttools.to_numpy(psik_dev)
         psi = ttools.to_numpy(psi_dev)
         return PropResult(psi, psik, energy, pops, file_name)

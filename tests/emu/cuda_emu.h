@@ -49,6 +49,8 @@ struct State {
     int cur = 0, nthreads = 0, alive = 0;
     int bar_arrived = 0;
     unsigned bar_gen = 0;
+    int nbar_arrived[16] = {0};
+    unsigned nbar_gen[16] = {0};
     std::vector<int> warp_arrived;
     std::vector<unsigned> warp_gen;
     std::vector<double> shfl_d[2];
@@ -83,6 +85,14 @@ inline void syncthreads() {
     unsigned g = s.bar_gen;
     if (++s.bar_arrived == s.nthreads) { s.bar_arrived = 0; s.bar_gen++; return; }
     while (s.bar_gen == g) yield();
+}
+// bar.sync id, count: the first `count` arrivals at barrier `id` form one generation
+inline void named_barrier(int id, int count) {
+    State& s = S();
+    if (id < 0 || id >= 16) { fprintf(stderr, "emu: barrier id %d\n", id); abort(); }
+    unsigned g = s.nbar_gen[id];
+    if (++s.nbar_arrived[id] == count) { s.nbar_arrived[id] = 0; s.nbar_gen[id]++; return; }
+    while (s.nbar_gen[id] == g) yield();
 }
 inline void warp_sync() {
     State& s = S();
@@ -121,6 +131,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, F f) {
     for (unsigned bx = 0; bx < grid.x; bx++) {
         s.bid.x = bx; s.bid.y = by; s.bid.z = bz;
         s.alive = s.nthreads; s.bar_arrived = 0;
+        for (int q = 0; q < 16; q++) s.nbar_arrived[q] = 0;
         std::fill(s.done.begin(), s.done.end(), 0);
         std::fill(s.warp_arrived.begin(), s.warp_arrived.end(), 0);
         for (int t = 0; t < s.nthreads; t++) {

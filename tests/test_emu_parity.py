@@ -98,6 +98,59 @@ def test_emulated_half_width_column_tiles():
     pl.close()
 
 
+def _seeded_problem(ny, nx, seed, coupling=0.7):
+    """A small random problem on an (ny, nx) mesh with separable operators (harmonic trap, shifted dispersion)."""
+    rng = np.random.default_rng(seed)
+    dr = (0.25, 0.2)
+    dk = (2 * np.pi / (nx * dr[0]), 2 * np.pi / (ny * dr[1]))
+    x = (np.arange(nx) - nx // 2) * dr[0]
+    y = (np.arange(ny) - ny // 2) * dr[1]
+    kx = (np.arange(nx) - nx // 2) * dk[0]
+    ky = (np.arange(ny) - ny // 2) * dk[1]
+    pot = 0.5 * (x[None, :] ** 2 + (1.3 * y[:, None]) ** 2)
+    kin = 0.5 * (kx[None, :] ** 2 + ky[:, None] ** 2)
+    kin_spin = np.stack([kin + 0.8 * kx[None, :], kin - 0.8 * kx[None, :]])
+    kin_spin -= kin_spin.min(axis=(1, 2), keepdims=True)
+    env = np.exp(-(x[None, :] ** 2 + y[:, None] ** 2) / 8.0)
+    psi = env * (rng.standard_normal((2, ny, nx)) + 1j * rng.standard_normal((2, ny, nx)))
+    dv_r, dv_k = dr[0] * dr[1], dk[0] * dk[1]
+    psik = orc.fft2(torch.as_tensor(psi), dr)
+    psik, _ = orc.normalise(psik, dv_k, 500.0)
+    return orc.Problem(psik.numpy(), kin_spin, np.stack([pot + 0.1 * y[:, None], pot - 0.1 * y[:, None]]),
+                       np.full((ny, nx), coupling), dr, dv_r, dv_k, [0.011, 0.0105, 0.0108], 500.0, x=x, kL=0.8,
+                       is_coupling=True, rot_coupling=False)
+
+
+@pytest.mark.parametrize('shape,mode,dtype,separable', [((256, 32), 'real', np.complex128, True),
+                                                         ((256, 32), 'imag', np.complex128, False),
+                                                         ((512, 32), 'imag', np.complex128, True),
+                                                         ((256, 64), 'real', np.complex64, True)])
+def test_emulated_two_barrier_groups_per_column_tile(shape, mode, dtype, separable):
+    """col_tile = 3 (columns of >= 256 points): the column tile is worked on by two independent barrier groups of
+    half the width (named barriers, own shared-memory image and partial-sum slot each) — same results as the
+    oracle, populations included, and the stand-alone transforms (non-FAST instantiation) as well."""
+    ny, nx = shape
+    prob = _seeded_problem(ny, nx, seed=ny + nx)
+    dt, n = (1 / 200, 3) if mode == 'real' else (1 / 50, 3)
+    want = orc.OraclePropagator(prob, dt, mode).run(n)
+    pl = plan_from_problem(prob, mode, dt, dtype=dtype, separable=separable)
+    pl.set_option('col_tile', 3)
+    pops = pl.full_steps(n)
+    tol = 1e-12 if dtype == np.complex128 else 2e-5
+    assert rel(pl.store()[0], want['psik']) < tol
+    np.testing.assert_allclose(pops[0], want['pops_vals'], rtol=tol)
+    # and the default kernel agrees to rounding (different summation order of the partial sums only)
+    pl0 = plan_from_problem(prob, mode, dt, dtype=dtype, separable=separable)
+    pl0.full_steps(n)
+    assert rel(pl.store()[0], pl0.store()[0]) < (1e-14 if dtype == np.complex128 else 1e-5)
+    rng = np.random.default_rng(5)
+    psi = rng.standard_normal((2, ny, nx)) + 1j * rng.standard_normal((2, ny, nx))
+    ref = orc.fft2(torch.as_tensor(psi), prob.dr).numpy()
+    assert rel(pl.fft2d(psi)[0], ref) < (1e-13 if dtype == np.complex128 else 1e-5)
+    pl.close()
+    pl0.close()
+
+
 def test_separability_detection():
     from spinor_gpe_b200._separable import split_separable
     y, x = np.meshgrid(np.linspace(-1, 1, 32), np.linspace(-2, 2, 64), indexing='ij')

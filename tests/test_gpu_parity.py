@@ -198,6 +198,39 @@ def test_bitwise_reproducible():
         assert torch.equal(o, outs[0])
 
 
+@pytest.mark.parametrize('mesh,mode,dt,cpl,precision', [((256, 256), 'imag', 1 / 50, 'zero', 'c128'),
+                                                        ((128, 1024), 'real', 1 / 2000, 'uniform', 'c128'),
+                                                        ((64, 2048), 'imag', 1 / 50, 'dense', 'c128'),
+                                                        ((64, 2048), 'real', 1 / 2000, 'uniform', 'c64'),
+                                                        ((32, 4096), 'imag', 1 / 50, 'zero', 'c128')])
+def test_two_barrier_groups_per_column_tile(mesh, mode, dt, cpl, precision):
+    """col_tile = 3 (two independent barrier groups per column tile) against the oracle and the default kernel;
+    repeated runs are bit-identical."""
+    from spinor_gpe_b200 import TensorPropagator
+    ps = make_ps(mesh, atom_num=1e4, r_sizes=(16, 16), g_sc={'uu': 1, 'dd': 0.98, 'ud': 1.02})
+    ps.coupling_setup(wavel=790.1e-9, kin_shift=True)
+    if cpl == 'uniform':
+        ps.coupling_uniform(1.5 * ps.EL_recoil)
+    elif cpl == 'dense':
+        ps.coupling_grad(slope=0.3, offset=2.0, axis=1)
+    ps.rot_coupling = cpl != 'uniform'
+    rng = np.random.default_rng(4242)
+    ps.psik = [p * (1 + 0.05 * (rng.standard_normal(p.shape) + 1j * rng.standard_normal(p.shape))) for p in ps.psik]
+    want = orc.OraclePropagator(problem_of(ps), dt, mode).run(3)
+    outs = []
+    for tile in (3, 3, 0):
+        prop = TensorPropagator(ps, dt, 3, 'cuda', time=mode, precision=precision)
+        prop._plan.set_option('col_tile', tile)
+        pops = torch.zeros((1, 3, 2), dtype=torch.float64, device='cuda')
+        prop._plan.full_steps(3, pops)
+        outs.append((torch.stack(prop.psik).clone(), pops.cpu().numpy()[0]))
+    tol = TOL_PSI if precision == 'c128' else TOL_PSI_C64
+    assert rel(outs[0][0].cpu().numpy(), want['psik']) < tol
+    np.testing.assert_allclose(outs[0][1], want['pops_vals'], rtol=TOL_SCALAR if precision == 'c128' else 1e-5)
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert rel(outs[0][0].cpu().numpy(), outs[2][0].cpu().numpy()) < (1e-13 if precision == 'c128' else 1e-5)
+
+
 def test_complex64_against_oracle():
     ps = make_ps((512, 512))
     ps.coupling_setup(wavel=790.1e-9, kin_shift=True)
