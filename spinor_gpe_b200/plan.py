@@ -173,12 +173,21 @@ class Plan:
         self._chk(self.lib.sgpe_full_steps(self.h, int(n), _dp(pops), stride, int(first), self.stream),
                   'sgpe_full_steps')
 
-    def run_host(self, psik_host, n_steps, want_pops=True):
-        """Host-buffer path (H2D + steps + D2H inside the call).  psik_host: CPU tensor/ndarray."""
+    def run_host(self, psik_host, n_steps, want_pops=True, out=None, pops=None):
+        """Host-buffer path (H2D + steps + D2H inside the call).  psik_host: CPU tensor/ndarray.  ``out`` / ``pops``:
+        optional caller-owned (ideally pinned) result buffers of the right shape, reused across calls."""
         a = torch.as_tensor(np.asarray(psik_host) if not isinstance(psik_host, torch.Tensor) else psik_host)
         a = a.to(dtype=self.cdtype).contiguous()
-        out = torch.empty_like(a, pin_memory=True)
-        pops = torch.zeros((self.batch, n_steps, 2), dtype=torch.float64, pin_memory=True) if want_pops else None
+        if out is None:
+            out = torch.empty_like(a, pin_memory=True)
+        elif out.dtype != a.dtype or out.numel() != a.numel() or not out.is_contiguous():
+            raise ValueError("out must be a contiguous buffer of the state's dtype and size")
+        if want_pops and pops is None:
+            pops = torch.zeros((self.batch, n_steps, 2), dtype=torch.float64, pin_memory=True)
+        elif want_pops and (pops.dtype != torch.float64 or pops.numel() != self.batch * n_steps * 2):
+            raise ValueError("pops must be a float64 buffer of (batch, n_steps, 2)")
+        elif not want_pops:
+            pops = None
         self._chk(self.lib.sgpe_run_host(self.h, _dp(a), _dp(out), int(n_steps), _dp(pops), self.stream),
                   'sgpe_run_host')
         return out, pops

@@ -218,8 +218,8 @@ class SlabPropagator:
         # Chunked pipelining of the fused exchange (four-step lines only: three local passes per direction, the last
         # one NVLink-bound).  The slab is cut into `chunks` windows; the scatter pass of window c runs on a second
         # stream with a few persistent CTAs per SM while the first two passes of window c + 1 run beside it.
-        if chunks is None:
-            chunks = 4 if (self.p2p and self.dev.type == 'cuda') else 1
+        if chunks is None:      # one rank has no link to hide: one window (measured: 52.5 vs 45.9 steps/s at 8192^2)
+            chunks = 4 if (self.p2p and self.dev.type == 'cuda' and self.P > 1) else 1
         self.chunks_x = chunks if (self.p2p and self.n1x > 1 and self.nyl % chunks == 0) else 1
         self.chunks_y = chunks if (self.p2p and self.n1y > 1 and self.nxl % (chunks * 32) == 0) else 1
         if scatter_ctas is None:

@@ -12,10 +12,12 @@ import torch
 from spinor_gpe_b200.slab import LongLinePlan, SeparableProblem
 
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+chunk_list = [int(v) for v in sys.argv[3].split(',')] if len(sys.argv) > 3 else [None]
 for n in [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else '8192,16384').split(',')]:
+  for chunks in chunk_list:
     for mode, dt in (('imag', 1 / 50), ('real', 1 / 5000)):
         prob = SeparableProblem((n, n), (64, 64), atom_num=1e4, coupling=1.0, kin_shift=True, rot_coupling=False)
-        pl = LongLinePlan(prob, dt, mode, 'cuda')
+        pl = LongLinePlan(prob, dt, mode, 'cuda', chunks=chunks)
         pops = torch.zeros((1, steps + 2, 2), dtype=torch.float64, device='cuda')
         pl.full_steps(2, pops, first=0)
         torch.cuda.synchronize()
