@@ -120,6 +120,13 @@ int sgpe_normalise(sgpe_plan* p, const void* in_dev, void* out_dev, double vol, 
 int sgpe_energy(sgpe_plan* p, const void* psik_dev, int unwrap_mode, double kl_term, double* out_dev,
                 sgpe_stream st);
 
+/* Spectral kinetic energy per component, out_dev[batch][2] = dv_k * sum_k kin_c(k) |psi_k,c(k)|^2  [hbar omega_x]:
+ * the k-space counterpart of the finite-difference / unwrapped-phase kinetic term of eng_expect
+ * (tensor_propagator.py:306-311), which needs no phase (no reference equivalent).  kin_c is the
+ * plan's kinetic operator (kin_eng_spin: Raman shift and "- min" offset included, pspinor.py:496-501).
+ * psik_dev == NULL evaluates the plan's current (normalised) state.  Asynchronous. */
+int sgpe_kinetic_spectral(sgpe_plan* p, const void* psik_dev, double* out_dev, sgpe_stream st);
+
 /* The same functional on a REAL-space state [batch][2][ny][nx] of the plan's dtype (eng_expect after its ifft_2d,
  * tensor_propagator.py:301-324).  Valid on line plans too (sgpe_plan_create_lines: ny = nlines rows of nx = len points,
  * potential / coupling / interactions set as for sgpe_pass_rows), which is how meshes beyond 4096 points per line get

@@ -1164,6 +1164,63 @@ __global__ void __launch_bounds__(256) sumsq_pass(SumsqArgs<T> a) {
     }
 }
 
+// Spectral kinetic energy  sum_k kin_c(k) |psi_k,c|^2  per component (times `scale` = dv_k): the k-space counterpart of
+// the finite-difference + unwrapped-phase expression of eng_expect (tensor_propagator.py:306-311) that needs no phase
+// at all.  kin_c is the propagator's own kinetic grid (dense, or separable kin_x[c][kx] + kin_y[c][ky]),
+// Raman shift and the reference's "- min" offset (pspinor.py:496-501) included.  Same two-stage fixed-order reduction
+// as sumsq_pass.
+template <typename T> struct KineticArgs {
+    typedef typename cx_of<T>::type C;
+    const C* in; int nx, ny; long long plane;
+    int kin_mode; const double* kin0; const double* kin1; long long kin_bstride;
+    const double* kin_x; const double* kin_y; long long kinx_bstride, kiny_bstride;
+    double scale;
+    double* partials; unsigned* counter; double* out;      // out [B][2]
+};
+template <typename T>
+__global__ void __launch_bounds__(256) kinetic_pass(KineticArgs<T> a) {
+    typedef typename cx_of<T>::type C;
+    SGPE_DYN_SMEM(smem_raw);
+    double* red = reinterpret_cast<double*>(smem_raw);
+    const int b = blockIdx.y, nblk = gridDim.x, tid = threadIdx.x;
+    double acc[2] = {0.0, 0.0};
+    for (int comp = 0; comp < 2; comp++) {
+        const C* p = a.in + ((long long)b * 2 + comp) * a.plane;
+        const double* kd = (comp == 0 ? a.kin0 : a.kin1) + (long long)b * a.kin_bstride;
+        const double* kx = a.kin_x + (long long)b * a.kinx_bstride + (long long)comp * a.nx;
+        const double* ky = a.kin_y + (long long)b * a.kiny_bstride + (long long)comp * a.ny;
+        for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < a.plane; i += (long long)nblk * blockDim.x) {
+            const C z = p[i];
+            double e;
+            if (a.kin_mode == 0) e = __ldg(&kd[i]);
+            else { const int iy = (int)(i / a.nx); e = __ldg(&kx[i - (long long)iy * a.nx]) + __ldg(&ky[iy]); }
+            acc[comp] += e * ((double)z.x * z.x + (double)z.y * z.y);
+        }
+    }
+    cta_reduce<2>(acc, red);
+    if (tid == 0) {
+        double* p = a.partials + ((long long)b * nblk + blockIdx.x) * 2;
+        p[0] = acc[0]; p[1] = acc[1];
+        __threadfence();
+        const unsigned ticket = atomicAdd(&a.counter[b], 1u);
+        red[0] = (ticket == (unsigned)(nblk - 1)) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const bool last = red[0] != 0.0;
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        double t2[2] = {0.0, 0.0};
+        const double* p = a.partials + (long long)b * nblk * 2;
+        for (int t = tid; t < nblk; t += blockDim.x) { t2[0] += __ldcg(&p[2 * t]); t2[1] += __ldcg(&p[2 * t + 1]); }
+        cta_reduce<2>(t2, red);
+        if (tid == 0) {
+            a.out[2 * b] = t2[0] * a.scale; a.out[2 * b + 1] = t2[1] * a.scale;
+            a.counter[b] = 0u;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Energy expectation (reference TensorPropagator.eng_expect, tensor_propagator.py:298-324) on the
 // real-space state.  Pass 1: per-component max density (the mask threshold of phase_comp,

@@ -395,6 +395,26 @@ int run_sumsq(sgpe_plan* p, const void* in, double* out2, cudaStream_t st) {
 }
 
 template <typename T>
+int run_kinetic(sgpe_plan* p, const void* psik, double* out, cudaStream_t st) {
+    typedef typename sgpe::cx_of<T>::type C;
+    sgpe::KineticArgs<T> a;
+    memset(&a, 0, sizeof(a));
+    a.in = static_cast<const C*>(psik); a.nx = p->nx; a.ny = p->ny; a.plane = p->plane;
+    a.kin_mode = p->kin_mode; a.kin0 = p->kin0; a.kin1 = p->kin1; a.kin_bstride = p->kin_bs;
+    a.kin_x = p->kin_x; a.kin_y = p->kin_y; a.kinx_bstride = p->kin_xbs; a.kiny_bstride = p->kin_ybs;
+    a.scale = p->dv_k;
+    a.partials = p->partials; a.counter = p->counter; a.out = out;
+    long long blocks = (p->plane + 256 * 8 - 1) / (256 * 8);
+    if (blocks > p->max_tiles) blocks = p->max_tiles;
+    if (blocks < 1) blocks = 1;
+    dim3 grid((unsigned)blocks, p->batch), block(256);
+    SGPE_LAUNCH((sgpe::kinetic_pass<T>), grid, block, 32 * 2 * sizeof(double), st, a);
+    p->launches++;
+    SGPE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
 int run_energy(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, double* out, cudaStream_t st) {
     typedef typename sgpe::cx_of<T>::type C;
     sgpe::MaxDensArgs<T> m;
@@ -1061,6 +1081,22 @@ int sgpe_energy(sgpe_plan* p, const void* psik, int unwrap_mode, double kl_term,
     }
     if ((rc = sgpe_fft2d(p, psik, p->scratch, 1, st))) return rc;
     return energy_of_real_space(p, p->scratch, unwrap_mode, kl_term, out, st);
+}
+
+int sgpe_kinetic_spectral(sgpe_plan* p, const void* psik, double* out, sgpe_stream st) {
+    if (!p || !out) return fail(SGPE_EINVAL, "null argument");
+    if (!(p->grid_set && p->kin_set)) return fail(SGPE_ESTATE, "set grid and kinetic operator first");
+    if (p->n1 != 1 || p->state == nullptr) return fail(SGPE_EINVAL, "not available on line plans");
+    DeviceGuard guard(p->device);
+    if (psik == nullptr) {
+        if (p->phase == sgpe_plan::EMPTY) return fail(SGPE_ESTATE, "no state loaded");
+        const size_t bytes = (size_t)p->batch * 2 * p->plane * p->csize;
+        if (!p->scratch && cudaMalloc(&p->scratch, bytes) != cudaSuccess) return fail(SGPE_ENOMEM, "scratch allocation failed");
+        int rc = sgpe_store_psik(p, p->scratch, st);
+        if (rc) return rc;
+        psik = p->scratch;
+    }
+    return SGPE_BY_DTYPE(p, run_kinetic, p, psik, out, (cudaStream_t)st);
 }
 
 int sgpe_energy_real_space(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, double* out, sgpe_stream st) {

@@ -225,6 +225,13 @@ class Plan:
         self._chk(self.lib.sgpe_energy(self.h, _dp(t), mode, float(kl_term), _dp(out), self.stream), 'sgpe_energy')
         return out
 
+    def kinetic_spectral(self, psik=None):
+        """dv_k * sum_k kin_c |psi_k,c|^2 per trajectory and component, (B, 2) float64 CUDA tensor."""
+        t = self._state(psik) if psik is not None else None
+        out = torch.zeros((self.batch, 2), dtype=torch.float64, device=self.device)
+        self._chk(self.lib.sgpe_kinetic_spectral(self.h, _dp(t), _dp(out), self.stream), 'sgpe_kinetic_spectral')
+        return out
+
     def energy_real_space(self, psi, kl_term=0.0, unwrap='none'):
         """The energy functional on a real-space state (B, 2, ny, nx) already on the device; also valid on line
         plans (meshes beyond 4096 points per line)."""

@@ -1,16 +1,13 @@
 """``PropResult`` — container returned by ``PSpinor.imaginary()/real()`` (reference
-spinor_gpe/pspinor/prop_result.py:50-88, 304-328).  Plotting needs matplotlib, which is optional here."""
+spinor_gpe/pspinor/prop_result.py:50-88, 304-328).  The figures need matplotlib, which is imported only when one is
+requested (``plotting_tools``)."""
+import os
+import sys
+
 import numpy as np
 
+from . import plotting_tools as ptools
 from . import tensor_tools as ttools
-
-
-def _need_matplotlib():
-    try:
-        import matplotlib  # noqa: F401
-    except ImportError as exc:      # pragma: no cover
-        raise ImportError("plotting needs matplotlib, which is not installed in this environment; "
-                          "the numerical results (psi, psik, pops, eng_final, dens, phase) do not") from exc
 
 
 class PropResult:
@@ -44,11 +41,76 @@ class PropResult:
         ny, nx = new_shape
         return [a.reshape(ny, a.shape[0] // ny, nx, a.shape[1] // nx).mean(-1).mean(1) for a in arr]
 
-    def plot_spins(self, *args, **kwargs):
-        _need_matplotlib()
-        raise NotImplementedError("figure generation is outside the propagator path (SURVEY.md 8f-4)")
+    def plot_spins(self, rscale=1.0, kscale=1.0, cmap='viridis', save=True, ext='.pdf', show=True, zoom=1.0):
+        """Densities and phases of both components (prop_result.py:90-125); returns (fig, all_plots)."""
+        return ptools.plot_spins(self.psi, self.psik, ptools.extents_of(self.space, rscale, kscale), self.paths,
+                                 cmap=cmap, save=save, ext=ext, show=show, zoom=zoom)
 
-    plot_total = plot_pops = make_movie = plot_spins
+    def plot_total(self, rscale=1.0, kscale=1.0, cmap='viridis', save=True, ext='.pdf', show=True, zoom=1.0):
+        """Total densities and phase (prop_result.py:127-163); returns (fig, all_plots)."""
+        return ptools.plot_total(self.psi, self.psik, ptools.extents_of(self.space, rscale, kscale), self.paths,
+                                 cmap=cmap, save=save, ext=ext, show=show, zoom=zoom)
+
+    def plot_pops(self, scaled=True, save=True, ext='.pdf'):
+        """Populations of both components against time, and the size of their step-to-step change on a log scale
+        (prop_result.py:169-214).  Saved as ``<data>/pop_evolution<i>-<folder><ext>``."""
+        plt = ptools._pyplot()
+        unit, label = (self.time_scale, 'Time [s]') if scaled else (1.0, 'Time [$1/\\omega_x$]')
+        times = self.pops['times'] * unit
+        fig = plt.figure(figsize=(12, 4))
+        left, right = fig.add_subplot(121), fig.add_subplot(122)
+        lines = left.plot(times, self.pops['vals'])
+        left.legend(lines, ('Pop. $| \\uparrow\\rangle$', 'Pop. $| \\downarrow\\rangle$'))
+        left.set_ylabel('Population')
+        right.plot(times, np.abs(np.diff(self.pops['vals'])))
+        right.set_ylabel('Abs. Population Difference')
+        right.set_yscale('log')
+        right.set_ylim(2e-16, None)
+        for ax in (left, right):
+            ax.set_xlabel(label)
+            ax.grid(alpha=0.5)
+        if save:
+            plt.savefig(ptools.next_available_path(self.paths['data'] + 'pop_evolution', self.paths['folder'], ext))
+        plt.show()
+
+    def make_movie(self, rscale=1.0, kscale=1.0, cmap='viridis', play=False, zoom=1.0, norm_type='all'):
+        """Animate the sampled wavefunctions (``psik_sampled*.npz`` written by ``prop_loop``) in the layout of
+        ``plot_spins``; saved as ``<data>/prop_movie<i>-<folder>.mp4`` through matplotlib's ffmpeg writer
+        (prop_result.py:220-302).  ``norm_type``: colour scale from the summed maxima ('all') or half of that."""
+        import subprocess
+        import warnings
+        if not os.path.exists(str(self.sampled_path)):
+            warnings.warn("Cannot generate propagation movie. No sampled wavefuntion data exists.")
+            return
+        divisor = {'all': 1.0, 'half': 2.0}[norm_type]
+        from matplotlib import animation
+        plt = ptools._pyplot()
+        with np.load(self.sampled_path) as sampled:
+            psiks = sampled['psiks']
+        fig, images = self.plot_spins(rscale, kscale, cmap, save=False, show=False, zoom=zoom)
+
+        def draw(frame):
+            psik = list(psiks[frame])
+            psi = ttools.ifft_2d(psik, self.space['dr'])
+            dens, densk = ttools.density(psi), ttools.density(psik)
+            for key, data in (('r', dens), ('ph', ttools.phase(psi, uwrap=False, dens=dens)), ('k', densk)):
+                for img, arr in zip(images[key], data):
+                    img.set_data(arr)
+            for key, data in (('r', dens), ('k', densk)):
+                top = sum(np.max(d) for d in data) / divisor
+                for img in images[key]:
+                    img.set_clim(0, top)
+            ptools.progress_message(frame, len(psiks))
+
+        movie = animation.FuncAnimation(fig, draw, frames=len(psiks), blit=False)
+        file_name = ptools.next_available_path(self.paths['data'] + 'prop_movie', self.paths['folder'], '.mp4')
+        movie.save(file_name, writer=animation.writers['ffmpeg'](fps=5, bitrate=-1))
+        plt.close(fig)
+        if play:
+            if sys.platform == 'win32':
+                os.startfile(file_name)          # pylint: disable=no-member
+            else:
+                subprocess.call(['open' if sys.platform == 'darwin' else 'xdg-open', file_name])
 
     def plot_eng(self):
         raise NotImplementedError()          # a stub in the reference as well (prop_result.py:165-167)

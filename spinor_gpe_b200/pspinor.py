@@ -15,6 +15,7 @@ from scipy.ndimage import fourier_shift
 from . import constants as const
 from . import tensor_tools as ttools
 from . import tensor_propagator as tprop
+from . import plotting_tools as ptools
 
 ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -273,12 +274,26 @@ class PSpinor:
     def seed_random_vortices(self, N):       # pylint: disable=invalid-name
         raise NotImplementedError()          # pspinor.py:754-756
 
-    # ------------------------------------------------------------------ plotting pass-throughs
-    def _no_plots(self, *args, **kwargs):
-        raise NotImplementedError("figures need matplotlib and are outside the propagator path "
-                                  "(SURVEY.md 8f-4); use ps.psi / ps.psik / PropResult arrays")
+    # ------------------------------------------------------------------ figures (host-side, need matplotlib)
+    def plot_rdens(self, psi=None, spin=None, cmap='viridis', scale=1.0):
+        """Real-space density (pspinor.py:758-787)."""
+        ptools.plot_dens(self.psi if psi is None else psi, spin, cmap, scale,
+                         extent=ptools.extents_of(self.space, rscale=scale)['r'])
 
-    plot_rdens = plot_kdens = plot_rphase = plot_spins = _no_plots
+    def plot_kdens(self, psik=None, spin=None, cmap='viridis', scale=1.0):
+        """Momentum-space density (pspinor.py:789-818)."""
+        ptools.plot_dens(self.psik if psik is None else psik, spin, cmap, scale,
+                         extent=ptools.extents_of(self.space, kscale=scale)['k'])
+
+    def plot_rphase(self, psi=None, spin=None, cmap='twilight_shifted', scale=1.0):
+        """Real-space phase (pspinor.py:820-851)."""
+        ptools.plot_phase(self.psi if psi is None else psi, spin, cmap, scale,
+                          extent=ptools.extents_of(self.space, rscale=scale)['r'])
+
+    def plot_spins(self, rscale=1.0, kscale=1.0, cmap='viridis', save=True, ext='.pdf', zoom=1.0):
+        """Densities and phases of both components (pspinor.py:853-888); returns (fig, all_plots)."""
+        return ptools.plot_spins(self.psi, self.psik, ptools.extents_of(self.space, rscale, kscale), self.paths,
+                                 cmap=cmap, save=save, ext=ext, zoom=zoom)
 
     # ------------------------------------------------------------------ propagation
     def _propagate(self, time, t_step, n_steps, device, is_sampling, n_samples, **kw):

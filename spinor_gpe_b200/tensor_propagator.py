@@ -28,6 +28,7 @@ import torch
 from . import _capi
 from . import tensor_tools as ttools
 from .plan import Plan
+from .plotting_tools import next_available_path      # names the sampled-wavefunction file (:199-200)
 from .prop_result import PropResult
 from ._separable import split_separable
 
@@ -40,15 +41,6 @@ MAGIC_GAMMA = 1 / (2 + 2 ** (1 / 3))        # tensor_propagator.py:101
 MAX_LINE = 4096                             # longest line one CTA transforms (sgpe_plan_create)
 # phase treatment of eng_expect when the caller does not choose one (see the module docstring)
 DEFAULT_UNWRAP = 'herraez'
-
-
-def next_available_path(file_name, trial_name, ext=''):
-    """First ``<file_name><i>-<trial_name><ext>`` (i = 1, 2, ...) that does not exist yet
-    (reference plotting_tools.py:13-37; decides the name of the sampled-wavefunction file)."""
-    idx = 1
-    while os.path.exists(f'{file_name}{idx}-{trial_name}{ext}'):
-        idx += 1
-    return f'{file_name}{idx}-{trial_name}{ext}'
 
 
 class _LazyTensors(dict):
@@ -347,3 +339,15 @@ class TensorPropagator:
         # the coupling energy uses the full coupling grid even where the step skips an all-zero one
         out = self._plan.energy(psik, kl_term=kl_term, unwrap=unwrap)
         return [float(v) for v in out[0].cpu().numpy()]
+
+    def kin_expect_spectral(self, psik=None):
+        """Kinetic energy per component from the k-space density, ``dv_k * sum kin_eng_spin[c] * abs(psik[c])**2``
+        [hbar omega_x] — an alternative to the finite-difference / unwrapped-phase kinetic term of ``eng_expect``
+        that needs no phase (no reference equivalent; the reference's number is a raw grid sum: multiply it by
+        ``dv_r`` to compare).  Not available on meshes beyond 4096 points per line."""
+        if self._long:
+            raise NotImplementedError("kin_expect_spectral is not available on long-line meshes")
+        if psik is not None:
+            comps = [torch.as_tensor(p) if not isinstance(p, torch.Tensor) else p for p in psik]
+            psik = torch.stack([c.to(self._dev) for c in comps]).reshape(1, 2, self._plan.ny, self._plan.nx)
+        return [float(v) for v in self._plan.kinetic_spectral(psik)[0].cpu().numpy()]

@@ -161,6 +161,12 @@ class EmuPlan:
         self._chk(self.lib.sgpe_unwrap_phase(self.h, _ptr(a), kind, nplanes, int(mask), _ptr(out), None), 'unwrap_phase')
         return out
 
+    def kinetic_spectral(self, psik=None):
+        a = self._state(psik) if psik is not None else None
+        out = np.zeros((self.batch, 2))
+        self._chk(self.lib.sgpe_kinetic_spectral(self.h, _ptr(a), _ptr(out), None), 'kinetic_spectral')
+        return out
+
     def energy(self, psik=None, kl_term=0.0, unwrap=0):
         a = self._state(psik) if psik is not None else None
         out = np.zeros((self.batch, 4))

@@ -256,6 +256,18 @@ def test_energy_of_ground_state_against_oracle():
     np.testing.assert_allclose(prop.eng_expect(None, unwrap='local'), want['energy'], rtol=1e-6)
 
 
+def test_spectral_kinetic_energy():
+    """TensorPropagator.kin_expect_spectral against NumPy on the same state (dense and separable operators)."""
+    ps = make_ps((256, 128), atom_num=1e4, r_sizes=(16, 16))
+    ps.coupling_setup(wavel=790.1e-9, kin_shift=True)
+    ps.coupling_uniform(1.5 * ps.EL_recoil)
+    for sep in (True, False):
+        res, prop = ps_copy_run(ps, sep)
+        want = [(np.asarray(ps.kin_eng_spin[c]) * np.abs(res.psik[c]) ** 2).sum() * ps.space['dv_k'] for c in range(2)]
+        np.testing.assert_allclose(prop.kin_expect_spectral(), want, rtol=TOL_SCALAR)
+        np.testing.assert_allclose(prop.kin_expect_spectral(res.psik), want, rtol=TOL_SCALAR)
+
+
 def test_batched_sweep_matches_individual_runs():
     """Config-4 style: several trajectories (coupling x detuning sweep) in one plan == one by one."""
     from spinor_gpe_b200 import _capi
