@@ -49,9 +49,12 @@ def _default_factory(nx, ny, batch, dtype, device):
 
 
 def run_sweep(ps, trajectories, t_step, n_steps, time='imag', device='cuda', batch=8, precision='c128',
-              keep_states=False, group=None, plan_factory=None, energy=True):
+              keep_states=False, group=None, plan_factory=None, energy=True, unwrap='none'):
     """Propagate every trajectory for ``n_steps`` full steps; returns on every rank the gathered dict
     ``{'pops': (n, n_steps, 2), 'energy': (n, 4) or None, 'psik': list or None, 'owner': (n,)}``.
+
+    ``unwrap``: phase treatment of the final energies — 'none' (default: stays on the device, asynchronous),
+    'local', or 'herraez' (the reference's unwrapped phase; the region merging of every trajectory runs on the host).
 
     ``ps`` supplies the shared grid, kinetic energy, interactions, atom number and (default) initial state.
     Works with any initialised ``torch.distributed`` group (NCCL on GPUs; gloo in the CPU tests, where
@@ -97,7 +100,7 @@ def run_sweep(ps, trajectories, t_step, n_steps, time='imag', device='cuda', bat
         pl.load(states)
         pops = torch.zeros((B, max(n_steps, 1), 2), dtype=torch.float64, device=device)
         pl.full_steps(n_steps, pops)
-        en = pl.energy(None, kl_term=2 * ps.kL_recoil * float(bool(ps.is_coupling))) if energy else None
+        en = pl.energy(None, kl_term=2 * ps.kL_recoil * float(bool(ps.is_coupling)), unwrap=unwrap) if energy else None
         final = pl.store() if keep_states else None
         pops_h = pops.cpu().numpy()[:, :n_steps]
         for k, i in enumerate(ids):

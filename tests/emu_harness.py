@@ -263,7 +263,8 @@ class EmuTorchPlan:
 
     def energy(self, psik=None, kl_term=0.0, unwrap='none'):
         import torch
-        return torch.from_numpy(self.p.energy(psik, kl_term, 0))
+        from spinor_gpe_b200.plan import UNWRAP_MODES
+        return torch.from_numpy(self.p.energy(psik, kl_term, UNWRAP_MODES[unwrap]))
 
     def store(self):
         import torch

@@ -64,3 +64,8 @@ def test_no_cpu_fallback():
         tt.fft_2d([torch.zeros(64, 64, dtype=torch.complex128)] * 2)
     # host-side NumPy helpers (set-up / analysis) do work
     assert len(tt.fft_2d([np.ones((32, 32), complex)] * 2)) == 2
+    assert tt.phase([np.ones((32, 32), complex)] * 2)[0].shape == (32, 32)
+    # ... except the phase unwrapping, which runs through the library (device kernels + host merging): no silent
+    # "wrapped phase instead" when there is no GPU
+    with pytest.raises(ExtensionMissing):
+        tt.phase([np.ones((32, 32), complex)] * 2, uwrap=True)
