@@ -94,6 +94,15 @@ int sgpe_store_psik(sgpe_plan* p, void* psik_dev, sgpe_stream st);
  * writes pops_dev[b*pops_stride + 2*(pops_first+i) + {0,1}].  Asynchronous. */
 int sgpe_full_steps(sgpe_plan* p, int n, double* pops_dev, int64_t pops_stride, int pops_first,
                     sgpe_stream st);
+/* The same with the energy expectation (eng_expect, tensor_propagator.py:273-324) of EVERY step boundary — the "energy
+ * tracking" of BASELINE configs[2]; the reference evaluates the energy once per run, on the CPU.  energy_dev is
+ * [batch][energy_stride] doubles, step i writes energy_dev[b*energy_stride + 4*(energy_first+i) + {0..3}] = E_total,
+ * E_kin, E_pot, E_int.  The junction pass that follows a full step stores the boundary state on the side; its inverse
+ * transform (with the normalisation and the density maxima folded into the last pass) and the stencil pass run
+ * behind it: three extra launches per step, nothing synchronises.  unwrap_mode 0 or 1 (see sgpe_energy). */
+int sgpe_full_steps_energy(sgpe_plan* p, int n, double* pops_dev, int64_t pops_stride, int pops_first,
+                           double* energy_dev, int64_t energy_stride, int energy_first, int unwrap_mode,
+                           double kl_term, sgpe_stream st);
 /* One TensorPropagator.single_step (tensor_propagator.py:224-271) of sub-step length dt_sub
  * (use sgpe_substeps for dt_out / dt_in). */
 int sgpe_single_step(sgpe_plan* p, double dt_sub, sgpe_stream st);

@@ -23,6 +23,8 @@ PROTOTYPES = {
     'sgpe_load_psik': (C.c_int, [c_plan, c_dptr, c_stream]),
     'sgpe_store_psik': (C.c_int, [c_plan, c_dptr, c_stream]),
     'sgpe_full_steps': (C.c_int, [c_plan, C.c_int, c_dptr, C.c_int64, C.c_int, c_stream]),
+    'sgpe_full_steps_energy': (C.c_int, [c_plan, C.c_int, c_dptr, C.c_int64, C.c_int, c_dptr, C.c_int64, C.c_int, C.c_int,
+                                         C.c_double, c_stream]),
     'sgpe_single_step': (C.c_int, [c_plan, C.c_double, c_stream]),
     'sgpe_substeps': (C.c_int, [c_plan, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     'sgpe_fft2d': (C.c_int, [c_plan, c_dptr, c_dptr, C.c_int, c_stream]),

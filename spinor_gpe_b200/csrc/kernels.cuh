@@ -126,6 +126,9 @@ template <typename T> struct ColArgs {
     double* totals;                // [B][4] : T, S0, S1, -
     double* pops; long long pops_bstride; int pops_slot;   // [B][n][2], slot < 0: don't record
     double atom_num;
+    C* aux;                        // optional second output [B][2][ny][nx]: the state right after FA — at a full-step
+                                   // junction that is the (un-normalised) k-space state of the step boundary, which
+                                   // per-step energy tracking transforms back on the side (sgpe_full_steps_energy)
 };
 
 // multiply by a factor: in imaginary time every factor is real (only .x is meaningful)
@@ -139,7 +142,7 @@ template <int TM, typename C> SGPE_DI C combine_factor(C f, C g) {
 }
 
 // FAST = 1: the steady-state junction (forward + factors + inverse, separable tables, no sign / scale) with the
-// other branches compiled out.
+// other branches compiled out.  FAST = 2: the same plus the store of the boundary state to `aux`.
 // G > 1: the CTA's tile of G * W adjacent columns is worked on by G independent barrier groups of W columns each
 // (own shared-memory image, own named barrier, own partial-sum slot).  Where the register file has room for one
 // CTA only (complex128 at 2048 points: 512 threads x 128 registers), the groups give the SM two instruction streams
@@ -209,6 +212,7 @@ __global__ void __launch_bounds__(G * W * N / E, (G * W * N / E <= 256) ? 2 : 1)
                 if (a.has_a) {
                     x = mul_factor<TM>(x, evo<TM, T, C>(e[m], a.ka_re, a.ka_im));
                     acc[0] += (double)x.x * x.x + (double)x.y * x.y;
+                    if (!FAST && a.aux != nullptr) SGPE_ST_STREAM(&a.aux[off + (long long)(j + m * NT) * a.nx], x);
                 }
                 if (a.has_b) {
                     x = mul_factor<TM>(x, evo<TM, T, C>(e[m], a.kb_re, a.kb_im));
@@ -229,6 +233,8 @@ __global__ void __launch_bounds__(G * W * N / E, (G * W * N / E <= 256) ? 2 : 1)
                 if (a.has_a) {
                     x = mul_factor<TM>(x, combine_factor<TM>(fxa, __ldg(&a.ya[oy + m * NT])));
                     acc[0] += (double)x.x * x.x + (double)x.y * x.y;
+                    if ((FAST == 2) || (!FAST && a.aux != nullptr))
+                        SGPE_ST_STREAM(&a.aux[off + (long long)(j + m * NT) * a.nx], x);
                 }
                 if (a.has_b) {
                     x = mul_factor<TM>(x, combine_factor<TM>(fxb, __ldg(&a.yb[oy + m * NT])));
@@ -329,6 +335,12 @@ template <typename T> struct RowArgs {
     const double* totals;          // [B][4], T at [0]
     double norm_c;                 // N_atoms / (dv_r * nx * ny)
     Scatter<C> sc;                 // slab mode: fused exchange on the store (non-FAST kernels only)
+    // non-FAST kernels, stand-alone inverse of an un-normalised k-space state (per-step energy tracking): the output
+    // is also multiplied by sqrt(scale_num / (scale_tot[b][1] + scale_tot[b][2])) — ttools.norm with the sums the
+    // junction pass left on the device — and the per-component maxima of |out|^2 are folded into maxbits[b][2]
+    // (bits of non-negative doubles: integer max == floating-point max, order independent; zeroed by the caller)
+    const double* scale_tot; double scale_num;
+    unsigned long long* maxbits;
 };
 
 // 2x2 coupling operator (reference tensor_tools.py:586-590) for theta = Omega*tc and exp(i phi) = ph
@@ -505,7 +517,30 @@ __global__ void __launch_bounds__(RPC * N / E, row_min_blocks<T>(RPC * N / E)) r
     }   // pass loop
     SGPE_MARK(4);
 
-    const T sc = FAST ? (T)1 : (T)a.scale_out;
+    T sc = FAST ? (T)1 : (T)a.scale_out;
+    if (!FAST && a.scale_tot != nullptr) {
+        const double* tot = a.scale_tot + (long long)b * 4;
+        sc = (T)((double)sc * sqrt(a.scale_num / (tot[1] + tot[2])));
+    }
+    if (!FAST && a.maxbits != nullptr) {
+        double mx0 = 0.0, mx1 = 0.0;
+        const double s2 = (double)sc * (double)sc;
+#pragma unroll
+        for (int m = 0; m < E; m++) {
+            const double d0 = ((double)v[0][m].x * v[0][m].x + (double)v[0][m].y * v[0][m].y) * s2;
+            const double d1 = ((double)v[1][m].x * v[1][m].x + (double)v[1][m].y * v[1][m].y) * s2;
+            mx0 = d0 > mx0 ? d0 : mx0; mx1 = d1 > mx1 ? d1 : mx1;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double t0 = __shfl_xor_sync(0xffffffffu, mx0, o), t1 = __shfl_xor_sync(0xffffffffu, mx1, o);
+            mx0 = t0 > mx0 ? t0 : mx0; mx1 = t1 > mx1 ? t1 : mx1;
+        }
+        if ((tid & 31) == 0) {
+            atomicMax(&a.maxbits[2 * b], (unsigned long long)__double_as_longlong(mx0));
+            atomicMax(&a.maxbits[2 * b + 1], (unsigned long long)__double_as_longlong(mx1));
+        }
+    }
     if (!FAST && a.sc.mode) {       // fused exchange: each run of `seg` columns goes to the rank that owns it
 #pragma unroll
         for (int m = 0; m < E; m++) {
@@ -1292,7 +1327,8 @@ template <typename T> struct EnergyArgs {
                                 // 2: unwrapped field = wrapped phase + 2 pi * inc (unwrap.cuh)
     const int* inc;             // mode 2: [B][2][ny][nx] multiples of 2 pi from the region merging
     const double* maxdens;
-    double* partials; unsigned* counter; double* out;        // out [B][4]: total, kin, pot, int
+    double* partials; unsigned* counter; double* out;        // out [b * out_bstride + {0..3}]: total, kin, pot, int
+    long long out_bstride;
 };
 
 SGPE_DI double sgpe_wrap_pi(double d) {
@@ -1414,7 +1450,7 @@ __global__ void __launch_bounds__(256) energy_pass(EnergyArgs<T> a) {
         cta_reduce<4>(t4, red);
         if (tid == 0) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) a.out[4 * b + q] = t4[q];
+            for (int q = 0; q < 4; q++) a.out[(long long)b * a.out_bstride + q] = t4[q];
             a.counter[b] = 0u;
         }
     }

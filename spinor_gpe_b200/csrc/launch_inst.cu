@@ -101,6 +101,7 @@ static int launch_col_w(const ColArgs<T>& a, int batch, cudaStream_t st) {
     if (!once) {
         allow_smem(col_pass<T, N, E, W, TM, 0>, smem);
         allow_smem(col_pass<T, N, E, W, TM, 1>, smem);
+        allow_smem(col_pass<T, N, E, W, TM, 2>, smem);
         ahead = resident_ctas(col_pass<T, N, E, W, TM, 1>, W * (N / E), smem);
         once = true;
     }
@@ -108,7 +109,9 @@ static int launch_col_w(const ColArgs<T>& a, int batch, cudaStream_t st) {
     ColArgs<T> a2 = a;
     if (a2.prefetch_ahead) a2.prefetch_ahead = ahead;
     const bool fast = a.do_fwd && a.do_inv && a.kin_mode == 1 && !a.sign_in && !a.sign_out && a.scale_out == 1.0;
-    if (fast) {
+    if (fast && a.aux != nullptr && a.has_a) {
+        SGPE_LAUNCH((col_pass<T, N, E, W, TM, 2>), grid, block, smem, st, a2);
+    } else if (fast) {
         SGPE_LAUNCH((col_pass<T, N, E, W, TM, 1>), grid, block, smem, st, a2);
     } else {
         SGPE_LAUNCH((col_pass<T, N, E, W, TM, 0>), grid, block, smem, st, a2);
@@ -134,7 +137,8 @@ static int launch_col_g(const ColArgs<T>& a, int batch, cudaStream_t st) {
     dim3 grid(2 * a.nx / (W * G), batch), block(G * W * (N / E));
     ColArgs<T> a2 = a;
     if (a2.prefetch_ahead) a2.prefetch_ahead = ahead;
-    const bool fast = a.do_fwd && a.do_inv && a.kin_mode == 1 && !a.sign_in && !a.sign_out && a.scale_out == 1.0;
+    const bool fast = a.do_fwd && a.do_inv && a.kin_mode == 1 && !a.sign_in && !a.sign_out && a.scale_out == 1.0 &&
+                      a.aux == nullptr;      // (the boundary-state store exists in the generic kernel only)
     if (fast) {
         SGPE_LAUNCH((col_pass<T, N, E, W, TM, 1, G>), grid, block, smem, st, a2);
     } else {

@@ -13,6 +13,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <vector>
@@ -101,6 +103,10 @@ struct sgpe_plan {
     double pending_dt = 0;
     bool scale_pending = false;
     double* pend_pops = nullptr; long long pend_stride = 0; int pend_slot = -1;
+    // per-step energy tracking (sgpe_full_steps_energy): where the energy of the step boundary that the NEXT junction
+    // pass materialises goes (slot < 0: none), and how it is evaluated
+    double* pend_energy = nullptr; long long pend_estride = 0; int pend_eslot = -1;
+    int track_unwrap = 0; double track_kl = 0.0;
     uint64_t launches = 0;
     // optional per-kernel timing (sgpe_profile_*): event pairs around column (kind 0) / row (kind 1) passes
     bool prof_on = false;
@@ -226,7 +232,7 @@ void invalidate_tables(sgpe_plan::FactorTable* slots, int n) { for (int i = 0; i
 template <typename T>
 int run_col(sgpe_plan* p, const void* in, void* out, bool fwd, bool has_a, double tau_a, bool has_b, double tau_b,
             bool inv, int sign_in, int sign_out, double scale_out, double* pops, long long pops_stride,
-            int pops_slot, cudaStream_t st) {
+            int pops_slot, cudaStream_t st, void* aux = nullptr) {
     typedef typename sgpe::cx_of<T>::type C;
     ColArgs<T> a;
     memset(&a, 0, sizeof(a));
@@ -259,6 +265,7 @@ int run_col(sgpe_plan* p, const void* in, void* out, bool fwd, bool has_a, doubl
     a.partials = p->partials; a.counter = p->counter; a.totals = p->totals;
     a.pops = pops; a.pops_bstride = pops_stride; a.pops_slot = pops_slot;
     a.atom_num = p->atom_num;
+    a.aux = static_cast<C*>(aux);
     ProfScope prof(p, 0, st);
     int rc = sgpe::launch_col(p->ny, p->dtype, p->tm, &a, p->batch, p->col_wsel, st);
     if (rc == -3) return fail(SGPE_EINVAL, "column pass variant not compiled in (build with -DSGPE_EXPERIMENTAL)");
@@ -271,7 +278,8 @@ int run_col(sgpe_plan* p, const void* in, void* out, bool fwd, bool has_a, doubl
 template <typename T>
 int run_row(sgpe_plan* p, const void* in, void* out, bool inv, bool pw, double dt_sub, bool fwd, int sign_in,
             int sign_out, double scale_out, cudaStream_t st, const double* totals_override = nullptr,
-            double norm_points = 0.0, bool scatter = false) {
+            double norm_points = 0.0, bool scatter = false, const double* scale_tot = nullptr, double scale_num = 0.0,
+            double* maxdens = nullptr) {
     typedef typename sgpe::cx_of<T>::type C;
     RowArgs<T> a;
     memset(&a, 0, sizeof(a));
@@ -304,6 +312,8 @@ int run_row(sgpe_plan* p, const void* in, void* out, bool inv, bool pw, double d
     a.totals = totals_override ? totals_override : p->totals;
     a.norm_c = p->atom_num / (p->dv_r * (norm_points > 0 ? norm_points : (double)p->nx * (double)p->ny));
     fill_scatter(p, scatter, &a.sc);
+    a.scale_tot = scale_tot; a.scale_num = scale_num;
+    a.maxbits = reinterpret_cast<unsigned long long*>(maxdens);
     ProfScope prof(p, 1, st);
     int rc = sgpe::launch_row(p->nx, p->dtype, p->tm, &a, p->batch, p->row_mode, st);
     if (rc == -3) return fail(SGPE_EINVAL, "row pass variant not compiled in (build with -DSGPE_EXPERIMENTAL)");
@@ -323,11 +333,21 @@ int ready_to_step(sgpe_plan* p) {
     return 0;
 }
 
+int energy_of_boundary(sgpe_plan* p, cudaStream_t st);
+
 int single_step_impl(sgpe_plan* p, double dt_sub, cudaStream_t st) {
     const bool mid = (p->phase == sgpe_plan::MID);
     const bool want_s = mid && p->pend_pops != nullptr && p->pend_slot >= 0;
+    const bool want_e = mid && p->pend_energy != nullptr && p->pend_eslot >= 0;
     int rc;
-    if (!mid) {
+    if (want_e) {
+        // energy tracking: the junction also stores the boundary state (after the trailing half-step) on the side;
+        // that needs the two factors separately in real time as well
+        rc = SGPE_BY_DTYPE(p, run_col, p, p->state, p->state, true, true, p->pending_dt / 2, true, dt_sub / 2, true,
+                           0, 0, 1.0, want_s ? p->pend_pops : nullptr, p->pend_stride, want_s ? p->pend_slot : -1, st,
+                           p->scratch);
+        if (!rc) rc = energy_of_boundary(p, st);
+    } else if (!mid) {
         // leading kinetic half-step only (tensor_propagator.py:242)
         rc = SGPE_BY_DTYPE(p, run_col, p, p->state, p->state, false, false, 0.0, true, dt_sub / 2, true, 0, 0, 1.0,
                            nullptr, 0, -1, st);
@@ -354,9 +374,11 @@ int single_step_impl(sgpe_plan* p, double dt_sub, cudaStream_t st) {
 
 int close_junction(sgpe_plan* p, cudaStream_t st) {
     if (p->phase != sgpe_plan::MID) return 0;
+    const bool want_e = p->pend_energy != nullptr && p->pend_eslot >= 0;
     int rc = SGPE_BY_DTYPE(p, run_col, p, p->state, p->state, true, true, p->pending_dt / 2, false, 0.0, false, 0, 0,
-                           1.0, p->pend_pops, p->pend_stride, p->pend_slot, st);
+                           1.0, p->pend_pops, p->pend_stride, p->pend_slot, st, want_e ? p->scratch : nullptr);
     if (rc) return rc;
+    if (want_e && (rc = energy_of_boundary(p, st))) return rc;
     p->pend_slot = -1;
     p->phase = sgpe_plan::KSPACE;
     p->scale_pending = true;
@@ -415,14 +437,15 @@ int run_kinetic(sgpe_plan* p, const void* psik, double* out, cudaStream_t st) {
 }
 
 template <typename T>
-int run_energy(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, double* out, cudaStream_t st) {
+int run_energy(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, double* out, cudaStream_t st,
+               long long out_bstride = 4, bool have_maxdens = false) {
     typedef typename sgpe::cx_of<T>::type C;
     sgpe::MaxDensArgs<T> m;
     m.psi = static_cast<const C*>(psi); m.plane = p->plane;
     m.partials = p->partials; m.counter = p->counter; m.maxdens = p->maxdens;
     long long blocks = (p->plane + 256 * 8 - 1) / (256 * 8);
     if (blocks > 1024) blocks = 1024;
-    {
+    if (!have_maxdens) {
         dim3 grid((unsigned)blocks, p->batch), block(256);
         SGPE_LAUNCH((sgpe::maxdens_pass<T>), grid, block, 256 * 2 * sizeof(double), st, m);
         p->launches++;
@@ -442,6 +465,7 @@ int run_energy(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, d
     a.unwrap_mode = unwrap_mode;
     a.inc = p->unwrap_inc;
     a.maxdens = p->maxdens; a.partials = p->partials; a.counter = p->counter; a.out = out;
+    a.out_bstride = out_bstride;
     long long tiles = (long long)(p->nx / 32) * (p->ny / 8);
     blocks = tiles < 888 ? tiles : 888;                     // six 256-thread CTAs per SM x 148 SMs
     if (blocks > p->max_tiles / 2) blocks = p->max_tiles / 2;   // four partial sums per CTA in `partials`
@@ -512,8 +536,21 @@ struct UnwrapBuffers {                       // device scratch of one unwrap cal
 
 unsigned unwrap_blocks(long long n) { long long b = (n + 255) / 256; return (unsigned)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b)); }
 
+int unwrap_increments_impl(sgpe_plan* p, const double* phi_dev, int nplanes, int* inc_dev, cudaStream_t st);
+
 // phi_dev: nplanes x [ny][nx] wrapped phases -> inc_dev: nplanes x [ny][nx] multiples of 2 pi.  Synchronises st.
+// (host containers and threads live behind this call: nothing may throw across the C boundary)
 int unwrap_increments(sgpe_plan* p, const double* phi_dev, int nplanes, int* inc_dev, cudaStream_t st) {
+    try {
+        return unwrap_increments_impl(p, phi_dev, nplanes, inc_dev, st);
+    } catch (const std::bad_alloc&) {
+        return fail(SGPE_ENOMEM, "phase unwrapping: host allocation failed");
+    } catch (const std::exception& e) {
+        return fail(SGPE_ECUDA, std::string("phase unwrapping: ") + e.what());
+    }
+}
+
+int unwrap_increments_impl(sgpe_plan* p, const double* phi_dev, int nplanes, int* inc_dev, cudaStream_t st) {
     const int nx = p->nx, ny = p->ny;
     const size_t plane = (size_t)p->plane;
     const size_t n_edges = (size_t)ny * (nx - 1) + (size_t)nx * (ny - 1);
@@ -791,6 +828,26 @@ static int run_unpack(sgpe_plan* p, const void* in, void* out, int P, int Bh, in
     return 0;
 }
 
+// Energy of the step boundary whose un-normalised k-space state the junction pass just stored to `scratch` (and whose
+// norm sums it left in `totals`): inverse transform on the side with ttools.norm folded into the last pass (device-side
+// scale) and the per-component density maxima gathered by the same pass, then the stencil pass.  Three launches and
+// no close / re-open of the junction, against six for sgpe_energy(NULL) between two sgpe_full_steps calls.
+int energy_of_boundary(sgpe_plan* p, cudaStream_t st) {
+    const double norm = p->dx * p->dy / (2.0 * M_PI);
+    double* out = p->pend_energy + 4LL * p->pend_eslot;
+    SGPE_CUDA(cudaMemsetAsync(p->maxdens, 0, sizeof(double) * 2 * p->batch, st));
+    int rc = SGPE_BY_DTYPE(p, run_col, p, p->scratch, p->scratch, false, false, 0.0, false, 0.0, true, 0, 0, 1.0, nullptr,
+                           0, -1, st);
+    if (rc) return rc;
+    rc = SGPE_BY_DTYPE(p, run_row, p, p->scratch, p->scratch, true, false, 0.0, false, 0, 3,
+                       1.0 / (norm * (double)p->nx * (double)p->ny), st, nullptr, 0.0, false, p->totals,
+                       p->atom_num / p->dv_k, p->maxdens);
+    if (rc) return rc;
+    rc = SGPE_BY_DTYPE(p, run_energy, p, p->scratch, p->track_unwrap, p->track_kl, out, st, p->pend_estride, true);
+    p->pend_eslot = -1;
+    return rc;
+}
+
 }  // namespace
 
 extern "C" {
@@ -950,7 +1007,7 @@ int sgpe_load_psik(sgpe_plan* p, const void* psik, sgpe_stream st) {
     DeviceGuard guard(p->device);
     SGPE_CUDA(cudaMemcpyAsync(p->state, psik, (size_t)p->batch * 2 * p->plane * p->csize, cudaMemcpyDeviceToDevice,
                               (cudaStream_t)st));
-    p->phase = sgpe_plan::KSPACE; p->scale_pending = false; p->pend_slot = -1;
+    p->phase = sgpe_plan::KSPACE; p->scale_pending = false; p->pend_slot = -1; p->pend_eslot = -1;
     return 0;
 }
 
@@ -991,6 +1048,32 @@ int sgpe_full_steps(sgpe_plan* p, int n, double* pops, int64_t pops_stride, int 
         p->pend_pops = pops; p->pend_stride = pops_stride; p->pend_slot = pops ? pops_first + i : -1;
     }
     // close the last junction so that the populations of the final step are recorded before returning
+    if (n > 0 && (rc = close_junction(p, s))) return rc;
+    return 0;
+}
+
+int sgpe_full_steps_energy(sgpe_plan* p, int n, double* pops, int64_t pops_stride, int pops_first, double* energy,
+                           int64_t energy_stride, int energy_first, int unwrap_mode, double kl_term, sgpe_stream st) {
+    int rc = ready_to_step(p);
+    if (rc) return rc;
+    if (n < 0) return fail(SGPE_EINVAL, "negative step count");
+    if (!energy) return fail(SGPE_EINVAL, "null energy buffer (use sgpe_full_steps)");
+    if (unwrap_mode != 0 && unwrap_mode != 1)
+        return fail(SGPE_EINVAL, "per-step tracking stays on the device: unwrap_mode 0 or 1 (sgpe_energy offers 2)");
+    DeviceGuard guard(p->device);
+    cudaStream_t s = (cudaStream_t)st;
+    const size_t bytes = (size_t)p->batch * 2 * p->plane * p->csize;
+    if (!p->scratch && cudaMalloc(&p->scratch, bytes) != cudaSuccess) return fail(SGPE_ENOMEM, "scratch allocation failed");
+    if (!p->maxdens && cudaMalloc((void**)&p->maxdens, sizeof(double) * 2 * p->batch) != cudaSuccess)
+        return fail(SGPE_ENOMEM, "scratch allocation failed");
+    p->track_unwrap = unwrap_mode; p->track_kl = kl_term;
+    for (int i = 0; i < n; i++) {
+        if ((rc = single_step_impl(p, p->dt_out, s))) return rc;
+        if ((rc = single_step_impl(p, p->dt_in, s))) return rc;
+        if ((rc = single_step_impl(p, p->dt_out, s))) return rc;
+        p->pend_pops = pops; p->pend_stride = pops_stride; p->pend_slot = pops ? pops_first + i : -1;
+        p->pend_energy = energy; p->pend_estride = energy_stride; p->pend_eslot = energy_first + i;
+    }
     if (n > 0 && (rc = close_junction(p, s))) return rc;
     return 0;
 }
@@ -1346,7 +1429,7 @@ int sgpe_run_host(sgpe_plan* p, const void* psik_in, void* psik_out, int n_steps
         p->pops_cap = pops_n;
     }
     SGPE_CUDA(cudaMemcpyAsync(p->state, psik_in, bytes, cudaMemcpyHostToDevice, s));
-    p->phase = sgpe_plan::KSPACE; p->scale_pending = false; p->pend_slot = -1;
+    p->phase = sgpe_plan::KSPACE; p->scale_pending = false; p->pend_slot = -1; p->pend_eslot = -1;
     int rc = sgpe_full_steps(p, n_steps, pops_host ? p->pops_buf : nullptr, 2LL * n_steps, 0, st);
     if (rc) return rc;
     rc = sgpe_store_psik(p, p->state, st);

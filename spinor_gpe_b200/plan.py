@@ -164,14 +164,22 @@ class Plan:
     def single_step(self, dt_sub):
         self._chk(self.lib.sgpe_single_step(self.h, float(dt_sub), self.stream), 'sgpe_single_step')
 
-    def full_steps(self, n, pops=None, first=0):
-        """pops: optional float64 CUDA tensor (B, n_total, 2); step i writes row first+i."""
+    def full_steps(self, n, pops=None, first=0, energy=None, kl_term=0.0, unwrap='none'):
+        """pops: optional float64 CUDA tensor (B, n_total, 2); step i writes row first+i.  energy: optional float64
+        CUDA tensor (B, n_total, 4) — the energy expectation [E_total, E_kin, E_pot, E_int] of every step boundary
+        (row first+i), evaluated behind the junction passes (``unwrap`` 'none' or 'local'; no synchronisation)."""
         stride = 0
         if pops is not None:
             assert pops.is_cuda and pops.dtype == torch.float64 and pops.is_contiguous()
             stride = pops.shape[1] * 2
-        self._chk(self.lib.sgpe_full_steps(self.h, int(n), _dp(pops), stride, int(first), self.stream),
-                  'sgpe_full_steps')
+        if energy is None:
+            self._chk(self.lib.sgpe_full_steps(self.h, int(n), _dp(pops), stride, int(first), self.stream),
+                      'sgpe_full_steps')
+            return
+        assert energy.is_cuda and energy.dtype == torch.float64 and energy.is_contiguous() and energy.shape[-1] == 4
+        self._chk(self.lib.sgpe_full_steps_energy(self.h, int(n), _dp(pops), stride, int(first), _dp(energy),
+                                                  energy.shape[1] * 4, int(first), UNWRAP_MODES[unwrap], float(kl_term),
+                                                  self.stream), 'sgpe_full_steps_energy')
 
     def run_host(self, psik_host, n_steps, want_pops=True, out=None, pops=None):
         """Host-buffer path (H2D + steps + D2H inside the call).  psik_host: CPU tensor/ndarray.  ``out`` / ``pops``:

@@ -19,6 +19,7 @@ class PropResult:
         self.eng_final = eng_final
         self.pops = pops
         self.sampled_path = sampled_path
+        self.eng_history = None      # (n_steps, 4) when the propagator tracked the energy of every step (extension)
 
         self.dens = ttools.density(self.psi)
         self.densk = ttools.density(self.psik)

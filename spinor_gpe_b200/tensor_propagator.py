@@ -98,8 +98,15 @@ class TensorPropagator:
 
     # pylint: disable=too-many-instance-attributes
     def __init__(self, spin, t_step, n_steps, device='cuda', time='imag', is_sampling=False, n_samples=1,
-                 precision='c128', progress=False, separable='auto', unwrap=None, long_lines=None):
+                 precision='c128', progress=False, separable='auto', unwrap=None, long_lines=None,
+                 track_energy=False):
         dev = torch.device(device)
+        # track_energy: prop_loop also records eng_expect of every step (PropResult.eng_history, (n_steps, 4)); pass
+        # 'none' or 'local' to choose the phase treatment (True = 'none'); it stays on the device, so the reference's
+        # host-side unwrapping is not available per step
+        self.track_energy = 'none' if track_energy is True else (track_energy or None)
+        if self.track_energy not in (None, 'none', 'local'):
+            raise ValueError("track_energy must be False, True, 'none' or 'local'")
         self.unwrap = DEFAULT_UNWRAP if unwrap is None else unwrap
         if self.unwrap not in ('none', 'local', 'herraez'):
             raise ValueError("unwrap must be 'none', 'local' or 'herraez'")
@@ -285,6 +292,13 @@ class TensorPropagator:
         energy; returns a PropResult."""
         pop_times = np.linspace(0, self.n_steps * np.abs(self.t_step), n_steps)
         pops_dev = torch.zeros((1, max(n_steps, 1), 2), dtype=torch.float64, device=self._dev)
+        track = {}
+        if self.track_energy is not None:
+            if self._long:
+                raise NotImplementedError("per-step energy tracking is not available on long-line meshes")
+            eng_dev = torch.zeros((1, max(n_steps, 1), 4), dtype=torch.float64, device=self._dev)
+            track = dict(energy=eng_dev, kl_term=2 * self.kL_recoil * float(bool(self.is_coupling)),
+                         unwrap=self.track_energy)
         done = 0
         if self.is_sampling:
             n_samples = int(n_steps / self.sample_rate)
@@ -298,10 +312,10 @@ class TensorPropagator:
             for idx in chunks:                               # sample BEFORE the step (:186-189)
                 snap = self._plan.store()
                 sampled_host[idx].copy_(snap[0].to(torch.complex128), non_blocking=True)
-                self._plan.full_steps(rate, pops_dev, first=done)
+                self._plan.full_steps(rate, pops_dev, first=done, **track)
                 done += rate
         if done < n_steps:
-            self._plan.full_steps(n_steps - done, pops_dev, first=done)
+            self._plan.full_steps(n_steps - done, pops_dev, first=done, **track)
         self._psik_cache = None
 
         energy = self.eng_expect(None)
@@ -324,7 +338,10 @@ class TensorPropagator:
             psi_dev = ttools.ifft_2d(psik_dev, self._dr)
         psik = ttools.to_numpy(psik_dev)
         psi = ttools.to_numpy(psi_dev)
-        return PropResult(psi, psik, energy, pops, file_name)
+        result = PropResult(psi, psik, energy, pops, file_name)
+        if track:
+            result.eng_history = track['energy'][0, :n_steps].cpu().numpy().copy()
+        return result
 
     def eng_expect(self, psik=None, unwrap=None):
         """tensor_propagator.py:273-324 — [<total>, <kin>, <pot>, <int>] (raw grid sums), on the GPU.

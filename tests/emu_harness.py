@@ -127,6 +127,13 @@ class EmuPlan:
         self._chk(self.lib.sgpe_full_steps(self.h, n, _ptr(pops), 2 * n, 0, None), 'full_steps')
         return pops
 
+    def full_steps_energy(self, n, kl_term=0.0, unwrap=0):
+        pops = np.zeros((self.batch, n, 2))
+        eng = np.zeros((self.batch, n, 4))
+        self._chk(self.lib.sgpe_full_steps_energy(self.h, n, _ptr(pops), 2 * n, 0, _ptr(eng), 4 * n, 0, unwrap, kl_term,
+                                                  None), 'full_steps_energy')
+        return pops, eng
+
     def fft2d(self, arr, inverse=False):
         a = self._state(arr)
         out = np.empty_like(a)

@@ -176,6 +176,36 @@ def test_emulated_spectral_kinetic_energy(separable):
     pl.close()
 
 
+@pytest.mark.parametrize('case,run', [('nocoupl_64', 0), ('cgrad_64', 0), ('cgrad_64', 1)])
+@pytest.mark.parametrize('separable', [False, True])
+def test_emulated_energy_tracking(case, run, separable):
+    """sgpe_full_steps_energy: the energy of every step boundary, evaluated from the state the junction pass stores on
+    the side, equals the oracle's eng_expect after each full step (and state / populations are unaffected)."""
+    z = np.load(os.path.join(GOLDEN, case + '.npz'))
+    pre = f'r{run}_'
+    prob = orc.Problem.from_golden(z, pre)
+    mode, dt, n = str(z[pre + 'mode']), float(z[pre + 'dt']), int(z[pre + 'n_steps'])
+    kl = 2 * prob.kL * prob.is_coupling
+    pl = plan_from_problem(prob, mode, dt, separable=separable)
+    pops, eng = pl.full_steps_energy(n, kl, 0)
+    assert rel(pl.store()[0], z[pre + 'psik_final']) < 1e-12
+    np.testing.assert_allclose(pops[0], z[pre + 'pops_vals'], rtol=1e-12)
+    o = orc.OraclePropagator(prob, dt, mode)
+    for i in range(n):
+        o.full_step()
+        np.testing.assert_allclose(eng[0, i], orc.energy(prob, o.psik), rtol=1e-10, err_msg=f'step {i}')
+    np.testing.assert_allclose(eng[0, -1], z[pre + 'energy_identity_unwrap'], rtol=1e-10)
+    # a second call continues (the first junction of the call emits nothing stale), 'local' differences are accepted
+    pops2, eng2 = pl.full_steps_energy(2, kl, 1)
+    o.full_step()
+    o.full_step()
+    assert rel(pl.store()[0], o.psik.numpy()) < 1e-12
+    assert np.isfinite(eng2).all()
+    with pytest.raises(Exception):
+        pl.full_steps_energy(1, kl, 2)              # host-side unwrapping is not available per step
+    pl.close()
+
+
 def test_separability_detection():
     from spinor_gpe_b200._separable import split_separable
     y, x = np.meshgrid(np.linspace(-1, 1, 32), np.linspace(-2, 2, 64), indexing='ij')
@@ -224,6 +254,23 @@ def test_emulated_batch_of_two():
     for b in range(2):
         assert rel(out[b], want[b]['psik']) < 1e-12
         np.testing.assert_allclose(pops[b], want[b]['pops_vals'], rtol=1e-12)
+    # energies of the whole batch (per-trajectory potential and coupling; unwrapping: 2 x batch planes, one host
+    # thread each) == the same state evaluated in a one-trajectory plan
+    kl = 2 * base.kL * base.is_coupling
+    for mode in (0, 1, 2):
+        e_batch = pl.energy(out, kl, mode)
+        for b in range(2):
+            one = EmuPlan(nx, ny)
+            one.set_grid(base.dr[0], base.dr[1], base.dv_r, base.dv_k, base.atom_num)
+            one.set_interactions((base.g_uu, base.g_dd, base.g_ud))
+            one.set_kinetic(base.kin.numpy())
+            one.set_potential(pots[b])
+            one.set_coupling(_capi.SGPE_COUPLING_UNIFORM, omega=np.array([omegas[b]]))
+            np.testing.assert_allclose(e_batch[b], one.energy(out[b], kl, mode)[0], rtol=1e-13)
+            one.close()
+    np.testing.assert_allclose(pl.kinetic_spectral(out),
+                               [[(base.kin[c].numpy() * np.abs(out[b, c]) ** 2).sum() * base.dv_k for c in range(2)]
+                                for b in range(2)], rtol=1e-13)
     pl.close()
 
 

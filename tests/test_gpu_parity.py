@@ -256,6 +256,32 @@ def test_energy_of_ground_state_against_oracle():
     np.testing.assert_allclose(prop.eng_expect(None, unwrap='local'), want['energy'], rtol=1e-6)
 
 
+@pytest.mark.parametrize('mode,dt,cpl', [('imag', 1 / 50, 'zero'), ('real', 1 / 2000, 'uniform'), ('real', 1 / 2000, 'dense')])
+def test_energy_tracking_every_step(mode, dt, cpl):
+    """PSpinor.imaginary/real(track_energy=True): PropResult.eng_history against the oracle's eng_expect after every
+    full step (wrapped phase), final state and populations unaffected."""
+    ps = make_ps((256, 128), atom_num=1e4, r_sizes=(16, 16), g_sc={'uu': 1, 'dd': 0.98, 'ud': 1.02},
+                 pop_frac=(0.6, 0.4), phase_factor=1j)
+    ps.coupling_setup(wavel=790.1e-9, kin_shift=(cpl != 'zero'))
+    if cpl == 'uniform':
+        ps.coupling_uniform(1.5 * ps.EL_recoil)
+    elif cpl == 'dense':
+        ps.coupling_grad(slope=0.3, offset=2.0, axis=1)
+    rng = np.random.default_rng(7)
+    ps.psik = [p * (1 + 0.05 * (rng.standard_normal(p.shape) + 1j * rng.standard_normal(p.shape))) for p in ps.psik]
+    prob = problem_of(ps)
+    n = 5
+    o = orc.OraclePropagator(prob, dt, mode)
+    want = []
+    for _ in range(n):
+        o.full_step()
+        want.append(orc.energy(prob, o.psik))
+    res, prop = (ps.imaginary if mode == 'imag' else ps.real)(dt, n, 'cuda', track_energy=True, unwrap='none')
+    assert rel(np.array(res.psik), o.psik.numpy()) < TOL_PSI
+    np.testing.assert_allclose(res.eng_history, np.array(want), rtol=TOL_SCALAR)
+    np.testing.assert_allclose(res.eng_history[-1], res.eng_final, rtol=TOL_SCALAR)
+
+
 def test_spectral_kinetic_energy():
     """TensorPropagator.kin_expect_spectral against NumPy on the same state (dense and separable operators)."""
     ps = make_ps((256, 128), atom_num=1e4, r_sizes=(16, 16))
