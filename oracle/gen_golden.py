@@ -116,6 +116,25 @@ CASES = {
                ('detuning_uniform', dict(value=0.8))],
         attrs=dict(rot_coupling=False),
         runs=[('real', 1 / 1000, 8), ('imag', 1 / 100, 4)]),
+    # Vortices imprinted on both components (seed_vortices, pspinor.py:680-745), no Raman coupling, real time:
+    # phase singularities, zeros of the density inside the cloud
+    'vortex_64': dict(
+        ctor=dict(atom_num=2e3, omeg={'x': W0, 'y': W0, 'z': 40 * W0},
+                  g_sc={'uu': 1, 'dd': 0.97, 'ud': 0.9}, pop_frac=(0.5, 0.5), r_sizes=(10, 10),
+                  mesh_points=(64, 64)),
+        setup=[('seed_vortices', dict(positions=[[1.5, 0.5], [-2.0, 1.0], [0.3, -2.2]], windings=[1, -1, 2]))],
+        attrs=dict(),
+        runs=[('real', 1 / 400, 8)]),
+    # Time of flight (example 2): relax in an anisotropic trap, switch the trap off, expand in real time
+    'tof_32x64': dict(
+        ctor=dict(atom_num=1e4, omeg={'x': W0, 'y': 4 * W0, 'z': 40 * W0},
+                  g_sc={'uu': 1, 'dd': 1, 'ud': 0.5}, pop_frac=(0.5, 0.5), r_sizes=(16, 16),
+                  mesh_points=(32, 64)),
+        setup=[('coupling_setup', dict(wavel=790.1e-9))],
+        attrs=dict(rand_seed=99999),
+        runs=[('imag', 1 / 50, 6),
+              ('zero', 'pot_eng'),
+              ('real', 1 / 500, 8)]),
 }
 
 
@@ -161,6 +180,9 @@ def run_case(name, spec, ref_spin, ref_tprop, ref_tt, out_dir):
         if run[0] == 'call':
             arg = _resolve(ps, run[2])
             getattr(ps, run[1])(*arg)
+            continue
+        if run[0] == 'zero':                       # e.g. ps.pot_eng = zeros: the trap is switched off
+            setattr(ps, run[1], np.zeros_like(getattr(ps, run[1])))
             continue
         mode, dt, n = run
         pre = f'r{run_idx}_'
