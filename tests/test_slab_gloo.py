@@ -61,6 +61,16 @@ def _worker(rank, world, port, outdir, mode, splits=(None, None), mesh=(128, 64)
         assert err < 1e-12, err
         np.testing.assert_allclose(pops.numpy(), want['pops_vals'], rtol=1e-12)
         assert sp.a2a_bytes > 0
+        if given and (mesh[0] * mesh[1] <= 128 * 64 or splits[1]):
+            # distributed inverse transform to real space (ttools.ifft_2d of the state): this rank's rows, and the
+            # k-space state is left untouched
+            rows = sp.real_space_rows().numpy()
+            nyl = mesh[1] // world
+            want_rows = want['psi'][:, rank * nyl:(rank + 1) * nyl]
+            err = np.linalg.norm(rows - want_rows) / np.linalg.norm(want_rows)
+            assert err < 1e-12, err
+            again = sp.gather_psik().numpy()
+            assert np.linalg.norm(again - want['psik']) / np.linalg.norm(want['psik']) < 1e-12
     finally:
         dist.destroy_process_group()
 
