@@ -287,7 +287,7 @@ def run_ours(args, rank, world, local_rank):
     t_e0, t_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_e = max(1, min(args.steps, 50))
     eng = torch.zeros((1, n_e, 4), dtype=torch.float64, device=dev)
-    pl.full_steps(2, pops, first=0, energy=eng, kl_term=2 * ps.kL_recoil)          # first-use allocations
+    pl.full_steps(min(2, n_e), pops, first=0, energy=eng, kl_term=2 * ps.kL_recoil)    # first-use allocations
     barrier()
     t_e0.record()
     pl.full_steps(n_e, pops, first=0, energy=eng, kl_term=2 * ps.kL_recoil)
