@@ -77,6 +77,12 @@ int sgpe_set_potential_separable(sgpe_plan* p, const double* pot_x_dev, const do
  *                  coupling is in the rotating frame (expon = 0, tensor_propagator.py:126-127). */
 int sgpe_set_coupling(sgpe_plan* p, int mode, const double* coupling_dev, int64_t batch_stride,
                       const double* omega_dev, const void* eiphi_dev);
+/* Coupling grid of the energy expectation when it is not the one the stepping applies: the reference's eng_expect
+ * adds Re(conj(psi0) psi1) * coupling from `self.coupling` whatever `is_coupling` says (tensor_propagator.py:319-321),
+ * while single_step applies the coupling operator only if is_coupling (:252, :258).  mode as in sgpe_set_coupling
+ * (the Raman phase plays no role in the energy); -1 = follow sgpe_set_coupling (default). */
+int sgpe_set_energy_coupling(sgpe_plan* p, int mode, const double* coupling_dev, int64_t batch_stride,
+                             const double* omega_dev);
 /* Tuning knobs.  "col_tile": 0 = default column-tile width (64-byte global segments, one CTA per SM at
  * 2048 points), 2 = half width (two CTAs per SM). */
 int sgpe_set_option(sgpe_plan* p, const char* name, int value);
@@ -246,7 +252,8 @@ int sgpe_step_accounting(const sgpe_plan* p, uint64_t* algorithmic_bytes, uint64
  * launch counts per kind (used by bench.py for the roofline of the dominant kernel). */
 int sgpe_profile_begin(sgpe_plan* p);
 int sgpe_profile_end(sgpe_plan* p, double* ms_col, uint64_t* n_col, double* ms_row, uint64_t* n_row);
-/* Dev tool: when buf_dev != NULL every row-pass CTA writes 8 uint64 (globaltimer at 6 phase boundaries, -, SM id). */
+/* Dev tool: when buf_dev != NULL every row-pass CTA (column-pass CTA after sgpe_set_option("timeline_kind", 1)) writes
+ * 8 uint64 (globaltimer at 6 phase boundaries, -, SM id). */
 int sgpe_debug_timeline(sgpe_plan* p, unsigned long long* buf_dev);
 /* Number of kernels this plan has launched since creation. */
 int sgpe_launch_count(const sgpe_plan* p, uint64_t* launches);

@@ -18,6 +18,7 @@ PROTOTYPES = {
     'sgpe_set_kinetic_separable': (C.c_int, [c_plan, c_dptr, c_dptr, C.c_int64, C.c_int64]),
     'sgpe_set_potential_separable': (C.c_int, [c_plan, c_dptr, c_dptr, C.c_int64, C.c_int64]),
     'sgpe_set_coupling': (C.c_int, [c_plan, C.c_int, c_dptr, C.c_int64, c_dptr, c_dptr]),
+    'sgpe_set_energy_coupling': (C.c_int, [c_plan, C.c_int, c_dptr, C.c_int64, c_dptr]),
     'sgpe_set_option': (C.c_int, [c_plan, C.c_char_p, C.c_int]),
     'sgpe_set_time': (C.c_int, [c_plan, C.c_int, C.c_double]),
     'sgpe_load_psik': (C.c_int, [c_plan, c_dptr, c_stream]),

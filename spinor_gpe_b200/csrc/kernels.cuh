@@ -126,6 +126,7 @@ template <typename T> struct ColArgs {
     double* totals;                // [B][4] : T, S0, S1, -
     double* pops; long long pops_bstride; int pops_slot;   // [B][n][2], slot < 0: don't record
     double atom_num;
+    unsigned long long* dbg;       // dev tool: per-CTA phase timestamps [nCTA][8] (null in production; generic kernel only)
     C* aux;                        // optional second output [B][2][ny][nx]: the state right after FA — at a full-step
                                    // junction that is the (un-normalised) k-space state of the step boundary, which
                                    // per-step energy tracking transforms back on the side (sgpe_full_steps_energy)
@@ -174,6 +175,9 @@ __global__ void __launch_bounds__(G * W * N / E, (G * W * N / E <= 256) ? 2 : 1)
     const int sign_in = FAST ? 0 : a.sign_in, sign_out = FAST ? 0 : a.sign_out;
     const long long off = ((long long)b * 2 + comp) * a.plane + col;
 
+#define SGPE_CMARK(k) do { if (!FAST && a.dbg != nullptr && tid == 0 && g == 0) a.dbg[(long long)blockIdx.x * 8 + (k)] = SGPE_GLOBALTIMER(); } while (0)
+    if (!FAST && a.dbg != nullptr && tid == 0 && g == 0) a.dbg[(long long)blockIdx.x * 8 + 7] = SGPE_SMID();
+    SGPE_CMARK(0);
     C v[1][E];
 #pragma unroll
     for (int m = 0; m < E; m++) v[0][m] = SGPE_LD_STREAM(&a.in[off + (long long)(j + m * NT) * a.nx]);
@@ -192,11 +196,13 @@ __global__ void __launch_bounds__(G * W * N / E, (G * W * N / E <= 256) ? 2 : 1)
     }
 
     C* const sms[1] = {sm};
+    if (!FAST && a.dbg != nullptr) { if (v[0][0].x == (T)1.2345e300 || v[0][E - 1].y == (T)1.2345e300) a.dbg[6] = 1; SGPE_CMARK(1); }
     // (the two-iteration-loop trick of row_pass was measured slower here: 16 elements per thread, more spills)
     if (do_fwd) {
         if constexpr (G == 1) cta_fft<T, N, E, -1, W, 1>(v, j, c, sms, a.tw + (E == 16 ? N : 0));
         else group_fft<T, N, E, -1, W>(v, j, c, sms, a.tw + (E == 16 ? N : 0), gbar);
     }
+    SGPE_CMARK(2);
     double acc[2] = {0.0, 0.0};   // S (after FA), T (after FB)
     const bool any_k = a.has_a || a.has_b;
 
@@ -262,10 +268,12 @@ __global__ void __launch_bounds__(G * W * N / E, (G * W * N / E <= 256) ? 2 : 1)
         }
     }
 
+    SGPE_CMARK(3);
     if (do_inv) {
         if constexpr (G == 1) cta_fft<T, N, E, +1, W, 1>(v, j, c, sms, a.tw + (E == 16 ? N : 0));
         else group_fft<T, N, E, +1, W>(v, j, c, sms, a.tw + (E == 16 ? N : 0), gbar);
     }
+    SGPE_CMARK(4);
 
     if (!FAST && (sign_out || a.scale_out != 1.0)) {
         const T sc = (T)a.scale_out;
@@ -277,6 +285,8 @@ __global__ void __launch_bounds__(G * W * N / E, (G * W * N / E <= 256) ? 2 : 1)
     }
 #pragma unroll
     for (int m = 0; m < E; m++) SGPE_ST_STREAM(&a.out[off + (long long)(j + m * NT) * a.nx], v[0][m]);
+    SGPE_CMARK(5);
+#undef SGPE_CMARK
 
     if (any_k) {
         if (tid == 0) red[0] = (ticket == (unsigned)(nslots - 1)) ? 1.0 : 0.0;

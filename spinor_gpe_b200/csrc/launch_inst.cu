@@ -108,7 +108,8 @@ static int launch_col_w(const ColArgs<T>& a, int batch, cudaStream_t st) {
     dim3 grid(2 * a.nx / W, batch), block(W * (N / E));
     ColArgs<T> a2 = a;
     if (a2.prefetch_ahead) a2.prefetch_ahead = ahead;
-    const bool fast = a.do_fwd && a.do_inv && a.kin_mode == 1 && !a.sign_in && !a.sign_out && a.scale_out == 1.0;
+    const bool fast = a.do_fwd && a.do_inv && a.kin_mode == 1 && !a.sign_in && !a.sign_out && a.scale_out == 1.0 &&
+                      a.dbg == nullptr;
     if (fast && a.aux != nullptr && a.has_a) {
         SGPE_LAUNCH((col_pass<T, N, E, W, TM, 2>), grid, block, smem, st, a2);
     } else if (fast) {
@@ -138,7 +139,7 @@ static int launch_col_g(const ColArgs<T>& a, int batch, cudaStream_t st) {
     ColArgs<T> a2 = a;
     if (a2.prefetch_ahead) a2.prefetch_ahead = ahead;
     const bool fast = a.do_fwd && a.do_inv && a.kin_mode == 1 && !a.sign_in && !a.sign_out && a.scale_out == 1.0 &&
-                      a.aux == nullptr;      // (the boundary-state store exists in the generic kernel only)
+                      a.aux == nullptr && a.dbg == nullptr;      // (the boundary-state store exists in the generic kernel only)
     if (fast) {
         SGPE_LAUNCH((col_pass<T, N, E, W, TM, 1, G>), grid, block, smem, st, a2);
     } else {

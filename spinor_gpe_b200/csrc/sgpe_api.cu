@@ -56,7 +56,9 @@ struct sgpe_plan {
     int nx = 0, ny = 0, batch = 0, dtype = 0, device = 0;
     size_t csize = 16;
     long long plane = 0;
-    void* state = nullptr;
+    void* state = nullptr;          // working state, allocated on first use (sgpe_load_psik / sgpe_run_host): plans that only
+                                    // serve transforms / reductions (tensor_tools helpers) never pay for it
+    bool line_plan = false;         // sgpe_plan_create_lines: caller-owned buffers, no k-space state
     void* tw_x = nullptr;
     void* tw_y = nullptr;
     double* partials = nullptr;
@@ -82,6 +84,7 @@ struct sgpe_plan {
     uint64_t tab_clock = 0;
     unsigned* sm_slots = nullptr;
     unsigned long long* dbg = nullptr;   // dev tool (sgpe_debug_timeline)
+    unsigned long long* dbg_col = nullptr; int dbg_kind = 0;   // option "timeline_kind": 0 row pass, 1 column pass
     int stagger_ns = 0;            // option "stagger_ns"
     int prefetch = 1;              // L2 prefetch of the next tile of each SM (option "prefetch")
     int row_mode = 0;              // 0: both components per thread, 1: split (one component per thread)
@@ -97,6 +100,9 @@ struct sgpe_plan {
     struct Peers { void* ptr[SGPE_MAX_PEERS]; int n = 0, mode = 0, seg = 0, drow = 0, base = 0; long long dplane = 0; } peers;
     int cpl_mode = 0; const double* cpl = nullptr; long long cpl_bs = 0;
     const double* omega = nullptr; const void* eiphi = nullptr;
+    // coupling grid of the energy expectation when it differs from what the stepping applies (sgpe_set_energy_coupling):
+    // eng_expect always adds Re(conj(p0) p1) * coupling (tensor_propagator.py:319-321), the step only if is_coupling
+    int ecpl_mode = -1; const double* ecpl = nullptr; long long ecpl_bs = 0; const double* eomega = nullptr;
     int tm = SGPE_TIME_IMAG; double dt = 0, dt_out = 0, dt_in = 0;
     // state machine
     enum Phase { EMPTY, KSPACE, MID } phase = EMPTY;
@@ -266,6 +272,7 @@ int run_col(sgpe_plan* p, const void* in, void* out, bool fwd, bool has_a, doubl
     a.pops = pops; a.pops_bstride = pops_stride; a.pops_slot = pops_slot;
     a.atom_num = p->atom_num;
     a.aux = static_cast<C*>(aux);
+    a.dbg = (fwd && inv) ? p->dbg_col : nullptr;
     ProfScope prof(p, 0, st);
     int rc = sgpe::launch_col(p->ny, p->dtype, p->tm, &a, p->batch, p->col_wsel, st);
     if (rc == -3) return fail(SGPE_EINVAL, "column pass variant not compiled in (build with -DSGPE_EXPERIMENTAL)");
@@ -324,6 +331,16 @@ int run_row(sgpe_plan* p, const void* in, void* out, bool inv, bool pw, double d
 }
 
 #define SGPE_BY_DTYPE(p, fn, ...) ((p)->dtype == SGPE_C128 ? fn<double>(__VA_ARGS__) : fn<float>(__VA_ARGS__))
+
+int ensure_state(sgpe_plan* p) {
+    if (p->state) return 0;
+    if (p->line_plan) return fail(SGPE_ESTATE, "line plans work on caller-owned buffers");
+    if (cudaMalloc(&p->state, (size_t)p->batch * 2 * p->plane * p->csize) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(SGPE_ENOMEM, "device allocation of the working state failed");
+    }
+    return 0;
+}
 
 int ready_to_step(sgpe_plan* p) {
     if (!p) return fail(SGPE_EINVAL, "null plan");
@@ -458,6 +475,7 @@ int run_energy(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, d
     a.pot_mode = p->pot_mode; a.pot_x = p->pot_x; a.pot_y = p->pot_y;
     a.potx_bstride = p->pot_xbs; a.poty_bstride = p->pot_ybs;
     a.cpl_mode = p->cpl_mode; a.coupling = p->cpl; a.cpl_bstride = p->cpl_bs; a.omega_b = p->omega;
+    if (p->ecpl_mode >= 0) { a.cpl_mode = p->ecpl_mode; a.coupling = p->ecpl; a.cpl_bstride = p->ecpl_bs; a.omega_b = p->eomega; }
     a.g_uu = p->g_uu; a.g_dd = p->g_dd; a.g_ud = p->g_ud;
     a.kl2 = kl_term;
     a.inv_h0 = 1.0 / p->dx;        // np.gradient(f, dx, dy): dx goes with axis 0 (tensor_tools.py:342)
@@ -878,7 +896,6 @@ int sgpe_plan_create(sgpe_plan** out, int nx, int ny, int batch, int dtype, int 
     if (p->max_tiles < 1024) p->max_tiles = 1024;
     int rc = 0;
     do {
-        if (cudaMalloc(&p->state, (size_t)batch * 2 * p->plane * p->csize) != cudaSuccess) { rc = SGPE_ENOMEM; break; }
         if (cudaMalloc((void**)&p->partials, sizeof(double) * 2 * (size_t)p->max_tiles * batch) != cudaSuccess) { rc = SGPE_ENOMEM; break; }
         if (cudaMalloc((void**)&p->counter, sizeof(unsigned) * batch) != cudaSuccess) { rc = SGPE_ENOMEM; break; }
         if (cudaMalloc((void**)&p->totals, sizeof(double) * 4 * batch) != cudaSuccess) { rc = SGPE_ENOMEM; break; }
@@ -960,6 +977,15 @@ int sgpe_set_coupling(sgpe_plan* p, int mode, const double* coupling, int64_t bs
     return 0;
 }
 
+int sgpe_set_energy_coupling(sgpe_plan* p, int mode, const double* coupling, int64_t bs, const double* omega) {
+    if (!p) return fail(SGPE_EINVAL, "null plan");
+    if (mode < -1 || mode > 2) return fail(SGPE_EINVAL, "bad coupling mode");
+    if (mode == SGPE_COUPLING_UNIFORM && !omega) return fail(SGPE_EINVAL, "uniform coupling needs omega_dev[batch]");
+    if (mode == SGPE_COUPLING_DENSE && !coupling) return fail(SGPE_EINVAL, "dense coupling needs coupling_dev");
+    p->ecpl_mode = mode; p->ecpl = coupling; p->ecpl_bs = bs; p->eomega = omega;
+    return 0;
+}
+
 int sgpe_set_option(sgpe_plan* p, const char* name, int value) {
     if (!p || !name) return fail(SGPE_EINVAL, "null argument");
     if (std::strcmp(name, "col_tile") == 0) {
@@ -969,6 +995,7 @@ int sgpe_set_option(sgpe_plan* p, const char* name, int value) {
         return 0;
     }
     if (std::strcmp(name, "stagger_ns") == 0) { p->stagger_ns = value; return 0; }
+    if (std::strcmp(name, "timeline_kind") == 0) { p->dbg_kind = value ? 1 : 0; return 0; }
     if (std::strcmp(name, "prefetch") == 0) { p->prefetch = value ? 1 : 0; return 0; }
     if (std::strcmp(name, "unwrap_sort") == 0) {
         if (value != 0 && value != 1) return fail(SGPE_EINVAL, "unwrap_sort: 0 (device radix sort) or 1 (host sort)");
@@ -1005,6 +1032,7 @@ int sgpe_substeps(const sgpe_plan* p, double* dt_out, double* dt_in) {
 int sgpe_load_psik(sgpe_plan* p, const void* psik, sgpe_stream st) {
     if (!p || !psik) return fail(SGPE_EINVAL, "null argument");
     DeviceGuard guard(p->device);
+    if (int rc = ensure_state(p)) return rc;
     SGPE_CUDA(cudaMemcpyAsync(p->state, psik, (size_t)p->batch * 2 * p->plane * p->csize, cudaMemcpyDeviceToDevice,
                               (cudaStream_t)st));
     p->phase = sgpe_plan::KSPACE; p->scale_pending = false; p->pend_slot = -1; p->pend_eslot = -1;
@@ -1152,7 +1180,7 @@ int sgpe_energy(sgpe_plan* p, const void* psik, int unwrap_mode, double kl_term,
     if (!p || !out) return fail(SGPE_EINVAL, "null argument");
     if (!(p->grid_set && p->g_set && p->pot_set)) return fail(SGPE_ESTATE, "set grid, interactions and potential first");
     if (unwrap_mode < 0 || unwrap_mode > 2) return fail(SGPE_EINVAL, "unwrap_mode must be 0, 1 or 2");
-    if (p->n1 != 1 || p->state == nullptr) return fail(SGPE_EINVAL, "line plans have no k-space state: use sgpe_energy_real_space");
+    if (p->n1 != 1 || p->line_plan) return fail(SGPE_EINVAL, "line plans have no k-space state: use sgpe_energy_real_space");
     DeviceGuard guard(p->device);
     const size_t bytes = (size_t)p->batch * 2 * p->plane * p->csize;
     if (!p->scratch && cudaMalloc(&p->scratch, bytes) != cudaSuccess) return fail(SGPE_ENOMEM, "scratch allocation failed");
@@ -1169,7 +1197,7 @@ int sgpe_energy(sgpe_plan* p, const void* psik, int unwrap_mode, double kl_term,
 int sgpe_kinetic_spectral(sgpe_plan* p, const void* psik, double* out, sgpe_stream st) {
     if (!p || !out) return fail(SGPE_EINVAL, "null argument");
     if (!(p->grid_set && p->kin_set)) return fail(SGPE_ESTATE, "set grid and kinetic operator first");
-    if (p->n1 != 1 || p->state == nullptr) return fail(SGPE_EINVAL, "not available on line plans");
+    if (p->n1 != 1 || p->line_plan) return fail(SGPE_EINVAL, "not available on line plans");
     DeviceGuard guard(p->device);
     if (psik == nullptr) {
         if (p->phase == sgpe_plan::EMPTY) return fail(SGPE_ESTATE, "no state loaded");
@@ -1345,7 +1373,7 @@ int sgpe_plan_create_lines(sgpe_plan** out, int len, int nlines, int n1, int dty
     if (dtype != SGPE_C128 && dtype != SGPE_C64) return fail(SGPE_EINVAL, "dtype must be 0 (c128) or 1 (c64)");
     DeviceGuard guard(device);
     sgpe_plan* p = new sgpe_plan();
-    p->nx = len; p->ny = nlines; p->batch = 1; p->dtype = dtype; p->device = device;
+    p->nx = len; p->ny = nlines; p->batch = 1; p->dtype = dtype; p->device = device; p->line_plan = true;
     p->csize = dtype == SGPE_C128 ? 16 : 8;
     p->plane = (long long)len * nlines;
     p->n1 = n1; p->n2 = n2;
@@ -1428,6 +1456,7 @@ int sgpe_run_host(sgpe_plan* p, const void* psik_in, void* psik_out, int n_steps
         SGPE_CUDA(cudaMalloc((void**)&p->pops_buf, sizeof(double) * pops_n));
         p->pops_cap = pops_n;
     }
+    if (int rc0 = ensure_state(p)) return rc0;
     SGPE_CUDA(cudaMemcpyAsync(p->state, psik_in, bytes, cudaMemcpyHostToDevice, s));
     p->phase = sgpe_plan::KSPACE; p->scale_pending = false; p->pend_slot = -1; p->pend_eslot = -1;
     int rc = sgpe_full_steps(p, n_steps, pops_host ? p->pops_buf : nullptr, 2LL * n_steps, 0, st);
@@ -1488,7 +1517,8 @@ int sgpe_profile_end(sgpe_plan* p, double* ms_col, uint64_t* n_col, double* ms_r
 
 int sgpe_debug_timeline(sgpe_plan* p, unsigned long long* buf_dev) {
     if (!p) return fail(SGPE_EINVAL, "null plan");
-    p->dbg = buf_dev;
+    if (p->dbg_kind == 1) { p->dbg_col = buf_dev; if (!buf_dev) p->dbg = nullptr; }
+    else { p->dbg = buf_dev; if (!buf_dev) p->dbg_col = nullptr; }
     return 0;
 }
 

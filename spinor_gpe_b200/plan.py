@@ -15,6 +15,27 @@ from ._lib import lib, require_cuda
 UNWRAP_MODES = {'none': 0, 'local': 1, 'herraez': 2}
 
 
+# line lengths the kernels transform: one CTA holds a line of up to 4096 points (register-resident Stockham, radix
+# 16 / 8 / 4 / 2); longer lines run as a four-step split n1 x n2 of two such lengths (slab.LongLinePlan)
+MIN_LINE, MAX_LINE, MAX_LONG_LINE = 32, 4096, 4096 * 1024
+
+
+def supported_mesh(n):
+    """(ok, reason) for a mesh size along one axis.  The reference asserts even sizes only (pspinor.py:331-332, its
+    message asks for powers of two) and leaves the rest to cuFFT / MKL."""
+    n = int(n)
+    if n % 2:
+        return False, "the number of mesh points must be even (pspinor.py:331-332)"
+    if n & (n - 1):
+        return False, ("the in-house FFT handles powers of two only; "
+                       f"nearest supported sizes: {1 << (n.bit_length() - 1)} and {1 << n.bit_length()}")
+    if n < MIN_LINE:
+        return False, f"lines shorter than {MIN_LINE} points are not supported"
+    if n > MAX_LONG_LINE:
+        return False, f"lines longer than {MAX_LONG_LINE} points are not supported"
+    return True, ''
+
+
 def _stream_ptr(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -137,6 +158,14 @@ class Plan:
             self.keep['eiphi'] = e
         self._chk(self.lib.sgpe_set_coupling(self.h, int(mode), _dp(c), self.nx * self.ny if batched else 0,
                                              _dp(o), _dp(e)), 'sgpe_set_coupling')
+
+    def set_energy_coupling(self, mode, coupling=None, omega=None, batched=False):
+        """Coupling grid of ``energy()`` when it is not what the stepping applies (the reference's eng_expect always
+        uses ``self.coupling``, tensor_propagator.py:319-321); mode -1 = follow ``set_coupling``."""
+        c = self._f64('e_coupling', coupling) if coupling is not None else None
+        o = self._f64('e_omega', omega) if omega is not None else None
+        self._chk(self.lib.sgpe_set_energy_coupling(self.h, int(mode), _dp(c), self.nx * self.ny if batched else 0,
+                                                    _dp(o)), 'sgpe_set_energy_coupling')
 
     def set_option(self, name, value):
         self._chk(self.lib.sgpe_set_option(self.h, name.encode(), int(value)), 'sgpe_set_option')

@@ -57,6 +57,24 @@ def digit_order(n, n1):
     return (p // n2) + n1 * (p % n2)
 
 
+def _all_ranks_are_peers(group, dev):
+    """True when every rank of ``group`` sits on this host and every pair of their devices can map the other's memory
+    (what sgpe_ipc_open needs).  One all-gather of (hostname, device index, peer-access row) over the group."""
+    import socket
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    n_dev = torch.cuda.device_count()
+    row = [bool(i == idx or torch.cuda.can_device_access_peer(idx, i)) for i in range(n_dev)]
+    mine = (socket.gethostname(), int(idx), row)
+    everyone = [None] * dist.get_world_size(group)
+    dist.all_gather_object(everyone, mine, group=group)
+    if any(host != mine[0] for host, _, _ in everyone):
+        return False
+    devices = [d for _, d, _ in everyone]
+    if len(set(devices)) != len(devices):
+        return False                      # two ranks on one device: nothing to exchange through peer memory
+    return all(r[d] for _, _, r in everyone for d in devices if d < len(r))
+
+
 class SeparableProblem:
     """A problem given by 1-D vectors only (no (Ny, Nx) host arrays) for grids too large to set up with
     ``PSpinor`` on the host: harmonic trap (+ optional linear detuning along y), free / Raman-shifted
@@ -130,8 +148,15 @@ class SlabPropagator:
             self.rank, self.P = dist.get_rank(group), dist.get_world_size(group)
         self.dev = torch.device(device)
         assert exchange in ('auto', 'nccl', 'p2p')
-        if exchange == 'auto':    # one node, one process per GPU: the fused exchange through peer memory
-            exchange = 'p2p' if (self.dev.type == 'cuda' or exchange_buffers is not None) else 'nccl'
+        if exchange == 'auto':
+            # the fused exchange stores into the other ranks' buffers (CUDA IPC): only when every rank of the group runs
+            # on this node and every pair of devices has peer access; otherwise the NCCL all-to-all
+            if exchange_buffers is not None or self.local:
+                exchange = 'p2p'
+            elif self.dev.type == 'cuda':
+                exchange = 'p2p' if _all_ranks_are_peers(self.group, self.dev) else 'nccl'
+            else:
+                exchange = 'nccl'
         self.exchange = exchange
         self.p2p = (exchange == 'p2p')
         self._ipc = []            # (lib, own pointers, opened pointers) to release
@@ -180,6 +205,8 @@ class SlabPropagator:
             cpl = np.asarray(spin.coupling, dtype=np.float64)
             if not spin.is_coupling or not np.any(cpl):
                 rp.set_coupling(_capi.SGPE_COUPLING_NONE)
+                if np.any(cpl):     # eng_expect adds the coupling energy whatever is_coupling says (:319-321)
+                    rp.set_energy_coupling(_capi.SGPE_COUPLING_DENSE, coupling=np.ascontiguousarray(cpl[ys]))
             elif np.all(cpl == cpl.flat[0]):
                 rp.set_coupling(_capi.SGPE_COUPLING_UNIFORM, omega=np.array([cpl.flat[0]]), eiphi=eiphi)
             else:

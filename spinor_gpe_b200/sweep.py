@@ -95,6 +95,9 @@ def run_sweep(ps, trajectories, t_step, n_steps, time='imag', device='cuda', bat
                             eiphi=eiphi)
         else:
             pl.set_coupling(_capi.SGPE_COUPLING_NONE)
+            omegas = np.array([trajectories[i].omega for i in ids], dtype=np.float64)
+            if np.any(omegas):      # eng_expect adds the coupling energy whatever is_coupling says (:319-321)
+                pl.set_energy_coupling(_capi.SGPE_COUPLING_UNIFORM, omega=omegas)
         pl.set_time(time, t_step)
         states = np.stack([base_psik if trajectories[i].psik is None else trajectories[i].psik for i in ids])
         pl.load(states)

@@ -43,6 +43,23 @@ MAX_LINE = 4096                             # longest line one CTA transforms (s
 DEFAULT_UNWRAP = 'herraez'
 
 
+def check_mesh(nx, ny):
+    """Mesh sizes the kernels transform: the reference asserts even sizes (pspinor.py:331-332); see ``supported_mesh``."""
+    from .plan import supported_mesh
+    for name, n in (('x', nx), ('y', ny)):
+        ok, why = supported_mesh(n)
+        if not ok:
+            raise ValueError(f"mesh_points along {name} = {n}: {why}")
+
+
+def _grid(arr, ny, nx, name):
+    """C-contiguous float64 (Ny, Nx) copy / view of a user-supplied operator grid."""
+    a = np.ascontiguousarray(np.asarray(arr), dtype=np.float64)
+    if a.shape != (ny, nx):
+        raise ValueError(f"{name} has shape {a.shape}, the mesh is ({ny}, {nx})")
+    return a
+
+
 class _LazyTensors(dict):
     """dict whose values are uploaded to the GPU on first access."""
 
@@ -147,19 +164,23 @@ class TensorPropagator:
 
         psik0 = np.asarray(spin.psik)
         ny, nx = psik0.shape[-2:]
-        self.kin_eng_spin = ttools.to_tensor([np.asarray(k) for k in spin.kin_eng_spin], dev=dev)
+        check_mesh(nx, ny)
+        # the kernels read row-major (Ny, Nx) float64 grids through raw pointers: whatever layout the user's arrays
+        # have (Fortran order, transposed views, other dtypes), the device copies are C-contiguous float64
+        self.kin_eng_spin = ttools.to_tensor([_grid(k, ny, nx, 'kin_eng_spin') for k in spin.kin_eng_spin], dev=dev)
         pot_shared = spin.pot_eng_spin[0] is spin.pot_eng_spin[1] or np.array_equal(spin.pot_eng_spin[0],
                                                                                     spin.pot_eng_spin[1])
         if pot_shared:
-            p0 = ttools.to_tensor(np.asarray(spin.pot_eng_spin[0]), dev=dev)
+            p0 = ttools.to_tensor(_grid(spin.pot_eng_spin[0], ny, nx, 'pot_eng_spin'), dev=dev)
             self.pot_eng_spin = [p0, p0]
         else:
-            self.pot_eng_spin = ttools.to_tensor([np.asarray(p) for p in spin.pot_eng_spin], dev=dev)
+            self.pot_eng_spin = ttools.to_tensor([_grid(p, ny, nx, 'pot_eng_spin') for p in spin.pot_eng_spin],
+                                                 dev=dev)
         keys_space = ['dr', 'dk', 'x_mesh', 'y_mesh', 'dv_r', 'dv_k']
         self.space = _LazyTensors(spin.space, keys_space, dev)
         self._dr = (float(spin.space['dr'][0]), float(spin.space['dr'][1]))
         self._dv_r, self._dv_k = float(spin.space['dv_r']), float(spin.space['dv_k'])
-        cpl_np = np.asarray(spin.coupling, dtype=np.float64)
+        cpl_np = _grid(spin.coupling, ny, nx, 'coupling')
         self.coupling = ttools.to_tensor(cpl_np, dev=dev)
 
         if self.is_sampling:                                # :131-134
@@ -194,9 +215,14 @@ class TensorPropagator:
         import ctypes
         pl = self._plan
         k0, k1 = self.kin_eng_spin
+        p0, p1 = self.pot_eng_spin
+        for t in (k0, k1, p0, p1, self.coupling):
+            assert t.is_contiguous() and t.dtype == torch.float64
+        # the plan borrows these device pointers: it keeps the tensors alive itself, so rebinding the public
+        # attributes (prop.pot_eng_spin = ...) cannot leave it with a dangling pointer
+        pl.keep['grids_ref'] = (k0, k1, p0, p1)
         pl._chk(pl.lib.sgpe_set_kinetic(pl.h, ctypes.c_void_p(k0.data_ptr()), ctypes.c_void_p(k1.data_ptr()), 0),
                 'sgpe_set_kinetic')
-        p0, p1 = self.pot_eng_spin
         pl._chk(pl.lib.sgpe_set_potential(pl.h, ctypes.c_void_p(p0.data_ptr()), ctypes.c_void_p(p1.data_ptr()), 0),
                 'sgpe_set_potential')
         # separable fast path (1-D factor tables) when the grids allow it; the dense path stays general
@@ -221,6 +247,13 @@ class TensorPropagator:
         if not self.is_coupling or not np.any(cpl_np):
             # Omega == 0 everywhere: the coupling operator is exactly the identity (cos 0 = 1, sin 0 = 0)
             pl.set_coupling(_capi.SGPE_COUPLING_NONE)
+            if np.any(cpl_np):
+                # is_coupling False with a non-zero grid: the step skips the operator (tensor_propagator.py:252, 258)
+                # but eng_expect still adds the coupling energy from self.coupling (:319-321)
+                if np.all(cpl_np == cpl_np.flat[0]):
+                    pl.set_energy_coupling(_capi.SGPE_COUPLING_UNIFORM, omega=np.array([cpl_np.flat[0]]))
+                else:
+                    pl.set_energy_coupling(_capi.SGPE_COUPLING_DENSE, coupling=self.coupling)
         elif np.all(cpl_np == cpl_np.flat[0]):
             pl.set_coupling(_capi.SGPE_COUPLING_UNIFORM, omega=np.array([cpl_np.flat[0]]), eiphi=eiphi)
         else:

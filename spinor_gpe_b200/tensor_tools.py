@@ -9,6 +9,7 @@ Wavefunctions are, as in the reference, lists of two (Ny, Nx) arrays.  Two kinds
   time-stepping path.
 """
 import operator
+from collections import OrderedDict
 from functools import reduce
 
 import numpy as np
@@ -17,16 +18,34 @@ import torch
 from . import _capi
 from .plan import Plan
 
-_PLANS = {}
+# Helper plans of the stand-alone transforms / reductions: twiddles and reduction scratch only (a plan allocates its
+# working state on the first sgpe_load_psik, which these never call), a handful kept, least recently used evicted.
+_PLANS = OrderedDict()
+_MAX_PLANS = 8
+
+
+def _cached_plan(nx, ny, dtype, device):
+    from .plan import supported_mesh
+    for name, n in (('x', nx), ('y', ny)):
+        ok, why = supported_mesh(n)
+        if ok and n > 4096:
+            ok, why = False, "the stand-alone helpers transform lines of up to 4096 points"
+        if not ok:
+            raise ValueError(f"{n} mesh points along {name}: {why}")
+    key = (nx, ny, dtype, device.index)
+    pl = _PLANS.pop(key, None)
+    if pl is None:
+        pl = Plan(nx, ny, 1, dtype, device)
+        while len(_PLANS) >= _MAX_PLANS:
+            _PLANS.popitem(last=False)[1].close()
+    _PLANS[key] = pl
+    return pl
 
 
 def _plan_for(t):
     """A cached bare plan (transforms / reductions only) matching a CUDA tensor's shape and dtype."""
     ny, nx = t.shape[-2:]
-    key = (nx, ny, t.dtype, t.device.index)
-    if key not in _PLANS:
-        _PLANS[key] = Plan(nx, ny, 1, t.dtype, t.device)
-    return _PLANS[key]
+    return _cached_plan(nx, ny, t.dtype, t.device)
 
 
 def _is_np(psi):
@@ -239,10 +258,7 @@ def _unwrap_plan(ny, nx):
     """A cached bare complex128 plan on the current CUDA device for the (ny, nx) mesh (raises without CUDA)."""
     from ._lib import require_cuda
     require_cuda()
-    key = (nx, ny, torch.complex128, torch.cuda.current_device())
-    if key not in _PLANS:
-        _PLANS[key] = Plan(nx, ny, 1, torch.complex128, torch.device('cuda', torch.cuda.current_device()))
-    return _PLANS[key]
+    return _cached_plan(nx, ny, torch.complex128, torch.device('cuda', torch.cuda.current_device()))
 
 
 def _unwrap_2d(ang):

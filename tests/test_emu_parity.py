@@ -48,8 +48,10 @@ def test_emulated_kernels_vs_golden(case, separable):
         final = pl.store()[0]
         assert rel(final, z[pre + 'psik_final']) < 1e-12          # tolerance of north_star: 1e-10
         np.testing.assert_allclose(pops[0], z[pre + 'pops_vals'], rtol=1e-12)
+        # E_pot / E_int depend on the densities only: pinned on every run; E_kin / E_tot where the phase is conditioned
+        e = pl.energy(z[pre + 'psik_final'], 2 * prob.kL * prob.is_coupling, 0)[0]
+        np.testing.assert_allclose(e[2:], z[pre + 'energy_identity_unwrap'][2:], rtol=1e-10)
         if (case, r) in ENERGY_OK:
-            e = pl.energy(z[pre + 'psik_final'], 2 * prob.kL * prob.is_coupling, 0)[0]
             np.testing.assert_allclose(e, z[pre + 'energy_identity_unwrap'], rtol=1e-10)
         out, pops2 = pl.run_host(prob.psik.numpy(), n)
         assert rel(out[0], z[pre + 'psik_final']) < 1e-12

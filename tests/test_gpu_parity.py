@@ -96,11 +96,14 @@ def test_golden_through_public_api(case):
             assert rel(smp['psiks'], z[pre + 'sampled_psiks']) < TOL_PSI
             np.testing.assert_array_equal(smp['times'], z[pre + 'sampled_times'])
         assert os.path.basename(res.sampled_path) == f"psik_sampled{run_idx + 1}-{ps.paths['folder']}.npz"
+        # the fixture's energy was generated with the identity in place of skimage's unwrap_phase (not installed
+        # where the reference ran); the unwrapped variant is checked in tests/test_unwrap.py.  E_pot and E_int
+        # (tensor_propagator.py:313-318) depend on the densities only: pinned on EVERY run.  E_kin / E_tot carry the
+        # finite-difference phase gradient, meaningful only where the wrapped phase is conditioned (ENERGY_OK).
+        got_e = prop.eng_expect(None, unwrap='none')
+        np.testing.assert_allclose(got_e[2:], z[pre + 'energy_identity_unwrap'][2:], rtol=TOL_SCALAR)
         if (case, run_idx) in ENERGY_OK:
-            # the fixture's energy was generated with the identity in place of skimage's unwrap_phase (not installed
-            # where the reference ran); the unwrapped variant is checked in tests/test_unwrap.py
-            np.testing.assert_allclose(prop.eng_expect(None, unwrap='none'), z[pre + 'energy_identity_unwrap'],
-                                       rtol=TOL_SCALAR)
+            np.testing.assert_allclose(got_e, z[pre + 'energy_identity_unwrap'], rtol=TOL_SCALAR)
         run_idx += 1
 
 
@@ -181,6 +184,102 @@ def test_against_oracle(mesh, mode, dt, n, cpl, rot, kshift, separable):
     assert rel(np.array(res.psik), want['psik']) < TOL_PSI
     np.testing.assert_allclose(res.pops['vals'], want['pops_vals'], rtol=TOL_SCALAR)
     assert abs(res.pops['vals'][-1].sum() / ps.atom_num - 1) < TOL_SCALAR
+
+
+def test_headline_config_against_oracle():
+    """BASELINE configs[2] itself — 2048^2 complex128, imaginary time, the benchmark's parameters
+    (benchmarks/benchmark_prop.py:50-67) — against the oracle: psi_k, per-step populations, atom number and the
+    energy of the final state (E_pot / E_int always; E_kin / E_tot for this smooth rotating-frame ground state)."""
+    import bench
+    ps = bench.build_problem(2048)
+    n = 3
+    want = orc.OraclePropagator(problem_of(ps), 1 / 50, 'imag').run(n)
+    res, prop = ps.imaginary(1 / 50, n, 'cuda', unwrap='none')
+    assert prop.separable == {'kin': True, 'pot': True}
+    assert rel(np.array(res.psik), want['psik']) < TOL_PSI
+    assert rel(np.array(res.psi), want['psi']) < TOL_PSI
+    np.testing.assert_allclose(res.pops['vals'], want['pops_vals'], rtol=TOL_SCALAR)
+    assert abs(res.pops['vals'][-1].sum() / ps.atom_num - 1) < TOL_SCALAR
+    np.testing.assert_allclose(res.eng_final[2:], want['energy'][2:], rtol=TOL_SCALAR)
+    np.testing.assert_allclose(res.eng_final, want['energy'], rtol=TOL_SCALAR)
+    # the general (dense-operator) kernels on the same configuration
+    ps2 = bench.build_problem(2048)
+    res2, prop2 = ps2.imaginary(1 / 50, n, 'cuda', unwrap='none', separable=False)
+    assert prop2.separable == {'kin': False, 'pot': False}
+    assert rel(np.array(res2.psik), want['psik']) < TOL_PSI
+    np.testing.assert_allclose(res2.pops['vals'], want['pops_vals'], rtol=TOL_SCALAR)
+
+
+def test_config2_raman_kick_real_time_against_oracle():
+    """BASELINE configs[1] as written (examples/3_raman_rabi.py:126-183 at 1024^2): Raman set-up with the
+    spin-dependent kinetic shift, momentum kick, laboratory-frame coupling phase, a short imaginary-time relaxation,
+    then real-time Rabi flopping under a uniform coupling — 12 steps against the oracle."""
+    ps = make_ps((1024, 1024), atom_num=1e4, g_sc={'uu': 1, 'dd': 1, 'ud': 0.0}, pop_frac=(1.0, 0.0),
+                 r_sizes=(16, 16))
+    ps.coupling_setup(wavel=790.1e-9, kin_shift=True)
+    ps.shift_momentum(scale=1.0, frac=(0, 1.0))
+    ps.rot_coupling = False
+    ps.rand_seed = 99999
+    o = orc.OraclePropagator(problem_of(ps), 1 / 50, 'imag')
+    relax = o.run(4)
+    res0, _ = ps.imaginary(1 / 50, 4, 'cuda', unwrap='none')
+    assert rel(np.array(res0.psik), relax['psik']) < TOL_PSI
+    np.testing.assert_allclose(res0.pops['vals'], relax['pops_vals'], rtol=TOL_SCALAR, atol=1e-9 * ps.atom_num)
+    ps.coupling_uniform(1.0 * ps.EL_recoil)
+    n = 12
+    want = orc.OraclePropagator(problem_of(ps), 1 / 5000, 'real').run(n, n_samples=3)
+    res1, prop1 = ps.real(1 / 5000, n, 'cuda', is_sampling=True, n_samples=3, unwrap='none')
+    assert rel(np.array(res1.psik), want['psik']) < TOL_PSI
+    assert rel(np.array(res1.psi), want['psi']) < TOL_PSI
+    np.testing.assert_allclose(res1.pops['vals'], want['pops_vals'], rtol=TOL_SCALAR, atol=1e-9 * ps.atom_num)
+    np.testing.assert_allclose(res1.pops['vals'].sum(axis=1), ps.atom_num, rtol=TOL_SCALAR)
+    with np.load(res1.sampled_path) as smp:
+        assert rel(smp['psiks'], want['sampled_psiks']) < TOL_PSI
+    np.testing.assert_allclose(res1.eng_final[2:], want['energy'][2:], rtol=TOL_SCALAR)
+    assert res1.pops['vals'][-1, 1] > 1e-3 * ps.atom_num       # the coupling does transfer population
+
+
+def test_user_grids_of_any_memory_layout():
+    """Operator grids set by the user as Fortran-ordered / transposed-view arrays (non-separable potential, dense
+    coupling, spin-dependent detuning) reach the kernels as row-major float64: same result as the oracle, which reads
+    them through NumPy indexing.  The plan keeps its own references to the device copies."""
+    ps = make_ps((128, 256), atom_num=1e4, r_sizes=(16, 16))
+    ps.coupling_setup(wavel=790.1e-9, kin_shift=True)
+    x, y = ps.space['x_mesh'], ps.space['y_mesh']
+    pot = np.asfortranarray(0.5 * (x ** 2 + y ** 2) + 0.3 * np.sin(x) * np.cos(0.7 * y) + 0.05 * x * y)
+    assert not pot.flags['C_CONTIGUOUS']
+    ps.pot_eng = pot
+    ps.detuning = np.ascontiguousarray((0.4 * x * y).T).T                 # transposed view, non-separable
+    ps.coupling = np.asfortranarray(1.5 * ps.EL_recoil * (1 + 0.2 * np.tanh(x * y / 10)))
+    ps.rot_coupling = False
+    want = orc.OraclePropagator(problem_of(ps), 1 / 2000, 'real').run(4)
+    res, prop = ps.real(1 / 2000, 4, 'cuda', unwrap='none')
+    assert prop.separable['pot'] is False
+    prop.pot_eng_spin = None                                              # the plan holds its own references
+    assert rel(np.array(res.psik), want['psik']) < TOL_PSI
+    np.testing.assert_allclose(res.pops['vals'], want['pops_vals'], rtol=TOL_SCALAR)
+    np.testing.assert_allclose(res.eng_final[2:], want['energy'][2:], rtol=TOL_SCALAR)
+    np.testing.assert_allclose(prop.eng_expect(None, unwrap='none')[2:], want['energy'][2:], rtol=TOL_SCALAR)
+
+
+def test_coupling_energy_without_coupling_setup():
+    """ps.coupling set without coupling_setup(): single_step skips the coupling operator (is_coupling False,
+    tensor_propagator.py:252) but eng_expect still adds the coupling energy from self.coupling (:319-321)."""
+    ps = make_ps((128, 128), atom_num=1e3, pop_frac=(0.7, 0.3))
+    assert not ps.is_coupling
+    x, y = ps.space['x_mesh'], ps.space['y_mesh']
+    for cpl in (np.full_like(x, 0.8), 0.8 + 0.1 * x):
+        ps.coupling = cpl
+        want = orc.OraclePropagator(problem_of(ps), 1 / 50, 'imag').run(3)
+        psik0 = [p.copy() for p in ps.psik]
+        res, prop = ps.imaginary(1 / 50, 3, 'cuda', unwrap='none')
+        ps.psik = psik0
+        assert rel(np.array(res.psik), want['psik']) < TOL_PSI
+        e_cpl_want = want['energy'][0] - sum(want['energy'][1:])
+        e_cpl_got = res.eng_final[0] - sum(res.eng_final[1:])
+        assert abs(e_cpl_want) > 1e-3 * abs(want['energy'][0])
+        np.testing.assert_allclose(e_cpl_got, e_cpl_want, rtol=1e-7)          # a difference of large sums
+        np.testing.assert_allclose(res.eng_final, want['energy'], rtol=TOL_SCALAR)
 
 
 def test_bitwise_reproducible():

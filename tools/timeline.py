@@ -19,19 +19,24 @@ pl.set_potential_separable(*split_separable(np.array(ps.pot_eng_spin)))
 pl.set_coupling(_capi.SGPE_COUPLING_NONE)
 pl.set_time('imag', 1 / 50)
 pl.load(np.array(ps.psik)[None])
-if len(sys.argv) > 1: pl.set_option('stagger_ns', int(sys.argv[1]))
+kind = sys.argv[1] if len(sys.argv) > 1 else 'row'
 pl.full_steps(3)
-dbg = torch.zeros((mesh, 8), dtype=torch.int64, device='cuda')
-pl.lib.sgpe_debug_timeline(pl.h, _dp(dbg))
+ncta = mesh if kind == 'row' else 2 * mesh // 4
+dbg = torch.zeros((ncta, 8), dtype=torch.int64, device='cuda')
+pl.set_option('timeline_kind', 1 if kind == 'col' else 0)
 dto, dti = pl.substeps()
-pl.single_step(dto)
+pl.single_step(dto)                 # open a junction: the next column pass is the full one (FFT, factors, sums, iFFT)
+pl.lib.sgpe_debug_timeline(pl.h, _dp(dbg))
+pl.single_step(dti)
 torch.cuda.synchronize()
 pl.lib.sgpe_debug_timeline(pl.h, None)
 d = dbg.cpu().numpy().astype(np.int64)
 t0 = d[:, 0].min()
 ph = d[:, :6] - t0
 dur = np.diff(ph, axis=1)
-names = ['issue loads', 'inverse FFT (incl. load wait)', 'point-wise', 'forward FFT', 'stores']
+names = (['issue loads', 'inverse FFT (incl. load wait)', 'point-wise', 'forward FFT', 'stores'] if kind == 'row' else
+         ['issue loads + wait', 'forward FFT', 'K factors + publish sums', 'inverse FFT', 'stores'])
+print('pass:', kind)
 print('kernel span %.1f us, CTAs %d' % ((ph[:, 5].max()) / 1e3, len(d)))
 for k, nme in enumerate(names):
     print('  %-32s mean %6.2f us  median %6.2f  p90 %6.2f' % (nme, dur[:, k].mean() / 1e3, np.median(dur[:, k]) / 1e3, np.percentile(dur[:, k], 90) / 1e3))
@@ -46,8 +51,9 @@ for s in np.unique(sm):
     ends = sorted(e for _, e in ev)
     starts = sorted(st for st, _ in ev)
     # gap between k-th end and (k+2)-th start (2 slots per SM)
-    for k in range(len(ends) - 2):
-        gaps.append(starts[k + 2] - ends[k])
+    per = 2 if kind == 'row' else 1
+    for k in range(len(ends) - per):
+        gaps.append(starts[k + per] - ends[k])
 gaps = np.array(gaps) / 1e3
 print('  slot turnaround (end of a CTA -> start of its successor on the SM): mean %.2f us median %.2f' % (gaps.mean(), np.median(gaps)))
 print('  CTAs per SM: min %d max %d' % (np.bincount(sm).min(), np.bincount(sm).max()))
