@@ -165,9 +165,17 @@ struct LineGeom {
     static constexpr int radix(int Ns) { return (N / Ns) < E ? (N / Ns) : E; }
 };
 
+// Where a stage reads its twiddles: global memory through the read-only path (plain pointer), or a copy of the tables
+// in shared memory (SmemTable: persistent kernels whose shared-memory footprint leaves no L1 to cache them in).
+template <typename C> struct SmemTable {
+    const C* p;
+    SGPE_DI SmemTable operator+(int o) const { SmemTable r; r.p = p + o; return r; }
+};
+template <typename C> SGPE_DI C tw_at(const C* __restrict__ p, int i) { return __ldg(&p[i]); }
+template <typename C> SGPE_DI C tw_at(SmemTable<C> t, int i) { return t.p[i]; }
 // twiddle + butterflies of the stage whose previous-radix product is Ns, on one line's registers
-template <typename T, int N, int E, int DIR, int Ns, typename C>
-SGPE_DI void stage_compute(C (&v)[E], int j, const C* __restrict__ tw) {
+template <typename T, int N, int E, int DIR, int Ns, typename C, typename TWP>
+SGPE_DI void stage_compute(C (&v)[E], int j, TWP tw) {
     constexpr int R = (N / Ns) < E ? (N / Ns) : E;
     constexpr int NB = E / R;
     constexpr int NT = N / E;
@@ -177,10 +185,9 @@ SGPE_DI void stage_compute(C (&v)[E], int j, const C* __restrict__ tw) {
             // per-stage table, [t-1][k] with k fastest (consecutive lanes read consecutive entries); the
             // stage with previous-radix product Ns starts at entry Ns - E (see sgpe_api.cu: upload_twiddles)
             const int k = (j + b * NT) & (Ns - 1);
-            const C* __restrict__ tws = tw + (Ns - E) + k;
 #pragma unroll
             for (int t = 1; t < R; t++) {
-                const C w = __ldg(&tws[(t - 1) * Ns]);
+                const C w = tw_at<C>(tw, (Ns - E) + k + (t - 1) * Ns);
                 v[b + t * NB] = (DIR < 0) ? cmul(v[b + t * NB], w) : cmulc(v[b + t * NB], w);
             }
         }
@@ -227,8 +234,8 @@ struct GroupBar {
 
 // Full transform of L lines per thread (each with its own shared-memory image); all threads of the
 // CTA (or of the barrier group) must call this together (it contains barriers).
-template <typename T, int N, int E, int DIR, int W, int L, int Ns, typename C, typename B>
-SGPE_DI void cta_fft_from(C (&v)[L][E], int j, int c, C* const (&sm)[L], const C* __restrict__ tw, const B& bar) {
+template <typename T, int N, int E, int DIR, int W, int L, int Ns, typename C, typename B, typename TWP>
+SGPE_DI void cta_fft_from(C (&v)[L][E], int j, int c, C* const (&sm)[L], TWP tw, const B& bar) {
     constexpr int R = (N / Ns) < E ? (N / Ns) : E;
 #pragma unroll
     for (int l = 0; l < L; l++) stage_compute<T, N, E, DIR, Ns>(v[l], j, tw);
@@ -243,12 +250,36 @@ SGPE_DI void cta_fft_from(C (&v)[L][E], int j, int c, C* const (&sm)[L], const C
     }
 }
 
+// product of the radices before the LAST stage of the length-N, E-per-thread plan (1 when there is a single stage)
+template <int N, int E, int Ns = 1> struct LastStage {
+    static constexpr int R = (N / Ns) < E ? (N / Ns) : E;
+    static constexpr int value = LastStage<N, E, (Ns * R >= N) ? 0 : Ns * R>::value == 0 ? Ns : LastStage<N, E, (Ns * R >= N) ? 0 : Ns * R>::value;
+};
+template <int N, int E> struct LastStage<N, E, 0> { static constexpr int value = 0; };
+// every stage from Ns on EXCEPT the butterflies of the last one: returns behind the barrier that follows the last
+// exchange read, i.e. at the point from which the shared-memory images are free again
+template <typename T, int N, int E, int DIR, int W, int L, int Ns, typename C, typename B, typename TWP>
+SGPE_DI void cta_fft_head(C (&v)[L][E], int j, int c, C* const (&sm)[L], TWP tw, const B& bar) {
+    constexpr int R = (N / Ns) < E ? (N / Ns) : E;
+    if constexpr (Ns * R < N) {
+#pragma unroll
+        for (int l = 0; l < L; l++) stage_compute<T, N, E, DIR, Ns>(v[l], j, tw);
+#pragma unroll
+        for (int l = 0; l < L; l++) stage_store<T, N, E, W, Ns>(v[l], j, c, sm[l]);
+        bar.sync();
+#pragma unroll
+        for (int l = 0; l < L; l++) stage_load<T, N, E, W>(v[l], j, c, sm[l]);
+        bar.sync();
+        cta_fft_head<T, N, E, DIR, W, L, Ns * R>(v, j, c, sm, tw, bar);
+    }
+}
+
 // Two lines per thread: software-pipelined exchange.  Line A's shared-memory read latency is covered by
 // line B's stores and vice versa, and each barrier serves one line's write->read and the other line's
 // read->write hazard, so the barrier count is unchanged (2 per stage) while the post-barrier bubble shrinks.
 // Precondition of a round: A's stage-Ns outputs are stored (not yet visible), B's are still in registers.
-template <typename T, int N, int E, int DIR, int W, int Ns, typename C>
-SGPE_DI void cta_fft2_round(C (&v)[2][E], int j, int c, C* const (&sm)[2], const C* __restrict__ tw) {
+template <typename T, int N, int E, int DIR, int W, int Ns, typename C, typename TWP>
+SGPE_DI void cta_fft2_round(C (&v)[2][E], int j, int c, C* const (&sm)[2], TWP tw) {
     constexpr int R = (N / Ns) < E ? (N / Ns) : E;
     constexpr int Ns2 = Ns * R;
     constexpr int R2 = (N / Ns2) < E ? (N / Ns2) : E;
@@ -264,8 +295,8 @@ SGPE_DI void cta_fft2_round(C (&v)[2][E], int j, int c, C* const (&sm)[2], const
     if constexpr (more) cta_fft2_round<T, N, E, DIR, W, Ns2>(v, j, c, sm, tw);
 }
 
-template <typename T, int N, int E, int DIR, int W, int L, typename C>
-SGPE_DI void cta_fft(C (&v)[L][E], int j, int c, C* const (&sm)[L], const C* __restrict__ tw) {
+template <typename T, int N, int E, int DIR, int W, int L, typename C, typename TWP>
+SGPE_DI void cta_fft(C (&v)[L][E], int j, int c, C* const (&sm)[L], TWP tw) {
     if constexpr (L == 2 && E < N) {
         // (a following cta_fft of the same two lines may start right away: it touches line A's image, whose
         // readers are past the last barrier, before its own first barrier, and line B's only after it)
@@ -278,9 +309,68 @@ SGPE_DI void cta_fft(C (&v)[L][E], int j, int c, C* const (&sm)[L], const C* __r
     }
 }
 // one line per thread, synchronising over a barrier group
-template <typename T, int N, int E, int DIR, int W, typename C, typename B>
-SGPE_DI void group_fft(C (&v)[1][E], int j, int c, C* const (&sm)[1], const C* __restrict__ tw, const B& bar) {
+template <typename T, int N, int E, int DIR, int W, typename C, typename B, typename TWP>
+SGPE_DI void group_fft(C (&v)[1][E], int j, int c, C* const (&sm)[1], TWP tw, const B& bar) {
     cta_fft_from<T, N, E, DIR, W, 1, 1>(v, j, c, sm, tw, bar);
+}
+
+// ---- split exchange: the real and the imaginary parts of a line travel through ONE real-valued image of the line,
+// one after the other (twice the barriers, half the shared memory of the complex image).  What the persistent passes
+// use for their second transform, so that the complex image can hold the asynchronously staged NEXT tile meanwhile.
+template <typename T, int N, int E, int W>
+struct SplitGeom {
+    static constexpr int PHASE = 128 / (int)sizeof(T);          // 8-byte (double) / 4-byte (float) elements per wavefront
+    static constexpr int MASK = (PHASE / W > 1) ? (PHASE / W - 1) : 0;
+    static constexpr int SH = LineGeom<T, N, E, W>::SH;
+    SGPE_DI static int swz(int n) { return n ^ ((n >> SH) & MASK); }
+};
+template <typename T, int N, int E, int W, int Ns, int PART, typename C>
+SGPE_DI void stage_store_part(const C (&v)[E], int j, int c, T* sm) {
+    typedef SplitGeom<T, N, E, W> G;
+    constexpr int R = (N / Ns) < E ? (N / Ns) : E;
+    constexpr int NB = E / R;
+    constexpr int NT = N / E;
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        const int jb = j + b * NT;
+        const int k = jb & (Ns - 1);
+        const int j0 = (jb - k) * R + k;
+#pragma unroll
+        for (int t = 0; t < R; t++) sm[G::swz(j0 + t * Ns) * W + c] = PART ? v[b + t * NB].y : v[b + t * NB].x;
+    }
+}
+template <typename T, int N, int E, int W, int PART, typename C>
+SGPE_DI void stage_load_part(C (&v)[E], int j, int c, const T* sm) {
+    typedef SplitGeom<T, N, E, W> G;
+    constexpr int NT = N / E;
+#pragma unroll
+    for (int m = 0; m < E; m++) {
+        if (PART) v[m].y = sm[G::swz(j + m * NT) * W + c];
+        else v[m].x = sm[G::swz(j + m * NT) * W + c];
+    }
+}
+// full transform of L lines per thread through real images sm[l] (N * W reals each); ends right after the last
+// butterflies (the images' readers are behind a barrier only when another exchange followed)
+template <typename T, int N, int E, int DIR, int W, int L, int Ns, typename C, typename B, typename TWP>
+SGPE_DI void cta_fft_split_from(C (&v)[L][E], int j, int c, T* const (&sm)[L], TWP tw, const B& bar) {
+    constexpr int R = (N / Ns) < E ? (N / Ns) : E;
+#pragma unroll
+    for (int l = 0; l < L; l++) stage_compute<T, N, E, DIR, Ns>(v[l], j, tw);
+    if constexpr (Ns * R < N) {
+        bar.sync();                         // the previous readers of the images are done
+#pragma unroll
+        for (int l = 0; l < L; l++) stage_store_part<T, N, E, W, Ns, 0>(v[l], j, c, sm[l]);
+        bar.sync();
+#pragma unroll
+        for (int l = 0; l < L; l++) stage_load_part<T, N, E, W, 0>(v[l], j, c, sm[l]);
+        bar.sync();
+#pragma unroll
+        for (int l = 0; l < L; l++) stage_store_part<T, N, E, W, Ns, 1>(v[l], j, c, sm[l]);
+        bar.sync();
+#pragma unroll
+        for (int l = 0; l < L; l++) stage_load_part<T, N, E, W, 1>(v[l], j, c, sm[l]);
+        cta_fft_split_from<T, N, E, DIR, W, L, Ns * R>(v, j, c, sm, tw, bar);
+    }
 }
 
 // ---- deterministic CTA reduction of NV doubles (warp shuffle, then shared memory in warp order)

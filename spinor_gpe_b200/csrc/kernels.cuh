@@ -125,8 +125,12 @@ template <typename T> struct ColArgs {
     unsigned* counter;             // [B]
     double* totals;                // [B][4] : T, S0, S1, -
     double* pops; long long pops_bstride; int pops_slot;   // [B][n][2], slot < 0: don't record
+    int* slot_ctr;                 // [B] or null.  Non-null (CUDA-graph replay of the steady-state step: node arguments
+                                   // are frozen): the slot is read from slot_ctr[b] and post-incremented by the fold
     double atom_num;
     unsigned long long* dbg;       // dev tool: per-CTA phase timestamps [nCTA][8] (null in production; generic kernel only)
+    const void* tile_map;          // host pointer to the SgpeTileMap of `in` (persistent kernel; read by the launcher only)
+    int kernel_sel;                // 0: one tile per CTA, 1 / 2: persistent CTAs with asynchronously staged tiles (col_pass_p)
     C* aux;                        // optional second output [B][2][ny][nx]: the state right after FA — at a full-step
                                    // junction that is the (un-normalised) k-space state of the step boundary, which
                                    // per-step energy tracking transforms back on the side (sgpe_full_steps_energy)
@@ -308,9 +312,392 @@ __global__ void __launch_bounds__(G * W * N / E, (G * W * N / E <= 256) ? 2 : 1)
                 tot[0] = t4[1] + t4[3];
                 tot[1] = t4[0];
                 tot[2] = t4[2];
-                if (a.pops != nullptr && a.pops_slot >= 0) {
+                int slot = a.pops_slot;
+                if (a.slot_ctr != nullptr) { slot = a.slot_ctr[b]; a.slot_ctr[b] = slot + 1; }
+                if (a.pops != nullptr && slot >= 0) {
                     // calc_pops of the normalised psi_k: N * S_c / (S_0 + S_1)   (tensor_tools.py:482)
-                    double* pp = a.pops + (long long)b * a.pops_bstride + 2LL * a.pops_slot;
+                    double* pp = a.pops + (long long)b * a.pops_bstride + 2LL * slot;
+                    const double inv = a.atom_num / (t4[0] + t4[2]);
+                    pp[0] = t4[0] * inv; pp[1] = t4[2] * inv;
+                }
+                a.counter[b] = 0u;
+            }
+        }
+    }
+}
+
+// the twiddle source of a kernel: the plan's tables in global memory, or the kernel's copy in shared memory
+template <typename C, int TWS> struct TwSource {
+    typedef const C* type;
+    SGPE_DI static type make(const C* global, const C*) { return global; }
+};
+template <typename C> struct TwSource<C, 1> {
+    typedef SmemTable<C> type;
+    SGPE_DI static type make(const C*, const C* shared) { type t; t.p = shared; return t; }
+};
+
+// k-space factors of one thread's E points of a column: v <- v FA (S += |v|^2, optional copy to aux), v <- v FB
+// (T += |v|^2); which of the two exist is a compile-time choice here (branches inside the unrolled loop keep the
+// compiler from batching the table loads: every load then waits out its own L2 round trip).
+template <typename T, int E, int NT, int TM, bool HAS_A, bool HAS_B, bool AUX, typename C>
+SGPE_DI void k_factors(C (&v)[E], C fxa, C fxb, const C* __restrict__ ya, const C* __restrict__ yb, C* aux, long long aux_stride,
+                       double (&acc)[2]) {
+    constexpr int CH = E < 4 ? E : 4;          // table loads in batches of four: latency overlapped, few registers
+#pragma unroll
+    for (int m0 = 0; m0 < E; m0 += CH) {
+        C fa[CH], fb[CH];
+#pragma unroll
+        for (int q = 0; q < CH; q++) {
+            if (HAS_A) fa[q] = __ldg(&ya[(m0 + q) * NT]);
+            if (HAS_B) fb[q] = __ldg(&yb[(m0 + q) * NT]);
+        }
+#pragma unroll
+        for (int q = 0; q < CH; q++) {
+            const int m = m0 + q;
+            C x = v[m];
+            if (HAS_A) {
+                x = mul_factor<TM>(x, combine_factor<TM>(fxa, fa[q]));
+                acc[0] += (double)x.x * x.x + (double)x.y * x.y;
+                if (AUX) SGPE_ST_STREAM(&aux[(long long)m * aux_stride], x);
+            }
+            if (HAS_B) {
+                x = mul_factor<TM>(x, combine_factor<TM>(fxb, fb[q]));
+                acc[1] += (double)x.x * x.x + (double)x.y * x.y;
+            }
+            v[m] = x;
+        }
+    }
+    if (!HAS_B) acc[1] = acc[0];
+    if (!HAS_A) acc[0] = acc[1];
+}
+
+// Persistent column pass of the steady-state junction (what FAST = 1 / 2 compute) with the NEXT tile staged
+// asynchronously: one CTA per SM slot walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ...; TMA (cp.async.bulk.tensor,
+// N / 256 boxes of 256 rows x 64 bytes, completion on an mbarrier) lands the CTA's next tile in shared memory while the
+// current one is still being worked on, so the global-load latency and the CTA turnaround of the one-tile-per-CTA
+// kernel (4 + 1 us of a 17 us tile at 2048 points, profiles/r02_timeline.txt) leave the critical path.
+//   S = complex image of a tile: TMA landing zone and exchange buffer.
+//   XSPLIT = 1: the inverse transform exchanges through a second, REAL image X (re and im one after the other, half
+//               the size): S is free - and refilled - right after the forward transform (a window of ~10 us);
+//   XSPLIT = 0: both transforms exchange through S; it is refilled behind the last exchange read of the inverse
+//               transform, while the last butterflies run and the tile is stored (a window of ~3 us, shared memory and
+//               L1 as in the one-tile-per-CTA kernel).
+// The partial sums of a tile are stored right away, the ticket (fence + atomic) is taken ONCE per CTA after its last
+// tile; the CTA that completes the count folds the partials in a fixed order as before.
+template <typename T, int N, int E, int W, int TM, int XSPLIT, int TWS>
+__global__ void __launch_bounds__(W * N / E, (W * N / E <= 256) ? 2 : 1)
+col_pass_p(const SGPE_GRID_CONSTANT SgpeTileMap tmap, ColArgs<T> a) {
+    typedef typename cx_of<T>::type C;
+    constexpr int NT = N / E;
+    constexpr int R0 = E;
+    constexpr int BOXR = N < 256 ? N : 256, NBOX = N / BOXR;
+    constexpr unsigned TILE_BYTES = (unsigned)(N * W * sizeof(C));
+    constexpr int LAST_NS = LastStage<N, E>::value;
+    SGPE_DYN_SMEM_128(smem_p);
+    C* const S = reinterpret_cast<C*>(smem_p);
+    T* const X = reinterpret_cast<T*>(smem_p + TILE_BYTES);
+    // TWS = 1: the twiddle tables of this plan (N entries) live in shared memory for the life of the CTA
+    C* const TW = reinterpret_cast<C*>(smem_p + TILE_BYTES + (XSPLIT ? TILE_BYTES / 2 : 0));
+    double* const red = reinterpret_cast<double*>(smem_p + TILE_BYTES + (XSPLIT ? TILE_BYTES / 2 : 0) + (TWS ? N * sizeof(C) : 0));
+    SgpeMbar* const mbar = reinterpret_cast<SgpeMbar*>(red + 32 * 4);
+    int* const flag = reinterpret_cast<int*>(mbar + 1);
+
+    const int b = blockIdx.y;
+    const int tiles_per_comp = a.nx / W;
+    const int ntiles = 2 * tiles_per_comp;
+    const bool any_k = a.has_a || a.has_b;
+
+    // stage tile `t` of this trajectory into S (one elected thread)
+    auto stage = [&](int t) {
+        sgpe_mbar_expect_tx(mbar, TILE_BYTES);
+#pragma unroll 1
+        for (int q = 0; q < NBOX; q++)
+            sgpe_tma_load_2d(S + (size_t)q * BOXR * W, &tmap, 2 * (t % tiles_per_comp) * W,
+                             (b * 2 + t / tiles_per_comp) * a.ny + q * BOXR, mbar, BOXR, (int)(W * sizeof(C)));
+    };
+
+    if (threadIdx.x == 0) sgpe_mbar_init(mbar, 1);
+    if (TWS) {
+        const C* src = a.tw + (E == 16 ? N : 0);
+        for (int i = threadIdx.x; i < N; i += W * NT) TW[i] = __ldg(&src[i]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) stage(blockIdx.x);
+    int done = 0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, done++) {
+        // (thread coordinates are re-derived per tile: nothing that depends on them stays live across the loop)
+        const int tid = threadIdx.x;
+        const int c = tid % W, j = tid / W;
+        typename TwSource<C, TWS>::type tw = TwSource<C, TWS>::make(a.tw + (E == 16 ? N : 0), TW);
+        const int comp = tile / tiles_per_comp;
+        const int col = (tile % tiles_per_comp) * W + c;
+        const long long off = ((long long)b * 2 + comp) * a.plane + col;
+
+#ifdef SGPE_TIMELINE     // dev build only (tools/timeline.py): phase timestamps of every tile
+        // (stamps go to shared memory and are flushed once per tile: no 64-bit address stays live across the pass)
+        unsigned long long* const marks = reinterpret_cast<unsigned long long*>(flag + 2);
+#define SGPE_PMARK(k) do { if (threadIdx.x == 0) marks[k] = SGPE_GLOBALTIMER(); } while (0)
+#else
+#define SGPE_PMARK(k) do { } while (0)
+#endif
+        SGPE_PMARK(0);
+        sgpe_mbar_wait(mbar, (unsigned)(done & 1));
+        SGPE_PMARK(1);
+        C v[1][E];
+#pragma unroll
+        for (int m = 0; m < E; m++) v[0][m] = S[(j + m * NT) * W + c];
+
+        // forward transform through S (first stage by hand: S must be read by everybody before it is overwritten)
+        C* const sms[1] = {S};
+        stage_compute<T, N, E, -1, 1>(v[0], j, tw);
+        __syncthreads();
+        if constexpr (R0 < N) {
+            stage_store<T, N, E, W, 1>(v[0], j, c, S);
+            __syncthreads();
+            stage_load<T, N, E, W>(v[0], j, c, S);
+            __syncthreads();
+            cta_fft_from<T, N, E, -1, W, 1, R0>(v, j, c, sms, tw, CtaBar());
+        }
+        if (XSPLIT && tid == 0 && tile + (int)gridDim.x < ntiles) {     // S is free: its last readers are behind a barrier
+            sgpe_fence_proxy_async();
+            stage(tile + (int)gridDim.x);
+        }
+
+        SGPE_PMARK(2);
+        double acc[2] = {0.0, 0.0};   // S (after FA), T (after FB)
+        if (any_k) {
+            const long long ox = (long long)b * a.sepx_bstride + (long long)comp * a.nx + col;
+            const long long oy = (long long)b * a.sepy_bstride + (long long)comp * a.ny + j;
+            C fxa, fxb;
+            fxa.x = (T)1; fxa.y = (T)0; fxb = fxa;
+            if (a.has_a) fxa = __ldg(&a.xa[ox]);
+            if (a.has_b) fxb = __ldg(&a.xb[ox]);
+            C* const aux = a.aux != nullptr ? a.aux + off + (long long)j * a.nx : nullptr;
+            const long long aux_stride = (long long)NT * a.nx;
+            if (a.has_a && a.has_b) {
+                if (aux != nullptr) k_factors<T, E, NT, TM, true, true, true>(v[0], fxa, fxb, a.ya + oy, a.yb + oy, aux, aux_stride, acc);
+                else k_factors<T, E, NT, TM, true, true, false>(v[0], fxa, fxb, a.ya + oy, a.yb + oy, aux, aux_stride, acc);
+            } else if (a.has_a) {
+                if (aux != nullptr) k_factors<T, E, NT, TM, true, false, true>(v[0], fxa, fxb, a.ya + oy, a.yb, aux, aux_stride, acc);
+                else k_factors<T, E, NT, TM, true, false, false>(v[0], fxa, fxb, a.ya + oy, a.yb, aux, aux_stride, acc);
+            } else {
+                k_factors<T, E, NT, TM, false, true, false>(v[0], fxa, fxb, a.ya, a.yb + oy, aux, aux_stride, acc);
+            }
+            cta_reduce<2>(acc, red);
+            if (tid == 0) {
+                double* p = a.partials + ((long long)b * ntiles + tile) * 2;
+                p[0] = acc[0]; p[1] = acc[1];
+            }
+        }
+
+        SGPE_PMARK(3);
+        if constexpr (XSPLIT) {
+            T* const xs[1] = {X};
+            cta_fft_split_from<T, N, E, +1, W, 1, 1>(v, j, c, xs, tw, CtaBar());
+        } else {
+            // (fresh copies of the thread coordinates: the exchange addresses of the two transforms are NOT shared, which
+            // would keep 32 of them live across the pass and spill)
+            int j2 = j, c2 = c;
+            SGPE_OPAQUE(j2); SGPE_OPAQUE(c2);
+            cta_fft_head<T, N, E, +1, W, 1, 1>(v, j2, c2, sms, tw, CtaBar());
+            if (tid == 0 && tile + (int)gridDim.x < ntiles) {           // behind the last exchange read: S is free
+                sgpe_fence_proxy_async();
+                stage(tile + (int)gridDim.x);
+            }
+            stage_compute<T, N, E, +1, LAST_NS>(v[0], j2, tw);
+        }
+        SGPE_PMARK(4);
+#pragma unroll
+        for (int m = 0; m < E; m++) SGPE_ST_STREAM(&a.out[off + (long long)(j + m * NT) * a.nx], v[0][m]);
+        SGPE_PMARK(5);
+#ifdef SGPE_TIMELINE
+        if (a.dbg != nullptr && threadIdx.x == 0) {
+            unsigned long long* d = a.dbg + ((long long)b * ntiles + tile) * 8;
+            for (int k = 0; k < 6; k++) d[k] = marks[k];
+            d[7] = SGPE_SMID();
+        }
+#endif
+#undef SGPE_PMARK
+    }
+
+    if (any_k) {
+        const int tid = threadIdx.x;
+        if (tid == 0) {
+            __threadfence();
+            const unsigned before = atomicAdd(&a.counter[b], (unsigned)done);
+            *flag = (before + (unsigned)done == (unsigned)ntiles) ? 1 : 0;
+        }
+        __syncthreads();
+        if (*flag) {      // the CTA that completed the count folds the partials in a fixed order
+            __threadfence();
+            double t4[4] = {0.0, 0.0, 0.0, 0.0};     // S0, T0, S1, T1
+            const double* p = a.partials + (long long)b * ntiles * 2;
+            for (int t = tid; t < ntiles; t += W * NT) {
+                const int cp = (t >= ntiles / 2) ? 2 : 0;
+                t4[cp + 0] += __ldcg(&p[2 * t]);
+                t4[cp + 1] += __ldcg(&p[2 * t + 1]);
+            }
+            cta_reduce<4>(t4, red);
+            if (tid == 0) {
+                double* tot = a.totals + (long long)b * 4;
+                tot[0] = t4[1] + t4[3];
+                tot[1] = t4[0];
+                tot[2] = t4[2];
+                int slot = a.pops_slot;
+                if (a.slot_ctr != nullptr) { slot = a.slot_ctr[b]; a.slot_ctr[b] = slot + 1; }
+                if (a.pops != nullptr && slot >= 0) {
+                    double* pp = a.pops + (long long)b * a.pops_bstride + 2LL * slot;
+                    const double inv = a.atom_num / (t4[0] + t4[2]);
+                    pp[0] = t4[0] * inv; pp[1] = t4[2] * inv;
+                }
+                a.counter[b] = 0u;
+            }
+        }
+    }
+}
+
+// Persistent column pass, two barrier groups per CTA.  The staged tile of W columns (64-byte rows, one TMA landing zone
+// S as in col_pass_p) is worked on by TWO independent groups of half the threads, W / 2 columns each, with their own
+// named barrier, their own real exchange image (both transforms use the split re / im exchange) and their own
+// partial-sum slot.  The groups drift out of phase - the scheduler prefers the higher warp ids, so one group's
+// butterflies run while the other waits at its exchange - which overlaps the FP64 pipe with the shared-memory pipe
+// inside one SM; the register file (one tile of complex128 data) has no room for a second CTA to do that.  The tile is
+// loaded by TMA whatever the group width, so the groups' 32-byte row halves cost nothing on the load side.
+// The second group to have read tile t out of S stages tile t + gridDim.x (shared-memory ticket).
+template <typename T, int N, int E, int W, int TM>
+__global__ void __launch_bounds__(W * N / E, 1)
+col_pass_pg(const SGPE_GRID_CONSTANT SgpeTileMap tmap, ColArgs<T> a) {
+    typedef typename cx_of<T>::type C;
+    constexpr int NT = N / E;
+    constexpr int WG = W / 2;                   // columns per group
+    constexpr int TG = WG * NT;                 // threads per group
+    constexpr int BOXR = N < 256 ? N : 256, NBOX = N / BOXR;
+    constexpr unsigned TILE_BYTES = (unsigned)(N * W * sizeof(C));
+    SGPE_DYN_SMEM_128(smem_p);
+    C* const S = reinterpret_cast<C*>(smem_p);
+    double* const red0 = reinterpret_cast<double*>(smem_p + TILE_BYTES + TILE_BYTES / 2);
+    SgpeMbar* const mbar = reinterpret_cast<SgpeMbar*>(red0 + 2 * 32 * 4);
+    unsigned* const ticket = reinterpret_cast<unsigned*>(mbar + 1);
+    int* const flag = reinterpret_cast<int*>(ticket + 1);           // [2]
+
+    const int b = blockIdx.y;
+    const int tiles_per_comp = a.nx / W;
+    const int ntiles = 2 * tiles_per_comp;
+    const int nslots = 2 * ntiles;
+    const bool any_k = a.has_a || a.has_b;
+
+    auto stage = [&](int t) {
+        sgpe_mbar_expect_tx(mbar, TILE_BYTES);
+#pragma unroll 1
+        for (int q = 0; q < NBOX; q++)
+            sgpe_tma_load_2d(S + (size_t)q * BOXR * W, &tmap, 2 * (t % tiles_per_comp) * W,
+                             (b * 2 + t / tiles_per_comp) * a.ny + q * BOXR, mbar, BOXR, (int)(W * sizeof(C)));
+    };
+
+    if (threadIdx.x == 0) { sgpe_mbar_init(mbar, 1); *ticket = 0u; }
+    __syncthreads();
+    if (threadIdx.x == 0) stage(blockIdx.x);
+    const int g = (int)threadIdx.x / TG;
+    const GroupBar gbar = {1 + g, TG};
+    T* const X = reinterpret_cast<T*>(smem_p + TILE_BYTES) + (size_t)g * N * WG;
+    double* const red = red0 + g * (32 * 4);
+    int done = 0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, done++) {
+        const int tid = (int)threadIdx.x - g * TG;
+        const int c = tid % WG, j = tid / WG;
+        const C* __restrict__ tw = a.tw + (E == 16 ? N : 0);
+        const int comp = tile / tiles_per_comp;
+        const int col = (tile % tiles_per_comp) * W + g * WG + c;
+        const long long off = ((long long)b * 2 + comp) * a.plane + col;
+
+        sgpe_mbar_wait(mbar, (unsigned)(done & 1));
+        C v[1][E];
+#pragma unroll
+        for (int m = 0; m < E; m++) v[0][m] = S[(j + m * NT) * W + g * WG + c];
+        stage_compute<T, N, E, -1, 1>(v[0], j, tw);
+        gbar.sync();                        // this group has its half of the tile in registers
+        if (tid == 0) {
+            const unsigned t0 = atomicAdd(ticket, 1u);
+            if ((t0 & 1u) && tile + (int)gridDim.x < ntiles) {      // the other group was first: S is free
+                sgpe_fence_proxy_async();
+                stage(tile + (int)gridDim.x);
+            }
+        }
+        T* const xs[1] = {X};
+        {   // forward transform: the stage-1 butterflies are done, continue with the exchange
+            constexpr int R0 = E;
+            if constexpr (R0 < N) {
+                stage_store_part<T, N, E, WG, 1, 0>(v[0], j, c, X);
+                gbar.sync();
+                stage_load_part<T, N, E, WG, 0>(v[0], j, c, X);
+                gbar.sync();
+                stage_store_part<T, N, E, WG, 1, 1>(v[0], j, c, X);
+                gbar.sync();
+                stage_load_part<T, N, E, WG, 1>(v[0], j, c, X);
+                cta_fft_split_from<T, N, E, -1, WG, 1, R0>(v, j, c, xs, tw, gbar);
+            }
+        }
+
+        double acc[2] = {0.0, 0.0};   // S (after FA), T (after FB)
+        if (any_k) {
+            const long long ox = (long long)b * a.sepx_bstride + (long long)comp * a.nx + col;
+            const long long oy = (long long)b * a.sepy_bstride + (long long)comp * a.ny + j;
+            C fxa, fxb;
+            fxa.x = (T)1; fxa.y = (T)0; fxb = fxa;
+            if (a.has_a) fxa = __ldg(&a.xa[ox]);
+            if (a.has_b) fxb = __ldg(&a.xb[ox]);
+            C* const aux = a.aux != nullptr ? a.aux + off + (long long)j * a.nx : nullptr;
+            const long long aux_stride = (long long)NT * a.nx;
+            if (a.has_a && a.has_b) {
+                if (aux != nullptr) k_factors<T, E, NT, TM, true, true, true>(v[0], fxa, fxb, a.ya + oy, a.yb + oy, aux, aux_stride, acc);
+                else k_factors<T, E, NT, TM, true, true, false>(v[0], fxa, fxb, a.ya + oy, a.yb + oy, aux, aux_stride, acc);
+            } else if (a.has_a) {
+                if (aux != nullptr) k_factors<T, E, NT, TM, true, false, true>(v[0], fxa, fxb, a.ya + oy, a.yb, aux, aux_stride, acc);
+                else k_factors<T, E, NT, TM, true, false, false>(v[0], fxa, fxb, a.ya + oy, a.yb, aux, aux_stride, acc);
+            } else {
+                k_factors<T, E, NT, TM, false, true, false>(v[0], fxa, fxb, a.ya, a.yb + oy, aux, aux_stride, acc);
+            }
+            group_reduce<2>(acc, red, tid, TG, gbar);
+            if (tid == 0) {
+                double* p = a.partials + ((long long)b * nslots + 2 * tile + g) * 2;
+                p[0] = acc[0]; p[1] = acc[1];
+            }
+        }
+
+        cta_fft_split_from<T, N, E, +1, WG, 1, 1>(v, j, c, xs, tw, gbar);
+#pragma unroll
+        for (int m = 0; m < E; m++) SGPE_ST_STREAM(&a.out[off + (long long)(j + m * NT) * a.nx], v[0][m]);
+    }
+
+    if (any_k) {
+        const int tid = (int)threadIdx.x - g * TG;
+        if (tid == 0) {
+            __threadfence();
+            const unsigned before = atomicAdd(&a.counter[b], (unsigned)done);
+            flag[g] = (before + (unsigned)done == (unsigned)nslots) ? 1 : 0;
+        }
+        gbar.sync();
+        if (flag[g]) {    // the group that completed the count folds the partials in a fixed order
+            __threadfence();
+            double t4[4] = {0.0, 0.0, 0.0, 0.0};     // S0, T0, S1, T1
+            const double* p = a.partials + (long long)b * nslots * 2;
+            for (int t = tid; t < nslots; t += TG) {
+                const int cp = (t >= nslots / 2) ? 2 : 0;
+                t4[cp + 0] += __ldcg(&p[2 * t]);
+                t4[cp + 1] += __ldcg(&p[2 * t + 1]);
+            }
+            group_reduce<4>(t4, red, tid, TG, gbar);
+            if (tid == 0) {
+                double* tot = a.totals + (long long)b * 4;
+                tot[0] = t4[1] + t4[3];
+                tot[1] = t4[0];
+                tot[2] = t4[2];
+                int slot = a.pops_slot;
+                if (a.slot_ctr != nullptr) { slot = a.slot_ctr[b]; a.slot_ctr[b] = slot + 1; }
+                if (a.pops != nullptr && slot >= 0) {
+                    double* pp = a.pops + (long long)b * a.pops_bstride + 2LL * slot;
                     const double inv = a.atom_num / (t4[0] + t4[2]);
                     pp[0] = t4[0] * inv; pp[1] = t4[2] * inv;
                 }
@@ -1123,6 +1510,13 @@ __global__ void __launch_bounds__(256) slab_unpack_transpose(UnpackArgs<T> a) {
         for (int k = 0; k < 4; k++) dst[(long long)(ty + 8 * k) * ((long long)a.P * a.Bh) + tx] = tile[tx * 33 + ty + 8 * k];
         __syncthreads();
     }
+}
+
+// out[i] = value, i < n (the slot counters of a graph replay)
+template <typename I>
+__global__ void __launch_bounds__(128) fill_value(I* out, I value, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = value;
 }
 
 // factor table: out[i] = exp(-i * e[i] * tau)   (separable operators: 1-D energy vectors -> 1-D factor tables)

@@ -120,6 +120,55 @@ static int launch_col_w(const ColArgs<T>& a, int batch, cudaStream_t st) {
     return 0;
 }
 
+// persistent column pass with TMA-staged tiles (col_pass_p): one CTA per resident slot, grid capped at the tile count
+template <typename T, int N, int TM, int W, int E, int XSPLIT, int TWS>
+static int launch_col_p(const ColArgs<T>& a, int batch, cudaStream_t st) {
+    typedef ColCfg<T, N> Cfg;
+    constexpr size_t tile = (size_t)N * W * Cfg::CB;
+    constexpr size_t smem = tile + (XSPLIT ? tile / 2 : 0) + (TWS ? (size_t)N * Cfg::CB : 0) + 32 * 4 * sizeof(double) + 64;
+    if (a.nx % W != 0 || a.tile_map == nullptr) return -2;
+    if (smem > 227 * 1024) return -2;
+    static bool once = false;
+    static int resident = 0;
+    if (!once) {
+        allow_smem(col_pass_p<T, N, E, W, TM, XSPLIT, TWS>, smem);
+        resident = resident_ctas(col_pass_p<T, N, E, W, TM, XSPLIT, TWS>, W * (N / E), smem);
+        once = true;
+    }
+    const int ntiles = 2 * a.nx / W;
+    int ctas = resident > 0 ? resident / (batch < 1 ? 1 : batch) : ntiles;      // the batch shares the device
+    if (ctas < 1) ctas = 1;
+    if (ctas > ntiles) ctas = ntiles;
+    dim3 grid(ctas, batch), block(W * (N / E));
+    const SgpeTileMap& map = *static_cast<const SgpeTileMap*>(a.tile_map);
+    SGPE_LAUNCH((col_pass_p<T, N, E, W, TM, XSPLIT, TWS>), grid, block, smem, st, map, a);
+    return 0;
+}
+
+// persistent column pass, two barrier groups per CTA (col_pass_pg)
+template <typename T, int N, int TM, int W, int E>
+static int launch_col_pg(const ColArgs<T>& a, int batch, cudaStream_t st) {
+    typedef ColCfg<T, N> Cfg;
+    constexpr size_t tile = (size_t)N * W * Cfg::CB;
+    constexpr size_t smem = tile + tile / 2 + 2 * 32 * 4 * sizeof(double) + 64;
+    if (a.nx % W != 0 || a.tile_map == nullptr) return -2;
+    static bool once = false;
+    static int resident = 0;
+    if (!once) {
+        allow_smem(col_pass_pg<T, N, E, W, TM>, smem);
+        resident = resident_ctas(col_pass_pg<T, N, E, W, TM>, W * (N / E), smem);
+        once = true;
+    }
+    const int ntiles = 2 * a.nx / W;
+    int ctas = resident > 0 ? resident / (batch < 1 ? 1 : batch) : ntiles;
+    if (ctas < 1) ctas = 1;
+    if (ctas > ntiles) ctas = ntiles;
+    dim3 grid(ctas, batch), block(W * (N / E));
+    const SgpeTileMap& map = *static_cast<const SgpeTileMap*>(a.tile_map);
+    SGPE_LAUNCH((col_pass_pg<T, N, E, W, TM>), grid, block, smem, st, map, a);
+    return 0;
+}
+
 // G barrier groups of W columns each in one CTA (col_pass<..., G>): same tile, same global segments, G instruction
 // streams per SM
 template <typename T, int N, int TM, int W, int E, int G>
@@ -170,6 +219,27 @@ static int launch_col_t(const ColArgs<T>& a, int batch, int wsel, cudaStream_t s
 #else
     if (wsel != 0 && wsel != 3) return -3;
 #endif
+    if constexpr (Cfg::E == 16) {
+        // the persistent kernel covers the steady-state junction: forward + factors + inverse, separable tables
+        const bool fast = a.do_fwd && a.do_inv && a.kin_mode == 1 && !a.sign_in && !a.sign_out && a.scale_out == 1.0 &&
+                          a.in == a.out;
+        if (a.kernel_sel == 1 && fast && a.tile_map != nullptr && wsel == 0)
+            return launch_col_p<T, N, TM, Cfg::W, Cfg::E, 1, 0>(a, batch, st);
+        if (a.kernel_sel == 2 && fast && a.tile_map != nullptr && wsel == 0)
+            return launch_col_p<T, N, TM, Cfg::W, Cfg::E, 0, 0>(a, batch, st);
+        if (a.kernel_sel == 4 && fast && a.tile_map != nullptr && wsel == 0) {
+            int rc4 = launch_col_p<T, N, TM, Cfg::W, Cfg::E, 1, 1>(a, batch, st);
+            return rc4 == -2 ? launch_col_p<T, N, TM, Cfg::W, Cfg::E, 1, 0>(a, batch, st) : rc4;
+        }
+        if constexpr (Cfg::W % 2 == 0 && (Cfg::W / 2) * Cfg::NT >= 32) {
+            if (a.kernel_sel == 5 && fast && a.tile_map != nullptr && wsel == 0)
+                return launch_col_p<T, N, TM, Cfg::W / 2, Cfg::E, 1, 0>(a, batch, st);
+        }
+        if constexpr (Cfg::W % 2 == 0 && (Cfg::W / 2) * Cfg::NT >= 32) {
+            if (a.kernel_sel == 3 && fast && a.tile_map != nullptr && wsel == 0)
+                return launch_col_pg<T, N, TM, Cfg::W, Cfg::E>(a, batch, st);
+        }
+    }
     return launch_col_w<T, N, TM, Cfg::W, Cfg::E>(a, batch, st);
 }
 

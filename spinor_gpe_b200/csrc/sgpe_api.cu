@@ -91,6 +91,9 @@ struct sgpe_plan {
     // long lines (four-step): nx = n1 * n2 with the strided part n1 (1 = ordinary plan)
     int n1 = 1, n2 = 0; void* tw_mid = nullptr; void* tw4 = nullptr;
     int col_wsel = 0;              // column tile width selector (sgpe_set_option "col_tile")
+    int col_kernel = 0;            // option "col_kernel": 0 = default choice, 1 = one tile per CTA, 2 / 3 = persistent + TMA staging
+    struct TileMap { const void* ptr = nullptr; int w = 0; SgpeTileMap* map = nullptr; };
+    std::vector<TileMap> tile_maps;   // column-tile descriptors of the buffers the persistent pass has run on
     int unwrap_sort = 0;           // edge sort of the phase unwrapping: 0 device radix sort, 1 host (option "unwrap_sort")
     int* unwrap_inc = nullptr;     // [B][2][ny][nx] multiples of 2 pi (sgpe_energy with unwrap_mode 2), on first use
     // fused exchange of the slab mode (sgpe_slab_set_peers): where the scatter stores of this plan's passes go
@@ -114,6 +117,18 @@ struct sgpe_plan {
     double* pend_energy = nullptr; long long pend_estride = 0; int pend_eslot = -1;
     int track_unwrap = 0; double track_kl = 0.0;
     uint64_t launches = 0;
+    // CUDA-graph replay of the steady-state full step (option "graph"): six kernel nodes whose arguments do not change
+    // from step to step (the populations slot comes from the device-side counter slot_ctr)
+    int use_graph = -1;            // -1: default choice (small meshes), 0 off, 1 on
+    uint64_t epoch = 0;            // bumped by every sgpe_set_* call: a captured graph is valid for one epoch
+    int* slot_ctr = nullptr;       // [batch]
+    bool capturing = false;
+#ifndef SGPE_EMU
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaStream_t cap_stream = nullptr;
+    struct GraphKey { uint64_t epoch = 0; const void* pops = nullptr; long long stride = 0; int tm = -1; double dt = 0;
+                      bool operator==(const GraphKey& o) const { return epoch == o.epoch && pops == o.pops && stride == o.stride && tm == o.tm && dt == o.dt; } } graph_key;
+#endif
     // optional per-kernel timing (sgpe_profile_*): event pairs around column (kind 0) / row (kind 1) passes
     bool prof_on = false;
 #ifndef SGPE_EMU
@@ -233,6 +248,59 @@ int factor_table(sgpe_plan* p, sgpe_plan::FactorTable* slots, int nslots, const 
 
 void invalidate_tables(sgpe_plan::FactorTable* slots, int n) { for (int i = 0; i < n; i++) slots[i].valid = false; }
 
+// Which column-pass kernel a plan uses unless sgpe_set_option("col_kernel") says otherwise (kernel_sel of ColArgs):
+// measured on B200 (profiles/r02_kernel_sweep.jsonl) — complex128: the persistent pass with TMA-staged tiles and the
+// split inverse exchange wins from 1024-point columns on (+5 % at 2048, +13 % at 4096; +12..17 % in real time) and for
+// batched plans (+6..8 % at 8 / 64 x 512^2); complex64: half-width persistent tiles, two CTAs per SM (+12..19 % at 2048).
+int default_col_kernel(const sgpe_plan* p) {
+    if (p->dtype == SGPE_C128) return (p->ny >= 1024 || (p->batch >= 2 && p->ny >= 512)) ? 1 : 0;
+    return p->ny >= 1024 ? 5 : 0;
+}
+
+// Descriptor of the column tiles of a state buffer [B][2][ny][nx] for the persistent column pass: the buffer seen as a
+// 2-D array of B*2*ny rows of 2*nx reals, boxes of 256 rows x one tile width (64 bytes).
+int tile_map_for(sgpe_plan* p, const void* buf, int w, const SgpeTileMap** out) {
+    for (auto& t : p->tile_maps)
+        if (t.ptr == buf && t.w == w) { *out = t.map; return 0; }
+    SgpeTileMap* m = new SgpeTileMap();
+#ifndef SGPE_EMU
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+            cudaGetLastError();
+            delete m;
+            return fail(SGPE_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        }
+        encode = (EncodeFn)fn;
+    }
+    const cuuint64_t dims[2] = {2ull * (cuuint64_t)p->nx, (cuuint64_t)p->batch * 2ull * (cuuint64_t)p->ny};
+    const cuuint64_t strides[1] = {(cuuint64_t)p->nx * p->csize};
+    const cuuint32_t box[2] = {(cuuint32_t)(2 * w), (cuuint32_t)(p->ny < 256 ? p->ny : 256)};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult rc = encode(&m->m, p->dtype == SGPE_C128 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                         const_cast<void*>(buf), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        delete m;
+        return fail(SGPE_ECUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)rc) + ")");
+    }
+#else
+    (void)w;
+    m->base = static_cast<const unsigned char*>(buf);
+    m->row_stride = (long long)p->nx * (long long)p->csize;
+    m->elem_bytes = (int)p->csize / 2;
+#endif
+    if (p->tile_maps.size() >= 8) { delete p->tile_maps.front().map; p->tile_maps.erase(p->tile_maps.begin()); }
+    p->tile_maps.push_back({buf, w, m});
+    *out = m;
+    return 0;
+}
+
 // Column pass.  tau_a / tau_b: time arguments of the k-space factors FA / FB (exp(-i kin tau)); has_a / has_b
 // select them.
 template <typename T>
@@ -270,9 +338,19 @@ int run_col(sgpe_plan* p, const void* in, void* out, bool fwd, bool has_a, doubl
     }
     a.partials = p->partials; a.counter = p->counter; a.totals = p->totals;
     a.pops = pops; a.pops_bstride = pops_stride; a.pops_slot = pops_slot;
+    a.slot_ctr = (p->capturing && pops != nullptr && pops_slot >= 0) ? p->slot_ctr : nullptr;
     a.atom_num = p->atom_num;
     a.aux = static_cast<C*>(aux);
     a.dbg = (fwd && inv) ? p->dbg_col : nullptr;
+    a.kernel_sel = p->col_kernel == 0 ? default_col_kernel(p) : p->col_kernel - 1;
+    if (a.kernel_sel >= 1 && fwd && inv && in == out && p->kin_mode == 1 && p->n1 == 1) {
+        const SgpeTileMap* tm = nullptr;
+        int w = sgpe::col_tile_width(p->ny, p->dtype);
+        if (a.kernel_sel == 5) w /= 2;                      // half-width tiles, two CTAs per SM
+        int rcm = tile_map_for(p, in, w, &tm);
+        if (rcm) return rcm;
+        a.tile_map = tm;
+    }
     ProfScope prof(p, 0, st);
     int rc = sgpe::launch_col(p->ny, p->dtype, p->tm, &a, p->batch, p->col_wsel, st);
     if (rc == -3) return fail(SGPE_EINVAL, "column pass variant not compiled in (build with -DSGPE_EXPERIMENTAL)");
@@ -922,6 +1000,12 @@ int sgpe_plan_destroy(sgpe_plan* p) {
     cudaFree(p->state); cudaFree(p->tw_x); cudaFree(p->tw_y); cudaFree(p->partials);
     cudaFree(p->counter); cudaFree(p->totals); cudaFree(p->totals_aux); cudaFree(p->pops_buf);
     cudaFree(p->scratch); cudaFree(p->maxdens); cudaFree(p->unwrap_inc); cudaFree(p->sm_slots); cudaFree(p->tw_mid); cudaFree(p->tw4);
+    for (auto& t : p->tile_maps) delete t.map;
+    cudaFree(p->slot_ctr);
+#ifndef SGPE_EMU
+    if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+    if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
+#endif
     for (auto& t : p->kin_tab) { cudaFree(t.x); cudaFree(t.y); }
     for (auto& t : p->pot_tab) { cudaFree(t.x); cudaFree(t.y); }
     delete p;
@@ -929,6 +1013,7 @@ int sgpe_plan_destroy(sgpe_plan* p) {
 }
 
 int sgpe_set_grid(sgpe_plan* p, double dx, double dy, double dv_r, double dv_k, double atom_num) {
+    if (p) p->epoch++;
     if (!p) return fail(SGPE_EINVAL, "null plan");
     if (!(dx > 0 && dy > 0 && dv_r > 0 && dv_k > 0 && atom_num > 0)) return fail(SGPE_EINVAL, "grid values must be positive");
     p->dx = dx; p->dy = dy; p->dv_r = dv_r; p->dv_k = dv_k; p->atom_num = atom_num; p->grid_set = true;
@@ -936,24 +1021,28 @@ int sgpe_set_grid(sgpe_plan* p, double dx, double dy, double dv_r, double dv_k, 
 }
 
 int sgpe_set_interactions(sgpe_plan* p, double g_uu, double g_dd, double g_ud) {
+    if (p) p->epoch++;
     if (!p) return fail(SGPE_EINVAL, "null plan");
     p->g_uu = g_uu; p->g_dd = g_dd; p->g_ud = g_ud; p->g_set = true;
     return 0;
 }
 
 int sgpe_set_kinetic(sgpe_plan* p, const double* kin0, const double* kin1, int64_t bs) {
+    if (p) p->epoch++;
     if (!p || !kin0 || !kin1) return fail(SGPE_EINVAL, "null argument");
     p->kin0 = kin0; p->kin1 = kin1; p->kin_bs = bs; p->kin_set = true; p->kin_mode = 0;
     return 0;
 }
 
 int sgpe_set_potential(sgpe_plan* p, const double* pot0, const double* pot1, int64_t bs) {
+    if (p) p->epoch++;
     if (!p || !pot0 || !pot1) return fail(SGPE_EINVAL, "null argument");
     p->pot0 = pot0; p->pot1 = pot1; p->pot_bs = bs; p->pot_set = true; p->pot_mode = 0;
     return 0;
 }
 
 int sgpe_set_kinetic_separable(sgpe_plan* p, const double* kin_x, const double* kin_y, int64_t xbs, int64_t ybs) {
+    if (p) p->epoch++;
     if (!p || !kin_x || !kin_y) return fail(SGPE_EINVAL, "null argument");
     p->kin_x = kin_x; p->kin_y = kin_y; p->kin_xbs = xbs; p->kin_ybs = ybs; p->kin_mode = 1; p->kin_set = true;
     invalidate_tables(p->kin_tab, 6);
@@ -961,6 +1050,7 @@ int sgpe_set_kinetic_separable(sgpe_plan* p, const double* kin_x, const double* 
 }
 
 int sgpe_set_potential_separable(sgpe_plan* p, const double* pot_x, const double* pot_y, int64_t xbs, int64_t ybs) {
+    if (p) p->epoch++;
     if (!p || !pot_x || !pot_y) return fail(SGPE_EINVAL, "null argument");
     p->pot_x = pot_x; p->pot_y = pot_y; p->pot_xbs = xbs; p->pot_ybs = ybs; p->pot_mode = 1; p->pot_set = true;
     invalidate_tables(p->pot_tab, 4);
@@ -969,6 +1059,7 @@ int sgpe_set_potential_separable(sgpe_plan* p, const double* pot_x, const double
 
 int sgpe_set_coupling(sgpe_plan* p, int mode, const double* coupling, int64_t bs, const double* omega,
                       const void* eiphi) {
+    if (p) p->epoch++;
     if (!p) return fail(SGPE_EINVAL, "null plan");
     if (mode == SGPE_COUPLING_UNIFORM && !omega) return fail(SGPE_EINVAL, "uniform coupling needs omega_dev[batch]");
     if (mode == SGPE_COUPLING_DENSE && !coupling) return fail(SGPE_EINVAL, "dense coupling needs coupling_dev");
@@ -978,6 +1069,7 @@ int sgpe_set_coupling(sgpe_plan* p, int mode, const double* coupling, int64_t bs
 }
 
 int sgpe_set_energy_coupling(sgpe_plan* p, int mode, const double* coupling, int64_t bs, const double* omega) {
+    if (p) p->epoch++;
     if (!p) return fail(SGPE_EINVAL, "null plan");
     if (mode < -1 || mode > 2) return fail(SGPE_EINVAL, "bad coupling mode");
     if (mode == SGPE_COUPLING_UNIFORM && !omega) return fail(SGPE_EINVAL, "uniform coupling needs omega_dev[batch]");
@@ -987,6 +1079,7 @@ int sgpe_set_energy_coupling(sgpe_plan* p, int mode, const double* coupling, int
 }
 
 int sgpe_set_option(sgpe_plan* p, const char* name, int value) {
+    if (p) p->epoch++;
     if (!p || !name) return fail(SGPE_EINVAL, "null argument");
     if (std::strcmp(name, "col_tile") == 0) {
         if (value != 0 && value != 2 && value != 3 && value != 8)
@@ -996,6 +1089,19 @@ int sgpe_set_option(sgpe_plan* p, const char* name, int value) {
     }
     if (std::strcmp(name, "stagger_ns") == 0) { p->stagger_ns = value; return 0; }
     if (std::strcmp(name, "timeline_kind") == 0) { p->dbg_kind = value ? 1 : 0; return 0; }
+    if (std::strcmp(name, "graph") == 0) {
+        if (value < -1 || value > 1) return fail(SGPE_EINVAL, "graph: -1 (default: small meshes), 0 (off) or 1 (on)");
+        p->use_graph = value;
+        return 0;
+    }
+    if (std::strcmp(name, "col_kernel") == 0) {
+        if (value < 0 || value > 6)
+            return fail(SGPE_EINVAL, "col_kernel: 0 (default), 1 (one tile per CTA), 2 (persistent, TMA-staged, split inverse "
+                                     "exchange), 3 (persistent, TMA-staged behind the inverse transform), 4 (persistent, "
+                                     "two barrier groups per CTA) 5 (as 2 with the twiddle tables in shared memory) or 6 (as 2 with half-width tiles, two CTAs per SM)");
+        p->col_kernel = value;
+        return 0;
+    }
     if (std::strcmp(name, "prefetch") == 0) { p->prefetch = value ? 1 : 0; return 0; }
     if (std::strcmp(name, "unwrap_sort") == 0) {
         if (value != 0 && value != 1) return fail(SGPE_EINVAL, "unwrap_sort: 0 (device radix sort) or 1 (host sort)");
@@ -1011,6 +1117,7 @@ int sgpe_set_option(sgpe_plan* p, const char* name, int value) {
 }
 
 int sgpe_set_time(sgpe_plan* p, int time_mode, double dt) {
+    if (p) p->epoch++;
     if (!p) return fail(SGPE_EINVAL, "null plan");
     if (time_mode != SGPE_TIME_REAL && time_mode != SGPE_TIME_IMAG) return fail(SGPE_EINVAL, "bad time mode");
     if (p->phase == sgpe_plan::MID && time_mode != p->tm)
@@ -1063,12 +1170,89 @@ int sgpe_single_step(sgpe_plan* p, double dt_sub, sgpe_stream st) {
     return single_step_impl(p, dt_sub, (cudaStream_t)st);
 }
 
+#ifndef SGPE_EMU
+// One steady-state full step (MID -> MID, the junction that opens it records the populations of the step before)
+// captured into an executable graph.  Called with every factor table the step needs already cached.
+static int capture_step_graph(sgpe_plan* p, double* pops, int64_t pops_stride) {
+    // (captured on a stream of the plan's own: the caller's may be the legacy default stream, which cannot capture;
+    // the executable graph is then launched on the caller's stream)
+    if (!p->cap_stream) SGPE_CUDA(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
+    cudaStream_t s = p->cap_stream;
+    if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+    if (!p->slot_ctr && cudaMalloc((void**)&p->slot_ctr, sizeof(int) * p->batch) != cudaSuccess)
+        return fail(SGPE_ENOMEM, "device allocation failed");
+    cudaGraph_t graph = nullptr;
+    SGPE_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    p->capturing = true;
+    p->pend_pops = pops; p->pend_stride = pops_stride; p->pend_slot = pops ? 0 : -1;     // slot value unused: counter
+    int rc = single_step_impl(p, p->dt_out, s);
+    if (!rc) rc = single_step_impl(p, p->dt_in, s);
+    if (!rc) rc = single_step_impl(p, p->dt_out, s);
+    p->capturing = false;
+    cudaError_t e = cudaStreamEndCapture(s, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(SGPE_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&p->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { p->graph_exec = nullptr; return fail(SGPE_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+    return 0;
+}
+#endif
+
+// should sgpe_full_steps replay a captured graph?  Default: meshes whose passes are launch-bound (<= 512^2 points
+// in the plan); long-line plans, profiling runs and streams that are already being captured never do.
+static bool graph_wanted(const sgpe_plan* p, int n, cudaStream_t s) {
+#ifdef SGPE_EMU
+    (void)p; (void)n; (void)s;
+    return false;
+#else
+    if (p->use_graph == 0 || n < 4 || p->prof_on || p->n1 != 1 || p->dbg || p->dbg_col) return false;
+    if (p->use_graph < 0 && !((long long)p->nx * p->ny * p->batch <= 512LL * 512LL)) return false;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return false; }
+    return true;
+#endif
+}
+
 int sgpe_full_steps(sgpe_plan* p, int n, double* pops, int64_t pops_stride, int pops_first, sgpe_stream st) {
     int rc = ready_to_step(p);
     if (rc) return rc;
     if (n < 0) return fail(SGPE_EINVAL, "negative step count");
     DeviceGuard guard(p->device);
     cudaStream_t s = (cudaStream_t)st;
+#ifndef SGPE_EMU
+    if (graph_wanted(p, n, s)) {
+        // steps 0 and 1 launch normally (they open the junction and leave every factor table of the steady state in
+        // the cache), steps 2 .. n-1 replay the captured step, the last junction is closed normally
+        for (int i = 0; i < 2; i++) {
+            if ((rc = single_step_impl(p, p->dt_out, s))) return rc;
+            if ((rc = single_step_impl(p, p->dt_in, s))) return rc;
+            if ((rc = single_step_impl(p, p->dt_out, s))) return rc;
+            p->pend_pops = pops; p->pend_stride = pops_stride; p->pend_slot = pops ? pops_first + i : -1;
+        }
+        sgpe_plan::GraphKey key;
+        key.epoch = p->epoch; key.pops = pops; key.stride = pops_stride; key.tm = p->tm; key.dt = p->dt;
+        if (!p->graph_exec || !(p->graph_key == key)) {
+            // (the capture itself executes nothing: the state machine is restored afterwards)
+            const sgpe_plan::Phase phase = p->phase; const double pend = p->pending_dt; const bool sc = p->scale_pending;
+            const uint64_t l0 = p->launches;
+            rc = capture_step_graph(p, pops, pops_stride);
+            p->phase = phase; p->pending_dt = pend; p->scale_pending = sc; p->launches = l0;
+            if (rc) return rc;
+            p->graph_key = key;
+        }
+        if (pops) {
+            sgpe::fill_value<int><<<(p->batch + 127) / 128, 128, 0, s>>>(p->slot_ctr, pops_first + 1, p->batch);
+            p->launches++;
+        }
+        for (int i = 2; i < n; i++) SGPE_CUDA(cudaGraphLaunch(p->graph_exec, s));
+        p->launches += 6ull * (uint64_t)(n - 2);
+        p->phase = sgpe_plan::MID; p->pending_dt = p->dt_out; p->scale_pending = false;
+        p->pend_pops = pops; p->pend_stride = pops_stride; p->pend_slot = pops ? pops_first + n - 1 : -1;
+        p->pend_eslot = -1;
+        return close_junction(p, s);
+    }
+#endif
     for (int i = 0; i < n; i++) {                       // tensor_propagator.py:220-222
         if ((rc = single_step_impl(p, p->dt_out, s))) return rc;
         if ((rc = single_step_impl(p, p->dt_in, s))) return rc;
@@ -1266,6 +1450,7 @@ int sgpe_pass_rows(sgpe_plan* p, void* buf, double dt_sub, const double* totals_
 
 int sgpe_slab_set_peers(sgpe_plan* p, void* const* peer_bufs, int nranks, int mode, int seg, int drow, int64_t dplane,
                         int base) {
+    if (p) p->epoch++;
     if (!p || !peer_bufs) return fail(SGPE_EINVAL, "null argument");
     if (nranks < 1 || nranks > SGPE_MAX_PEERS) return fail(SGPE_EINVAL, "1..16 ranks");
     if (mode != 1 && mode != 2) return fail(SGPE_EINVAL, "mode must be 1 (split along x) or 2 (split along y)");

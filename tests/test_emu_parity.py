@@ -123,6 +123,39 @@ def _seeded_problem(ny, nx, seed, coupling=0.7):
                        is_coupling=True, rot_coupling=False)
 
 
+@pytest.mark.parametrize('shape,mode,dtype,kernel', [
+    ((256, 32), 'real', np.complex128, 2), ((512, 32), 'imag', np.complex128, 2), ((2048, 32), 'imag', np.complex128, 2),
+    ((256, 64), 'real', np.complex64, 2), ((1024, 32), 'imag', np.complex64, 6),
+    ((512, 32), 'imag', np.complex128, 3), ((256, 32), 'real', np.complex128, 4), ((256, 64), 'real', np.complex64, 4),
+    ((512, 32), 'imag', np.complex128, 5), ((256, 32), 'real', np.complex128, 6), ((512, 32), 'imag', np.complex128, 6)])
+def test_emulated_persistent_column_pass(shape, mode, dtype, kernel):
+    """col_kernel = 2 / 3: persistent column-pass CTAs, tiles staged asynchronously (TMA + mbarrier on the device, a copy
+    at issue time in the emulation); 2: forward exchange through the staging image, split re / im exchange for the
+    inverse; 3: both exchanges through the staging image, refilled behind the last exchange read; one ticket per CTA.  Same results as the oracle and as the one-tile-per-CTA kernel, energy tracking included."""
+    ny, nx = shape
+    prob = _seeded_problem(ny, nx, seed=3 * ny + nx)
+    dt, n = (1 / 200, 3) if mode == 'real' else (1 / 50, 3)
+    want = orc.OraclePropagator(prob, dt, mode).run(n)
+    pl = plan_from_problem(prob, mode, dt, dtype=dtype, separable=True)
+    pl.set_option('col_kernel', kernel)
+    pops = pl.full_steps(n)
+    tol = 1e-12 if dtype == np.complex128 else 2e-5
+    assert rel(pl.store()[0], want['psik']) < tol
+    np.testing.assert_allclose(pops[0], want['pops_vals'], rtol=tol)
+    pl0 = plan_from_problem(prob, mode, dt, dtype=dtype, separable=True)
+    pl0.set_option('col_kernel', 1)
+    pops0 = pl0.full_steps(n)
+    assert rel(pl.store()[0], pl0.store()[0]) < (1e-14 if dtype == np.complex128 else 1e-5)
+    np.testing.assert_allclose(pops[0], pops0[0], rtol=1e-13 if dtype == np.complex128 else 1e-5)
+    if dtype == np.complex128:
+        # the junction that also stores the boundary state for per-step energy tracking
+        pl.load(prob.psik.numpy()); pl0.load(prob.psik.numpy())
+        _, e1 = pl.full_steps_energy(2, 2 * prob.kL, 0)
+        _, e0 = pl0.full_steps_energy(2, 2 * prob.kL, 0)
+        np.testing.assert_allclose(e1, e0, rtol=1e-12)
+    pl.close(); pl0.close()
+
+
 @pytest.mark.parametrize('shape,mode,dtype,separable', [((256, 32), 'real', np.complex128, True),
                                                          ((256, 32), 'imag', np.complex128, False),
                                                          ((512, 32), 'imag', np.complex128, True),

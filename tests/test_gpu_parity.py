@@ -333,6 +333,87 @@ def test_two_barrier_groups_per_column_tile(mesh, mode, dt, cpl, precision):
     assert rel(outs[0][0].cpu().numpy(), outs[2][0].cpu().numpy()) < (1e-13 if precision == 'c128' else 1e-5)
 
 
+@pytest.mark.parametrize('mesh,mode,dt,cpl,precision', [((256, 256), 'imag', 1 / 50, 'zero', 'c128'),
+                                                        ((128, 1024), 'real', 1 / 2000, 'uniform', 'c128'),
+                                                        ((512, 2048), 'imag', 1 / 50, 'dense', 'c128'),
+                                                        ((64, 2048), 'real', 1 / 2000, 'uniform', 'c64'),
+                                                        ((32, 4096), 'imag', 1 / 50, 'zero', 'c128'),
+                                                        ((2048, 512), 'imag', 1 / 50, 'zero', 'c64')])
+@pytest.mark.parametrize('kernel', [2, 3, 4, 5, 6])
+def test_persistent_column_pass(mesh, mode, dt, cpl, precision, kernel):
+    """col_kernel = 2 / 3 (persistent column-pass CTAs, TMA-staged tiles; 2: split inverse exchange, 3: staging behind
+    the inverse transform) against the oracle and the
+    one-tile-per-CTA kernel; repeated runs are bit-identical; per-step energy tracking through it as well."""
+    from spinor_gpe_b200 import TensorPropagator
+    ps = make_ps(mesh, atom_num=1e4, r_sizes=(16, 16), g_sc={'uu': 1, 'dd': 0.98, 'ud': 1.02})
+    ps.coupling_setup(wavel=790.1e-9, kin_shift=True)
+    if cpl == 'uniform':
+        ps.coupling_uniform(1.5 * ps.EL_recoil)
+    elif cpl == 'dense':
+        ps.coupling_grad(slope=0.3, offset=2.0, axis=1)
+    ps.rot_coupling = cpl != 'uniform'
+    rng = np.random.default_rng(4243)
+    ps.psik = [p * (1 + 0.05 * (rng.standard_normal(p.shape) + 1j * rng.standard_normal(p.shape))) for p in ps.psik]
+    want = orc.OraclePropagator(problem_of(ps), dt, mode).run(3)
+    outs = []
+    for kern in (kernel, kernel, 1):
+        prop = TensorPropagator(ps, dt, 3, 'cuda', time=mode, precision=precision)
+        prop._plan.set_option('col_kernel', kern)
+        pops = torch.zeros((1, 3, 2), dtype=torch.float64, device='cuda')
+        eng = torch.zeros((1, 3, 4), dtype=torch.float64, device='cuda')
+        prop._plan.full_steps(3, pops, energy=eng, kl_term=2 * ps.kL_recoil)
+        outs.append((torch.stack(prop.psik).clone(), pops.cpu().numpy()[0], eng.cpu().numpy()[0]))
+    tol = TOL_PSI if precision == 'c128' else TOL_PSI_C64
+    assert rel(outs[0][0].cpu().numpy(), want['psik']) < tol
+    np.testing.assert_allclose(outs[0][1], want['pops_vals'], rtol=TOL_SCALAR if precision == 'c128' else 1e-5)
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert rel(outs[0][0].cpu().numpy(), outs[2][0].cpu().numpy()) < (1e-13 if precision == 'c128' else 1e-5)
+    np.testing.assert_allclose(outs[0][2][:, 2:], outs[2][2][:, 2:], rtol=1e-9 if precision == 'c128' else 1e-4)
+
+
+@pytest.mark.parametrize('mesh,mode,dt,batch', [((256, 256), 'imag', 1 / 50, 1), ((128, 64), 'real', 1 / 2000, 3),
+                                                 ((1024, 512), 'imag', 1 / 50, 1)])
+def test_graph_replay_matches_plain_launches(mesh, mode, dt, batch):
+    """Option graph = 1: from the third step on sgpe_full_steps replays ONE captured steady-state step (six kernel
+    nodes, the populations slot read from a device-side counter).  Bit-identical state and populations, also across
+    several calls on the same plan (slot offsets) and after an operator change (re-capture); oracle parity."""
+    from spinor_gpe_b200 import _capi
+    from spinor_gpe_b200._separable import split_separable
+    from spinor_gpe_b200.plan import Plan
+    ps = make_ps(mesh, atom_num=1e4, r_sizes=(16, 16), g_sc={'uu': 1, 'dd': 0.98, 'ud': 1.02})
+    ps.coupling_setup(wavel=790.1e-9, kin_shift=True)
+    rng = np.random.default_rng(11)
+    ps.psik = [p * (1 + 0.05 * (rng.standard_normal(p.shape) + 1j * rng.standard_normal(p.shape))) for p in ps.psik]
+    n1, n2 = 7, 5
+    outs = []
+    for graph in (1, 0):
+        pl = Plan(mesh[0], mesh[1], batch)
+        pl.set_grid(ps.space['dr'][0], ps.space['dr'][1], ps.space['dv_r'], ps.space['dv_k'], ps.atom_num)
+        pl.set_interactions(ps.g_sc['uu'], ps.g_sc['dd'], ps.g_sc['ud'])
+        pl.set_kinetic_separable(*split_separable(np.array(ps.kin_eng_spin)))
+        pl.set_potential_separable(*split_separable(np.array(ps.pot_eng_spin)))
+        pl.set_coupling(_capi.SGPE_COUPLING_UNIFORM, omega=np.linspace(0.5, 1.5, batch) * ps.EL_recoil)
+        pl.set_time(mode, dt)
+        pl.set_option('graph', graph)
+        pl.load(np.stack([np.array(ps.psik)] * batch))
+        pops = torch.zeros((batch, n1 + 2 * n2, 2), dtype=torch.float64, device='cuda')
+        l0 = pl.launch_count()
+        pl.full_steps(n1, pops, first=0)
+        pl.full_steps(n2, pops, first=n1)                      # same graph, other slots
+        pl.set_interactions(ps.g_sc['uu'], ps.g_sc['dd'], 0.5 * ps.g_sc['ud'])     # invalidates the captured step
+        pl.full_steps(n2, pops, first=n1 + n2)
+        outs.append((pl.store().clone(), pops.clone(), pl.launch_count() - l0))
+        pl.close()
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+    assert float(outs[0][1].abs().min()) > 0                   # every slot was written
+    if batch == 1:
+        ps.coupling_uniform(0.5 * ps.EL_recoil)
+        o = orc.OraclePropagator(problem_of(ps), dt, mode)
+        want = o.run(n1 + n2)
+        np.testing.assert_allclose(outs[0][1][0, :n1 + n2].cpu().numpy(), want['pops_vals'], rtol=TOL_SCALAR)
+
+
 def test_complex64_against_oracle():
     ps = make_ps((512, 512))
     ps.coupling_setup(wavel=790.1e-9, kin_shift=True)

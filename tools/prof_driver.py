@@ -26,6 +26,9 @@ if os.environ.get('SGPE_DENSE', '0') != '1':
     pl.set_potential_separable(*split_separable(np.array(ps.pot_eng_spin)))
 if os.environ.get('SGPE_COL_TILE'):
     pl.set_option('col_tile', int(os.environ['SGPE_COL_TILE']))
+for kv in filter(None, os.environ.get('SGPE_OPTS', '').split(',')):      # e.g. SGPE_OPTS=col_kernel=2,prefetch=0
+    k, v = kv.split('=')
+    pl.set_option(k, int(v))
 pl.set_coupling(_capi.SGPE_COUPLING_NONE)
 pl.set_time(mode, 1 / 50 if mode == 'imag' else 1 / 5000)
 pl.load(np.array(ps.psik)[None])

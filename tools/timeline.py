@@ -4,6 +4,10 @@ import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
+from spinor_gpe_b200 import _lib
+tl = os.path.join(ROOT, 'spinor_gpe_b200', 'libsgpe_timeline.so')     # make -C spinor_gpe_b200/csrc timeline
+if os.path.exists(tl):
+    _lib.LIB_PATH = tl
 from spinor_gpe_b200 import _capi
 from spinor_gpe_b200.plan import Plan, _dp
 from spinor_gpe_b200._separable import split_separable
@@ -20,6 +24,9 @@ pl.set_coupling(_capi.SGPE_COUPLING_NONE)
 pl.set_time('imag', 1 / 50)
 pl.load(np.array(ps.psik)[None])
 kind = sys.argv[1] if len(sys.argv) > 1 else 'row'
+for kv in filter(None, os.environ.get('SGPE_OPTS', '').split(',')):      # e.g. SGPE_OPTS=col_kernel=3
+    k, v = kv.split('=')
+    pl.set_option(k, int(v))
 pl.full_steps(3)
 ncta = mesh if kind == 'row' else 2 * mesh // 4
 dbg = torch.zeros((ncta, 8), dtype=torch.int64, device='cuda')
@@ -35,7 +42,7 @@ t0 = d[:, 0].min()
 ph = d[:, :6] - t0
 dur = np.diff(ph, axis=1)
 names = (['issue loads', 'inverse FFT (incl. load wait)', 'point-wise', 'forward FFT', 'stores'] if kind == 'row' else
-         ['issue loads + wait', 'forward FFT', 'K factors + publish sums', 'inverse FFT', 'stores'])
+         ['issue loads + wait (persistent: wait for the staged tile)', 'forward FFT', 'K factors + publish sums', 'inverse FFT', 'stores'])
 print('pass:', kind)
 print('kernel span %.1f us, CTAs %d' % ((ph[:, 5].max()) / 1e3, len(d)))
 for k, nme in enumerate(names):
@@ -54,6 +61,8 @@ for s in np.unique(sm):
     per = 2 if kind == 'row' else 1
     for k in range(len(ends) - per):
         gaps.append(starts[k + per] - ends[k])
+    if not gaps:
+        gaps.append(0)
 gaps = np.array(gaps) / 1e3
 print('  slot turnaround (end of a CTA -> start of its successor on the SM): mean %.2f us median %.2f' % (gaps.mean(), np.median(gaps)))
 print('  CTAs per SM: min %d max %d' % (np.bincount(sm).min(), np.bincount(sm).max()))
