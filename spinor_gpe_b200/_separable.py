@@ -5,6 +5,8 @@ reference's PSpinor builds by default: the harmonic trap (pspinor.py:426-428), t
 dispersions (:429-430, :496-501) and uniform / linear-gradient detunings (:574-575, :660, :678).  For such
 grids the kernels multiply by products of 1-D factor tables instead of evaluating exp / sincos per point.
 """
+import os
+
 import numpy as np
 
 RTOL = 1e-13
@@ -26,7 +28,28 @@ def split_separable(grids, rtol=RTOL):
         i0 = int(np.argmin(col))
         gy[c] = col - col[i0]
         gx[c] = g[c, i0, :]
-    err = np.abs(g - (gx[:, None, :] + gy[:, :, None])).max()
-    if err <= rtol * max(float(np.abs(g).max()), 1e-300):
+    # a cheap look at a coarse sub-grid rejects most non-separable grids before the full check
+    sy, sx = max(1, g.shape[1] // 64), max(1, g.shape[2] // 64)
+    coarse = g[:, ::sy, ::sx]
+    scale = max(float(np.abs(coarse).max()), 1e-300)
+    if np.abs(coarse - (gx[:, None, ::sx] + gy[:, ::sy, None])).max() > rtol * scale * 4:
+        return None
+    # full check in cache-sized row blocks (no full-size temporaries), a few host threads (NumPy releases the GIL)
+    rows = max(1, (1 << 19) // max(1, g.shape[2]))
+    blocks = [(c, r) for c in range(g.shape[0]) for r in range(0, g.shape[1], rows)]
+
+    def check(job):
+        c, r = job
+        blk = g[c, r:r + rows]
+        return (float(np.abs(blk - gx[c] - gy[c, r:r + rows, None]).max()), float(np.abs(blk).max()))
+
+    if len(blocks) > 4:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+            res = list(pool.map(check, blocks))
+    else:
+        res = [check(b) for b in blocks]
+    err = max(r[0] for r in res)
+    if err <= rtol * max(max(r[1] for r in res), 1e-300):
         return gx, gy
     return None

@@ -21,13 +21,46 @@ class PropResult:
         self.sampled_path = sampled_path
         self.eng_history = None      # (n_steps, 4) when the propagator tracked the energy of every step (extension)
 
-        self.dens = ttools.density(self.psi)
-        self.densk = ttools.density(self.psik)
-        self.phase = ttools.phase(self.psi, uwrap=False, dens=self.dens)
+        # densities and phase (prop_result.py:68-72) are evaluated when first read: at 2048^2 they cost more host time
+        # than the whole propagation takes on the GPU
+        self._dens = self._densk = self._phase = None
 
         self.paths = dict()
         self.time_scale = None
         self.space = dict()
+
+    @property
+    def dens(self):
+        """Real-space densities of both components (prop_result.py:68)."""
+        if self._dens is None:
+            self._dens = ttools.density(self.psi)
+        return self._dens
+
+    @dens.setter
+    def dens(self, value):
+        self._dens = value
+
+    @property
+    def densk(self):
+        """Momentum-space densities (prop_result.py:69)."""
+        if self._densk is None:
+            self._densk = ttools.density(self.psik)
+        return self._densk
+
+    @densk.setter
+    def densk(self, value):
+        self._densk = value
+
+    @property
+    def phase(self):
+        """Wrapped phases, zeroed where the density is below 1e-6 of its maximum (prop_result.py:70-72)."""
+        if self._phase is None:
+            self._phase = ttools.phase(self.psi, uwrap=False, dens=self.dens)
+        return self._phase
+
+    @phase.setter
+    def phase(self, value):
+        self._phase = value
 
     def calc_separation(self):
         """Phase separation 1 - <n0 n1> / sqrt(<n0^2><n1^2>) (prop_result.py:84-88)."""

@@ -60,6 +60,16 @@ def _grid(arr, ny, nx, name):
     return a
 
 
+def _to_host(comps):
+    """Two (Ny, Nx) device tensors -> two NumPy arrays, through page-locked staging (the pageable path of
+    ``Tensor.cpu()`` runs at ~2 GB/s; torch keeps the pinned blocks for the next call)."""
+    host = [torch.empty(c.shape, dtype=c.dtype, pin_memory=True) for c in comps]
+    for h, c in zip(host, comps):
+        h.copy_(c, non_blocking=True)
+    torch.cuda.current_stream(comps[0].device).synchronize()
+    return [h.numpy() for h in host]
+
+
 class _LazyTensors(dict):
     """dict whose values are uploaded to the GPU on first access."""
 
@@ -167,21 +177,19 @@ class TensorPropagator:
         check_mesh(nx, ny)
         # the kernels read row-major (Ny, Nx) float64 grids through raw pointers: whatever layout the user's arrays
         # have (Fortran order, transposed views, other dtypes), the device copies are C-contiguous float64
-        self.kin_eng_spin = ttools.to_tensor([_grid(k, ny, nx, 'kin_eng_spin') for k in spin.kin_eng_spin], dev=dev)
+        # (uploaded when first needed: with separable grids the kernels work from 1-D factor tables and the 2-D device
+        # copies exist only if somebody reads the public attributes kin_eng_spin / pot_eng_spin / coupling)
+        self._kin_np = [_grid(k, ny, nx, 'kin_eng_spin') for k in spin.kin_eng_spin]
         pot_shared = spin.pot_eng_spin[0] is spin.pot_eng_spin[1] or np.array_equal(spin.pot_eng_spin[0],
                                                                                     spin.pot_eng_spin[1])
-        if pot_shared:
-            p0 = ttools.to_tensor(_grid(spin.pot_eng_spin[0], ny, nx, 'pot_eng_spin'), dev=dev)
-            self.pot_eng_spin = [p0, p0]
-        else:
-            self.pot_eng_spin = ttools.to_tensor([_grid(p, ny, nx, 'pot_eng_spin') for p in spin.pot_eng_spin],
-                                                 dev=dev)
+        p0 = _grid(spin.pot_eng_spin[0], ny, nx, 'pot_eng_spin')
+        self._pot_np = [p0, p0] if pot_shared else [p0, _grid(spin.pot_eng_spin[1], ny, nx, 'pot_eng_spin')]
+        self._kin_dev = self._pot_dev = self._cpl_dev = None
         keys_space = ['dr', 'dk', 'x_mesh', 'y_mesh', 'dv_r', 'dv_k']
         self.space = _LazyTensors(spin.space, keys_space, dev)
         self._dr = (float(spin.space['dr'][0]), float(spin.space['dr'][1]))
         self._dv_r, self._dv_k = float(spin.space['dv_r']), float(spin.space['dv_k'])
-        cpl_np = _grid(spin.coupling, ny, nx, 'coupling')
-        self.coupling = ttools.to_tensor(cpl_np, dev=dev)
+        cpl_np = self._cpl_np = _grid(spin.coupling, ny, nx, 'coupling')
 
         if self.is_sampling:                                # :131-134
             assert self.n_steps % n_samples == 0, (
@@ -210,32 +218,71 @@ class TensorPropagator:
         self.eng_out = _OperatorView(self, self.dt_out, outer=True)      # :138-143
         self.eng_in = _OperatorView(self, self.dt_in, outer=False)       # :144-149
 
+    # ------------------------------------------------------------------ public 2-D operator grids (tensor_propagator.py:111-122)
+    @property
+    def kin_eng_spin(self):
+        if self._kin_dev is None:
+            self._kin_dev = ttools.to_tensor(self._kin_np, dev=self._dev)
+        return self._kin_dev
+
+    @kin_eng_spin.setter
+    def kin_eng_spin(self, value):
+        self._kin_dev = value
+
+    @property
+    def pot_eng_spin(self):
+        if self._pot_dev is None:
+            if self._pot_np[0] is self._pot_np[1]:
+                p0 = ttools.to_tensor(self._pot_np[0], dev=self._dev)
+                self._pot_dev = [p0, p0]
+            else:
+                self._pot_dev = ttools.to_tensor(self._pot_np, dev=self._dev)
+        return self._pot_dev
+
+    @pot_eng_spin.setter
+    def pot_eng_spin(self, value):
+        self._pot_dev = value
+
+    @property
+    def coupling(self):
+        if self._cpl_dev is None:
+            self._cpl_dev = ttools.to_tensor(self._cpl_np, dev=self._dev)
+        return self._cpl_dev
+
+    @coupling.setter
+    def coupling(self, value):
+        self._cpl_dev = value
+
     # ------------------------------------------------------------------ set-up helpers
     def _bind_operators(self, cpl_np, spin):
         import ctypes
         pl = self._plan
-        k0, k1 = self.kin_eng_spin
-        p0, p1 = self.pot_eng_spin
-        for t in (k0, k1, p0, p1, self.coupling):
-            assert t.is_contiguous() and t.dtype == torch.float64
-        # the plan borrows these device pointers: it keeps the tensors alive itself, so rebinding the public
-        # attributes (prop.pot_eng_spin = ...) cannot leave it with a dangling pointer
-        pl.keep['grids_ref'] = (k0, k1, p0, p1)
-        pl._chk(pl.lib.sgpe_set_kinetic(pl.h, ctypes.c_void_p(k0.data_ptr()), ctypes.c_void_p(k1.data_ptr()), 0),
-                'sgpe_set_kinetic')
-        pl._chk(pl.lib.sgpe_set_potential(pl.h, ctypes.c_void_p(p0.data_ptr()), ctypes.c_void_p(p1.data_ptr()), 0),
-                'sgpe_set_potential')
         # separable fast path (1-D factor tables) when the grids allow it; the dense path stays general
         self.separable = {'kin': False, 'pot': False}
+        ksep = psep = None
         if self._separable_opt:
-            ksep = split_separable(np.array([np.asarray(k) for k in spin.kin_eng_spin]))
-            if ksep is not None:
-                pl.set_kinetic_separable(*ksep)
-                self.separable['kin'] = True
-            psep = split_separable(np.array([np.asarray(v) for v in spin.pot_eng_spin]))
-            if psep is not None:
-                pl.set_potential_separable(*psep)
-                self.separable['pot'] = True
+            ksep = split_separable(np.stack(self._kin_np))
+            psep = split_separable(np.stack(self._pot_np))
+        # the plan borrows the device pointers of the dense grids: it keeps the tensors alive itself, so rebinding
+        # the public attributes (prop.pot_eng_spin = ...) cannot leave it with a dangling pointer
+        if ksep is not None:
+            pl.set_kinetic_separable(*ksep)
+            self.separable['kin'] = True
+        else:
+            k0, k1 = self.kin_eng_spin
+            assert k0.is_contiguous() and k1.is_contiguous() and k0.dtype == torch.float64
+            pl.keep['kin_ref'] = (k0, k1)
+            pl._chk(pl.lib.sgpe_set_kinetic(pl.h, ctypes.c_void_p(k0.data_ptr()), ctypes.c_void_p(k1.data_ptr()), 0),
+                    'sgpe_set_kinetic')
+        if psep is not None:
+            pl.set_potential_separable(*psep)
+            self.separable['pot'] = True
+        else:
+            p0, p1 = self.pot_eng_spin
+            assert p0.is_contiguous() and p1.is_contiguous() and p0.dtype == torch.float64
+            pl.keep['pot_ref'] = (p0, p1)
+            pl._chk(pl.lib.sgpe_set_potential(pl.h, ctypes.c_void_p(p0.data_ptr()), ctypes.c_void_p(p1.data_ptr()), 0),
+                    'sgpe_set_potential')
         eiphi = None
         if self.is_coupling and not self._rot_coupling:
             # expon = 2 kL x_mesh (tensor_propagator.py:129) depends on x only: ship exp(i expon) along x
@@ -369,8 +416,8 @@ class TensorPropagator:
             psi_dev = [rs[0], rs[1]]
         else:
             psi_dev = ttools.ifft_2d(psik_dev, self._dr)
-        psik = ttools.to_numpy(psik_dev)
-        psi = ttools.to_numpy(psi_dev)
+        psik = _to_host(psik_dev)
+        psi = _to_host(psi_dev)
         result = PropResult(psi, psik, energy, pops, file_name)
         if track:
             result.eng_history = track['energy'][0, :n_steps].cpu().numpy().copy()
