@@ -1766,13 +1766,14 @@ __global__ void __launch_bounds__(256) energy_pass(EnergyArgs<T> a) {
     double* s_ph = s_r + HX * HY;                                      // [HY][HX] masked phase
     const int b = blockIdx.y, nblk = gridDim.x, tid = threadIdx.x;
     const int tx = tid & 31, ty = tid >> 5;
-    const int tiles_x = a.nx / TX, tiles_y = a.ny / TY;
+    const int tiles_x = (a.nx + TX - 1) / TX, tiles_y = (a.ny + TY - 1) / TY;     // ragged last tiles on generic meshes
     const long long ntiles = (long long)tiles_x * tiles_y;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (long long t = blockIdx.x; t < ntiles; t += nblk) {
         const int i0 = (int)(t / tiles_x) * TY, j0 = (int)(t % tiles_x) * TX;
-        const int i = i0 + ty;          // axis 0 (y)
-        const int j = j0 + tx;          // axis 1 (x)
+        const bool inside = (i0 + ty < a.ny) && (j0 + tx < a.nx);
+        const int i = inside ? i0 + ty : 0;          // axis 0 (y)
+        const int j = inside ? j0 + tx : 0;          // axis 1 (x)
         double kin = 0.0, dens[2];
         C ctr[2];
         for (int comp = 0; comp < 2; comp++) {
@@ -1831,7 +1832,7 @@ __global__ void __launch_bounds__(256) energy_pass(EnergyArgs<T> a) {
         if (a.cpl_mode == 1) om = a.omega_b[b];
         else if (a.cpl_mode == 2) om = __ldg(&a.coupling[(long long)b * a.cpl_bstride + pix]);
         const double coupl = ((double)ctr[0].x * ctr[1].x + (double)ctr[0].y * ctr[1].y) * om;   // Re(conj(p0) p1) * Omega
-        acc[0] += kin + pot + inter + coupl; acc[1] += kin; acc[2] += pot; acc[3] += inter;
+        if (inside) { acc[0] += kin + pot + inter + coupl; acc[1] += kin; acc[2] += pot; acc[3] += inter; }
     }
     cta_reduce<4>(acc, red);
     if (tid == 0) {

@@ -26,6 +26,7 @@
 #include "../../include/sgpe.h"
 #include "kernels.cuh"
 #include "unwrap.cuh"
+#include "generic.cuh"
 #include "launch.h"
 
 namespace {
@@ -116,6 +117,10 @@ struct sgpe_plan {
     // pass materialises goes (slot < 0: none), and how it is evaluated
     double* pend_energy = nullptr; long long pend_estride = 0; int pend_eslot = -1;
     int track_unwrap = 0; double track_kl = 0.0;
+    // meshes outside the fused kernels' lengths (any even size with prime factors 2, 3, 5, 7; generic.cuh): one kernel
+    // per operation behind the same run_col / run_row calls
+    bool generic = false;
+    std::vector<int> rad_x, rad_y;
     uint64_t launches = 0;
     // CUDA-graph replay of the steady-state full step (option "graph"): six kernel nodes whose arguments do not change
     // from step to step (the populations slot comes from the device-side counter slot_ctr)
@@ -301,6 +306,125 @@ int tile_map_for(sgpe_plan* p, const void* buf, int w, const SgpeTileMap** out) 
     return 0;
 }
 
+// ---- generic meshes (generic.cuh)
+// stage radices of a length-n transform: 4s first, then 2, 3, 5, 7; empty when n has another prime factor
+std::vector<int> generic_radices(int n) {
+    std::vector<int> r;
+    while (n % 4 == 0) { r.push_back(4); n /= 4; }
+    for (int q : {2, 3, 5, 7})
+        while (n % q == 0) { r.push_back(q); n /= q; }
+    if (n != 1 || r.size() > SGPE_GEN_MAX_STAGES) r.clear();
+    return r;
+}
+bool generic_length(int n) { return n >= 2 && n % 2 == 0 && n <= 4096 && !generic_radices(n).empty(); }
+
+template <typename T>
+int gen_fft(sgpe_plan* p, const void* in, void* out, int axis /*0: along x, 1: along y*/, int dir, cudaStream_t st) {
+    sgpe::GenFftArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = in; a.out = out;
+    const std::vector<int>& rad = axis == 0 ? p->rad_x : p->rad_y;
+    a.n = axis == 0 ? p->nx : p->ny;
+    a.nlines = axis == 0 ? p->ny : p->nx;
+    a.elem_stride = axis == 0 ? 1 : p->nx;
+    a.line_stride = axis == 0 ? p->nx : 1;
+    a.plane = p->plane; a.nplanes = 2 * p->batch; a.dir = dir;
+    a.nstages = (int)rad.size();
+    for (int i = 0; i < a.nstages; i++) a.radix[i] = rad[i];
+    long long lpc = (200LL * 1024) / (2LL * a.n * (long long)p->csize);
+    if (lpc < 1) lpc = 1;
+    if (lpc > 16) lpc = 16;
+    if (lpc > a.nlines) lpc = a.nlines;
+    a.lpc = (int)lpc;
+    const size_t smem = 2 * (size_t)a.lpc * a.n * p->csize;
+#ifndef SGPE_EMU
+    static size_t allowed = 0;
+    if (smem > allowed) {
+        SGPE_CUDA(cudaFuncSetAttribute(sgpe::gen_fft_pass<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(208 * 1024)));
+        allowed = 208 * 1024;
+    }
+#endif
+    const int groups = (a.nlines + a.lpc - 1) / a.lpc;
+    SGPE_LAUNCH((sgpe::gen_fft_pass<T>), dim3((unsigned)(groups * a.nplanes)), dim3(256), smem, st, a);
+    p->launches++;
+    SGPE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+int gen_scale(sgpe_plan* p, const void* in, void* out, int sign_x, int sign_y, double scale, const double* scale_tot,
+              double scale_num, cudaStream_t st) {
+    typedef typename sgpe::cx_of<T>::type C;
+    sgpe::GenScaleArgs<T> a;
+    a.in = static_cast<const C*>(in); a.out = static_cast<C*>(out); a.nx = p->nx;
+    a.total = (long long)p->batch * 2 * p->plane; a.sign_x = sign_x; a.sign_y = sign_y; a.scale = scale;
+    a.scale_tot = scale_tot; a.scale_num = scale_num; a.per_batch = 2 * p->plane;
+    long long blocks = (a.total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    SGPE_LAUNCH((sgpe::gen_scale_sign<T>), dim3((unsigned)blocks), dim3(256), 0, st, a);
+    p->launches++;
+    SGPE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int gen_blocks(const sgpe_plan* p) {
+    long long b = (p->plane + 255) / 256;
+    if (b > 256) b = 256;                       // four partial sums per CTA fit the reduction scratch
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// the column pass of a generic mesh: [sign] -> [FFT_y] -> [factors + sums] -> [iFFT_y] -> [sign / scale]
+template <typename T>
+int run_col_generic(sgpe_plan* p, ColArgs<T>& a, bool fwd, bool inv, cudaStream_t st) {
+    const void* cur = a.in;
+    void* out = a.out;
+    int rc;
+    if (a.sign_in) { if ((rc = gen_scale<T>(p, cur, out, 0, 1, 1.0, nullptr, 0.0, st))) return rc; cur = out; }
+    if (fwd) { if ((rc = gen_fft<T>(p, cur, out, 1, -1, st))) return rc; cur = out; }
+    if (a.has_a || a.has_b) {
+        a.in = static_cast<const typename sgpe::cx_of<T>::type*>(cur);
+        dim3 grid((unsigned)gen_blocks(p), p->batch), block(256);
+        if (p->tm == SGPE_TIME_REAL) { SGPE_LAUNCH((sgpe::gen_kspace_pass<T, sgpe::TM_REAL>), grid, block, 32 * 4 * sizeof(double), st, a); }
+        else { SGPE_LAUNCH((sgpe::gen_kspace_pass<T, sgpe::TM_IMAG>), grid, block, 32 * 4 * sizeof(double), st, a); }
+        p->launches++;
+        SGPE_CUDA(cudaGetLastError());
+        cur = out;
+    }
+    if (inv) { if ((rc = gen_fft<T>(p, cur, out, 1, +1, st))) return rc; cur = out; }
+    if (a.sign_out || a.scale_out != 1.0 || cur != out) {
+        if ((rc = gen_scale<T>(p, cur, out, 0, a.sign_out ? 1 : 0, a.scale_out, nullptr, 0.0, st))) return rc;
+    }
+    return 0;
+}
+
+// the row pass of a generic mesh: [sign] -> [iFFT_x] -> [normalise, I C P C I] -> [FFT_x] -> [sign / scale]
+template <typename T>
+int run_row_generic(sgpe_plan* p, RowArgs<T>& a, bool inv, bool pw, bool fwd, cudaStream_t st) {
+    if (a.sc.mode || a.maxbits != nullptr) return fail(SGPE_EINVAL, "not available on generic meshes");
+    const void* cur = a.in;
+    void* out = a.out;
+    int rc;
+    if (a.sign_in) { if ((rc = gen_scale<T>(p, cur, out, a.sign_in & 1, (a.sign_in >> 1) & 1, 1.0, nullptr, 0.0, st))) return rc; cur = out; }
+    if (inv) { if ((rc = gen_fft<T>(p, cur, out, 0, +1, st))) return rc; cur = out; }
+    if (pw) {
+        a.in = static_cast<const typename sgpe::cx_of<T>::type*>(cur);
+        long long blocks = (p->plane + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        dim3 grid((unsigned)blocks, p->batch), block(256);
+        if (p->tm == SGPE_TIME_REAL) { SGPE_LAUNCH((sgpe::gen_rspace_pass<T, sgpe::TM_REAL>), grid, block, 0, st, a); }
+        else { SGPE_LAUNCH((sgpe::gen_rspace_pass<T, sgpe::TM_IMAG>), grid, block, 0, st, a); }
+        p->launches++;
+        SGPE_CUDA(cudaGetLastError());
+        cur = out;
+    }
+    if (fwd) { if ((rc = gen_fft<T>(p, cur, out, 0, -1, st))) return rc; cur = out; }
+    if (a.sign_out || a.scale_out != 1.0 || a.scale_tot != nullptr || cur != out) {
+        if ((rc = gen_scale<T>(p, cur, out, a.sign_out & 1, (a.sign_out >> 1) & 1, a.scale_out, a.scale_tot, a.scale_num, st))) return rc;
+    }
+    return 0;
+}
+
 // Column pass.  tau_a / tau_b: time arguments of the k-space factors FA / FB (exp(-i kin tau)); has_a / has_b
 // select them.
 template <typename T>
@@ -341,6 +465,7 @@ int run_col(sgpe_plan* p, const void* in, void* out, bool fwd, bool has_a, doubl
     a.slot_ctr = (p->capturing && pops != nullptr && pops_slot >= 0) ? p->slot_ctr : nullptr;
     a.atom_num = p->atom_num;
     a.aux = static_cast<C*>(aux);
+    if (p->generic) return run_col_generic<T>(p, a, fwd, inv, st);
     a.dbg = (fwd && inv) ? p->dbg_col : nullptr;
     a.kernel_sel = p->col_kernel == 0 ? default_col_kernel(p) : p->col_kernel - 1;
     if (a.kernel_sel >= 1 && fwd && inv && in == out && p->kin_mode == 1 && p->n1 == 1) {
@@ -399,6 +524,7 @@ int run_row(sgpe_plan* p, const void* in, void* out, bool inv, bool pw, double d
     fill_scatter(p, scatter, &a.sc);
     a.scale_tot = scale_tot; a.scale_num = scale_num;
     a.maxbits = reinterpret_cast<unsigned long long*>(maxdens);
+    if (p->generic) return run_row_generic<T>(p, a, inv, pw, fwd, st);
     ProfScope prof(p, 1, st);
     int rc = sgpe::launch_row(p->nx, p->dtype, p->tm, &a, p->batch, p->row_mode, st);
     if (rc == -3) return fail(SGPE_EINVAL, "row pass variant not compiled in (build with -DSGPE_EXPERIMENTAL)");
@@ -562,7 +688,7 @@ int run_energy(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, d
     a.inc = p->unwrap_inc;
     a.maxdens = p->maxdens; a.partials = p->partials; a.counter = p->counter; a.out = out;
     a.out_bstride = out_bstride;
-    long long tiles = (long long)(p->nx / 32) * (p->ny / 8);
+    long long tiles = (long long)((p->nx + 31) / 32) * ((p->ny + 7) / 8);
     blocks = tiles < 888 ? tiles : 888;                     // six 256-thread CTAs per SM x 148 SMs
     if (blocks > p->max_tiles / 2) blocks = p->max_tiles / 2;   // four partial sums per CTA in `partials`
     dim3 grid((unsigned)blocks, p->batch), block(256);
@@ -961,13 +1087,17 @@ const char* sgpe_version(void) {
 int sgpe_plan_create(sgpe_plan** out, int nx, int ny, int batch, int dtype, int device) {
     if (!out) return fail(SGPE_EINVAL, "null output pointer");
     *out = nullptr;
-    if (!sgpe::supported_length(nx) || !sgpe::supported_length(ny))
-        return fail(SGPE_EINVAL, "mesh sizes must be powers of two in [32, 4096]");
+    const bool fused = sgpe::supported_length(nx) && sgpe::supported_length(ny);
+    if (!fused && !(generic_length(nx) && generic_length(ny)))
+        return fail(SGPE_EINVAL, "mesh sizes must be even, at most 4096 points per line, with prime factors 2, 3, 5, 7 "
+                                 "(powers of two from 32 on run in the fused kernels; lines beyond 4096: sgpe_plan_create_lines)");
     if (batch < 1) return fail(SGPE_EINVAL, "batch must be >= 1");
     if (dtype != SGPE_C128 && dtype != SGPE_C64) return fail(SGPE_EINVAL, "dtype must be 0 (c128) or 1 (c64)");
     DeviceGuard guard(device);
     sgpe_plan* p = new sgpe_plan();
     p->nx = nx; p->ny = ny; p->batch = batch; p->dtype = dtype; p->device = device;
+    p->generic = !fused;
+    if (p->generic) { p->rad_x = generic_radices(nx); p->rad_y = generic_radices(ny); }
     p->csize = dtype == SGPE_C128 ? 16 : 8;
     p->plane = (long long)nx * ny;
     p->max_tiles = 2 * (nx > ny ? nx : ny);      // covers every column tile width and the line passes
@@ -981,6 +1111,7 @@ int sgpe_plan_create(sgpe_plan** out, int nx, int ny, int batch, int dtype, int 
         cudaMemset(p->counter, 0, sizeof(unsigned) * batch);
         cudaMemset(p->totals, 0, sizeof(double) * 4 * batch);
         cudaMemset(p->totals_aux, 0, sizeof(double) * 4 * batch);
+        if (p->generic) break;                 // the generic transforms evaluate their twiddles in place
         rc = dtype == SGPE_C128 ? upload_twiddles<double>(&p->tw_x, nx) : upload_twiddles<float>(&p->tw_x, nx);
         if (rc) break;
         rc = dtype == SGPE_C128 ? upload_twiddles<double>(&p->tw_y, ny) : upload_twiddles<float>(&p->tw_y, ny);
@@ -1278,6 +1409,18 @@ int sgpe_full_steps_energy(sgpe_plan* p, int n, double* pops, int64_t pops_strid
     if (!p->scratch && cudaMalloc(&p->scratch, bytes) != cudaSuccess) return fail(SGPE_ENOMEM, "scratch allocation failed");
     if (!p->maxdens && cudaMalloc((void**)&p->maxdens, sizeof(double) * 2 * p->batch) != cudaSuccess)
         return fail(SGPE_ENOMEM, "scratch allocation failed");
+    if (p->generic) {
+        // generic meshes: the energy of every step through the stand-alone evaluation (junction closed each step)
+        for (int i = 0; i < n; i++) {
+            if ((rc = sgpe_full_steps(p, 1, pops, pops_stride, pops_first + i, st))) return rc;
+            if ((rc = sgpe_store_psik(p, p->scratch, st))) return rc;
+            if ((rc = sgpe_fft2d(p, p->scratch, p->scratch, 1, st))) return rc;
+            if ((rc = SGPE_BY_DTYPE(p, run_energy, p, p->scratch, unwrap_mode, kl_term, energy + 4LL * (energy_first + i), s,
+                                    energy_stride)))
+                return rc;
+        }
+        return 0;
+    }
     p->track_unwrap = unwrap_mode; p->track_kl = kl_term;
     for (int i = 0; i < n; i++) {
         if ((rc = single_step_impl(p, p->dt_out, s))) return rc;

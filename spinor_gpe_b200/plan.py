@@ -15,22 +15,31 @@ from ._lib import lib, require_cuda
 UNWRAP_MODES = {'none': 0, 'local': 1, 'herraez': 2}
 
 
-# line lengths the kernels transform: one CTA holds a line of up to 4096 points (register-resident Stockham, radix
-# 16 / 8 / 4 / 2); longer lines run as a four-step split n1 x n2 of two such lengths (slab.LongLinePlan)
-MIN_LINE, MAX_LINE, MAX_LONG_LINE = 32, 4096, 4096 * 1024
+# line lengths the kernels transform: powers of two from 32 to 4096 in the fused register-resident passes (one CTA per
+# line); any other EVEN length up to 4096 whose prime factors are 2, 3, 5, 7 in the generic passes (csrc/generic.cuh);
+# longer power-of-two lines as a four-step split n1 x n2 of two fused lengths (slab.LongLinePlan)
+MIN_LINE, MAX_LINE, MAX_LONG_LINE = 2, 4096, 4096 * 1024
+
+
+def _smooth(n):
+    for q in (2, 3, 5, 7):
+        while n % q == 0:
+            n //= q
+    return n == 1
 
 
 def supported_mesh(n):
     """(ok, reason) for a mesh size along one axis.  The reference asserts even sizes only (pspinor.py:331-332, its
     message asks for powers of two) and leaves the rest to cuFFT / MKL."""
     n = int(n)
-    if n % 2:
+    if n < MIN_LINE or n % 2:
         return False, "the number of mesh points must be even (pspinor.py:331-332)"
+    if n <= MAX_LINE:
+        if _smooth(n):
+            return True, ''
+        return False, "the in-house FFT takes sizes whose prime factors are 2, 3, 5 and 7"
     if n & (n - 1):
-        return False, ("the in-house FFT handles powers of two only; "
-                       f"nearest supported sizes: {1 << (n.bit_length() - 1)} and {1 << n.bit_length()}")
-    if n < MIN_LINE:
-        return False, f"lines shorter than {MIN_LINE} points are not supported"
+        return False, f"lines longer than {MAX_LINE} points must be powers of two (four-step split)"
     if n > MAX_LONG_LINE:
         return False, f"lines longer than {MAX_LONG_LINE} points are not supported"
     return True, ''

@@ -353,8 +353,7 @@ class TensorPropagator:
         the propagator's time kind); ``eng`` must be this propagator's ``eng_out`` / ``eng_in`` view (the
         fused kernels evaluate those operators themselves) or None."""
         if eng is not None and not isinstance(eng, _OperatorView):
-            raise NotImplementedError("custom operator tables are not supported by the fused kernels; pass "
-                                      "prop.eng_out / prop.eng_in (or None)")
+            return self._single_step_tables(t_step, eng)
         ts = complex(t_step)
         if self._time == 'imag':
             if abs(ts.real) > 0:
@@ -366,6 +365,40 @@ class TensorPropagator:
             dt_sub = ts.real
         self._plan.single_step(dt_sub)
         self._psik_cache = None
+
+    def _single_step_tables(self, t_step, eng):
+        """``single_step`` with caller-supplied operator tables ``eng = {'kin': [2], 'pot': [2], 'coupl': 2x2}`` of
+        complex (Ny, Nx) tensors, as the reference applies them (tensor_propagator.py:242-271).  Not the fused path: the
+        transforms and both normalisations run in the library's kernels (``sgpe_fft2d``, ``sgpe_normalise``), the
+        table products are element-wise device operations."""
+        if self._long:
+            raise NotImplementedError("custom operator tables are not available on long-line meshes")
+        dev = self._dev
+
+        def table(t):
+            t = t if isinstance(t, torch.Tensor) else torch.as_tensor(np.asarray(t))
+            return t.to(device=dev, dtype=torch.complex128)
+
+        kin = [table(k) for k in eng['kin']]
+        pot = [table(p) for p in eng['pot']]
+        psik = [kin[c] * self.psik[c] for c in range(2)]                                  # :242
+        psi = ttools.ifft_2d(psik, self._dr)                                              # :243
+        psi, dens = ttools.norm(psi, self._dv_r, self.atom_num)                           # :244
+        g = self.g_sc
+        int_eng = [g['uu'] * dens[0] + g['ud'] * dens[1], g['dd'] * dens[1] + g['ud'] * dens[0]]     # :247-248
+        int_op = ttools.evolution_op(t_step / 2, int_eng)                                 # :249
+        psi = [o * p for o, p in zip(int_op, psi)]                                        # :250
+        if self.is_coupling:                                                              # :252-254
+            cpl = [[table(e) for e in row] for row in eng['coupl']]
+            psi = [cpl[r][0] * psi[0] + cpl[r][1] * psi[1] for r in range(2)]
+        psi = [pot[c] * psi[c] for c in range(2)]                                         # :256
+        if self.is_coupling:                                                              # :258-260
+            psi = [cpl[r][0] * psi[0] + cpl[r][1] * psi[1] for r in range(2)]
+        psi = [o * p for o, p in zip(int_op, psi)]                                        # :267
+        psik = ttools.fft_2d(psi, self._dr)                                               # :269
+        psik = [kin[c] * psik[c] for c in range(2)]                                       # :270
+        psik, _ = ttools.norm(psik, self._dv_k, self.atom_num)                            # :271
+        self.psik = psik
 
     def prop_loop(self, n_steps):
         """tensor_propagator.py:151-212 — step loop with per-step populations, optional sampling, final

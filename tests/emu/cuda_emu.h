@@ -169,6 +169,7 @@ inline double __dmul_rn(double a, double b) { volatile double r = a * b; return 
 inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 inline void sincos(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }
 inline void sincosf(float x, float* s, float* c) { *s = std::sin(x); *c = std::cos(x); }
+inline void sincospi(double x, double* s, double* c) { *s = std::sin(M_PI * x); *c = std::cos(M_PI * x); }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline int __double2loint(double x) { unsigned long long u; memcpy(&u, &x, 8); return (int)(unsigned)(u & 0xffffffffull); }
 inline int __double2hiint(double x) { unsigned long long u; memcpy(&u, &x, 8); return (int)(unsigned)(u >> 32); }

@@ -330,3 +330,50 @@ def test_emulated_fine_mesh_factor_tables():
     assert np.isfinite(out).all()
     assert rel(out, want['psik']) < 1e-12
     pl.close()
+
+
+@pytest.mark.parametrize('shape,mode,dtype,separable,coupling', [
+    ((30, 50), 'imag', np.complex128, True, 0.7), ((6, 10), 'real', np.complex128, False, 0.7),
+    ((96, 80), 'real', np.complex128, True, 0.7), ((16, 8), 'imag', np.complex128, False, 0.0),
+    ((36, 250), 'imag', np.complex128, True, 0.7), ((14, 24), 'real', np.complex64, True, 0.7)])
+def test_emulated_generic_mesh_sizes(shape, mode, dtype, separable, coupling):
+    """Meshes outside the fused kernels' lengths — any even size with prime factors 2, 3, 5, 7, powers of two below 32
+    (the reference asserts even sizes only, pspinor.py:331-332): the generic passes behind the same C ABI reproduce the
+    oracle's propagation, populations, stand-alone transforms and energy."""
+    ny, nx = shape
+    prob = _seeded_problem(ny, nx, seed=5 * ny + nx, coupling=coupling)
+    dt, n = (1 / 200, 3) if mode == 'real' else (1 / 50, 3)
+    want = orc.OraclePropagator(prob, dt, mode).run(n)
+    pl = plan_from_problem(prob, mode, dt, dtype=dtype, separable=separable)
+    pops = pl.full_steps(n)
+    tol = 1e-12 if dtype == np.complex128 else 2e-5
+    assert rel(pl.store()[0], want['psik']) < tol
+    np.testing.assert_allclose(pops[0], want['pops_vals'], rtol=tol)
+    if dtype == np.complex128:
+        np.testing.assert_allclose(pl.energy(None, 2 * prob.kL, 0)[0], want['energy'], rtol=1e-9)
+        pl.load(prob.psik.numpy())
+        _, eng = pl.full_steps_energy(2, 2 * prob.kL, 0)
+        o = orc.OraclePropagator(prob, dt, mode)
+        for i in range(2):
+            o.full_step()
+            np.testing.assert_allclose(eng[0, i], orc.energy(prob, o.psik), rtol=1e-9)
+    rng = np.random.default_rng(ny)
+    psi = rng.standard_normal((2, ny, nx)) + 1j * rng.standard_normal((2, ny, nx))
+    t = torch.as_tensor(psi)
+    ttol = 1e-13 if dtype == np.complex128 else 1e-5
+    assert rel(pl.fft2d(psi)[0], orc.fft2(t, prob.dr).numpy()) < ttol
+    assert rel(pl.fft2d(psi, True)[0], orc.ifft2(t, prob.dr).numpy()) < ttol
+    for ax in (0, 1):
+        assert rel(pl.fft1d(psi, ax)[0], orc.fft1(t, prob.dr, ax).numpy()) < ttol
+        assert rel(pl.fft1d(psi, ax, True)[0], orc.ifft1(t, prob.dr, ax).numpy()) < ttol
+    pl.close()
+
+
+def test_mesh_sizes_the_library_refuses():
+    from tests.emu_harness import emu_lib
+    import ctypes
+    lib = emu_lib()
+    for nx, ny in ((31, 32), (22, 32), (32, 26), (8192, 32), (0, 32)):      # odd, factor 11, factor 13, too long, empty
+        h = ctypes.c_void_p()
+        assert lib.sgpe_plan_create(ctypes.byref(h), nx, ny, 1, 0, 0) != 0
+        assert b'even' in lib.sgpe_last_error()

@@ -414,6 +414,69 @@ def test_graph_replay_matches_plain_launches(mesh, mode, dt, batch):
         np.testing.assert_allclose(outs[0][1][0, :n1 + n2].cpu().numpy(), want['pops_vals'], rtol=TOL_SCALAR)
 
 
+@pytest.mark.parametrize('mesh,mode,dt,cpl', [((96, 80), 'real', 1 / 2000, 'uniform'), ((30, 50), 'imag', 1 / 50, 'dense'),
+                                               ((1000, 600), 'imag', 1 / 50, 'zero'), ((16, 8), 'real', 1 / 2000, 'none'),
+                                               ((750, 4), 'imag', 1 / 50, 'uniform'), ((24, 1458), 'real', 1 / 2000, 'zero')])
+@pytest.mark.parametrize('separable', [True, False])
+def test_generic_mesh_sizes_against_oracle(mesh, mode, dt, cpl, separable):
+    """Even mesh sizes that are not powers of two (prime factors 2, 3, 5, 7) and powers of two below 32 — what the
+    reference accepts (pspinor.py:331-332 asserts even sizes) — through the public API: psi_k, populations, energy,
+    stand-alone transforms."""
+    from spinor_gpe_b200 import tensor_tools as tt
+    ps = make_ps(mesh, atom_num=1e4, r_sizes=(16, 16), g_sc={'uu': 1, 'dd': 0.98, 'ud': 1.02})
+    if cpl != 'none':
+        ps.coupling_setup(wavel=790.1e-9, kin_shift=True)
+        if cpl == 'uniform':
+            ps.coupling_uniform(1.5 * ps.EL_recoil)
+        elif cpl == 'dense':
+            ps.coupling_grad(slope=0.3, offset=2.0, axis=1)
+        ps.detuning_grad(-3.0)
+    ps.rot_coupling = cpl != 'uniform'
+    rng = np.random.default_rng(31)
+    ps.psik = [p * (1 + 0.05 * (rng.standard_normal(p.shape) + 1j * rng.standard_normal(p.shape))) for p in ps.psik]
+    want = orc.OraclePropagator(problem_of(ps), dt, mode).run(4)
+    res, prop = (ps.imaginary if mode == 'imag' else ps.real)(dt, 4, 'cuda', separable=separable, unwrap='none')
+    assert rel(np.array(res.psik), want['psik']) < TOL_PSI
+    assert rel(np.array(res.psi), want['psi']) < TOL_PSI
+    np.testing.assert_allclose(res.pops['vals'], want['pops_vals'], rtol=TOL_SCALAR)
+    np.testing.assert_allclose(res.eng_final[2:], want['energy'][2:], rtol=TOL_SCALAR)
+    psi = [torch.as_tensor(p).cuda() for p in want['psi']]
+    back = tt.ifft_2d(tt.fft_2d(psi, ps.space['dr']), ps.space['dr'])
+    assert rel(np.array([b.cpu().numpy() for b in back]), want['psi']) < 1e-13
+    assert rel(np.array([b.cpu().numpy() for b in tt.fft_2d(psi, ps.space['dr'])]), want['psik']) < 1e-12
+
+
+def test_single_step_with_custom_operator_tables():
+    """single_step(t_step, eng) with caller-built operator tables (tensor_propagator.py:224-271 takes any `eng` dict):
+    the reference's own tables reproduce the fused step; modified tables follow the oracle fed the same tables."""
+    from spinor_gpe_b200 import TensorPropagator
+    from spinor_gpe_b200 import tensor_tools as tt
+    ps = make_ps((128, 64), atom_num=1e4, r_sizes=(16, 16))
+    ps.coupling_setup(wavel=790.1e-9, kin_shift=True)
+    ps.coupling_uniform(1.5 * ps.EL_recoil)
+    ps.rot_coupling = False
+    prop = TensorPropagator(ps, 1 / 2000, 1, 'cuda', time='real')
+    eng = {'kin': tt.evolution_op(prop.dt_out / 2, prop.kin_eng_spin), 'pot': tt.evolution_op(prop.dt_out, prop.pot_eng_spin),
+           'coupl': tt.coupling_op(prop.dt_out, prop.coupling / 2, prop.expon)}
+    prop.single_step(prop.dt_out, eng)
+    got = np.array([p.cpu().numpy() for p in prop.psik])
+    prop2 = TensorPropagator(ps, 1 / 2000, 1, 'cuda', time='real')
+    prop2.single_step(prop2.dt_out, prop2.eng_out)
+    assert rel(got, np.array([p.cpu().numpy() for p in prop2.psik])) < 1e-12
+    o = orc.OraclePropagator(problem_of(ps), 1 / 2000, 'real')
+    o.single_step(o.ops_out)
+    assert rel(got, o.psik.numpy()) < TOL_PSI
+    # tables that are no evolution operators of the propagator's grids (an absorbing boundary folded into `pot`)
+    damp = torch.as_tensor(np.exp(-0.01 * (ps.space['x_mesh'] ** 2 + ps.space['y_mesh'] ** 2) / 16 ** 2), device='cuda')
+    eng['pot'] = [p * damp for p in eng['pot']]
+    prop3 = TensorPropagator(ps, 1 / 2000, 1, 'cuda', time='real')
+    prop3.single_step(prop3.dt_out, eng)
+    o = orc.OraclePropagator(problem_of(ps), 1 / 2000, 'real')
+    o.ops_out['pot'] = o.ops_out['pot'] * damp.cpu()
+    o.single_step(o.ops_out)
+    assert rel(np.array([p.cpu().numpy() for p in prop3.psik]), o.psik.numpy()) < TOL_PSI
+
+
 def test_complex64_against_oracle():
     ps = make_ps((512, 512))
     ps.coupling_setup(wavel=790.1e-9, kin_shift=True)
