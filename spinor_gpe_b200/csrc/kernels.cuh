@@ -371,6 +371,36 @@ SGPE_DI void k_factors(C (&v)[E], C fxa, C fxb, const C* __restrict__ ya, const 
     if (!HAS_A) acc[0] = acc[1];
 }
 
+// the same with dense kinetic grids: the factors exp(-i kin tau) are evaluated per point (general operators)
+template <typename T, int E, int TM, bool HAS_A, bool HAS_B, bool AUX, typename C>
+SGPE_DI void k_factors_dense(C (&v)[E], const double* __restrict__ kin, long long kin_stride, double ka_re, double ka_im,
+                             double kb_re, double kb_im, C* aux, long long aux_stride, double (&acc)[2]) {
+    constexpr int CH = E < 4 ? E : 4;
+#pragma unroll
+    for (int m0 = 0; m0 < E; m0 += CH) {
+        double e[CH];
+#pragma unroll
+        for (int q = 0; q < CH; q++) e[q] = __ldg(&kin[(long long)(m0 + q) * kin_stride]);
+#pragma unroll
+        for (int q = 0; q < CH; q++) {
+            const int m = m0 + q;
+            C x = v[m];
+            if (HAS_A) {
+                x = mul_factor<TM>(x, evo<TM, T, C>(e[q], ka_re, ka_im));
+                acc[0] += (double)x.x * x.x + (double)x.y * x.y;
+                if (AUX) SGPE_ST_STREAM(&aux[(long long)m * aux_stride], x);
+            }
+            if (HAS_B) {
+                x = mul_factor<TM>(x, evo<TM, T, C>(e[q], kb_re, kb_im));
+                acc[1] += (double)x.x * x.x + (double)x.y * x.y;
+            }
+            v[m] = x;
+        }
+    }
+    if (!HAS_B) acc[1] = acc[0];
+    if (!HAS_A) acc[0] = acc[1];
+}
+
 // Persistent column pass of the steady-state junction (what FAST = 1 / 2 compute) with the NEXT tile staged
 // asynchronously: one CTA per SM slot walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ...; TMA (cp.async.bulk.tensor,
 // N / 256 boxes of 256 rows x 64 bytes, completion on an mbarrier) lands the CTA's next tile in shared memory while the
@@ -384,7 +414,7 @@ SGPE_DI void k_factors(C (&v)[E], C fxa, C fxb, const C* __restrict__ ya, const 
 //               L1 as in the one-tile-per-CTA kernel).
 // The partial sums of a tile are stored right away, the ticket (fence + atomic) is taken ONCE per CTA after its last
 // tile; the CTA that completes the count folds the partials in a fixed order as before.
-template <typename T, int N, int E, int W, int TM, int XSPLIT, int TWS>
+template <typename T, int N, int E, int W, int TM, int XSPLIT, int TWS, int KM = 1>
 __global__ void __launch_bounds__(W * N / E, (W * N / E <= 256) ? 2 : 1)
 col_pass_p(const SGPE_GRID_CONSTANT SgpeTileMap tmap, ColArgs<T> a) {
     typedef typename cx_of<T>::type C;
@@ -471,11 +501,22 @@ col_pass_p(const SGPE_GRID_CONSTANT SgpeTileMap tmap, ColArgs<T> a) {
             const long long oy = (long long)b * a.sepy_bstride + (long long)comp * a.ny + j;
             C fxa, fxb;
             fxa.x = (T)1; fxa.y = (T)0; fxb = fxa;
-            if (a.has_a) fxa = __ldg(&a.xa[ox]);
-            if (a.has_b) fxb = __ldg(&a.xb[ox]);
+            if (KM != 0 && a.has_a) fxa = __ldg(&a.xa[ox]);
+            if (KM != 0 && a.has_b) fxb = __ldg(&a.xb[ox]);
             C* const aux = a.aux != nullptr ? a.aux + off + (long long)j * a.nx : nullptr;
             const long long aux_stride = (long long)NT * a.nx;
-            if (a.has_a && a.has_b) {
+            if (KM == 0) {                  // dense kinetic grids, stored (shifted) k order like the state
+                const double* kin = (comp == 0 ? a.kin0 : a.kin1) + (long long)b * a.kin_bstride + col + (long long)j * a.nx;
+                if (a.has_a && a.has_b) {
+                    if (aux != nullptr) k_factors_dense<T, E, TM, true, true, true>(v[0], kin, aux_stride, a.ka_re, a.ka_im, a.kb_re, a.kb_im, aux, aux_stride, acc);
+                    else k_factors_dense<T, E, TM, true, true, false>(v[0], kin, aux_stride, a.ka_re, a.ka_im, a.kb_re, a.kb_im, aux, aux_stride, acc);
+                } else if (a.has_a) {
+                    if (aux != nullptr) k_factors_dense<T, E, TM, true, false, true>(v[0], kin, aux_stride, a.ka_re, a.ka_im, a.kb_re, a.kb_im, aux, aux_stride, acc);
+                    else k_factors_dense<T, E, TM, true, false, false>(v[0], kin, aux_stride, a.ka_re, a.ka_im, a.kb_re, a.kb_im, aux, aux_stride, acc);
+                } else {
+                    k_factors_dense<T, E, TM, false, true, false>(v[0], kin, aux_stride, a.ka_re, a.ka_im, a.kb_re, a.kb_im, aux, aux_stride, acc);
+                }
+            } else if (a.has_a && a.has_b) {
                 if (aux != nullptr) k_factors<T, E, NT, TM, true, true, true>(v[0], fxa, fxb, a.ya + oy, a.yb + oy, aux, aux_stride, acc);
                 else k_factors<T, E, NT, TM, true, true, false>(v[0], fxa, fxb, a.ya + oy, a.yb + oy, aux, aux_stride, acc);
             } else if (a.has_a) {
@@ -780,7 +821,8 @@ __global__ void __launch_bounds__(RPC * N / E, row_min_blocks<T>(RPC * N / E)) r
     const int r = tid / NT, j = tid % NT;
     const int y = blockIdx.x * RPC + r;
     const int b = blockIdx.y;
-    const int cpl_mode = FAST ? 0 : a.cpl_mode, pot_mode = FAST ? 1 : a.pot_mode;
+    // FAST = 2: the same specialisation for DENSE potential grids (factors evaluated per point, no coupling)
+    const int cpl_mode = FAST ? 0 : a.cpl_mode, pot_mode = FAST == 1 ? 1 : (FAST == 2 ? 0 : a.pot_mode);
     const int sign_in = FAST ? 0 : a.sign_in, sign_out = FAST ? 0 : a.sign_out;
     const bool do_inv = FAST ? true : (a.do_inv != 0), do_pw = FAST ? true : (a.do_pw != 0);
     const bool do_fwd = FAST ? true : (a.do_fwd != 0);
@@ -1733,6 +1775,7 @@ template <typename T> struct EnergyArgs {
     const double* maxdens;
     double* partials; unsigned* counter; double* out;        // out [b * out_bstride + {0..3}]: total, kin, pot, int
     long long out_bstride;
+    int rows;                   // streaming kernel: rows per CTA band
 };
 
 SGPE_DI double sgpe_wrap_pi(double d) {
@@ -1833,6 +1876,160 @@ __global__ void __launch_bounds__(256) energy_pass(EnergyArgs<T> a) {
         else if (a.cpl_mode == 2) om = __ldg(&a.coupling[(long long)b * a.cpl_bstride + pix]);
         const double coupl = ((double)ctr[0].x * ctr[1].x + (double)ctr[0].y * ctr[1].y) * om;   // Re(conj(p0) p1) * Omega
         if (inside) { acc[0] += kin + pot + inter + coupl; acc[1] += kin; acc[2] += pot; acc[3] += inter; }
+    }
+    cta_reduce<4>(acc, red);
+    if (tid == 0) {
+        double* p = a.partials + ((long long)b * nblk + blockIdx.x) * 4;
+        p[0] = acc[0]; p[1] = acc[1]; p[2] = acc[2]; p[3] = acc[3];
+        __threadfence();
+        red[0] = (atomicAdd(&a.counter[b], 1u) == (unsigned)(nblk - 1)) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const bool last = red[0] != 0.0;
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        double t4[4] = {0.0, 0.0, 0.0, 0.0};
+        const double* p = a.partials + (long long)b * nblk * 4;
+        for (int t = tid; t < nblk; t += blockDim.x) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) t4[q] += __ldcg(&p[4 * t + q]);
+        }
+        cta_reduce<4>(t4, red);
+        if (tid == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) a.out[(long long)b * a.out_bstride + q] = t4[q];
+            a.counter[b] = 0u;
+        }
+    }
+}
+
+// The same functional, streaming: a CTA owns a band of `rows` rows x 256 columns and walks down the rows with a
+// three-row window in registers; sqrt(n) and the masked phase of a pixel are evaluated ONCE (the tiled kernel above pays a
+// 33 % halo and two barriers per tile and component, and was latency-bound at 160 us for 2048^2), the x-neighbours come
+// from a double-buffered shared-memory row (one barrier per row), the y-neighbours are the thread's own previous rows.
+// Loads are full coalesced row segments, the next row is fetched while the current one is worked on.
+template <typename T>
+__global__ void __launch_bounds__(256, 2) energy_stream_pass(EnergyArgs<T> a) {
+    typedef typename cx_of<T>::type C;
+    constexpr int BX = 256, RW = BX + 2;
+    SGPE_DYN_SMEM(smem_raw);
+    double* red = reinterpret_cast<double*>(smem_raw);                 // [32 * 4]
+    double* s_row = red + 32 * 4;                                      // [2 buffers][2 components][r, ph][RW]
+    const int b = blockIdx.y, nblk = gridDim.x, tid = threadIdx.x;
+    const int nxb = (a.nx + BX - 1) / BX;
+    const int x0 = (int)(blockIdx.x % nxb) * BX, y0 = (int)(blockIdx.x / nxb) * a.rows;
+    const int y1 = (y0 + a.rows < a.ny) ? y0 + a.rows : a.ny;
+    const int x = x0 + tid;
+    const bool col_ok = x < a.nx;
+    const int xc = col_ok ? x : a.nx - 1;
+    // the two halo columns of the band are looked after by threads 0 (left) and 1 (right)
+    const int xh = tid == 0 ? (x0 > 0 ? x0 - 1 : 0) : ((x0 + BX < a.nx) ? x0 + BX : a.nx - 1);
+    const C* p0 = a.psi + ((long long)b * 2) * a.plane;
+    const C* p1 = p0 + a.plane;
+    const int* inc0 = a.unwrap_mode == 2 ? a.inc + ((long long)b * 2) * a.plane : nullptr;
+    const int* inc1 = a.unwrap_mode == 2 ? inc0 + a.plane : nullptr;
+    const double thr0 = a.maxdens[2 * b] * 1e-6, thr1 = a.maxdens[2 * b + 1] * 1e-6;
+    double om_u = 0.0;
+    if (a.cpl_mode == 1) om_u = a.omega_b[b];
+
+    auto prep = [&](C z, double thr, const int* inc, long long pix, double& r, double& ph) {
+        const double n = (double)z.x * z.x + (double)z.y * z.y;
+        r = sqrt(n);
+        ph = 0.0;
+        if (!(n < thr)) {
+            ph = atan2((double)z.y, (double)z.x);
+            if (inc != nullptr) ph = __dadd_rn(ph, __dmul_rn(6.283185307179586, (double)inc[pix]));
+        }
+    };
+
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    // window: index 0 = two rows back, 1 = previous row; per component r, ph; of the previous row also the x-derivatives,
+    // the density and the wavefunction itself
+    double wr[2][2], wph[2][2], gxr[2], gxph[2];
+    C zprev[2];
+    wr[0][0] = wr[0][1] = wr[1][0] = wr[1][1] = 0.0; wph[0][0] = wph[0][1] = wph[1][0] = wph[1][1] = 0.0;
+    gxr[0] = gxr[1] = gxph[0] = gxph[1] = 0.0;
+    zprev[0].x = zprev[0].y = zprev[1].x = zprev[1].y = (T)0;
+
+    int yl = y0 - 1 < 0 ? 0 : y0 - 1;
+    C zn0 = p0[(long long)yl * a.nx + xc], zn1 = p1[(long long)yl * a.nx + xc];
+    C hn0 = zn0, hn1 = zn1;                              // threads 0 / 1: the halo pixels of the next row
+    if (tid < 2) { hn0 = p0[(long long)yl * a.nx + xh]; hn1 = p1[(long long)yl * a.nx + xh]; }
+    int it = 0;
+    for (int yy = y0 - 1; yy <= y1; yy++, it++) {
+        const C z0 = zn0, z1 = zn1, h0 = hn0, h1 = hn1;
+        const int ycur = yy < 0 ? 0 : (yy > a.ny - 1 ? a.ny - 1 : yy);
+        if (yy < y1) {                                   // fetch the next row while this one is worked on
+            const int yn = yy + 1 > a.ny - 1 ? a.ny - 1 : yy + 1;
+            zn0 = p0[(long long)yn * a.nx + xc]; zn1 = p1[(long long)yn * a.nx + xc];
+            if (tid < 2) { hn0 = p0[(long long)yn * a.nx + xh]; hn1 = p1[(long long)yn * a.nx + xh]; }
+            // (one row ahead in registers does not cover the DRAM latency: rows further down are pulled into L2)
+            const int yf = yy + 6;
+            if (yf <= y1 && yf < a.ny && (tid & 1) == 0) {
+                SGPE_PREFETCH_L2(&p0[(long long)yf * a.nx + xc]);
+                SGPE_PREFETCH_L2(&p1[(long long)yf * a.nx + xc]);
+            }
+        }
+        const long long pix = (long long)ycur * a.nx + xc;
+        double r[2], ph[2];
+        prep(z0, thr0, inc0, pix, r[0], ph[0]);
+        prep(z1, thr1, inc1, pix, r[1], ph[1]);
+        double* buf = s_row + (it & 1) * (4 * RW);
+        buf[0 * RW + tid + 1] = r[0]; buf[1 * RW + tid + 1] = ph[0];
+        buf[2 * RW + tid + 1] = r[1]; buf[3 * RW + tid + 1] = ph[1];
+        if (tid < 2) {
+            const long long hp = (long long)ycur * a.nx + xh;
+            double hr, hph;
+            const int slot = tid == 0 ? 0 : RW - 1;
+            prep(h0, thr0, inc0, hp, hr, hph); buf[0 * RW + slot] = hr; buf[1 * RW + slot] = hph;
+            prep(h1, thr1, inc1, hp, hr, hph); buf[2 * RW + slot] = hr; buf[3 * RW + slot] = hph;
+        }
+        __syncthreads();
+        // finish the previous row: its y-derivatives need this row
+        if (yy - 1 >= y0 && yy - 1 < y1 && col_ok) {
+            const int i = yy - 1;
+            double kin = 0.0, dens[2];
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const double gyr = sgpe_grad3(wr[0][c], wr[1][c], r[c], i, a.ny, a.inv_h0);
+                const double gyph = a.unwrap_mode != 1 ? sgpe_grad3(wph[0][c], wph[1][c], ph[c], i, a.ny, a.inv_h0)
+                                                       : sgpe_grad3_wrapped(wph[0][c], wph[1][c], ph[c], i, a.ny, a.inv_h0);
+                const double n0 = (double)zprev[c].x * zprev[c].x + (double)zprev[c].y * zprev[c].y;
+                kin += (gyr * gyr + gxr[c] * gxr[c]) + n0 * (gyph * gyph + gxph[c] * gxph[c]) + n0 * gyph * a.kl2;
+                dens[c] = n0;
+            }
+            kin *= 0.5;
+            const long long pp = (long long)i * a.nx + x;
+            double v0, v1;
+            if (a.pot_mode == 0) {
+                v0 = __ldg(&a.pot0[(long long)b * a.pot_bstride + pp]);
+                v1 = __ldg(&a.pot1[(long long)b * a.pot_bstride + pp]);
+            } else {
+                const double* px = a.pot_x + (long long)b * a.potx_bstride;
+                const double* py = a.pot_y + (long long)b * a.poty_bstride;
+                v0 = __ldg(&px[x]) + __ldg(&py[i]);
+                v1 = __ldg(&px[a.nx + x]) + __ldg(&py[a.ny + i]);
+            }
+            const double pot = dens[0] * v0 + dens[1] * v1;
+            const double inter = a.g_uu * dens[0] * dens[0] + a.g_dd * dens[1] * dens[1] + a.g_ud * dens[0] * dens[1];
+            double om = om_u;
+            if (a.cpl_mode == 2) om = __ldg(&a.coupling[(long long)b * a.cpl_bstride + pp]);
+            const double coupl = ((double)zprev[0].x * zprev[1].x + (double)zprev[0].y * zprev[1].y) * om;
+            acc[0] += kin + pot + inter + coupl; acc[1] += kin; acc[2] += pot; acc[3] += inter;
+        }
+        // x-derivatives of this row (from the shared row), then shift the window
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const double rm = buf[(2 * c) * RW + tid], rp = buf[(2 * c) * RW + tid + 2];
+            const double pm = buf[(2 * c + 1) * RW + tid], pq = buf[(2 * c + 1) * RW + tid + 2];
+            gxr[c] = sgpe_grad3(rm, r[c], rp, xc, a.nx, a.inv_h1);
+            gxph[c] = a.unwrap_mode != 1 ? sgpe_grad3(pm, ph[c], pq, xc, a.nx, a.inv_h1)
+                                         : sgpe_grad3_wrapped(pm, ph[c], pq, xc, a.nx, a.inv_h1);
+            wr[0][c] = wr[1][c]; wph[0][c] = wph[1][c];
+            wr[1][c] = r[c]; wph[1][c] = ph[c];
+        }
+        zprev[0] = z0; zprev[1] = z1;
     }
     cta_reduce<4>(acc, red);
     if (tid == 0) {

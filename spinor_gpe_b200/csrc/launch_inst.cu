@@ -74,6 +74,7 @@ static int launch_row_t(const RowArgs<T>& a, int batch, cudaStream_t st) {
     if (!once) {
         allow_smem(row_pass<T, N, Cfg::E, Cfg::RPC, TM, 0>, Cfg::SMEM);
         allow_smem(row_pass<T, N, Cfg::E, Cfg::RPC, TM, 1>, Cfg::SMEM);
+        allow_smem(row_pass<T, N, Cfg::E, Cfg::RPC, TM, 2>, Cfg::SMEM);
         ahead = resident_ctas(row_pass<T, N, Cfg::E, Cfg::RPC, TM, 1>, Cfg::THREADS, Cfg::SMEM);
         once = true;
     }
@@ -81,10 +82,13 @@ static int launch_row_t(const RowArgs<T>& a, int batch, cudaStream_t st) {
     RowArgs<T> a2 = a;
     if (a2.prefetch_ahead) a2.prefetch_ahead = ahead;
     a2.resident = ahead;
-    const bool fast = a.do_inv && a.do_pw && a.do_fwd && a.cpl_mode == 0 && a.pot_mode == 1 && !a.sign_in &&
-                      !a.sign_out && a.scale_out == 1.0 && a.stagger_ns == 0 && a.dbg == nullptr && a.sc.mode == 0;
-    if (fast) {
+    const bool fast = a.do_inv && a.do_pw && a.do_fwd && a.cpl_mode == 0 && !a.sign_in &&
+                      !a.sign_out && a.scale_out == 1.0 && a.stagger_ns == 0 && a.dbg == nullptr && a.sc.mode == 0 &&
+                      a.scale_tot == nullptr && a.maxbits == nullptr;
+    if (fast && a.pot_mode == 1) {
         SGPE_LAUNCH((row_pass<T, N, Cfg::E, Cfg::RPC, TM, 1>), grid, block, Cfg::SMEM, st, a2);
+    } else if (fast && a.pot_mode == 0) {
+        SGPE_LAUNCH((row_pass<T, N, Cfg::E, Cfg::RPC, TM, 2>), grid, block, Cfg::SMEM, st, a2);
     } else {
         SGPE_LAUNCH((row_pass<T, N, Cfg::E, Cfg::RPC, TM, 0>), grid, block, Cfg::SMEM, st, a2);
     }
@@ -121,7 +125,7 @@ static int launch_col_w(const ColArgs<T>& a, int batch, cudaStream_t st) {
 }
 
 // persistent column pass with TMA-staged tiles (col_pass_p): one CTA per resident slot, grid capped at the tile count
-template <typename T, int N, int TM, int W, int E, int XSPLIT, int TWS>
+template <typename T, int N, int TM, int W, int E, int XSPLIT, int TWS, int KM = 1>
 static int launch_col_p(const ColArgs<T>& a, int batch, cudaStream_t st) {
     typedef ColCfg<T, N> Cfg;
     constexpr size_t tile = (size_t)N * W * Cfg::CB;
@@ -131,8 +135,8 @@ static int launch_col_p(const ColArgs<T>& a, int batch, cudaStream_t st) {
     static bool once = false;
     static int resident = 0;
     if (!once) {
-        allow_smem(col_pass_p<T, N, E, W, TM, XSPLIT, TWS>, smem);
-        resident = resident_ctas(col_pass_p<T, N, E, W, TM, XSPLIT, TWS>, W * (N / E), smem);
+        allow_smem(col_pass_p<T, N, E, W, TM, XSPLIT, TWS, KM>, smem);
+        resident = resident_ctas(col_pass_p<T, N, E, W, TM, XSPLIT, TWS, KM>, W * (N / E), smem);
         once = true;
     }
     const int ntiles = 2 * a.nx / W;
@@ -141,7 +145,7 @@ static int launch_col_p(const ColArgs<T>& a, int batch, cudaStream_t st) {
     if (ctas > ntiles) ctas = ntiles;
     dim3 grid(ctas, batch), block(W * (N / E));
     const SgpeTileMap& map = *static_cast<const SgpeTileMap*>(a.tile_map);
-    SGPE_LAUNCH((col_pass_p<T, N, E, W, TM, XSPLIT, TWS>), grid, block, smem, st, map, a);
+    SGPE_LAUNCH((col_pass_p<T, N, E, W, TM, XSPLIT, TWS, KM>), grid, block, smem, st, map, a);
     return 0;
 }
 
@@ -221,10 +225,12 @@ static int launch_col_t(const ColArgs<T>& a, int batch, int wsel, cudaStream_t s
 #endif
     if constexpr (Cfg::E == 16) {
         // the persistent kernel covers the steady-state junction: forward + factors + inverse, separable tables
-        const bool fast = a.do_fwd && a.do_inv && a.kin_mode == 1 && !a.sign_in && !a.sign_out && a.scale_out == 1.0 &&
-                          a.in == a.out;
+        const bool fast = a.do_fwd && a.do_inv && !a.sign_in && !a.sign_out && a.scale_out == 1.0 && a.in == a.out;
+        // (the first persistent variant also evaluates dense kinetic grids; the others take factor tables only)
+        if (a.kernel_sel >= 2 && a.kin_mode != 1) return launch_col_w<T, N, TM, Cfg::W, Cfg::E>(a, batch, st);
         if (a.kernel_sel == 1 && fast && a.tile_map != nullptr && wsel == 0)
-            return launch_col_p<T, N, TM, Cfg::W, Cfg::E, 1, 0>(a, batch, st);
+            return a.kin_mode == 1 ? launch_col_p<T, N, TM, Cfg::W, Cfg::E, 1, 0, 1>(a, batch, st)
+                                   : launch_col_p<T, N, TM, Cfg::W, Cfg::E, 1, 0, 0>(a, batch, st);
         if (a.kernel_sel == 2 && fast && a.tile_map != nullptr && wsel == 0)
             return launch_col_p<T, N, TM, Cfg::W, Cfg::E, 0, 0>(a, batch, st);
         if (a.kernel_sel == 4 && fast && a.tile_map != nullptr && wsel == 0) {

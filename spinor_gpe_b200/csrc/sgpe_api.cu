@@ -124,6 +124,7 @@ struct sgpe_plan {
     uint64_t launches = 0;
     // CUDA-graph replay of the steady-state full step (option "graph"): six kernel nodes whose arguments do not change
     // from step to step (the populations slot comes from the device-side counter slot_ctr)
+    int energy_kernel = 0;         // option "energy_kernel": 0 streaming (default), 1 tiled
     int use_graph = -1;            // -1: default choice (small meshes), 0 off, 1 on
     uint64_t epoch = 0;            // bumped by every sgpe_set_* call: a captured graph is valid for one epoch
     int* slot_ctr = nullptr;       // [batch]
@@ -468,7 +469,7 @@ int run_col(sgpe_plan* p, const void* in, void* out, bool fwd, bool has_a, doubl
     if (p->generic) return run_col_generic<T>(p, a, fwd, inv, st);
     a.dbg = (fwd && inv) ? p->dbg_col : nullptr;
     a.kernel_sel = p->col_kernel == 0 ? default_col_kernel(p) : p->col_kernel - 1;
-    if (a.kernel_sel >= 1 && fwd && inv && in == out && p->kin_mode == 1 && p->n1 == 1) {
+    if (a.kernel_sel >= 1 && fwd && inv && in == out && p->n1 == 1) {
         const SgpeTileMap* tm = nullptr;
         int w = sgpe::col_tile_width(p->ny, p->dtype);
         if (a.kernel_sel == 5) w /= 2;                      // half-width tiles, two CTAs per SM
@@ -688,11 +689,28 @@ int run_energy(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, d
     a.inc = p->unwrap_inc;
     a.maxdens = p->maxdens; a.partials = p->partials; a.counter = p->counter; a.out = out;
     a.out_bstride = out_bstride;
-    long long tiles = (long long)((p->nx + 31) / 32) * ((p->ny + 7) / 8);
-    blocks = tiles < 888 ? tiles : 888;                     // six 256-thread CTAs per SM x 148 SMs
-    if (blocks > p->max_tiles / 2) blocks = p->max_tiles / 2;   // four partial sums per CTA in `partials`
-    dim3 grid((unsigned)blocks, p->batch), block(256);
-    SGPE_LAUNCH((sgpe::energy_pass<T>), grid, block, (32 * 4 + 2 * 34 * 10) * sizeof(double), st, a);
+    if (p->energy_kernel == 1) {       // the tiled kernel of round 1 (option "energy_kernel", cross-checks)
+        long long tiles = (long long)((p->nx + 31) / 32) * ((p->ny + 7) / 8);
+        blocks = tiles < 888 ? tiles : 888;                     // six 256-thread CTAs per SM x 148 SMs
+        if (blocks > p->max_tiles / 2) blocks = p->max_tiles / 2;   // four partial sums per CTA in `partials`
+        dim3 grid((unsigned)blocks, p->batch), block(256);
+        SGPE_LAUNCH((sgpe::energy_pass<T>), grid, block, (32 * 4 + 2 * 34 * 10) * sizeof(double), st, a);
+        p->launches++;
+        SGPE_CUDA(cudaGetLastError());
+        return 0;
+    }
+    // streaming kernel: bands of `rows` rows x 256 columns, ~4 CTAs per SM, at most max_tiles / 2 of them
+    const int nxb = (p->nx + 255) / 256;
+    long long want = 592 / nxb;
+    if (want > p->max_tiles / 2 / nxb) want = p->max_tiles / 2 / nxb;
+    if (want < 1) want = 1;
+    int rows = (int)((p->ny + want - 1) / want);
+    if (rows < 8) rows = 8;
+    if (rows > p->ny) rows = p->ny;
+    a.rows = rows;
+    const int nyb = (p->ny + rows - 1) / rows;
+    dim3 grid((unsigned)(nxb * nyb), p->batch), block(256);
+    SGPE_LAUNCH((sgpe::energy_stream_pass<T>), grid, block, (32 * 4 + 2 * 4 * 258) * sizeof(double), st, a);
     p->launches++;
     SGPE_CUDA(cudaGetLastError());
     return 0;
@@ -1220,6 +1238,7 @@ int sgpe_set_option(sgpe_plan* p, const char* name, int value) {
     }
     if (std::strcmp(name, "stagger_ns") == 0) { p->stagger_ns = value; return 0; }
     if (std::strcmp(name, "timeline_kind") == 0) { p->dbg_kind = value ? 1 : 0; return 0; }
+    if (std::strcmp(name, "energy_kernel") == 0) { p->energy_kernel = value ? 1 : 0; return 0; }
     if (std::strcmp(name, "graph") == 0) {
         if (value < -1 || value > 1) return fail(SGPE_EINVAL, "graph: -1 (default: small meshes), 0 (off) or 1 (on)");
         p->use_graph = value;

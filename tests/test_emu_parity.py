@@ -136,6 +136,13 @@ def test_emulated_persistent_column_pass(shape, mode, dtype, kernel):
     prob = _seeded_problem(ny, nx, seed=3 * ny + nx)
     dt, n = (1 / 200, 3) if mode == 'real' else (1 / 50, 3)
     want = orc.OraclePropagator(prob, dt, mode).run(n)
+    if kernel == 2:      # this variant also takes dense kinetic grids (factors evaluated per point)
+        pld = plan_from_problem(prob, mode, dt, dtype=dtype, separable=False)
+        pld.set_option('col_kernel', kernel)
+        popsd = pld.full_steps(n)
+        assert rel(pld.store()[0], want['psik']) < (1e-12 if dtype == np.complex128 else 2e-5)
+        np.testing.assert_allclose(popsd[0], want['pops_vals'], rtol=1e-12 if dtype == np.complex128 else 2e-5)
+        pld.close()
     pl = plan_from_problem(prob, mode, dt, dtype=dtype, separable=True)
     pl.set_option('col_kernel', kernel)
     pops = pl.full_steps(n)
