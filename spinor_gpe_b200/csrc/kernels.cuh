@@ -48,6 +48,29 @@ SGPE_DI double sgpe_exp(double x) {
     return __longlong_as_double(__double_as_longlong(p) + ((long long)k << 52));
 }
 
+// exp(x) for |x| <= 1/16: Taylor polynomial of degree 9 (truncation 2.5e-19 relative), no range reduction, nine FMAs
+// against the ~20 floating-point and integer operations of sgpe_exp.  What the non-linear factor of an imaginary-time
+// sub-step asks for when g n dt / 2 is small (the benchmark's: <= 0.03) — two of them per pixel in the row pass.
+SGPE_DI double sgpe_exp_small(double x) {
+    double p = 2.7557319223985893e-06;            // 1 / 9!
+    p = fma(p, x, 2.4801587301587302e-05);        // 1 / 8!
+    p = fma(p, x, 1.9841269841269841e-04);        // 1 / 7!
+    p = fma(p, x, 1.3888888888888889e-03);        // 1 / 6!
+    p = fma(p, x, 8.3333333333333332e-03);        // 1 / 5!
+    p = fma(p, x, 4.1666666666666664e-02);        // 1 / 4!
+    p = fma(p, x, 1.6666666666666666e-01);        // 1 / 3!
+    p = fma(p, x, 0.5);
+    p = fma(p, x, 1.0);
+    p = fma(p, x, 1.0);
+    return p;
+}
+// the two interaction factors of a pixel in imaginary time (double precision): the short polynomial when both arguments
+// are small, sgpe_exp otherwise (both within one ulp of exp)
+SGPE_DI void sgpe_exp_pair(double x0, double x1, double& e0, double& e1) {
+    if (fabs(x0) <= 0.0625 && fabs(x1) <= 0.0625) { e0 = sgpe_exp_small(x0); e1 = sgpe_exp_small(x1); }
+    else { e0 = sgpe_exp(x0); e1 = sgpe_exp(x1); }
+}
+
 // exp(-i * e * tau), tau = (tr, ti):  real time tau = (dt, 0);  imaginary time tau = (0, -dt)
 template <int TM, typename T, typename C> SGPE_DI C evo(double e, double tr, double ti) {
     C r;
@@ -371,6 +394,29 @@ SGPE_DI void k_factors(C (&v)[E], C fxa, C fxb, const C* __restrict__ ya, const 
     if (!HAS_A) acc[0] = acc[1];
 }
 
+// imaginary time, the y-dependent factor tables of the launch held in shared memory (real factors): no L2 round trips
+// in the K phase of a persistent CTA whose shared-memory footprint leaves no L1 to cache the tables in
+template <typename T, int E, int NT, bool HAS_A, bool HAS_B, bool AUX, typename C>
+SGPE_DI void k_factors_smem_imag(C (&v)[E], T fxa, T fxb, const T* ya, const T* yb, C* aux, long long aux_stride,
+                                 double (&acc)[2]) {
+#pragma unroll
+    for (int m = 0; m < E; m++) {
+        C x = v[m];
+        if (HAS_A) {
+            x = cscale(x, fxa * ya[m * NT]);
+            acc[0] += (double)x.x * x.x + (double)x.y * x.y;
+            if (AUX) SGPE_ST_STREAM(&aux[(long long)m * aux_stride], x);
+        }
+        if (HAS_B) {
+            x = cscale(x, fxb * yb[m * NT]);
+            acc[1] += (double)x.x * x.x + (double)x.y * x.y;
+        }
+        v[m] = x;
+    }
+    if (!HAS_B) acc[1] = acc[0];
+    if (!HAS_A) acc[0] = acc[1];
+}
+
 // the same with dense kinetic grids: the factors exp(-i kin tau) are evaluated per point (general operators)
 template <typename T, int E, int TM, bool HAS_A, bool HAS_B, bool AUX, typename C>
 SGPE_DI void k_factors_dense(C (&v)[E], const double* __restrict__ kin, long long kin_stride, double ka_re, double ka_im,
@@ -426,8 +472,12 @@ col_pass_p(const SGPE_GRID_CONSTANT SgpeTileMap tmap, ColArgs<T> a) {
     SGPE_DYN_SMEM_128(smem_p);
     C* const S = reinterpret_cast<C*>(smem_p);
     T* const X = reinterpret_cast<T*>(smem_p + TILE_BYTES);
-    // TWS = 1: the twiddle tables of this plan (N entries) live in shared memory for the life of the CTA
+    // TWS = 1: the twiddle tables of this plan (N entries) live in shared memory for the life of the CTA.
+    // TWS = 2 (imaginary time, factor tables): the same bytes hold the y-dependent k factors of the launch instead,
+    // real parts only, [FA | FB] of the component the CTA is working on
     C* const TW = reinterpret_cast<C*>(smem_p + TILE_BYTES + (XSPLIT ? TILE_BYTES / 2 : 0));
+    T* const KT = reinterpret_cast<T*>(TW);
+    static_assert(TWS != 2 || (TM == TM_IMAG && KM == 1), "shared-memory k factors: imaginary time, factor tables");
     double* const red = reinterpret_cast<double*>(smem_p + TILE_BYTES + (XSPLIT ? TILE_BYTES / 2 : 0) + (TWS ? N * sizeof(C) : 0));
     SgpeMbar* const mbar = reinterpret_cast<SgpeMbar*>(red + 32 * 4);
     int* const flag = reinterpret_cast<int*>(mbar + 1);
@@ -437,7 +487,7 @@ col_pass_p(const SGPE_GRID_CONSTANT SgpeTileMap tmap, ColArgs<T> a) {
     const int ntiles = 2 * tiles_per_comp;
     const bool any_k = a.has_a || a.has_b;
 
-    // stage tile `t` of this trajectory into S (one elected thread)
+    // stage tile `t` of this trajectory into S (one elected thread) 
     auto stage = [&](int t) {
         sgpe_mbar_expect_tx(mbar, TILE_BYTES);
 #pragma unroll 1
@@ -447,20 +497,41 @@ col_pass_p(const SGPE_GRID_CONSTANT SgpeTileMap tmap, ColArgs<T> a) {
     };
 
     if (threadIdx.x == 0) sgpe_mbar_init(mbar, 1);
-    if (TWS) {
+    if (TWS == 1) {
         const C* src = a.tw + (E == 16 ? N : 0);
         for (int i = threadIdx.x; i < N; i += W * NT) TW[i] = __ldg(&src[i]);
     }
     __syncthreads();
     if (threadIdx.x == 0) stage(blockIdx.x);
     int done = 0;
+    int kt_comp = -1;
 #pragma unroll 1
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, done++) {
         // (thread coordinates are re-derived per tile: nothing that depends on them stays live across the loop)
         const int tid = threadIdx.x;
         const int c = tid % W, j = tid / W;
-        typename TwSource<C, TWS>::type tw = TwSource<C, TWS>::make(a.tw + (E == 16 ? N : 0), TW);
+        typename TwSource<C, TWS == 1>::type tw = TwSource<C, TWS == 1>::make(a.tw + (E == 16 ? N : 0), TW);
         const int comp = tile / tiles_per_comp;
+        // the x-dependent factors of this tile's W columns: fetched by W threads NOW, read by everybody in the K phase
+        // (behind the barriers of the forward transform) - as plain loads at the head of the K phase they stalled the
+        // whole CTA for an L2 round trip per tile
+        C* const FX = reinterpret_cast<C*>(mbar + 16);           // [2][W], behind the barrier word, flag and stamps
+        if (KM == 1 && any_k && tid < 2 * W) {
+            const int which = tid / W, cc = tid % W;
+            const long long oxx = (long long)b * a.sepx_bstride + (long long)comp * a.nx + (tile % tiles_per_comp) * W + cc;
+            C one; one.x = (T)1; one.y = (T)0;
+            FX[which * W + cc] = which == 0 ? (a.has_a ? __ldg(&a.xa[oxx]) : one) : (a.has_b ? __ldg(&a.xb[oxx]) : one);
+        }
+        if (TWS == 2 && any_k && comp != kt_comp) {
+            // (the barriers of the forward transform order these stores before the K phase reads them, those of the
+            // previous tile's inverse transform ordered its reads before them)
+            kt_comp = comp;
+            const long long oyb = (long long)b * a.sepy_bstride + (long long)comp * a.ny;
+            for (int i = tid; i < N; i += W * NT) {
+                KT[i] = a.has_a ? __ldg(&a.ya[oyb + i]).x : (T)1;
+                KT[N + i] = a.has_b ? __ldg(&a.yb[oyb + i]).x : (T)1;
+            }
+        }
         const int col = (tile % tiles_per_comp) * W + c;
         const long long off = ((long long)b * 2 + comp) * a.plane + col;
 
@@ -501,8 +572,8 @@ col_pass_p(const SGPE_GRID_CONSTANT SgpeTileMap tmap, ColArgs<T> a) {
             const long long oy = (long long)b * a.sepy_bstride + (long long)comp * a.ny + j;
             C fxa, fxb;
             fxa.x = (T)1; fxa.y = (T)0; fxb = fxa;
-            if (KM != 0 && a.has_a) fxa = __ldg(&a.xa[ox]);
-            if (KM != 0 && a.has_b) fxb = __ldg(&a.xb[ox]);
+            if (KM != 0) { fxa = FX[c]; fxb = FX[W + c]; }
+            (void)ox;
             C* const aux = a.aux != nullptr ? a.aux + off + (long long)j * a.nx : nullptr;
             const long long aux_stride = (long long)NT * a.nx;
             if (KM == 0) {                  // dense kinetic grids, stored (shifted) k order like the state
@@ -515,6 +586,17 @@ col_pass_p(const SGPE_GRID_CONSTANT SgpeTileMap tmap, ColArgs<T> a) {
                     else k_factors_dense<T, E, TM, true, false, false>(v[0], kin, aux_stride, a.ka_re, a.ka_im, a.kb_re, a.kb_im, aux, aux_stride, acc);
                 } else {
                     k_factors_dense<T, E, TM, false, true, false>(v[0], kin, aux_stride, a.ka_re, a.ka_im, a.kb_re, a.kb_im, aux, aux_stride, acc);
+                }
+            } else if (TWS == 2) {
+                const T* const ka = KT + j; const T* const kb = KT + N + j;
+                if (a.has_a && a.has_b) {
+                    if (aux != nullptr) k_factors_smem_imag<T, E, NT, true, true, true>(v[0], fxa.x, fxb.x, ka, kb, aux, aux_stride, acc);
+                    else k_factors_smem_imag<T, E, NT, true, true, false>(v[0], fxa.x, fxb.x, ka, kb, aux, aux_stride, acc);
+                } else if (a.has_a) {
+                    if (aux != nullptr) k_factors_smem_imag<T, E, NT, true, false, true>(v[0], fxa.x, fxb.x, ka, kb, aux, aux_stride, acc);
+                    else k_factors_smem_imag<T, E, NT, true, false, false>(v[0], fxa.x, fxb.x, ka, kb, aux, aux_stride, acc);
+                } else {
+                    k_factors_smem_imag<T, E, NT, false, true, false>(v[0], fxa.x, fxb.x, ka, kb, aux, aux_stride, acc);
                 }
             } else if (a.has_a && a.has_b) {
                 if (aux != nullptr) k_factors<T, E, NT, TM, true, true, true>(v[0], fxa, fxb, a.ya + oy, a.yb + oy, aux, aux_stride, acc);
@@ -911,6 +993,8 @@ __global__ void __launch_bounds__(RPC * N / E, row_min_blocks<T>(RPC * N / E)) r
             C p = cscale(v[0][m], alpha), q = cscale(v[1][m], alpha);
             const double n0 = (double)p.x * p.x + (double)p.y * p.y;
             const double n1 = (double)q.x * q.x + (double)q.y * q.y;
+            // (a short polynomial for small arguments - sgpe_exp_pair - was measured SLOWER here: 107 vs 103 us, the second
+            // code path costs more in registers and instruction cache than the nine saved FMAs per factor return)
             const C i0 = evo<TM, T, C>(a.g_uu * n0 + a.g_ud * n1, a.ti_re, a.ti_im);
             const C i1 = evo<TM, T, C>(a.g_dd * n1 + a.g_ud * n0, a.ti_re, a.ti_im);
             p = mul_factor<TM>(p, i0); q = mul_factor<TM>(q, i1);

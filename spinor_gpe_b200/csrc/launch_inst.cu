@@ -129,7 +129,7 @@ template <typename T, int N, int TM, int W, int E, int XSPLIT, int TWS, int KM =
 static int launch_col_p(const ColArgs<T>& a, int batch, cudaStream_t st) {
     typedef ColCfg<T, N> Cfg;
     constexpr size_t tile = (size_t)N * W * Cfg::CB;
-    constexpr size_t smem = tile + (XSPLIT ? tile / 2 : 0) + (TWS ? (size_t)N * Cfg::CB : 0) + 32 * 4 * sizeof(double) + 64;
+    constexpr size_t smem = tile + (XSPLIT ? tile / 2 : 0) + (TWS ? (size_t)N * Cfg::CB : 0) + 32 * 4 * sizeof(double) + 512;
     if (a.nx % W != 0 || a.tile_map == nullptr) return -2;
     if (smem > 227 * 1024) return -2;
     static bool once = false;
@@ -236,6 +236,15 @@ static int launch_col_t(const ColArgs<T>& a, int batch, int wsel, cudaStream_t s
         if (a.kernel_sel == 4 && fast && a.tile_map != nullptr && wsel == 0) {
             int rc4 = launch_col_p<T, N, TM, Cfg::W, Cfg::E, 1, 1>(a, batch, st);
             return rc4 == -2 ? launch_col_p<T, N, TM, Cfg::W, Cfg::E, 1, 0>(a, batch, st) : rc4;
+        }
+        if constexpr (TM == TM_IMAG) {       // k factors of the launch in shared memory (imaginary time)
+            if (a.kernel_sel == 6 && fast && a.tile_map != nullptr && wsel == 0) {
+                int rc6 = launch_col_p<T, N, TM, Cfg::W, Cfg::E, 1, 2>(a, batch, st);
+                return rc6 == -2 ? launch_col_p<T, N, TM, Cfg::W, Cfg::E, 1, 0>(a, batch, st) : rc6;
+            }
+        } else {
+            if (a.kernel_sel == 6 && fast && a.tile_map != nullptr && wsel == 0)
+                return launch_col_p<T, N, TM, Cfg::W, Cfg::E, 1, 0>(a, batch, st);
         }
         if constexpr (Cfg::W % 2 == 0 && (Cfg::W / 2) * Cfg::NT >= 32) {
             if (a.kernel_sel == 5 && fast && a.tile_map != nullptr && wsel == 0)

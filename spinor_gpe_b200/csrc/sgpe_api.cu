@@ -1245,10 +1245,11 @@ int sgpe_set_option(sgpe_plan* p, const char* name, int value) {
         return 0;
     }
     if (std::strcmp(name, "col_kernel") == 0) {
-        if (value < 0 || value > 6)
+        if (value < 0 || value > 7)
             return fail(SGPE_EINVAL, "col_kernel: 0 (default), 1 (one tile per CTA), 2 (persistent, TMA-staged, split inverse "
                                      "exchange), 3 (persistent, TMA-staged behind the inverse transform), 4 (persistent, "
-                                     "two barrier groups per CTA) 5 (as 2 with the twiddle tables in shared memory) or 6 (as 2 with half-width tiles, two CTAs per SM)");
+                                     "two barrier groups per CTA) 5 (as 2 with the twiddle tables in shared memory), 6 (as 2 with half-width tiles, two CTAs per SM) or 7 (as 2 "
+                                     "with the k factors of the launch in shared memory, imaginary time)");
         p->col_kernel = value;
         return 0;
     }

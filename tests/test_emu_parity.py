@@ -127,7 +127,8 @@ def _seeded_problem(ny, nx, seed, coupling=0.7):
     ((256, 32), 'real', np.complex128, 2), ((512, 32), 'imag', np.complex128, 2), ((2048, 32), 'imag', np.complex128, 2),
     ((256, 64), 'real', np.complex64, 2), ((1024, 32), 'imag', np.complex64, 6),
     ((512, 32), 'imag', np.complex128, 3), ((256, 32), 'real', np.complex128, 4), ((256, 64), 'real', np.complex64, 4),
-    ((512, 32), 'imag', np.complex128, 5), ((256, 32), 'real', np.complex128, 6), ((512, 32), 'imag', np.complex128, 6)])
+    ((512, 32), 'imag', np.complex128, 5), ((256, 32), 'real', np.complex128, 6), ((512, 32), 'imag', np.complex128, 6),
+    ((512, 32), 'imag', np.complex128, 7), ((256, 32), 'real', np.complex128, 7)])
 def test_emulated_persistent_column_pass(shape, mode, dtype, kernel):
     """col_kernel = 2 / 3: persistent column-pass CTAs, tiles staged asynchronously (TMA + mbarrier on the device, a copy
     at issue time in the emulation); 2: forward exchange through the staging image, split re / im exchange for the

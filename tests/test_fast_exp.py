@@ -18,6 +18,7 @@ static inline long long __double_as_longlong(double x) { long long r; std::memcp
 static inline double __longlong_as_double(long long x) { double r; std::memcpy(&r, &x, 8); return r; }
 %s
 extern "C" void run(const double* x, double* y, long n) { for (long i = 0; i < n; i++) y[i] = sgpe_exp(x[i]); }
+extern "C" void run_small(const double* x, double* y, long n) { for (long i = 0; i < n; i++) y[i] = sgpe_exp_small(x[i]); }
 '''
 
 
@@ -25,13 +26,16 @@ def _build():
     src = open(os.path.join(ROOT, 'spinor_gpe_b200', 'csrc', 'kernels.cuh')).read()
     a = src.index('SGPE_DI double sgpe_exp(double x) {')
     b = src.index('}\n', a) + 2
+    a2 = src.index('SGPE_DI double sgpe_exp_small(double x) {')
+    b2 = src.index('}\n', a2) + 2
     tmp = tempfile.mkdtemp(prefix='sgpe_exp_')
     with open(os.path.join(tmp, 'e.cpp'), 'w') as f:
-        f.write(HARNESS % src[a:b])
+        f.write(HARNESS % (src[a:b] + src[a2:b2]))
     so = os.path.join(tmp, 'e.so')
     subprocess.run(['g++', '-O2', '-shared', '-fPIC', '-o', so, os.path.join(tmp, 'e.cpp')], check=True)
     lib = ctypes.CDLL(so)
     lib.run.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
+    lib.run_small.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
     return lib
 
 
@@ -54,3 +58,15 @@ def test_sgpe_exp_out_of_range_saturates():
     y = np.empty_like(x)
     lib.run(x.ctypes.data, y.ctypes.data, x.size)
     assert np.all(np.isfinite(y)) and np.all(y[:2] < 1e-290) and np.all(y[:2] > 0) and np.all(y[2:] > 1e290)
+
+
+def test_sgpe_exp_small_within_one_ulp():
+    """The degree-9 polynomial the row pass uses for interaction factors with |argument| <= 1/16."""
+    lib = _build()
+    rng = np.random.default_rng(8)
+    x = np.concatenate([rng.uniform(-0.0625, 0.0625, 500000), -rng.uniform(0, 1e-6, 1000), np.array([0.0, 0.0625, -0.0625])])
+    y = np.empty_like(x)
+    lib.run_small(x.ctypes.data, y.ctypes.data, x.size)
+    want = np.exp(x.astype(np.longdouble))
+    rel = np.abs((y.astype(np.longdouble) - want) / want).astype(np.float64)
+    assert rel.max() < 2.0 ** -52, rel.max()

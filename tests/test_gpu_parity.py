@@ -339,7 +339,7 @@ def test_two_barrier_groups_per_column_tile(mesh, mode, dt, cpl, precision):
                                                         ((64, 2048), 'real', 1 / 2000, 'uniform', 'c64'),
                                                         ((32, 4096), 'imag', 1 / 50, 'zero', 'c128'),
                                                         ((2048, 512), 'imag', 1 / 50, 'zero', 'c64')])
-@pytest.mark.parametrize('kernel', [2, 3, 4, 5, 6])
+@pytest.mark.parametrize('kernel', [2, 3, 4, 5, 6, 7])
 def test_persistent_column_pass(mesh, mode, dt, cpl, precision, kernel):
     """col_kernel = 2 / 3 (persistent column-pass CTAs, TMA-staged tiles; 2: split inverse exchange, 3: staging behind
     the inverse transform) against the oracle and the
