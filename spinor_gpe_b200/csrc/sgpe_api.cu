@@ -8,6 +8,7 @@
 // A single step is  col_pass(FFT_y, K_a(pending), sums, K_b(this), sums, iFFT_y) ; row_pass(...)  i.e.
 // two HBM round trips; the junction is closed (col_pass with FFT_y, K_a only) when the k-space state is
 // needed.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -96,6 +97,13 @@ struct sgpe_plan {
     struct TileMap { const void* ptr = nullptr; int w = 0; SgpeTileMap* map = nullptr; };
     std::vector<TileMap> tile_maps;   // column-tile descriptors of the buffers the persistent pass has run on
     int unwrap_sort = 0;           // edge sort of the phase unwrapping: 0 device radix sort, 1 host (option "unwrap_sort")
+    struct UnwrapCache {           // scratch of the phase unwrapping, kept between evaluations (unwrap_scratch)
+        double* rel = nullptr; unsigned long long* keys = nullptr; unsigned long long* keys_sorted = nullptr;
+        unsigned* vals = nullptr; unsigned* vals_sorted = nullptr; void* tmp = nullptr; size_t tmp_bytes = 0;
+        uint32_t* order_host = nullptr; int32_t* inc_host = nullptr;
+        int nplanes = 0; size_t plane = 0; bool device_sort = false;
+    } unwrap;
+    double* unwrap_phi = nullptr;  // [B][2][ny][nx] wrapped phases of sgpe_energy(unwrap_mode 2), on first use
     int* unwrap_inc = nullptr;     // [B][2][ny][nx] multiples of 2 pi (sgpe_energy with unwrap_mode 2), on first use
     // fused exchange of the slab mode (sgpe_slab_set_peers): where the scatter stores of this plan's passes go
     // window of the slab the next line passes work on (sgpe_slab_window): lines [first, first + count), reduction
@@ -768,12 +776,6 @@ void unwrap_merge(int nx, int ny, const uint32_t* order, size_t n_edges, int32_t
     for (size_t i = 0; i < plane; i++) { int32_t a; f.find((int32_t)i, &a); inc[i] = a; }
 }
 
-struct UnwrapBuffers {                       // device scratch of one unwrap call
-    double* rel = nullptr; unsigned long long* keys = nullptr; unsigned long long* keys_sorted = nullptr;
-    unsigned* vals = nullptr; unsigned* vals_sorted = nullptr; void* tmp = nullptr;
-    ~UnwrapBuffers() { cudaFree(rel); cudaFree(keys); cudaFree(keys_sorted); cudaFree(vals); cudaFree(vals_sorted); cudaFree(tmp); }
-};
-
 unsigned unwrap_blocks(long long n) { long long b = (n + 255) / 256; return (unsigned)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b)); }
 
 int unwrap_increments_impl(sgpe_plan* p, const double* phi_dev, int nplanes, int* inc_dev, cudaStream_t st);
@@ -790,78 +792,115 @@ int unwrap_increments(sgpe_plan* p, const double* phi_dev, int nplanes, int* inc
     }
 }
 
-int unwrap_increments_impl(sgpe_plan* p, const double* phi_dev, int nplanes, int* inc_dev, cudaStream_t st) {
-    const int nx = p->nx, ny = p->ny;
-    const size_t plane = (size_t)p->plane;
-    const size_t n_edges = (size_t)ny * (nx - 1) + (size_t)nx * (ny - 1);
-    UnwrapBuffers w;
+// host staging of the phase unwrapping: plain pageable memory.  (Page-locked buffers were measured: cudaHostAlloc of the
+// ~100 MB costs 50 ms per plan, more than the pageable copies of 4 ms worth of device work ever did; the evaluation is
+// bound by the host-side region merging, ~245 ms per 2048^2 plane on the GPU box's cores.)
+static void* host_pinned(size_t bytes) { return malloc(bytes); }
+static void host_pinned_free(void* q) { free(q); }
+
+void unwrap_release(sgpe_plan::UnwrapCache& w) {
+    cudaFree(w.rel); cudaFree(w.keys); cudaFree(w.keys_sorted); cudaFree(w.vals); cudaFree(w.vals_sorted); cudaFree(w.tmp);
+    host_pinned_free(w.order_host); host_pinned_free(w.inc_host);
+    w = sgpe_plan::UnwrapCache();
+}
+
+// the scratch of the phase unwrapping lives with the plan (device buffers, the sort's work space, page-locked staging
+// for the edge order going down and the increments coming up): nothing is allocated per evaluation
+static int unwrap_scratch(sgpe_plan* p, int nplanes, size_t plane, size_t n_edges, bool device_sort, cudaStream_t st) {
+    sgpe_plan::UnwrapCache& w = p->unwrap;
+    if (w.nplanes >= nplanes && w.plane == plane && w.device_sort == device_sort && w.rel) return 0;
+    unwrap_release(w);
     if (cudaMalloc((void**)&w.rel, plane * sizeof(double)) != cudaSuccess ||
         cudaMalloc((void**)&w.keys, n_edges * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc((void**)&w.vals, n_edges * sizeof(unsigned)) != cudaSuccess)
         return fail(SGPE_ENOMEM, "unwrap scratch allocation failed");
-    bool device_sort = false;
 #ifndef SGPE_EMU
-    device_sort = p->unwrap_sort == 0;
-    size_t tmp_bytes = 0;
     if (device_sort) {
         if (cudaMalloc((void**)&w.keys_sorted, n_edges * sizeof(unsigned long long)) != cudaSuccess ||
             cudaMalloc((void**)&w.vals_sorted, n_edges * sizeof(unsigned)) != cudaSuccess)
             return fail(SGPE_ENOMEM, "unwrap scratch allocation failed");
-        SGPE_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, w.keys, w.keys_sorted, w.vals, w.vals_sorted,
+        SGPE_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, w.tmp_bytes, w.keys, w.keys_sorted, w.vals, w.vals_sorted,
                                                   (long long)n_edges, 0, 64, st));
-        if (cudaMalloc(&w.tmp, tmp_bytes ? tmp_bytes : 1) != cudaSuccess)
+        if (cudaMalloc(&w.tmp, w.tmp_bytes ? w.tmp_bytes : 1) != cudaSuccess)
             return fail(SGPE_ENOMEM, "unwrap scratch allocation failed");
     }
+#else
+    (void)st;
 #endif
-    std::vector<std::vector<uint32_t>> order((size_t)nplanes);
+    w.order_host = static_cast<uint32_t*>(host_pinned((size_t)nplanes * n_edges * sizeof(uint32_t)));
+    w.inc_host = static_cast<int32_t*>(host_pinned((size_t)nplanes * plane * sizeof(int32_t)));
+    if (!w.order_host || !w.inc_host) return fail(SGPE_ENOMEM, "unwrap host staging allocation failed");
+    w.nplanes = nplanes; w.plane = plane; w.device_sort = device_sort;
+    return 0;
+}
+
+int unwrap_increments_impl(sgpe_plan* p, const double* phi_dev, int nplanes, int* inc_dev, cudaStream_t st) {
+    const int nx = p->nx, ny = p->ny;
+    const size_t plane = (size_t)p->plane;
+    const size_t n_edges = (size_t)ny * (nx - 1) + (size_t)nx * (ny - 1);
+    bool device_sort = false;
+#ifndef SGPE_EMU
+    device_sort = p->unwrap_sort == 0;
+#endif
+    const bool timing = getenv("SGPE_UNWRAP_TIMING") != nullptr;       // dev: phase times on stderr
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    int rc = unwrap_scratch(p, nplanes, plane, n_edges, device_sort, st);
+    if (rc) return rc;
+    if (timing) { cudaStreamSynchronize(st); fprintf(stderr, "unwrap: scratch %.1f ms\n", now() - t_begin); }
+    sgpe_plan::UnwrapCache& w = p->unwrap;
     std::vector<unsigned long long> host_keys;
+    // The region merging of a plane (host, sequential) starts as soon as its edge order has arrived and runs beside the
+    // device work of the next plane; the planes are independent.
+    std::vector<std::thread> pool;
+    struct Joiner { std::vector<std::thread>& t; ~Joiner() { for (auto& th : t) if (th.joinable()) th.join(); } } joiner{pool};
+    const unsigned max_threads = std::max(1u, std::thread::hardware_concurrency());
     for (int pl = 0; pl < nplanes; pl++) {
         const double* phi = phi_dev + (size_t)pl * plane;
+        uint32_t* order = w.order_host + (size_t)pl * n_edges;
         SGPE_LAUNCH((sgpe::unwrap_reliab_pass), dim3(unwrap_blocks((long long)plane)), dim3(256), 0, st, phi, nx, ny, w.rel);
         SGPE_LAUNCH((sgpe::unwrap_edge_pass), dim3(unwrap_blocks((long long)plane)), dim3(256), 0, st, phi, w.rel, nx, ny,
                     w.keys, w.vals);
         p->launches += 2;
         SGPE_CUDA(cudaGetLastError());
-        order[pl].resize(n_edges);
         if (device_sort) {
 #ifndef SGPE_EMU
             // least-significant-digit radix sort: stable, so equal keys stay in edge-id order
-            SGPE_CUDA(cub::DeviceRadixSort::SortPairs(w.tmp, tmp_bytes, w.keys, w.keys_sorted, w.vals, w.vals_sorted,
+            SGPE_CUDA(cub::DeviceRadixSort::SortPairs(w.tmp, w.tmp_bytes, w.keys, w.keys_sorted, w.vals, w.vals_sorted,
                                                       (long long)n_edges, 0, 64, st));
             p->launches++;
-            SGPE_CUDA(cudaMemcpyAsync(order[pl].data(), w.vals_sorted, n_edges * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            SGPE_CUDA(cudaMemcpyAsync(order, w.vals_sorted, n_edges * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
             SGPE_CUDA(cudaStreamSynchronize(st));
 #endif
         } else {
             host_keys.resize(n_edges);
+            std::vector<uint32_t> vals(n_edges);
             SGPE_CUDA(cudaMemcpyAsync(host_keys.data(), w.keys, n_edges * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-            SGPE_CUDA(cudaMemcpyAsync(order[pl].data(), w.vals, n_edges * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            SGPE_CUDA(cudaMemcpyAsync(vals.data(), w.vals, n_edges * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
             SGPE_CUDA(cudaStreamSynchronize(st));
             std::vector<uint32_t> perm(n_edges);
             for (size_t k = 0; k < n_edges; k++) perm[k] = (uint32_t)k;
             const unsigned long long* hk = host_keys.data();
             std::sort(perm.begin(), perm.end(), [hk](uint32_t a, uint32_t b) { return hk[a] != hk[b] ? hk[a] < hk[b] : a < b; });
-            std::vector<uint32_t> sorted(n_edges);
-            for (size_t k = 0; k < n_edges; k++) sorted[k] = order[pl][perm[k]];
-            order[pl].swap(sorted);
+            for (size_t k = 0; k < n_edges; k++) order[k] = vals[perm[k]];
+        }
+        int32_t* inc = w.inc_host + (size_t)pl * plane;
+        if (timing) fprintf(stderr, "unwrap: plane %d order on the host at %.1f ms\n", pl, now() - t_begin);
+        if (max_threads > 1 && nplanes > 1) {
+            if (pool.size() >= max_threads) { pool.front().join(); pool.erase(pool.begin()); }
+            pool.emplace_back([=]() {
+                const double t0 = now();
+                unwrap_merge(nx, ny, order, n_edges, inc);
+                if (timing) fprintf(stderr, "unwrap: merge of plane %d %.1f ms\n", pl, now() - t0);
+            });
+        } else {
+            unwrap_merge(nx, ny, order, n_edges, inc);
         }
     }
-    // region merging: the planes are independent, one host thread each (bounded by the hardware)
-    std::vector<int32_t> inc((size_t)nplanes * plane);
-    unsigned nthreads = std::thread::hardware_concurrency();
-    if (nthreads < 1) nthreads = 1;
-    if (nthreads > (unsigned)nplanes) nthreads = (unsigned)nplanes;
-    auto work = [&](unsigned t) {
-        for (int pl = (int)t; pl < nplanes; pl += (int)nthreads)
-            unwrap_merge(nx, ny, order[pl].data(), n_edges, inc.data() + (size_t)pl * plane);
-    };
-    if (nthreads == 1) work(0);
-    else {
-        std::vector<std::thread> pool;
-        for (unsigned t = 0; t < nthreads; t++) pool.emplace_back(work, t);
-        for (auto& th : pool) th.join();
-    }
-    SGPE_CUDA(cudaMemcpyAsync(inc_dev, inc.data(), inc.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    for (auto& th : pool) th.join();
+    pool.clear();
+    if (timing) fprintf(stderr, "unwrap: merged at %.1f ms\n", now() - t_begin);
+    SGPE_CUDA(cudaMemcpyAsync(inc_dev, w.inc_host, (size_t)nplanes * plane * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     SGPE_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
@@ -1149,6 +1188,8 @@ int sgpe_plan_destroy(sgpe_plan* p) {
     cudaFree(p->state); cudaFree(p->tw_x); cudaFree(p->tw_y); cudaFree(p->partials);
     cudaFree(p->counter); cudaFree(p->totals); cudaFree(p->totals_aux); cudaFree(p->pops_buf);
     cudaFree(p->scratch); cudaFree(p->maxdens); cudaFree(p->unwrap_inc); cudaFree(p->sm_slots); cudaFree(p->tw_mid); cudaFree(p->tw4);
+    unwrap_release(p->unwrap);
+    cudaFree(p->unwrap_phi);
     for (auto& t : p->tile_maps) delete t.map;
     cudaFree(p->slot_ctr);
 #ifndef SGPE_EMU
@@ -1513,11 +1554,10 @@ static int energy_of_real_space(sgpe_plan* p, const void* psi, int unwrap_mode, 
         const long long total = (long long)p->batch * 2 * p->plane;
         if (!p->unwrap_inc && cudaMalloc((void**)&p->unwrap_inc, sizeof(int) * total) != cudaSuccess)
             return fail(SGPE_ENOMEM, "unwrap allocation failed");
-        double* phi = nullptr;
-        if (cudaMalloc((void**)&phi, sizeof(double) * total) != cudaSuccess) return fail(SGPE_ENOMEM, "unwrap allocation failed");
-        int rc = SGPE_BY_DTYPE(p, run_unwrap_angles, p, psi, total, phi, (cudaStream_t)st);
-        if (!rc) rc = unwrap_increments(p, phi, 2 * p->batch, p->unwrap_inc, (cudaStream_t)st);
-        cudaFree(phi);
+        if (!p->unwrap_phi && cudaMalloc((void**)&p->unwrap_phi, sizeof(double) * total) != cudaSuccess)
+            return fail(SGPE_ENOMEM, "unwrap allocation failed");
+        int rc = SGPE_BY_DTYPE(p, run_unwrap_angles, p, psi, total, p->unwrap_phi, (cudaStream_t)st);
+        if (!rc) rc = unwrap_increments(p, p->unwrap_phi, 2 * p->batch, p->unwrap_inc, (cudaStream_t)st);
         if (rc) return rc;
     }
     return SGPE_BY_DTYPE(p, run_energy, p, psi, unwrap_mode, kl_term, out, (cudaStream_t)st);
