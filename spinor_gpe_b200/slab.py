@@ -623,8 +623,26 @@ class LongLinePlan:
     def single_step(self, dt_sub):
         self.sp.single_step(float(dt_sub))
 
-    def full_steps(self, n, pops=None, first=0):
-        self.sp.full_steps(int(n), None if pops is None else pops[0, first:first + n])
+    def full_steps(self, n, pops=None, first=0, energy=None, kl_term=0.0, unwrap='none'):
+        """As ``Plan.full_steps``.  With ``energy`` (float64 (1, n_total, 4)) the energy expectation of every step
+        boundary is evaluated too — here through the stand-alone evaluation after each step (the fused side chain of
+        the short-line kernels does not exist for four-step lines)."""
+        if energy is None:
+            self.sp.full_steps(int(n), None if pops is None else pops[0, first:first + n])
+            return
+        for i in range(int(n)):
+            self.sp.full_steps(1, None if pops is None else pops[0, first + i:first + i + 1])
+            energy[0, first + i].copy_(self.energy(None, kl_term=kl_term, unwrap=unwrap)[0])
+
+    def kinetic_spectral(self, psik=None, kin_x=None, kin_y=None):
+        """dv_k * sum_k kin_c |psi_k,c|^2 per component from the separable kinetic grid kin_c = kin_x[c][kx] +
+        kin_y[c][ky], (1, 2) float64: two marginal sums of the k-space density on the device."""
+        full = self.store() if psik is None else psik.reshape(1, 2, self.ny, self.nx).to(self.device)
+        dens = full[0].real.double() ** 2 + full[0].imag.double() ** 2            # (2, ny, nx)
+        kx = torch.as_tensor(kin_x, dtype=torch.float64, device=self.device)
+        ky = torch.as_tensor(kin_y, dtype=torch.float64, device=self.device)
+        out = (dens.sum(1) * kx).sum(1) + (dens.sum(2) * ky).sum(1)
+        return (out * self.sp.dv_k).reshape(1, 2)
 
     def real_space(self):
         """(1, 2, ny, nx) normalised real-space state (ttools.ifft_2d of the current state)."""

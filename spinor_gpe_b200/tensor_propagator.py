@@ -407,8 +407,6 @@ class TensorPropagator:
         pops_dev = torch.zeros((1, max(n_steps, 1), 2), dtype=torch.float64, device=self._dev)
         track = {}
         if self.track_energy is not None:
-            if self._long:
-                raise NotImplementedError("per-step energy tracking is not available on long-line meshes")
             eng_dev = torch.zeros((1, max(n_steps, 1), 4), dtype=torch.float64, device=self._dev)
             track = dict(energy=eng_dev, kl_term=2 * self.kL_recoil * float(bool(self.is_coupling)),
                          unwrap=self.track_energy)
@@ -474,10 +472,13 @@ class TensorPropagator:
         """Kinetic energy per component from the k-space density, ``dv_k * sum kin_eng_spin[c] * abs(psik[c])**2``
         [hbar omega_x] — an alternative to the finite-difference / unwrapped-phase kinetic term of ``eng_expect``
         that needs no phase (no reference equivalent; the reference's number is a raw grid sum: multiply it by
-        ``dv_r`` to compare).  Not available on meshes beyond 4096 points per line."""
-        if self._long:
-            raise NotImplementedError("kin_expect_spectral is not available on long-line meshes")
+        ``dv_r`` to compare)."""
         if psik is not None:
             comps = [torch.as_tensor(p) if not isinstance(p, torch.Tensor) else p for p in psik]
             psik = torch.stack([c.to(self._dev) for c in comps]).reshape(1, 2, self._plan.ny, self._plan.nx)
+        if self._long:
+            ksep = split_separable(np.stack(self._kin_np))
+            if ksep is None:
+                raise NotImplementedError("long-line meshes need a separable kinetic grid")
+            return [float(v) for v in self._plan.kinetic_spectral(psik, ksep[0], ksep[1])[0].cpu().numpy()]
         return [float(v) for v in self._plan.kinetic_spectral(psik)[0].cpu().numpy()]

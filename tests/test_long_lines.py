@@ -142,3 +142,25 @@ def test_gpu_long_lines_energy_and_ground_state():
     assert rel(np.array(res.psik), want['psik']) < 1e-10
     np.testing.assert_allclose(prop.eng_expect(None, unwrap='none'), want['energy'], rtol=1e-9)
     np.testing.assert_allclose(res.eng_final, orc.energy(prob, want['psik'], unwrap=oracle_unwrap), rtol=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('mesh,long_lines', [((1024, 64), {'split_x': 32}), ((8192, 64), None)])
+def test_gpu_long_lines_energy_tracking_and_spectral_kinetic(mesh, long_lines):
+    """Per-step energy (PropResult.eng_history) and the spectral kinetic energy on four-step lines, against the oracle
+    and NumPy."""
+    ps = make_ps(mesh)
+    prob = problem_of(ps)
+    n = 3
+    o = orc.OraclePropagator(prob, 1 / 50, 'imag')
+    want = []
+    for _ in range(n):
+        o.full_step()
+        want.append(orc.energy(prob, o.psik))
+    res, prop = ps.imaginary(1 / 50, n, 'cuda', long_lines=long_lines, unwrap='none', track_energy=True)
+    assert prop._long
+    assert rel(np.array(res.psik), o.psik.numpy()) < 1e-10
+    np.testing.assert_allclose(res.eng_history[:, 2:], np.array(want)[:, 2:], rtol=1e-9)
+    np.testing.assert_allclose(res.eng_history[-1], res.eng_final, rtol=1e-9)
+    kin = [(np.asarray(prob.kin[c]) * np.abs(res.psik[c]) ** 2).sum() * prob.dv_k for c in range(2)]
+    np.testing.assert_allclose(prop.kin_expect_spectral(), kin, rtol=1e-9)
