@@ -8,7 +8,9 @@ import os
 from . import _capi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libsgpe.so')
+# (SGPE_LIB: a differently built copy of the same library - timeline stamps, build-time kernel experiments - for the dev
+# tools; it is the CUDA library either way)
+LIB_PATH = os.environ.get('SGPE_LIB') or os.path.join(_HERE, 'libsgpe.so')
 _lib = None
 
 

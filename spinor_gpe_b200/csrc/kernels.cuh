@@ -889,11 +889,14 @@ SGPE_DI void coupling_entries(double theta, C ph, T& diag, C& off01, C& off10) {
 #ifndef SGPE_F32_THREADS_PER_SM
 #define SGPE_F32_THREADS_PER_SM 768
 #endif
-template <typename T> constexpr int row_min_blocks(int threads) {
-    return sizeof(T) == 8 ? (threads <= 256 ? 2 : 1) : (threads <= SGPE_F32_THREADS_PER_SM ? SGPE_F32_THREADS_PER_SM / threads : 1);
+template <typename T, int E = 8> constexpr int row_min_blocks(int threads) {
+    // (complex64 with 16 elements per thread holds 64 data registers: 512 threads, 128 registers each)
+    return sizeof(T) == 8 ? (threads <= 256 ? 2 : 1)
+         : (E == 16 ? (threads <= 512 ? 512 / threads : 1)
+                    : (threads <= SGPE_F32_THREADS_PER_SM ? SGPE_F32_THREADS_PER_SM / threads : 1));
 }
 template <typename T, int N, int E, int RPC, int TM, int FAST>
-__global__ void __launch_bounds__(RPC * N / E, row_min_blocks<T>(RPC * N / E)) row_pass(RowArgs<T> a) {
+__global__ void __launch_bounds__(RPC * N / E, row_min_blocks<T, E>(RPC * N / E)) row_pass(RowArgs<T> a) {
     typedef typename cx_of<T>::type C;
     constexpr int NT = N / E;
     SGPE_DYN_SMEM(smem_raw);

@@ -9,8 +9,11 @@
 
 namespace sgpe {
 
-template <typename T, int N> struct RowCfg {
-    static constexpr int E = 8;
+// elements per thread of the row / line passes: 8 (three exchanges at 2048 points); complex64 in imaginary time runs 16
+// (two exchanges, 64 data registers, four CTAs per SM): 55.9 -> 50.2 us at 2048^2, while with the sincos of real time in
+// the point-wise phase the same change loses 4 % (profiles/r02_variants.md)
+template <typename T, int N, int TM = TM_REAL> struct RowCfg {
+    static constexpr int E = (sizeof(T) == 4 && N >= 256 && TM == TM_IMAG) ? 16 : 8;
     static constexpr int NT = N / E;
     static constexpr int RPC = (NT >= 128) ? 1 : (128 / NT);          // >= 128 threads per CTA
     static constexpr int THREADS = RPC * NT;
@@ -67,7 +70,7 @@ static int launch_row_split_t(const RowArgs<T>& a, int batch, cudaStream_t st) {
 
 template <typename T, int N, int TM>
 static int launch_row_t(const RowArgs<T>& a, int batch, cudaStream_t st) {
-    typedef RowCfg<T, N> Cfg;
+    typedef RowCfg<T, N, TM> Cfg;
     if (a.ny % Cfg::RPC != 0) return -2;
     static bool once = false;
     static int ahead = 0;
