@@ -457,6 +457,9 @@ def run_ours(args, rank, world, local_rank):
             options[name] = val
     if args.no_prefetch:
         options['prefetch'] = 0
+    for kv in args.opt or []:          # tuning runs: any sgpe_set_option selector
+        k, v = kv.split('=')
+        options[k] = int(v)
 
     pl = plan_for(ps, dev, args.precision, MODE, dense=args.dense, options=options)
     pops = torch.zeros((1, args.steps + args.warmup, 2), dtype=torch.float64, device=dev)
@@ -663,6 +666,7 @@ def main():
     ap.add_argument('--col-tile', type=int, default=0, choices=[0, 2, 3, 8])
     ap.add_argument('--col-kernel', type=int, default=None, help='column-pass kernel selector (sgpe_set_option)')
     ap.add_argument('--row-kernel', type=int, default=None, help='row-pass kernel selector (sgpe_set_option)')
+    ap.add_argument('--opt', action='append', help='name=value for sgpe_set_option (tuning runs; repeatable)')
     ap.add_argument('--graph', type=int, default=None, help='CUDA-graph replay of the steady-state step (0 / 1)')
     ap.add_argument('--mode', default='imag', choices=['imag', 'real'])
     args = ap.parse_args()

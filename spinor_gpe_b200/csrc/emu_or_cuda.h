@@ -20,6 +20,12 @@
 #define SGPE_TID_X() ((int)threadIdx.x)
 #define SGPE_OPAQUE(x) ((void)(x))
 #define SGPE_DYN_SMEM_128(name) unsigned char* name = ::emu::dyn_smem()
+// (the hardware reciprocal seed carries ~20 bits: the emulation truncates 1 / d to the upper word as well)
+inline double sgpe_rcp_seed_emu(double d) { double r = 1.0 / d; unsigned long long u; memcpy(&u, &r, 8); u &= 0xffffffff00000000ull; memcpy(&r, &u, 8); return r; }
+#define SGPE_RCP_SEED(d) sgpe_rcp_seed_emu(d)
+inline double sgpe_rsqrt_seed_emu(double d) { double r = 1.0 / sqrt(d); unsigned long long u; memcpy(&u, &r, 8); u &= 0xffffffff00000000ull; memcpy(&r, &u, 8); return r; }
+#define SGPE_RSQRT_SEED(d) sgpe_rsqrt_seed_emu(d)
+#define SGPE_D2I_RN(x) ((int)nearbyint(x))
 struct SgpeTileMap { const unsigned char* base; long long row_stride; int elem_bytes; };
 struct SgpeMbar { int pending; unsigned phase; };
 inline void sgpe_mbar_init(SgpeMbar* b, unsigned) { b->pending = 0; b->phase = 0; }
@@ -67,6 +73,11 @@ __device__ __forceinline__ int sgpe_tid_x() { int r; asm volatile("mov.u32 %0, %
 // the compiler forgets what it knows about an integer (no common sub-expressions across this point)
 #define SGPE_OPAQUE(x) asm volatile("" : "+r"(x))
 #define SGPE_DYN_SMEM_128(name) extern __shared__ __align__(128) unsigned char name[]
+__device__ __forceinline__ double sgpe_rcp_seed(double d) { double r; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d)); return r; }
+#define SGPE_RCP_SEED(d) sgpe_rcp_seed(d)
+__device__ __forceinline__ double sgpe_rsqrt_seed(double d) { double r; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d)); return r; }
+#define SGPE_RSQRT_SEED(d) sgpe_rsqrt_seed(d)
+#define SGPE_D2I_RN(x) __double2int_rn(x)
 struct alignas(64) SgpeTileMap { CUtensorMap m; };
 typedef unsigned long long SgpeMbar;
 __device__ __forceinline__ unsigned sgpe_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }

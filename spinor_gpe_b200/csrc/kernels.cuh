@@ -71,6 +71,60 @@ SGPE_DI void sgpe_exp_pair(double x0, double x1, double& e0, double& e1) {
     else { e0 = sgpe_exp(x0); e1 = sgpe_exp(x1); }
 }
 
+// reciprocal to (nearly) full precision without the library's special cases: hardware seed (~20 bits) + two Newton steps
+SGPE_DI double sgpe_rcp(double d) {
+    double r = SGPE_RCP_SEED(d);
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+// sqrt(n) for the same store: hardware seed of 1/sqrt (~20 bits), two coupled Newton steps on g ~ sqrt(n), h ~ 1/(2 sqrt(n)),
+// and a final residual correction (< 1 ulp in tests/test_fast_exp.py); n below 1e-290 (always masked) gives 0
+SGPE_DI double sgpe_sqrt(double n) {
+    const double y = SGPE_RSQRT_SEED(n);
+    double g = n * y, h = 0.5 * y;
+    double e = fma(-h, g, 0.5);
+    g = fma(g, e, g); h = fma(h, e, h);
+    e = fma(-h, g, 0.5);
+    g = fma(g, e, g); h = fma(h, e, h);
+    g = fma(fma(-g, g, n), h, g);
+    return n > 1e-290 ? g : 0.0;
+}
+
+// atan2(y, x) for the polar store of the energy tracking (two per pixel and step).  t = min / max of the magnitudes lies
+// in [0, 1]; with c = i / 16 the nearest sixteenth, atan t = atan c + atan s, s = (min - c max) / (max + c min),
+// |s| <= 1/32, so ONE division and a degree-11 odd Taylor polynomial (truncation 3e-21) replace the library's
+// division + degree-~40 polynomial: about half the FP64 instructions, < 2 ulp (tests/test_fast_exp.py).
+// Magnitudes below 1e-280 (always masked: n < 1e-6 max n) return 0.
+__device__ const double sgpe_atan_tab[17] = {0.0, 0.06241880999595735, 0.12435499454676144, 0.18534794999569476, 0.24497866312686414, 0.3028848683749714, 0.35877067027057225, 0.4124104415973873, 0.4636476090008061, 0.5123894603107377, 0.5585993153435624, 0.6022873461349642, 0.6435011087932844, 0.6823165548747481, 0.7188299996216245, 0.7531512809621944, 0.7853981633974483};
+SGPE_DI double sgpe_atan2(double y, double x) {
+    const double ax = fabs(x), ay = fabs(y);
+    const bool swap = ay > ax;
+    const double mx = swap ? ay : ax, mn = swap ? ax : ay;
+    const double t0 = mn * SGPE_RCP_SEED(mx);
+    int i = SGPE_D2I_RN(t0 * 16.0);
+    i = i < 0 ? 0 : (i > 16 ? 16 : i);
+    const double c = (double)i * 0.0625;
+    const double num = fma(-c, mx, mn), den = fma(c, mn, mx);
+    const double rd = sgpe_rcp(den);
+    double q = num * rd;
+    q = fma(fma(-den, q, num), rd, q);
+    const double s2 = q * q;
+    double p = -1.0 / 11.0;
+    p = fma(p, s2, 1.0 / 9.0);
+    p = fma(p, s2, -1.0 / 7.0);
+    p = fma(p, s2, 1.0 / 5.0);
+    p = fma(p, s2, -1.0 / 3.0);
+    double a = fma(q * s2, p, q) + sgpe_atan_tab[i];
+    if (swap) a = 1.5707963267948966 - a;
+    if (x < 0.0) a = 3.141592653589793 - a;
+    if (!(mx > 1e-280)) a = 0.0;
+    return copysign(a, y);
+}
+
 // exp(-i * e * tau), tau = (tr, ti):  real time tau = (dt, 0);  imaginary time tau = (0, -dt)
 template <int TM, typename T, typename C> SGPE_DI C evo(double e, double tr, double ti) {
     C r;
@@ -154,6 +208,7 @@ template <typename T> struct ColArgs {
     unsigned long long* dbg;       // dev tool: per-CTA phase timestamps [nCTA][8] (null in production; generic kernel only)
     const void* tile_map;          // host pointer to the SgpeTileMap of `in` (persistent kernel; read by the launcher only)
     int kernel_sel;                // 0: one tile per CTA, 1 / 2: persistent CTAs with asynchronously staged tiles (col_pass_p)
+    unsigned long long* zero2;     // optional [B][2] words cleared by the first CTA (the density maxima the NEXT pass folds)
     C* aux;                        // optional second output [B][2][ny][nx]: the state right after FA — at a full-step
                                    // junction that is the (un-normalised) k-space state of the step boundary, which
                                    // per-step energy tracking transforms back on the side (sgpe_full_steps_energy)
@@ -198,6 +253,7 @@ __global__ void __launch_bounds__(G * W * N / E, (G * W * N / E <= 256) ? 2 : 1)
     const GroupBar gbar = {1 + g, TG};
     const int b = blockIdx.y;
     const bool do_fwd = FAST ? true : (a.do_fwd != 0), do_inv = FAST ? true : (a.do_inv != 0);
+    if (!FAST && a.zero2 != nullptr && blockIdx.x == 0 && threadIdx.x < 2) a.zero2[2 * b + threadIdx.x] = 0ull;
     const int kin_mode = FAST ? 1 : a.kin_mode;
     const int sign_in = FAST ? 0 : a.sign_in, sign_out = FAST ? 0 : a.sign_out;
     const long long off = ((long long)b * 2 + comp) * a.plane + col;
@@ -485,7 +541,10 @@ col_pass_p(const SGPE_GRID_CONSTANT SgpeTileMap tmap, ColArgs<T> a) {
     const int b = blockIdx.y;
     const int tiles_per_comp = a.nx / W;
     const int ntiles = 2 * tiles_per_comp;
-    const bool any_k = a.has_a || a.has_b;
+    // KM = 2: inverse transform only (the boundary state of per-step energy tracking on its way back to real space):
+    // the staged tile goes from S to the registers, S is refilled at once, the transform exchanges through X
+    static_assert(KM != 2 || XSPLIT == 1, "the inverse-only pass exchanges through the real image");
+    const bool any_k = KM != 2 && (a.has_a || a.has_b);
 
     // stage tile `t` of this trajectory into S (one elected thread) 
     auto stage = [&](int t) {
@@ -497,6 +556,7 @@ col_pass_p(const SGPE_GRID_CONSTANT SgpeTileMap tmap, ColArgs<T> a) {
     };
 
     if (threadIdx.x == 0) sgpe_mbar_init(mbar, 1);
+    if (KM == 2 && a.zero2 != nullptr && blockIdx.x == 0 && threadIdx.x < 2) a.zero2[2 * b + threadIdx.x] = 0ull;
     if (TWS == 1) {
         const C* src = a.tw + (E == 16 ? N : 0);
         for (int i = threadIdx.x; i < N; i += W * NT) TW[i] = __ldg(&src[i]);
@@ -551,14 +611,18 @@ col_pass_p(const SGPE_GRID_CONSTANT SgpeTileMap tmap, ColArgs<T> a) {
 
         // forward transform through S (first stage by hand: S must be read by everybody before it is overwritten)
         C* const sms[1] = {S};
-        stage_compute<T, N, E, -1, 1>(v[0], j, tw);
-        __syncthreads();
-        if constexpr (R0 < N) {
-            stage_store<T, N, E, W, 1>(v[0], j, c, S);
+        if constexpr (KM != 2) {
+            stage_compute<T, N, E, -1, 1>(v[0], j, tw);
             __syncthreads();
-            stage_load<T, N, E, W>(v[0], j, c, S);
-            __syncthreads();
-            cta_fft_from<T, N, E, -1, W, 1, R0>(v, j, c, sms, tw, CtaBar());
+            if constexpr (R0 < N) {
+                stage_store<T, N, E, W, 1>(v[0], j, c, S);
+                __syncthreads();
+                stage_load<T, N, E, W>(v[0], j, c, S);
+                __syncthreads();
+                cta_fft_from<T, N, E, -1, W, 1, R0>(v, j, c, sms, tw, CtaBar());
+            }
+        } else {
+            __syncthreads();              // everybody has read the staged tile
         }
         if (XSPLIT && tid == 0 && tile + (int)gridDim.x < ntiles) {     // S is free: its last readers are behind a barrier
             sgpe_fence_proxy_async();
@@ -861,7 +925,16 @@ template <typename T> struct RowArgs {
     // (bits of non-negative doubles: integer max == floating-point max, order independent; zeroed by the caller)
     const double* scale_tot; double scale_num;
     unsigned long long* maxbits;
+    int polar;                     // store (sqrt(re^2 + im^2), atan2(im, re)) instead of (re, im): input of the energy stencils
 };
+
+// (|z|, arg z) packed as a complex number
+template <typename T, typename C> SGPE_DI C to_polar(C z) {
+    C o;
+    if constexpr (sizeof(T) == 8) { o.x = sgpe_sqrt(z.x * z.x + z.y * z.y); o.y = sgpe_atan2(z.y, z.x); }
+    else { o.x = (T)sqrt(z.x * z.x + z.y * z.y); o.y = (T)atan2(z.y, z.x); }
+    return o;
+}
 
 // 2x2 coupling operator (reference tensor_tools.py:586-590) for theta = Omega*tc and exp(i phi) = ph
 template <int TM, typename T, typename C>
@@ -889,14 +962,18 @@ SGPE_DI void coupling_entries(double theta, C ph, T& diag, C& off01, C& off10) {
 #ifndef SGPE_F32_THREADS_PER_SM
 #define SGPE_F32_THREADS_PER_SM 768
 #endif
-template <typename T, int E = 8> constexpr int row_min_blocks(int threads) {
+#ifndef SGPE_INVP_BLOCKS
+#define SGPE_INVP_BLOCKS 2
+#endif
+template <typename T, int E = 8> constexpr int row_min_blocks(int threads, int fast = 0) {
     // (complex64 with 16 elements per thread holds 64 data registers: 512 threads, 128 registers each)
-    return sizeof(T) == 8 ? (threads <= 256 ? 2 : 1)
+    // (SGPE_INVP_BLOCKS: resident CTAs asked for the inverse-only polar pass, whose point-wise phase holds no operators)
+    return sizeof(T) == 8 ? (threads <= 256 ? ((fast == 3 && threads == 256) ? SGPE_INVP_BLOCKS : 2) : 1)
          : (E == 16 ? (threads <= 512 ? 512 / threads : 1)
                     : (threads <= SGPE_F32_THREADS_PER_SM ? SGPE_F32_THREADS_PER_SM / threads : 1));
 }
 template <typename T, int N, int E, int RPC, int TM, int FAST>
-__global__ void __launch_bounds__(RPC * N / E, row_min_blocks<T, E>(RPC * N / E)) row_pass(RowArgs<T> a) {
+__global__ void __launch_bounds__(RPC * N / E, row_min_blocks<T, E>(RPC * N / E, FAST)) row_pass(RowArgs<T> a) {
     typedef typename cx_of<T>::type C;
     constexpr int NT = N / E;
     SGPE_DYN_SMEM(smem_raw);
@@ -907,10 +984,13 @@ __global__ void __launch_bounds__(RPC * N / E, row_min_blocks<T, E>(RPC * N / E)
     const int y = blockIdx.x * RPC + r;
     const int b = blockIdx.y;
     // FAST = 2: the same specialisation for DENSE potential grids (factors evaluated per point, no coupling)
-    const int cpl_mode = FAST ? 0 : a.cpl_mode, pot_mode = FAST == 1 ? 1 : (FAST == 2 ? 0 : a.pot_mode);
-    const int sign_in = FAST ? 0 : a.sign_in, sign_out = FAST ? 0 : a.sign_out;
-    const bool do_inv = FAST ? true : (a.do_inv != 0), do_pw = FAST ? true : (a.do_pw != 0);
-    const bool do_fwd = FAST ? true : (a.do_fwd != 0);
+    // FAST = 3: the stand-alone inverse of per-step energy tracking (inverse transform only, device-side scale, density
+    // maxima, sign on the store, POLAR output: (sqrt(n), atan2) instead of (re, im) - see RowArgs::polar)
+    constexpr bool GEN = (FAST == 0), INVP = (FAST == 3);
+    const int cpl_mode = GEN ? a.cpl_mode : 0, pot_mode = FAST == 1 ? 1 : (FAST == 2 ? 0 : a.pot_mode);
+    const int sign_in = GEN ? a.sign_in : 0, sign_out = (GEN || INVP) ? a.sign_out : 0;
+    const bool do_inv = GEN ? (a.do_inv != 0) : true, do_pw = GEN ? (a.do_pw != 0) : !INVP;
+    const bool do_fwd = GEN ? (a.do_fwd != 0) : !INVP;
     // everything the point-wise phase needs from memory is pulled into L1 before the transforms start
     // (prefetches cost no registers; holding the values across the FFT made the kernel spill)
     if (do_pw) {
@@ -921,7 +1001,7 @@ __global__ void __launch_bounds__(RPC * N / E, row_min_blocks<T, E>(RPC * N / E)
             SGPE_PREFETCH_L1(&a.py[oy + a.ny]);
         }
     }
-    if (!FAST && a.stagger_ns > 0) {
+    if (GEN && a.stagger_ns > 0) {
         // co-resident CTAs launched together run in lock-step (same phase -> they fight for the same unit);
         // delaying the second arrival on every SM by ~half a CTA lifetime interleaves their phases for good
         if (tid == 0 && (atomicAdd(&a.sm_slots[SGPE_SMID()], 1u) == 1u)) SGPE_NANOSLEEP((unsigned)a.stagger_ns);
@@ -929,8 +1009,8 @@ __global__ void __launch_bounds__(RPC * N / E, row_min_blocks<T, E>(RPC * N / E)
     }
     const long long off0 = ((long long)b * 2) * a.plane + (long long)y * a.nx;
     const long long off1 = off0 + a.plane;
-#define SGPE_MARK(k) do { if (!FAST && a.dbg != nullptr && tid == 0) a.dbg[(long long)blockIdx.x * 8 + (k)] = SGPE_GLOBALTIMER(); } while (0)
-    if (!FAST && a.dbg != nullptr && tid == 0) a.dbg[(long long)blockIdx.x * 8 + 7] = SGPE_SMID();
+#define SGPE_MARK(k) do { if (GEN && a.dbg != nullptr && tid == 0) a.dbg[(long long)blockIdx.x * 8 + (k)] = SGPE_GLOBALTIMER(); } while (0)
+    if (GEN && a.dbg != nullptr && tid == 0) a.dbg[(long long)blockIdx.x * 8 + 7] = SGPE_SMID();
     SGPE_MARK(0);
 
     C v[2][E];
@@ -960,7 +1040,7 @@ __global__ void __launch_bounds__(RPC * N / E, row_min_blocks<T, E>(RPC * N / E)
         }
     }
     C* const sms[2] = {smem + (size_t)(2 * r) * N, smem + (size_t)(2 * r + 1) * N};
-    if (!FAST && a.dbg != nullptr) { if (v[0][0].x == (T)1.2345e300 || v[1][E - 1].y == (T)1.2345e300) a.dbg[6] = 1; SGPE_MARK(1); }
+    if (GEN && a.dbg != nullptr) { if (v[0][0].x == (T)1.2345e300 || v[1][E - 1].y == (T)1.2345e300) a.dbg[6] = 1; SGPE_MARK(1); }
 
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
@@ -1043,12 +1123,12 @@ __global__ void __launch_bounds__(RPC * N / E, row_min_blocks<T, E>(RPC * N / E)
     }   // pass loop
     SGPE_MARK(4);
 
-    T sc = FAST ? (T)1 : (T)a.scale_out;
-    if (!FAST && a.scale_tot != nullptr) {
+    T sc = (GEN || INVP) ? (T)a.scale_out : (T)1;
+    if (INVP || (GEN && a.scale_tot != nullptr)) {
         const double* tot = a.scale_tot + (long long)b * 4;
         sc = (T)((double)sc * sqrt(a.scale_num / (tot[1] + tot[2])));
     }
-    if (!FAST && a.maxbits != nullptr) {
+    if (INVP || (GEN && a.maxbits != nullptr)) {
         double mx0 = 0.0, mx1 = 0.0;
         const double s2 = (double)sc * (double)sc;
 #pragma unroll
@@ -1067,11 +1147,22 @@ __global__ void __launch_bounds__(RPC * N / E, row_min_blocks<T, E>(RPC * N / E)
             atomicMax(&a.maxbits[2 * b + 1], (unsigned long long)__double_as_longlong(mx1));
         }
     }
-    if (!FAST && a.sc.mode) {       // fused exchange: each run of `seg` columns goes to the rank that owns it
+    if (GEN && a.sc.mode) {       // fused exchange: each run of `seg` columns goes to the rank that owns it
 #pragma unroll
         for (int m = 0; m < E; m++) {
             SGPE_ST_STREAM(scatter_ptr(a.sc, 0, y, j + m * NT), v[0][m]);
             SGPE_ST_STREAM(scatter_ptr(a.sc, 1, y, j + m * NT), v[1][m]);
+        }
+    } else if (INVP || (GEN && a.polar)) {
+        // polar store for the energy functional: the square roots and arctangents of eng_expect (tensor_propagator.py:
+        // 306-311) are evaluated HERE, sixteen independent chains per thread beside the other CTA's memory phases,
+        // instead of one dependent chain per pixel in the stencil pass
+#pragma unroll
+        for (int m = 0; m < E; m++) {
+            T s = sc;
+            if ((((sign_out & 1) ? (j + m * NT) : 0) + ((sign_out & 2) ? y : 0)) & 1) s = -s;
+            SGPE_ST_STREAM(&a.out[off0 + j + m * NT], to_polar<T>(cscale(v[0][m], s)));
+            SGPE_ST_STREAM(&a.out[off1 + j + m * NT], to_polar<T>(cscale(v[1][m], s)));
         }
     } else {
 #pragma unroll
@@ -1863,6 +1954,7 @@ template <typename T> struct EnergyArgs {
     double* partials; unsigned* counter; double* out;        // out [b * out_bstride + {0..3}]: total, kin, pot, int
     long long out_bstride;
     int rows;                   // streaming kernel: rows per CTA band
+    int polar;                  // streaming kernel: `psi` holds (|psi|, arg psi) (RowArgs::polar)
 };
 
 SGPE_DI double sgpe_wrap_pi(double d) {
@@ -1996,7 +2088,9 @@ __global__ void __launch_bounds__(256) energy_pass(EnergyArgs<T> a) {
 // 33 % halo and two barriers per tile and component, and was latency-bound at 160 us for 2048^2), the x-neighbours come
 // from a double-buffered shared-memory row (one barrier per row), the y-neighbours are the thread's own previous rows.
 // Loads are full coalesced row segments, the next row is fetched while the current one is worked on.
-template <typename T>
+// POLAR: `psi` holds (sqrt(n), atan2(im, re)) per pixel - what row_pass<..., FAST = 3> stores - and the pass is left with the
+// mask, the stencils and the sums.
+template <typename T, bool POLAR>
 __global__ void __launch_bounds__(256, 2) energy_stream_pass(EnergyArgs<T> a) {
     typedef typename cx_of<T>::type C;
     constexpr int BX = 256, RW = BX + 2;
@@ -2021,11 +2115,12 @@ __global__ void __launch_bounds__(256, 2) energy_stream_pass(EnergyArgs<T> a) {
     if (a.cpl_mode == 1) om_u = a.omega_b[b];
 
     auto prep = [&](C z, double thr, const int* inc, long long pix, double& r, double& ph) {
-        const double n = (double)z.x * z.x + (double)z.y * z.y;
-        r = sqrt(n);
+        double n;
+        if (POLAR) { r = (double)z.x; n = r * r; }
+        else { n = (double)z.x * z.x + (double)z.y * z.y; r = sqrt(n); }
         ph = 0.0;
         if (!(n < thr)) {
-            ph = atan2((double)z.y, (double)z.x);
+            ph = POLAR ? (double)z.y : atan2((double)z.y, (double)z.x);
             if (inc != nullptr) ph = __dadd_rn(ph, __dmul_rn(6.283185307179586, (double)inc[pix]));
         }
     };
@@ -2082,7 +2177,8 @@ __global__ void __launch_bounds__(256, 2) energy_stream_pass(EnergyArgs<T> a) {
                 const double gyr = sgpe_grad3(wr[0][c], wr[1][c], r[c], i, a.ny, a.inv_h0);
                 const double gyph = a.unwrap_mode != 1 ? sgpe_grad3(wph[0][c], wph[1][c], ph[c], i, a.ny, a.inv_h0)
                                                        : sgpe_grad3_wrapped(wph[0][c], wph[1][c], ph[c], i, a.ny, a.inv_h0);
-                const double n0 = (double)zprev[c].x * zprev[c].x + (double)zprev[c].y * zprev[c].y;
+                const double n0 = POLAR ? (double)zprev[c].x * zprev[c].x
+                                        : (double)zprev[c].x * zprev[c].x + (double)zprev[c].y * zprev[c].y;
                 kin += (gyr * gyr + gxr[c] * gxr[c]) + n0 * (gyph * gyph + gxph[c] * gxph[c]) + n0 * gyph * a.kl2;
                 dens[c] = n0;
             }
@@ -2102,7 +2198,9 @@ __global__ void __launch_bounds__(256, 2) energy_stream_pass(EnergyArgs<T> a) {
             const double inter = a.g_uu * dens[0] * dens[0] + a.g_dd * dens[1] * dens[1] + a.g_ud * dens[0] * dens[1];
             double om = om_u;
             if (a.cpl_mode == 2) om = __ldg(&a.coupling[(long long)b * a.cpl_bstride + pp]);
-            const double coupl = ((double)zprev[0].x * zprev[1].x + (double)zprev[0].y * zprev[1].y) * om;
+            double coupl = 0.0;                          // Re(conj(p0) p1) * Omega
+            if (!POLAR) coupl = ((double)zprev[0].x * zprev[1].x + (double)zprev[0].y * zprev[1].y) * om;
+            else if (om != 0.0) coupl = (double)zprev[0].x * zprev[1].x * cos((double)zprev[0].y - (double)zprev[1].y) * om;
             acc[0] += kin + pot + inter + coupl; acc[1] += kin; acc[2] += pot; acc[3] += inter;
         }
         // x-derivatives of this row (from the shared row), then shift the window
@@ -2117,6 +2215,147 @@ __global__ void __launch_bounds__(256, 2) energy_stream_pass(EnergyArgs<T> a) {
             wr[1][c] = r[c]; wph[1][c] = ph[c];
         }
         zprev[0] = z0; zprev[1] = z1;
+    }
+    cta_reduce<4>(acc, red);
+    if (tid == 0) {
+        double* p = a.partials + ((long long)b * nblk + blockIdx.x) * 4;
+        p[0] = acc[0]; p[1] = acc[1]; p[2] = acc[2]; p[3] = acc[3];
+        __threadfence();
+        red[0] = (atomicAdd(&a.counter[b], 1u) == (unsigned)(nblk - 1)) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const bool last = red[0] != 0.0;
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        double t4[4] = {0.0, 0.0, 0.0, 0.0};
+        const double* p = a.partials + (long long)b * nblk * 4;
+        for (int t = tid; t < nblk; t += blockDim.x) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) t4[q] += __ldcg(&p[4 * t + q]);
+        }
+        cta_reduce<4>(t4, red);
+        if (tid == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) a.out[(long long)b * a.out_bstride + q] = t4[q];
+            a.counter[b] = 0u;
+        }
+    }
+}
+
+// The stencil pass for POLAR input, without shared memory or CTA barriers: a WARP owns a band of `rows` rows x 30 columns
+// (lanes 0 and 31 carry the halo columns), the x-neighbours come from warp shuffles, the y-neighbours are the lane's own
+// previous rows, FOUR rows are in flight per lane (a ring of named registers: rotating them by copies would wait for
+// every load) and every warp of the SM runs on its own.  Loads beyond the mesh are clamped to the edge pixel, which
+// turns np.gradient's one-sided edge differences into the SAME expression (f[+1] - f[-1]) * c with c = 1/h instead of
+// 1/(2h): no edge branches or selects.  WRAPPED: differences of the phase taken modulo 2 pi (unwrap_mode 1).
+// (unwrap_mode 2 - a field of 2 pi multiples from the region merging - goes through energy_stream_pass.)
+template <typename T, bool WRAPPED>
+__global__ void __launch_bounds__(256, 2) energy_polar_pass(EnergyArgs<T> a) {
+    typedef typename cx_of<T>::type C;
+    SGPE_DYN_SMEM(smem_raw);
+    double* red = reinterpret_cast<double*>(smem_raw);                 // [32 * 4]
+    const int b = blockIdx.y, nblk = gridDim.x, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int ncb = (a.nx + 29) / 30, ncb8 = (ncb + 7) / 8;
+    const int cb = (int)(blockIdx.x % ncb8) * 8 + warp;
+    // (the bands are handed out from the bottom of the mesh upwards: the rows the preceding pass wrote last are still in L2)
+    const int y0 = (int)((gridDim.x - 1 - blockIdx.x) / ncb8) * a.rows;
+    const int y1 = (y0 + a.rows < a.ny) ? y0 + a.rows : a.ny;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    {   // (no branch around the body: a warp past the last column band works on the last one and adds nothing, so that
+        // the compiler sees the shuffles in convergent code; y0 < ny by the construction of the grid)
+        const int xr = (cb < ncb ? cb : ncb - 1) * 30 - 1 + lane;
+        const int x = xr < 0 ? 0 : (xr > a.nx - 1 ? a.nx - 1 : xr);
+        const bool out_ok = lane >= 1 && lane <= 30 && xr < a.nx && cb < ncb;
+        const double cx = (x == 0 || x == a.nx - 1) ? a.inv_h1 : 0.5 * a.inv_h1;
+        const C* p0 = a.psi + ((long long)b * 2) * a.plane + x;
+        const double thr0 = a.maxdens[2 * b] * 1e-6, thr1 = a.maxdens[2 * b + 1] * 1e-6;
+        double om_u = 0.0;
+        if (a.cpl_mode == 1) om_u = a.omega_b[b];
+        const bool dense_pot = a.pot_mode == 0, dense_cpl = a.cpl_mode == 2;
+        double vx0 = 0.0, vx1 = 0.0;
+        // (every batch / column offset is folded into these pointers once: nothing but the row index is left for the loop)
+        const double* const py0 = a.pot_y + (long long)b * a.poty_bstride;
+        const double* const py1 = py0 + a.ny;
+        const double* const pd0 = dense_pot ? a.pot0 + (long long)b * a.pot_bstride + x : nullptr;
+        const double* const pd1 = dense_pot ? a.pot1 + (long long)b * a.pot_bstride + x : nullptr;
+        const double* const cpd = dense_cpl ? a.coupling + (long long)b * a.cpl_bstride + x : nullptr;
+        const int nx = a.nx, ny = a.ny;
+        const double inv_h0 = a.inv_h0, half_h0 = 0.5 * a.inv_h0, kl2 = a.kl2, g_uu = a.g_uu, g_dd = a.g_dd, g_ud = a.g_ud;
+        if (!dense_pot) {
+            const double* px = a.pot_x + (long long)b * a.potx_bstride;
+            vx0 = __ldg(&px[x]); vx1 = __ldg(&px[a.nx + x]);
+        }
+        // window: w?0 = two rows back, w?1 = previous row (per component |psi| and masked phase); of the previous row also
+        // the x-derivatives and the raw phases (coupling term)
+        double wr0[2] = {0.0, 0.0}, wr1[2] = {0.0, 0.0}, wp0[2] = {0.0, 0.0}, wp1[2] = {0.0, 0.0};
+        double gxr[2] = {0.0, 0.0}, gxph[2] = {0.0, 0.0}, rawp[2] = {0.0, 0.0};
+        struct Row { C z0, z1; };
+        // running fetch pointers: row fy clamped to the mesh (rows past the band are fetched and never used: no branch)
+        int fy = y0 - 1;
+        const C* f0 = p0 + (long long)(fy < 0 ? 0 : fy) * a.nx;
+        const long long plane = a.plane;
+        auto fetch = [&](Row& q) {
+            q.z0 = SGPE_LD_STREAM(&f0[0]); q.z1 = SGPE_LD_STREAM(&f0[plane]);
+            if (fy >= 0 && fy < ny - 1) f0 += nx;
+            fy++;
+        };
+        auto process = [&](int yy, const Row& q) {
+            double r[2], ph[2];
+            r[0] = (double)q.z0.x; r[1] = (double)q.z1.x;
+            ph[0] = (r[0] * r[0] < thr0) ? 0.0 : (double)q.z0.y;
+            ph[1] = (r[1] * r[1] < thr1) ? 0.0 : (double)q.z1.y;
+            const int i = yy - 1;                     // the previous row is finished now: its y-derivatives need this row
+            if (i >= y0 && i < y1 && out_ok) {
+                const double cy = (i == 0 || i == ny - 1) ? inv_h0 : half_h0;
+                double kin = 0.0, dens[2];
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    const double gyr = (r[c] - wr0[c]) * cy;
+                    const double gyph = WRAPPED ? (sgpe_wrap_pi(ph[c] - wp1[c]) + sgpe_wrap_pi(wp1[c] - wp0[c])) * cy
+                                                : (ph[c] - wp0[c]) * cy;
+                    const double n0 = wr1[c] * wr1[c];
+                    kin += (gyr * gyr + gxr[c] * gxr[c]) + n0 * (gyph * gyph + gxph[c] * gxph[c]) + n0 * gyph * kl2;
+                    dens[c] = n0;
+                }
+                kin *= 0.5;
+                double v0, v1;
+                if (dense_pot) {
+                    const long long pp = (long long)i * nx;
+                    v0 = __ldg(&pd0[pp]); v1 = __ldg(&pd1[pp]);
+                } else {
+                    v0 = vx0 + __ldg(&py0[i]); v1 = vx1 + __ldg(&py1[i]);
+                }
+                const double pot = dens[0] * v0 + dens[1] * v1;
+                const double inter = g_uu * dens[0] * dens[0] + g_dd * dens[1] * dens[1] + g_ud * dens[0] * dens[1];
+                double om = om_u;
+                if (dense_cpl) om = __ldg(&cpd[(long long)i * nx]);
+                double coupl = 0.0;                      // Re(conj(p0) p1) * Omega
+                if (om != 0.0) coupl = wr1[0] * wr1[1] * cos(rawp[0] - rawp[1]) * om;
+                acc[0] += kin + pot + inter + coupl; acc[1] += kin; acc[2] += pot; acc[3] += inter;
+            }
+            // x-derivatives of this row from the neighbouring lanes, then shift the window
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const double rm = __shfl_up_sync(0xffffffffu, r[c], 1), rp = __shfl_down_sync(0xffffffffu, r[c], 1);
+                const double pm = __shfl_up_sync(0xffffffffu, ph[c], 1), pq = __shfl_down_sync(0xffffffffu, ph[c], 1);
+                gxr[c] = (rp - rm) * cx;
+                gxph[c] = WRAPPED ? (sgpe_wrap_pi(pq - ph[c]) + sgpe_wrap_pi(ph[c] - pm)) * cx : (pq - pm) * cx;
+                wr0[c] = wr1[c]; wp0[c] = wp1[c];
+                wr1[c] = r[c]; wp1[c] = ph[c];
+            }
+            rawp[0] = (double)q.z0.y; rawp[1] = (double)q.z1.y;
+        };
+        Row qa, qb, qc, qd;
+        fetch(qa); fetch(qb); fetch(qc); fetch(qd);
+#pragma unroll 1
+        for (int yy = y0 - 1; yy <= y1; yy += 4) {     // (rows past y1 are processed into nothing: i >= y1)
+            process(yy, qa);     fetch(qa);
+            process(yy + 1, qb); fetch(qb);
+            process(yy + 2, qc); fetch(qc);
+            process(yy + 3, qd); fetch(qd);
+        }
     }
     cta_reduce<4>(acc, red);
     if (tid == 0) {

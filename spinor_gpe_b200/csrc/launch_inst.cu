@@ -78,6 +78,7 @@ static int launch_row_t(const RowArgs<T>& a, int batch, cudaStream_t st) {
         allow_smem(row_pass<T, N, Cfg::E, Cfg::RPC, TM, 0>, Cfg::SMEM);
         allow_smem(row_pass<T, N, Cfg::E, Cfg::RPC, TM, 1>, Cfg::SMEM);
         allow_smem(row_pass<T, N, Cfg::E, Cfg::RPC, TM, 2>, Cfg::SMEM);
+        allow_smem(row_pass<T, N, Cfg::E, Cfg::RPC, TM, 3>, Cfg::SMEM);
         ahead = resident_ctas(row_pass<T, N, Cfg::E, Cfg::RPC, TM, 1>, Cfg::THREADS, Cfg::SMEM);
         once = true;
     }
@@ -87,8 +88,13 @@ static int launch_row_t(const RowArgs<T>& a, int batch, cudaStream_t st) {
     a2.resident = ahead;
     const bool fast = a.do_inv && a.do_pw && a.do_fwd && a.cpl_mode == 0 && !a.sign_in &&
                       !a.sign_out && a.scale_out == 1.0 && a.stagger_ns == 0 && a.dbg == nullptr && a.sc.mode == 0 &&
-                      a.scale_tot == nullptr && a.maxbits == nullptr;
-    if (fast && a.pot_mode == 1) {
+                      a.scale_tot == nullptr && a.maxbits == nullptr && !a.polar;
+    // the stand-alone inverse of per-step energy tracking: device-side scale, density maxima, polar store
+    const bool invp = a.do_inv && !a.do_pw && !a.do_fwd && !a.sign_in && a.stagger_ns == 0 && a.dbg == nullptr &&
+                      a.sc.mode == 0 && a.scale_tot != nullptr && a.maxbits != nullptr && a.polar;
+    if (invp) {
+        SGPE_LAUNCH((row_pass<T, N, Cfg::E, Cfg::RPC, TM, 3>), grid, block, Cfg::SMEM, st, a2);
+    } else if (fast && a.pot_mode == 1) {
         SGPE_LAUNCH((row_pass<T, N, Cfg::E, Cfg::RPC, TM, 1>), grid, block, Cfg::SMEM, st, a2);
     } else if (fast && a.pot_mode == 0) {
         SGPE_LAUNCH((row_pass<T, N, Cfg::E, Cfg::RPC, TM, 2>), grid, block, Cfg::SMEM, st, a2);
@@ -229,6 +235,17 @@ static int launch_col_t(const ColArgs<T>& a, int batch, int wsel, cudaStream_t s
     if constexpr (Cfg::E == 16) {
         // the persistent kernel covers the steady-state junction: forward + factors + inverse, separable tables
         const bool fast = a.do_fwd && a.do_inv && !a.sign_in && !a.sign_out && a.scale_out == 1.0 && a.in == a.out;
+        // the stand-alone inverse of per-step energy tracking: persistent CTAs, staged tiles, no forward / K phase
+        const bool inv_only = !a.do_fwd && a.do_inv && !a.has_a && !a.has_b && !a.sign_in && !a.sign_out &&
+                              a.scale_out == 1.0 && a.in == a.out && a.tile_map != nullptr && wsel == 0;
+        if (inv_only && a.kernel_sel >= 1) {
+            int rci = -2;
+            if constexpr (Cfg::W % 2 == 0 && (Cfg::W / 2) * Cfg::NT >= 32) {
+                if (a.kernel_sel == 5) rci = launch_col_p<T, N, TM, Cfg::W / 2, Cfg::E, 1, 0, 2>(a, batch, st);
+            }
+            if (a.kernel_sel != 5) rci = launch_col_p<T, N, TM, Cfg::W, Cfg::E, 1, 0, 2>(a, batch, st);
+            if (rci != -2) return rci;
+        }
         // (the first persistent variant also evaluates dense kinetic grids; the others take factor tables only)
         if (a.kernel_sel >= 2 && a.kin_mode != 1) return launch_col_w<T, N, TM, Cfg::W, Cfg::E>(a, batch, st);
         if (a.kernel_sel == 1 && fast && a.tile_map != nullptr && wsel == 0)

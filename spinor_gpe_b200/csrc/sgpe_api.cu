@@ -133,6 +133,7 @@ struct sgpe_plan {
     // CUDA-graph replay of the steady-state full step (option "graph"): six kernel nodes whose arguments do not change
     // from step to step (the populations slot comes from the device-side counter slot_ctr)
     int energy_kernel = 0;         // option "energy_kernel": 0 streaming (default), 1 tiled
+    int energy_polar = 1;          // option "energy_polar": per-step tracking hands (|psi|, arg psi) to the stencil pass
     int use_graph = -1;            // -1: default choice (small meshes), 0 off, 1 on
     uint64_t epoch = 0;            // bumped by every sgpe_set_* call: a captured graph is valid for one epoch
     int* slot_ctr = nullptr;       // [batch]
@@ -439,7 +440,7 @@ int run_row_generic(sgpe_plan* p, RowArgs<T>& a, bool inv, bool pw, bool fwd, cu
 template <typename T>
 int run_col(sgpe_plan* p, const void* in, void* out, bool fwd, bool has_a, double tau_a, bool has_b, double tau_b,
             bool inv, int sign_in, int sign_out, double scale_out, double* pops, long long pops_stride,
-            int pops_slot, cudaStream_t st, void* aux = nullptr) {
+            int pops_slot, cudaStream_t st, void* aux = nullptr, double* zero2 = nullptr) {
     typedef typename sgpe::cx_of<T>::type C;
     ColArgs<T> a;
     memset(&a, 0, sizeof(a));
@@ -474,10 +475,12 @@ int run_col(sgpe_plan* p, const void* in, void* out, bool fwd, bool has_a, doubl
     a.slot_ctr = (p->capturing && pops != nullptr && pops_slot >= 0) ? p->slot_ctr : nullptr;
     a.atom_num = p->atom_num;
     a.aux = static_cast<C*>(aux);
+    a.zero2 = reinterpret_cast<unsigned long long*>(zero2);
     if (p->generic) return run_col_generic<T>(p, a, fwd, inv, st);
     a.dbg = (fwd && inv) ? p->dbg_col : nullptr;
     a.kernel_sel = p->col_kernel == 0 ? default_col_kernel(p) : p->col_kernel - 1;
-    if (a.kernel_sel >= 1 && fwd && inv && in == out && p->n1 == 1) {
+    const bool inv_only = !fwd && inv && !has_a && !has_b && !sign_in && !sign_out && scale_out == 1.0;
+    if (a.kernel_sel >= 1 && (fwd || inv_only) && inv && in == out && p->n1 == 1) {
         const SgpeTileMap* tm = nullptr;
         int w = sgpe::col_tile_width(p->ny, p->dtype);
         if (a.kernel_sel == 5) w /= 2;                      // half-width tiles, two CTAs per SM
@@ -498,7 +501,7 @@ template <typename T>
 int run_row(sgpe_plan* p, const void* in, void* out, bool inv, bool pw, double dt_sub, bool fwd, int sign_in,
             int sign_out, double scale_out, cudaStream_t st, const double* totals_override = nullptr,
             double norm_points = 0.0, bool scatter = false, const double* scale_tot = nullptr, double scale_num = 0.0,
-            double* maxdens = nullptr) {
+            double* maxdens = nullptr, bool polar = false) {
     typedef typename sgpe::cx_of<T>::type C;
     RowArgs<T> a;
     memset(&a, 0, sizeof(a));
@@ -533,6 +536,7 @@ int run_row(sgpe_plan* p, const void* in, void* out, bool inv, bool pw, double d
     fill_scatter(p, scatter, &a.sc);
     a.scale_tot = scale_tot; a.scale_num = scale_num;
     a.maxbits = reinterpret_cast<unsigned long long*>(maxdens);
+    a.polar = polar ? 1 : 0;
     if (p->generic) return run_row_generic<T>(p, a, inv, pw, fwd, st);
     ProfScope prof(p, 1, st);
     int rc = sgpe::launch_row(p->nx, p->dtype, p->tm, &a, p->batch, p->row_mode, st);
@@ -668,7 +672,7 @@ int run_kinetic(sgpe_plan* p, const void* psik, double* out, cudaStream_t st) {
 
 template <typename T>
 int run_energy(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, double* out, cudaStream_t st,
-               long long out_bstride = 4, bool have_maxdens = false) {
+               long long out_bstride = 4, bool have_maxdens = false, bool polar = false) {
     typedef typename sgpe::cx_of<T>::type C;
     sgpe::MaxDensArgs<T> m;
     m.psi = static_cast<const C*>(psi); m.plane = p->plane;
@@ -697,12 +701,33 @@ int run_energy(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, d
     a.inc = p->unwrap_inc;
     a.maxdens = p->maxdens; a.partials = p->partials; a.counter = p->counter; a.out = out;
     a.out_bstride = out_bstride;
+    a.polar = polar ? 1 : 0;
+    if (polar && p->energy_kernel == 1) return fail(SGPE_EINVAL, "the tiled energy kernel takes (re, im) input");
     if (p->energy_kernel == 1) {       // the tiled kernel of round 1 (option "energy_kernel", cross-checks)
         long long tiles = (long long)((p->nx + 31) / 32) * ((p->ny + 7) / 8);
         blocks = tiles < 888 ? tiles : 888;                     // six 256-thread CTAs per SM x 148 SMs
         if (blocks > p->max_tiles / 2) blocks = p->max_tiles / 2;   // four partial sums per CTA in `partials`
         dim3 grid((unsigned)blocks, p->batch), block(256);
         SGPE_LAUNCH((sgpe::energy_pass<T>), grid, block, (32 * 4 + 2 * 34 * 10) * sizeof(double), st, a);
+        p->launches++;
+        SGPE_CUDA(cudaGetLastError());
+        return 0;
+    }
+    if (polar && p->energy_polar == 1 && unwrap_mode != 2) {
+        // warp-per-band stencil pass on (|psi|, arg psi): CTAs of 8 warps x 30 columns, bands of `rows` rows, three
+        // resident CTAs per SM, at most max_tiles / 2 of them (four partial sums per CTA)
+        const int ncb8 = ((p->nx + 29) / 30 + 7) / 8;
+        long long want = 296 / ncb8;
+        if (want > p->max_tiles / 2 / ncb8) want = p->max_tiles / 2 / ncb8;
+        if (want < 1) want = 1;
+        int rows = (int)((p->ny + want - 1) / want);
+        if (rows < 8) rows = 8;
+        if (rows > p->ny) rows = p->ny;
+        a.rows = rows;
+        const int nyb = (p->ny + rows - 1) / rows;
+        dim3 grid((unsigned)(ncb8 * nyb), p->batch), block(256);
+        if (unwrap_mode == 1) { SGPE_LAUNCH((sgpe::energy_polar_pass<T, true>), grid, block, 32 * 4 * sizeof(double), st, a); }
+        else { SGPE_LAUNCH((sgpe::energy_polar_pass<T, false>), grid, block, 32 * 4 * sizeof(double), st, a); }
         p->launches++;
         SGPE_CUDA(cudaGetLastError());
         return 0;
@@ -718,7 +743,8 @@ int run_energy(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, d
     a.rows = rows;
     const int nyb = (p->ny + rows - 1) / rows;
     dim3 grid((unsigned)(nxb * nyb), p->batch), block(256);
-    SGPE_LAUNCH((sgpe::energy_stream_pass<T>), grid, block, (32 * 4 + 2 * 4 * 258) * sizeof(double), st, a);
+    if (polar) { SGPE_LAUNCH((sgpe::energy_stream_pass<T, true>), grid, block, (32 * 4 + 2 * 4 * 258) * sizeof(double), st, a); }
+    else { SGPE_LAUNCH((sgpe::energy_stream_pass<T, false>), grid, block, (32 * 4 + 2 * 4 * 258) * sizeof(double), st, a); }
     p->launches++;
     SGPE_CUDA(cudaGetLastError());
     return 0;
@@ -1114,15 +1140,18 @@ static int run_unpack(sgpe_plan* p, const void* in, void* out, int P, int Bh, in
 int energy_of_boundary(sgpe_plan* p, cudaStream_t st) {
     const double norm = p->dx * p->dy / (2.0 * M_PI);
     double* out = p->pend_energy + 4LL * p->pend_eslot;
-    SGPE_CUDA(cudaMemsetAsync(p->maxdens, 0, sizeof(double) * 2 * p->batch, st));
+    // (the density maxima of the row pass are cleared by the column pass before it: no memset node)
     int rc = SGPE_BY_DTYPE(p, run_col, p, p->scratch, p->scratch, false, false, 0.0, false, 0.0, true, 0, 0, 1.0, nullptr,
-                           0, -1, st);
+                           0, -1, st, nullptr, p->maxdens);
     if (rc) return rc;
+    // (option "energy_polar", default on: the last inverse pass stores (|psi|, arg psi) and the stencil pass is left
+    // without square roots and arctangents; 0 = (re, im) through the tiled / streaming kernels as in round 1)
+    const bool polar = p->energy_polar && p->energy_kernel == 0 && !p->generic;
     rc = SGPE_BY_DTYPE(p, run_row, p, p->scratch, p->scratch, true, false, 0.0, false, 0, 3,
                        1.0 / (norm * (double)p->nx * (double)p->ny), st, nullptr, 0.0, false, p->totals,
-                       p->atom_num / p->dv_k, p->maxdens);
+                       p->atom_num / p->dv_k, p->maxdens, polar);
     if (rc) return rc;
-    rc = SGPE_BY_DTYPE(p, run_energy, p, p->scratch, p->track_unwrap, p->track_kl, out, st, p->pend_estride, true);
+    rc = SGPE_BY_DTYPE(p, run_energy, p, p->scratch, p->track_unwrap, p->track_kl, out, st, p->pend_estride, true, polar);
     p->pend_eslot = -1;
     return rc;
 }
@@ -1280,6 +1309,11 @@ int sgpe_set_option(sgpe_plan* p, const char* name, int value) {
     if (std::strcmp(name, "stagger_ns") == 0) { p->stagger_ns = value; return 0; }
     if (std::strcmp(name, "timeline_kind") == 0) { p->dbg_kind = value ? 1 : 0; return 0; }
     if (std::strcmp(name, "energy_kernel") == 0) { p->energy_kernel = value ? 1 : 0; return 0; }
+    if (std::strcmp(name, "energy_polar") == 0) {     // 0: (re, im); 1: polar + warp-per-band stencils; 2: polar + streaming kernel
+        if (value < 0 || value > 2) return fail(SGPE_EINVAL, "energy_polar: 0, 1 or 2");
+        p->energy_polar = value;
+        return 0;
+    }
     if (std::strcmp(name, "graph") == 0) {
         if (value < -1 || value > 1) return fail(SGPE_EINVAL, "graph: -1 (default: small meshes), 0 (off) or 1 (on)");
         p->use_graph = value;

@@ -111,6 +111,16 @@ inline double shfl_xor(double v, int m) {
     return s.shfl_d[p][s.cur ^ m];
 }
 
+// value of lane `src` of the caller's warp (every lane of the warp calls)
+inline double shfl_from(double v, int src) {
+    State& s = S();
+    int w = s.cur / 32;
+    int p = s.warp_gen[w] & 1;
+    s.shfl_d[p][s.cur] = v;
+    warp_sync();
+    return s.shfl_d[p][w * 32 + src];
+}
+
 template <typename F>
 inline void launch(dim3 grid, dim3 block, size_t smem_bytes, F f) {
     State& s = S();
@@ -159,6 +169,8 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, F f) {
 inline void __syncthreads() { ::emu::syncthreads(); }
 inline void __threadfence() {}
 inline double __shfl_xor_sync(unsigned, double v, int m) { return ::emu::shfl_xor(v, m); }
+inline double __shfl_up_sync(unsigned, double v, int d) { int l = ::emu::S().cur & 31; return ::emu::shfl_from(v, l >= d ? l - d : l); }
+inline double __shfl_down_sync(unsigned, double v, int d) { int l = ::emu::S().cur & 31; return ::emu::shfl_from(v, l + d <= 31 ? l + d : l); }
 template <typename T> inline T __ldg(const T* p) { return *p; }
 inline long long __double_as_longlong(double x) { long long r; std::memcpy(&r, &x, 8); return r; }
 inline double __longlong_as_double(long long x) { double r; std::memcpy(&r, &x, 8); return r; }
