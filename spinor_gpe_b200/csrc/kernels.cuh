@@ -1955,6 +1955,8 @@ template <typename T> struct EnergyArgs {
     long long out_bstride;
     int rows;                   // streaming kernel: rows per CTA band
     int polar;                  // streaming kernel: `psi` holds (|psi|, arg psi) (RowArgs::polar)
+    int* slot_ctr;              // [B] or null.  Non-null (graph replay): the result goes to out[b * out_bstride + 4 * slot + q]
+                                // with the slot read from slot_ctr[b] and post-incremented by the fold
 };
 
 SGPE_DI double sgpe_wrap_pi(double d) {
@@ -2076,8 +2078,10 @@ __global__ void __launch_bounds__(256) energy_pass(EnergyArgs<T> a) {
         }
         cta_reduce<4>(t4, red);
         if (tid == 0) {
+            long long slot = 0;
+            if (a.slot_ctr != nullptr) { slot = a.slot_ctr[b]; a.slot_ctr[b] = (int)slot + 1; }
 #pragma unroll
-            for (int q = 0; q < 4; q++) a.out[(long long)b * a.out_bstride + q] = t4[q];
+            for (int q = 0; q < 4; q++) a.out[(long long)b * a.out_bstride + 4 * slot + q] = t4[q];
             a.counter[b] = 0u;
         }
     }
@@ -2236,8 +2240,10 @@ __global__ void __launch_bounds__(256, 2) energy_stream_pass(EnergyArgs<T> a) {
         }
         cta_reduce<4>(t4, red);
         if (tid == 0) {
+            long long slot = 0;
+            if (a.slot_ctr != nullptr) { slot = a.slot_ctr[b]; a.slot_ctr[b] = (int)slot + 1; }
 #pragma unroll
-            for (int q = 0; q < 4; q++) a.out[(long long)b * a.out_bstride + q] = t4[q];
+            for (int q = 0; q < 4; q++) a.out[(long long)b * a.out_bstride + 4 * slot + q] = t4[q];
             a.counter[b] = 0u;
         }
     }
@@ -2377,8 +2383,10 @@ __global__ void __launch_bounds__(256, 2) energy_polar_pass(EnergyArgs<T> a) {
         }
         cta_reduce<4>(t4, red);
         if (tid == 0) {
+            long long slot = 0;
+            if (a.slot_ctr != nullptr) { slot = a.slot_ctr[b]; a.slot_ctr[b] = (int)slot + 1; }
 #pragma unroll
-            for (int q = 0; q < 4; q++) a.out[(long long)b * a.out_bstride + q] = t4[q];
+            for (int q = 0; q < 4; q++) a.out[(long long)b * a.out_bstride + 4 * slot + q] = t4[q];
             a.counter[b] = 0u;
         }
     }

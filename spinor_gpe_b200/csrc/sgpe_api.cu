@@ -134,15 +134,19 @@ struct sgpe_plan {
     // from step to step (the populations slot comes from the device-side counter slot_ctr)
     int energy_kernel = 0;         // option "energy_kernel": 0 streaming (default), 1 tiled
     int energy_polar = 1;          // option "energy_polar": per-step tracking hands (|psi|, arg psi) to the stencil pass
-    int use_graph = -1;            // -1: default choice (small meshes), 0 off, 1 on
+    int use_graph = -1;            // -1: default choice (on), 0 off, 1 on
     uint64_t epoch = 0;            // bumped by every sgpe_set_* call: a captured graph is valid for one epoch
     int* slot_ctr = nullptr;       // [batch]
+    int* eslot_ctr = nullptr;      // [batch] energy slot of the replayed step
     bool capturing = false;
 #ifndef SGPE_EMU
     cudaGraphExec_t graph_exec = nullptr;
+    cudaGraphExec_t graph_exec_e = nullptr;      // the same step with the energy side chain (sgpe_full_steps_energy)
     cudaStream_t cap_stream = nullptr;
     struct GraphKey { uint64_t epoch = 0; const void* pops = nullptr; long long stride = 0; int tm = -1; double dt = 0;
-                      bool operator==(const GraphKey& o) const { return epoch == o.epoch && pops == o.pops && stride == o.stride && tm == o.tm && dt == o.dt; } } graph_key;
+                      const void* energy = nullptr; long long estride = 0; int unwrap = 0; double kl = 0;
+                      bool operator==(const GraphKey& o) const { return epoch == o.epoch && pops == o.pops && stride == o.stride && tm == o.tm && dt == o.dt &&
+                                                                        energy == o.energy && estride == o.estride && unwrap == o.unwrap && kl == o.kl; } } graph_key, graph_key_e;
 #endif
     // optional per-kernel timing (sgpe_profile_*): event pairs around column (kind 0) / row (kind 1) passes
     bool prof_on = false;
@@ -672,7 +676,7 @@ int run_kinetic(sgpe_plan* p, const void* psik, double* out, cudaStream_t st) {
 
 template <typename T>
 int run_energy(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, double* out, cudaStream_t st,
-               long long out_bstride = 4, bool have_maxdens = false, bool polar = false) {
+               long long out_bstride = 4, bool have_maxdens = false, bool polar = false, int* slot_ctr = nullptr) {
     typedef typename sgpe::cx_of<T>::type C;
     sgpe::MaxDensArgs<T> m;
     m.psi = static_cast<const C*>(psi); m.plane = p->plane;
@@ -702,6 +706,8 @@ int run_energy(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, d
     a.maxdens = p->maxdens; a.partials = p->partials; a.counter = p->counter; a.out = out;
     a.out_bstride = out_bstride;
     a.polar = polar ? 1 : 0;
+    a.slot_ctr = slot_ctr;
+    if (slot_ctr && p->energy_kernel == 1) return fail(SGPE_EINVAL, "the tiled energy kernel has no replay slot");
     if (polar && p->energy_kernel == 1) return fail(SGPE_EINVAL, "the tiled energy kernel takes (re, im) input");
     if (p->energy_kernel == 1) {       // the tiled kernel of round 1 (option "energy_kernel", cross-checks)
         long long tiles = (long long)((p->nx + 31) / 32) * ((p->ny + 7) / 8);
@@ -1139,7 +1145,9 @@ static int run_unpack(sgpe_plan* p, const void* in, void* out, int P, int Bh, in
 // no close / re-open of the junction, against six for sgpe_energy(NULL) between two sgpe_full_steps calls.
 int energy_of_boundary(sgpe_plan* p, cudaStream_t st) {
     const double norm = p->dx * p->dy / (2.0 * M_PI);
-    double* out = p->pend_energy + 4LL * p->pend_eslot;
+    // (graph replay: node arguments are frozen, the slot comes from a device-side counter the stencil pass advances)
+    int* const ectr = p->capturing ? p->eslot_ctr : nullptr;
+    double* out = p->pend_energy + (ectr ? 0LL : 4LL * p->pend_eslot);
     // (the density maxima of the row pass are cleared by the column pass before it: no memset node)
     int rc = SGPE_BY_DTYPE(p, run_col, p, p->scratch, p->scratch, false, false, 0.0, false, 0.0, true, 0, 0, 1.0, nullptr,
                            0, -1, st, nullptr, p->maxdens);
@@ -1151,7 +1159,7 @@ int energy_of_boundary(sgpe_plan* p, cudaStream_t st) {
                        1.0 / (norm * (double)p->nx * (double)p->ny), st, nullptr, 0.0, false, p->totals,
                        p->atom_num / p->dv_k, p->maxdens, polar);
     if (rc) return rc;
-    rc = SGPE_BY_DTYPE(p, run_energy, p, p->scratch, p->track_unwrap, p->track_kl, out, st, p->pend_estride, true, polar);
+    rc = SGPE_BY_DTYPE(p, run_energy, p, p->scratch, p->track_unwrap, p->track_kl, out, st, p->pend_estride, true, polar, ectr);
     p->pend_eslot = -1;
     return rc;
 }
@@ -1221,8 +1229,10 @@ int sgpe_plan_destroy(sgpe_plan* p) {
     cudaFree(p->unwrap_phi);
     for (auto& t : p->tile_maps) delete t.map;
     cudaFree(p->slot_ctr);
+    cudaFree(p->eslot_ctr);
 #ifndef SGPE_EMU
     if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+    if (p->graph_exec_e) cudaGraphExecDestroy(p->graph_exec_e);
     if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
 #endif
     for (auto& t : p->kin_tab) { cudaFree(t.x); cudaFree(t.y); }
@@ -1315,7 +1325,7 @@ int sgpe_set_option(sgpe_plan* p, const char* name, int value) {
         return 0;
     }
     if (std::strcmp(name, "graph") == 0) {
-        if (value < -1 || value > 1) return fail(SGPE_EINVAL, "graph: -1 (default: small meshes), 0 (off) or 1 (on)");
+        if (value < -1 || value > 1) return fail(SGPE_EINVAL, "graph: -1 (default: on), 0 (off) or 1 (on)");
         p->use_graph = value;
         return 0;
     }
@@ -1399,18 +1409,22 @@ int sgpe_single_step(sgpe_plan* p, double dt_sub, sgpe_stream st) {
 #ifndef SGPE_EMU
 // One steady-state full step (MID -> MID, the junction that opens it records the populations of the step before)
 // captured into an executable graph.  Called with every factor table the step needs already cached.
-static int capture_step_graph(sgpe_plan* p, double* pops, int64_t pops_stride) {
+static int capture_step_graph(sgpe_plan* p, double* pops, int64_t pops_stride, double* energy = nullptr, int64_t energy_stride = 0) {
     // (captured on a stream of the plan's own: the caller's may be the legacy default stream, which cannot capture;
     // the executable graph is then launched on the caller's stream)
     if (!p->cap_stream) SGPE_CUDA(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
     cudaStream_t s = p->cap_stream;
-    if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+    cudaGraphExec_t& exec = energy ? p->graph_exec_e : p->graph_exec;
+    if (exec) { cudaGraphExecDestroy(exec); exec = nullptr; }
     if (!p->slot_ctr && cudaMalloc((void**)&p->slot_ctr, sizeof(int) * p->batch) != cudaSuccess)
+        return fail(SGPE_ENOMEM, "device allocation failed");
+    if (!p->eslot_ctr && cudaMalloc((void**)&p->eslot_ctr, sizeof(int) * p->batch) != cudaSuccess)
         return fail(SGPE_ENOMEM, "device allocation failed");
     cudaGraph_t graph = nullptr;
     SGPE_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     p->capturing = true;
     p->pend_pops = pops; p->pend_stride = pops_stride; p->pend_slot = pops ? 0 : -1;     // slot value unused: counter
+    p->pend_energy = energy; p->pend_estride = energy_stride; p->pend_eslot = energy ? 0 : -1;
     int rc = single_step_impl(p, p->dt_out, s);
     if (!rc) rc = single_step_impl(p, p->dt_in, s);
     if (!rc) rc = single_step_impl(p, p->dt_out, s);
@@ -1418,22 +1432,22 @@ static int capture_step_graph(sgpe_plan* p, double* pops, int64_t pops_stride) {
     cudaError_t e = cudaStreamEndCapture(s, &graph);
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess) return fail(SGPE_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-    e = cudaGraphInstantiate(&p->graph_exec, graph, 0);
+    e = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
-    if (e != cudaSuccess) { p->graph_exec = nullptr; return fail(SGPE_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { exec = nullptr; return fail(SGPE_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
     return 0;
 }
 #endif
 
-// should sgpe_full_steps replay a captured graph?  Default: meshes whose passes are launch-bound (<= 512^2 points
-// in the plan); long-line plans, profiling runs and streams that are already being captured never do.
+// should sgpe_full_steps replay a captured graph?  Default: yes from four steps on (launch-bound small meshes gain 20 %,
+// 2048^2 still 1.6 %: 1596 -> 1622 steps/s); long-line plans, profiling runs and streams that are already being captured
+// never do.
 static bool graph_wanted(const sgpe_plan* p, int n, cudaStream_t s) {
 #ifdef SGPE_EMU
     (void)p; (void)n; (void)s;
     return false;
 #else
     if (p->use_graph == 0 || n < 4 || p->prof_on || p->n1 != 1 || p->dbg || p->dbg_col) return false;
-    if (p->use_graph < 0 && !((long long)p->nx * p->ny * p->batch <= 512LL * 512LL)) return false;
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return false; }
     return true;
@@ -1517,6 +1531,39 @@ int sgpe_full_steps_energy(sgpe_plan* p, int n, double* pops, int64_t pops_strid
         return 0;
     }
     p->track_unwrap = unwrap_mode; p->track_kl = kl_term;
+#ifndef SGPE_EMU
+    if (graph_wanted(p, n, s) && p->energy_kernel == 0) {
+        // as in sgpe_full_steps: two steps launched normally, the steady-state step (junction with the side store, the
+        // three passes of the energy chain, five more passes) replayed n - 2 times, the last junction closed normally
+        for (int i = 0; i < 2; i++) {
+            if ((rc = single_step_impl(p, p->dt_out, s))) return rc;
+            if ((rc = single_step_impl(p, p->dt_in, s))) return rc;
+            if ((rc = single_step_impl(p, p->dt_out, s))) return rc;
+            p->pend_pops = pops; p->pend_stride = pops_stride; p->pend_slot = pops ? pops_first + i : -1;
+            p->pend_energy = energy; p->pend_estride = energy_stride; p->pend_eslot = energy_first + i;
+        }
+        sgpe_plan::GraphKey key;
+        key.epoch = p->epoch; key.pops = pops; key.stride = pops_stride; key.tm = p->tm; key.dt = p->dt;
+        key.energy = energy; key.estride = energy_stride; key.unwrap = unwrap_mode; key.kl = kl_term;
+        if (!p->graph_exec_e || !(p->graph_key_e == key)) {
+            const sgpe_plan::Phase phase = p->phase; const double pend = p->pending_dt; const bool sc = p->scale_pending;
+            const uint64_t l0 = p->launches;
+            rc = capture_step_graph(p, pops, pops_stride, energy, energy_stride);
+            p->phase = phase; p->pending_dt = pend; p->scale_pending = sc; p->launches = l0;
+            if (rc) return rc;
+            p->graph_key_e = key;
+        }
+        if (pops) sgpe::fill_value<int><<<(p->batch + 127) / 128, 128, 0, s>>>(p->slot_ctr, pops_first + 1, p->batch);
+        sgpe::fill_value<int><<<(p->batch + 127) / 128, 128, 0, s>>>(p->eslot_ctr, energy_first + 1, p->batch);
+        p->launches += pops ? 2 : 1;
+        for (int i = 2; i < n; i++) SGPE_CUDA(cudaGraphLaunch(p->graph_exec_e, s));
+        p->launches += 9ull * (uint64_t)(n - 2);
+        p->phase = sgpe_plan::MID; p->pending_dt = p->dt_out; p->scale_pending = false;
+        p->pend_pops = pops; p->pend_stride = pops_stride; p->pend_slot = pops ? pops_first + n - 1 : -1;
+        p->pend_energy = energy; p->pend_estride = energy_stride; p->pend_eslot = energy_first + n - 1;
+        return close_junction(p, s);
+    }
+#endif
     for (int i = 0; i < n; i++) {
         if ((rc = single_step_impl(p, p->dt_out, s))) return rc;
         if ((rc = single_step_impl(p, p->dt_in, s))) return rc;

@@ -402,11 +402,18 @@ def test_graph_replay_matches_plain_launches(mesh, mode, dt, batch):
         pl.full_steps(n2, pops, first=n1)                      # same graph, other slots
         pl.set_interactions(ps.g_sc['uu'], ps.g_sc['dd'], 0.5 * ps.g_sc['ud'])     # invalidates the captured step
         pl.full_steps(n2, pops, first=n1 + n2)
-        outs.append((pl.store().clone(), pops.clone(), pl.launch_count() - l0))
+        # the same replay with the energy side chain (nine kernel nodes, energy slot from a second device-side counter)
+        eng = torch.zeros((batch, n1 + n2, 4), dtype=torch.float64, device='cuda')
+        pops_e = torch.zeros((batch, n1 + n2, 2), dtype=torch.float64, device='cuda')
+        pl.full_steps(n1, pops_e, first=0, energy=eng, kl_term=2 * ps.kL_recoil)
+        pl.full_steps(n2, pops_e, first=n1, energy=eng, kl_term=2 * ps.kL_recoil)
+        outs.append((pl.store().clone(), pops.clone(), pl.launch_count() - l0, eng.clone(), pops_e.clone()))
         pl.close()
     assert torch.equal(outs[0][0], outs[1][0])
     assert torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][3], outs[1][3]) and torch.equal(outs[0][4], outs[1][4])
     assert float(outs[0][1].abs().min()) > 0                   # every slot was written
+    assert float(outs[0][3][:, :, 0].abs().min()) > 0 and float(outs[0][4].abs().min()) > 0
     if batch == 1:
         ps.coupling_uniform(0.5 * ps.EL_recoil)
         o = orc.OraclePropagator(problem_of(ps), dt, mode)
