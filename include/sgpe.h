@@ -142,6 +142,14 @@ int sgpe_energy(sgpe_plan* p, const void* psik_dev, int unwrap_mode, double kl_t
  * psik_dev == NULL evaluates the plan's current (normalised) state.  Asynchronous. */
 int sgpe_kinetic_spectral(sgpe_plan* p, const void* psik_dev, double* out_dev, sgpe_stream st);
 
+/* ttools.grad_comp (tensor_tools.py:331-350: np.gradient(psi_comp, *delta_r); the reference raises for tensors, :343-345)
+ * on ONE (ny, nx) field of the plan's mesh that lives on the device: f_dev holds reals of the plan's precision
+ * (is_complex = 0) or complex numbers (is_complex = 1: both parts are differentiated).  g0_dev = d/d(axis 0) with
+ * spacing h0, g1_dev = d/d(axis 1) with spacing h1 — np.gradient's argument order, second-order central differences
+ * inside, first-order one-sided at the edges.  Same element type and shape as f_dev; f must not alias g0 / g1. */
+int sgpe_gradient(sgpe_plan* p, const void* f_dev, int is_complex, double h0, double h1, void* g0_dev, void* g1_dev,
+                  sgpe_stream st);
+
 /* The same functional on a REAL-space state [batch][2][ny][nx] of the plan's dtype (eng_expect after its ifft_2d,
  * tensor_propagator.py:301-324).  Valid on line plans too (sgpe_plan_create_lines: ny = nlines rows of nx = len points,
  * potential / coupling / interactions set as for sgpe_pass_rows), which is how meshes beyond 4096 points per line get

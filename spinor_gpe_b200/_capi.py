@@ -34,6 +34,7 @@ PROTOTYPES = {
     'sgpe_normalise': (C.c_int, [c_plan, c_dptr, c_dptr, C.c_double, c_stream]),
     'sgpe_energy': (C.c_int, [c_plan, c_dptr, C.c_int, C.c_double, c_dptr, c_stream]),
     'sgpe_kinetic_spectral': (C.c_int, [c_plan, c_dptr, c_dptr, c_stream]),
+    'sgpe_gradient': (C.c_int, [c_plan, c_dptr, C.c_int, C.c_double, C.c_double, c_dptr, c_dptr, c_stream]),
     'sgpe_energy_real_space': (C.c_int, [c_plan, c_dptr, C.c_int, C.c_double, c_dptr, c_stream]),
     'sgpe_unwrap_phase': (C.c_int, [c_plan, c_dptr, C.c_int, C.c_int, C.c_int, c_dptr, c_stream]),
     'sgpe_plan_create_lines': (C.c_int, [C.POINTER(c_plan), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -1977,6 +1977,24 @@ SGPE_DI double sgpe_grad3_wrapped(double fm, double f0, double fp, int i, int n,
     return (sgpe_wrap_pi(fp - f0) + sgpe_wrap_pi(f0 - fm)) * (0.5 * inv_h);
 }
 
+// ---------------------------------------------------------------------------------------------
+// np.gradient of one (ny, nx) field (reference ttools.grad_comp, tensor_tools.py:331-350, which hands NumPy arrays to
+// np.gradient and raises for tensors): second-order central differences inside, first-order one-sided at the edges.
+// nc = 1 real field, nc = 2 complex field seen as interleaved (re, im) - np.gradient differentiates both parts alike.
+// g0 = d / d(axis 0) with spacing 1 / inv_h0, g1 = d / d(axis 1) with spacing 1 / inv_h1.
+template <typename R>
+__global__ void __launch_bounds__(256) gradient_pass(const R* f, int ny, int nx, int nc, double inv_h0, double inv_h1, R* g0, R* g1) {
+    const long long row = (long long)nx * nc, n = (long long)ny * row;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / row), j = (int)((idx - (long long)i * row) / nc);
+        const double c = (double)f[idx];
+        const double up = (double)f[i > 0 ? idx - row : idx], dn = (double)f[i < ny - 1 ? idx + row : idx];
+        const double lf = (double)f[j > 0 ? idx - nc : idx], rt = (double)f[j < nx - 1 ? idx + nc : idx];
+        g0[idx] = (R)sgpe_grad3(up, c, dn, i, ny, inv_h0);
+        g1[idx] = (R)sgpe_grad3(lf, c, rt, j, nx, inv_h1);
+    }
+}
+
 // Each CTA walks 32 x 8 pixel tiles.  sqrt(n) and the masked phase are evaluated ONCE per pixel of the tile plus its
 // one-pixel halo (340 points for 256 outputs) into shared memory and the stencils read them from there: the
 // square roots and arctangents were 5x redundant when every pixel evaluated its own neighbours (FP64-bound).

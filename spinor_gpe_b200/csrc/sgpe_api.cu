@@ -1678,6 +1678,27 @@ int sgpe_kinetic_spectral(sgpe_plan* p, const void* psik, double* out, sgpe_stre
     return SGPE_BY_DTYPE(p, run_kinetic, p, psik, out, (cudaStream_t)st);
 }
 
+int sgpe_gradient(sgpe_plan* p, const void* f, int is_complex, double h0, double h1, void* g0, void* g1, sgpe_stream st) {
+    if (!p || !f || !g0 || !g1) return fail(SGPE_EINVAL, "null argument");
+    if (p->nx < 2 || p->ny < 2) return fail(SGPE_EINVAL, "np.gradient needs at least two points per axis");
+    if (!(h0 != 0.0) || !(h1 != 0.0)) return fail(SGPE_EINVAL, "zero spacing");
+    DeviceGuard guard(p->device);
+    const int nc = is_complex ? 2 : 1;
+    const long long n = (long long)p->plane * nc;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (p->dtype == SGPE_C128) {
+        SGPE_LAUNCH((sgpe::gradient_pass<double>), dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)st,
+                    static_cast<const double*>(f), p->ny, p->nx, nc, 1.0 / h0, 1.0 / h1, static_cast<double*>(g0), static_cast<double*>(g1));
+    } else {
+        SGPE_LAUNCH((sgpe::gradient_pass<float>), dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)st,
+                    static_cast<const float*>(f), p->ny, p->nx, nc, 1.0 / h0, 1.0 / h1, static_cast<float*>(g0), static_cast<float*>(g1));
+    }
+    p->launches++;
+    SGPE_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int sgpe_energy_real_space(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, double* out, sgpe_stream st) {
     if (!p || !psi || !out) return fail(SGPE_EINVAL, "null argument");
     if (!(p->grid_set && p->g_set && p->pot_set)) return fail(SGPE_ESTATE, "set grid, interactions and potential first");

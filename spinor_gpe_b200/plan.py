@@ -278,6 +278,19 @@ class Plan:
         self._chk(self.lib.sgpe_kinetic_spectral(self.h, _dp(t), _dp(out), self.stream), 'sgpe_kinetic_spectral')
         return out
 
+    def gradient(self, field, h0, h1):
+        """np.gradient(field, h0, h1) of ONE (ny, nx) field on the device (real or complex, converted to the plan's
+        precision): [d/d(axis 0), d/d(axis 1)] as two tensors of the field's shape."""
+        is_c = field.is_complex()
+        rdtype = torch.float64 if self.cdtype == torch.complex128 else torch.float32
+        f = field.to(device=self.device, dtype=self.cdtype if is_c else rdtype).contiguous()
+        if tuple(f.shape) != (self.ny, self.nx):
+            raise ValueError(f"field of {tuple(f.shape)}, plan has ({self.ny}, {self.nx})")
+        g0, g1 = torch.empty_like(f), torch.empty_like(f)
+        self._chk(self.lib.sgpe_gradient(self.h, _dp(f), int(is_c), float(h0), float(h1), _dp(g0), _dp(g1), self.stream),
+                  'sgpe_gradient')
+        return [g0, g1]
+
     def energy_real_space(self, psi, kl_term=0.0, unwrap='none'):
         """The energy functional on a real-space state (B, 2, ny, nx) already on the device; also valid on line
         plans (meshes beyond 4096 points per line)."""

@@ -211,11 +211,21 @@ def norm(psi, vol_elem, atom_num, pop_frac=None):
 
 # ----------------------------------------------------------------------------- host-side analysis (NumPy, as in the reference)
 def grad_comp(psi_comp, delta_r):
-    """tensor_tools.py:331-350."""
+    """tensor_tools.py:331-350.  NumPy arrays go to np.gradient as in the reference.  Beyond the reference (which raises
+    for tensors, :343-345), a CUDA tensor is differentiated on the device (``sgpe_gradient``: the same stencils) and
+    the two derivatives stay there."""
     if isinstance(psi_comp, np.ndarray):
         return np.gradient(psi_comp, *np.array(delta_r))
-    raise NotImplementedError("Spatial gradients for tensors are not implemented (reference :343-345); "
-                              "the fused energy kernel (TensorPropagator.eng_expect) covers the propagator's use.")
+    if isinstance(psi_comp, torch.Tensor):
+        if not psi_comp.is_cuda:
+            raise RuntimeError("spinor_gpe_b200 computes on CUDA tensors only (no CPU fallback)")
+        if psi_comp.dim() != 2:
+            raise ValueError("grad_comp takes one (Ny, Nx) component")
+        h0, h1 = (float(d) for d in np.array(delta_r))
+        cdtype = torch.complex64 if psi_comp.dtype in (torch.complex64, torch.float32) else torch.complex128
+        ny, nx = psi_comp.shape
+        return _cached_plan(nx, ny, cdtype, psi_comp.device).gradient(psi_comp, h0, h1)
+    raise TypeError(f"`psi_comp` is of type {type(psi_comp)}")
 
 
 def grad(psi, delta_r):

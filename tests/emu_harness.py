@@ -174,6 +174,14 @@ class EmuPlan:
         self._chk(self.lib.sgpe_kinetic_spectral(self.h, _ptr(a), _ptr(out), None), 'kinetic_spectral')
         return out
 
+    def gradient(self, field, h0, h1):
+        is_c = np.iscomplexobj(field)
+        rd = np.float64 if self.cdtype == np.complex128 else np.float32
+        f = np.ascontiguousarray(field, dtype=self.cdtype if is_c else rd)
+        g0, g1 = np.empty_like(f), np.empty_like(f)
+        self._chk(self.lib.sgpe_gradient(self.h, _ptr(f), int(is_c), float(h0), float(h1), _ptr(g0), _ptr(g1), None), 'gradient')
+        return [g0, g1]
+
     def energy(self, psik=None, kl_term=0.0, unwrap=0):
         a = self._state(psik) if psik is not None else None
         out = np.zeros((self.batch, 4))

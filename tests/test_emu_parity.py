@@ -219,6 +219,20 @@ def test_emulated_spectral_kinetic_energy(separable):
     pl.close()
 
 
+@pytest.mark.parametrize('shape', [(32, 64), (2, 32), (96, 80)])
+def test_emulated_gradient(shape):
+    """sgpe_gradient = np.gradient(f, h0, h1) (ttools.grad_comp, tensor_tools.py:331-350) for real and complex fields."""
+    ny, nx = shape
+    rng = np.random.default_rng(ny * 7 + nx)
+    pl = EmuPlan(nx, ny)
+    for f in (rng.standard_normal(shape), rng.standard_normal(shape) + 1j * rng.standard_normal(shape)):
+        got = pl.gradient(f, 0.37, 1.9)
+        want = np.gradient(f, 0.37, 1.9)
+        for g, w in zip(got, want):
+            np.testing.assert_allclose(g, w, rtol=1e-13, atol=1e-13)
+    pl.close()
+
+
 @pytest.mark.parametrize('case,run', [('nocoupl_64', 0), ('cgrad_64', 0), ('cgrad_64', 1)])
 @pytest.mark.parametrize('separable', [False, True])
 def test_emulated_energy_tracking(case, run, separable):

@@ -125,6 +125,34 @@ def test_tensor_tools_vectors_on_gpu():
         np.testing.assert_allclose(tt.calc_pops(psi, 0.125), z[f'{tag}_pops'], rtol=1e-12)
 
 
+def test_gradients_and_phase_of_cuda_tensors():
+    """ttools.grad / grad_sq / phase on CUDA tensors (the reference raises for tensors, tensor_tools.py:343-345, 533-536):
+    the device stencils of sgpe_gradient against np.gradient on the same data, NumPy inputs untouched."""
+    from spinor_gpe_b200 import tensor_tools as tt
+    rng = np.random.default_rng(5)
+    for shape, dr in (((64, 128), (0.25, 0.5)), ((2048, 256), (0.01, 0.02)), ((30, 50), (1.0, 3.0))):
+        psi = [rng.standard_normal(shape) + 1j * rng.standard_normal(shape) for _ in range(2)]
+        want = tt.grad(psi, dr)                                  # NumPy branch = the reference's
+        got = tt.grad([torch.as_tensor(p).cuda() for p in psi], dr)
+        for gc, wc in zip(got, want):
+            for g, w in zip(gc, wc):
+                assert g.is_cuda and rel(g.cpu().numpy(), w) < 1e-14
+        dens = [np.abs(p) ** 2 for p in psi]
+        got_sq = tt.grad_sq([torch.as_tensor(np.sqrt(d)).cuda() for d in dens], dr)
+        want_sq = tt.grad_sq([np.sqrt(d) for d in dens], dr)
+        for g, w in zip(got_sq, want_sq):
+            assert rel(g.cpu().numpy(), w) < 1e-13
+        ph = tt.phase([torch.as_tensor(p).cuda() for p in psi], uwrap=False, dens=[torch.as_tensor(d).cuda() for d in dens])
+        ph_want = tt.phase(psi, uwrap=False, dens=dens)
+        for g, w in zip(ph, ph_want):
+            np.testing.assert_allclose(g.cpu().numpy(), w, rtol=0, atol=1e-15)
+    f32 = torch.as_tensor(rng.standard_normal((64, 64)).astype(np.float32)).cuda()
+    g32 = tt.grad_comp(f32, (0.5, 0.5))
+    assert g32[0].dtype == torch.float32 and rel(g32[1].cpu().numpy(), np.gradient(f32.cpu().numpy(), 0.5, 0.5)[1]) < 1e-6
+    with pytest.raises(RuntimeError):
+        tt.grad_comp(torch.zeros(8, 8), (1, 1))                  # no CPU fallback for tensors
+
+
 def test_reference_fft_invariants_on_gpu():
     """Port of the reference's own tests (spinor_gpe/tests/fft_func_tests.py:27-472): all-ones grids of
     128..1024 points, delta_r=(1,1): round trip, 1-D x 1-D == 2-D, Parseval with vol_elem 4 pi^2 / N."""
