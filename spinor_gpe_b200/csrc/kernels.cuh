@@ -125,6 +125,12 @@ SGPE_DI double sgpe_atan2(double y, double x) {
     return copysign(a, y);
 }
 
+// |x|^2 as a double for the norm sums: complex128 in double; complex64 squared in single precision (two FP32 operations
+// and one conversion instead of two conversions and two FP64 operations per element - the FP64 pipe of the B200 has a
+// quarter of the FP32 lanes) and ACCUMULATED in double: the sum over the mesh keeps its 1e-7 / sqrt(points) accuracy.
+SGPE_DI double abs_sq(double2 x) { return x.x * x.x + x.y * x.y; }
+SGPE_DI double abs_sq(float2 x) { return (double)fmaf(x.x, x.x, x.y * x.y); }
+
 // exp(-i * e * tau), tau = (tr, ti):  real time tau = (dt, 0);  imaginary time tau = (0, -dt)
 template <int TM, typename T, typename C> SGPE_DI C evo(double e, double tr, double ti) {
     C r;
@@ -300,12 +306,12 @@ __global__ void __launch_bounds__(G * W * N / E, (G * W * N / E <= 256) ? 2 : 1)
                 C x = v[0][m];
                 if (a.has_a) {
                     x = mul_factor<TM>(x, evo<TM, T, C>(e[m], a.ka_re, a.ka_im));
-                    acc[0] += (double)x.x * x.x + (double)x.y * x.y;
+                    acc[0] += abs_sq(x);
                     if (!FAST && a.aux != nullptr) SGPE_ST_STREAM(&a.aux[off + (long long)(j + m * NT) * a.nx], x);
                 }
                 if (a.has_b) {
                     x = mul_factor<TM>(x, evo<TM, T, C>(e[m], a.kb_re, a.kb_im));
-                    acc[1] += (double)x.x * x.x + (double)x.y * x.y;
+                    acc[1] += abs_sq(x);
                 }
                 v[0][m] = x;
             }
@@ -321,13 +327,13 @@ __global__ void __launch_bounds__(G * W * N / E, (G * W * N / E <= 256) ? 2 : 1)
                 C x = v[0][m];
                 if (a.has_a) {
                     x = mul_factor<TM>(x, combine_factor<TM>(fxa, __ldg(&a.ya[oy + m * NT])));
-                    acc[0] += (double)x.x * x.x + (double)x.y * x.y;
+                    acc[0] += abs_sq(x);
                     if ((FAST == 2) || (!FAST && a.aux != nullptr))
                         SGPE_ST_STREAM(&a.aux[off + (long long)(j + m * NT) * a.nx], x);
                 }
                 if (a.has_b) {
                     x = mul_factor<TM>(x, combine_factor<TM>(fxb, __ldg(&a.yb[oy + m * NT])));
-                    acc[1] += (double)x.x * x.x + (double)x.y * x.y;
+                    acc[1] += abs_sq(x);
                 }
                 v[0][m] = x;
             }
@@ -436,12 +442,12 @@ SGPE_DI void k_factors(C (&v)[E], C fxa, C fxb, const C* __restrict__ ya, const 
             C x = v[m];
             if (HAS_A) {
                 x = mul_factor<TM>(x, combine_factor<TM>(fxa, fa[q]));
-                acc[0] += (double)x.x * x.x + (double)x.y * x.y;
+                acc[0] += abs_sq(x);
                 if (AUX) SGPE_ST_STREAM(&aux[(long long)m * aux_stride], x);
             }
             if (HAS_B) {
                 x = mul_factor<TM>(x, combine_factor<TM>(fxb, fb[q]));
-                acc[1] += (double)x.x * x.x + (double)x.y * x.y;
+                acc[1] += abs_sq(x);
             }
             v[m] = x;
         }
@@ -460,12 +466,12 @@ SGPE_DI void k_factors_smem_imag(C (&v)[E], T fxa, T fxb, const T* ya, const T* 
         C x = v[m];
         if (HAS_A) {
             x = cscale(x, fxa * ya[m * NT]);
-            acc[0] += (double)x.x * x.x + (double)x.y * x.y;
+            acc[0] += abs_sq(x);
             if (AUX) SGPE_ST_STREAM(&aux[(long long)m * aux_stride], x);
         }
         if (HAS_B) {
             x = cscale(x, fxb * yb[m * NT]);
-            acc[1] += (double)x.x * x.x + (double)x.y * x.y;
+            acc[1] += abs_sq(x);
         }
         v[m] = x;
     }
@@ -489,12 +495,12 @@ SGPE_DI void k_factors_dense(C (&v)[E], const double* __restrict__ kin, long lon
             C x = v[m];
             if (HAS_A) {
                 x = mul_factor<TM>(x, evo<TM, T, C>(e[q], ka_re, ka_im));
-                acc[0] += (double)x.x * x.x + (double)x.y * x.y;
+                acc[0] += abs_sq(x);
                 if (AUX) SGPE_ST_STREAM(&aux[(long long)m * aux_stride], x);
             }
             if (HAS_B) {
                 x = mul_factor<TM>(x, evo<TM, T, C>(e[q], kb_re, kb_im));
-                acc[1] += (double)x.x * x.x + (double)x.y * x.y;
+                acc[1] += abs_sq(x);
             }
             v[m] = x;
         }
@@ -516,8 +522,13 @@ SGPE_DI void k_factors_dense(C (&v)[E], const double* __restrict__ kin, long lon
 //               L1 as in the one-tile-per-CTA kernel).
 // The partial sums of a tile are stored right away, the ticket (fence + atomic) is taken ONCE per CTA after its last
 // tile; the CTA that completes the count folds the partials in a fixed order as before.
+// (resident CTAs asked of the compiler: complex64 tiles of half the width are meant to run two to an SM - 512 threads at
+// 64 registers; without the bound ptxas takes 128 and only one fits.  SGPE_F32_COL_BLOCKS = 2 asks for the two.)
+#ifndef SGPE_F32_COL_BLOCKS
+#define SGPE_F32_COL_BLOCKS 1
+#endif
 template <typename T, int N, int E, int W, int TM, int XSPLIT, int TWS, int KM = 1>
-__global__ void __launch_bounds__(W * N / E, (W * N / E <= 256) ? 2 : 1)
+__global__ void __launch_bounds__(W * N / E, (W * N / E <= 256 || (SGPE_F32_COL_BLOCKS == 2 && sizeof(T) == 4 && W * N / E <= 512 && W * N * 2 * sizeof(T) <= 64 * 1024)) ? 2 : 1)
 col_pass_p(const SGPE_GRID_CONSTANT SgpeTileMap tmap, ColArgs<T> a) {
     typedef typename cx_of<T>::type C;
     constexpr int NT = N / E;
@@ -1372,13 +1383,13 @@ __global__ void __launch_bounds__(RPC * N / E, (RPC * N / E <= 256) ? 2 : 1) kli
                     const C f = (a.kin_mode == 0) ? evo<TM, T, C>(__ldg(&kin[off0 + pos]), a.ka_re, a.ka_im)
                                                   : combine_factor<TM>(la, __ldg(&a.pa[pbase + pos]));
                     x = mul_factor<TM>(x, f);
-                    acc[2 * comp] += (double)x.x * x.x + (double)x.y * x.y;
+                    acc[2 * comp] += abs_sq(x);
                 }
                 if (a.has_b) {
                     const C f = (a.kin_mode == 0) ? evo<TM, T, C>(__ldg(&kin[off0 + pos]), a.kb_re, a.kb_im)
                                                   : combine_factor<TM>(lb, __ldg(&a.pb[pbase + pos]));
                     x = mul_factor<TM>(x, f);
-                    acc[2 * comp + 1] += (double)x.x * x.x + (double)x.y * x.y;
+                    acc[2 * comp + 1] += abs_sq(x);
                 }
                 v[comp][m] = x;
             }
@@ -1635,14 +1646,14 @@ __global__ void __launch_bounds__(W * N / E) kcol_pass(KColArgs<T> a) {
                     ? evo<TM, T, C>(__ldg(&kin[((long long)g * N + pos) * a.inner + col]), a.ka_re, a.ka_im)
                     : combine_factor<TM>(la, __ldg(&a.pa[pbase + pos]));
                 x = mul_factor<TM>(x, f);
-                acc[0] += (double)x.x * x.x + (double)x.y * x.y;
+                acc[0] += abs_sq(x);
             }
             if (a.has_b) {
                 const C f = (a.kin_mode == 0)
                     ? evo<TM, T, C>(__ldg(&kin[((long long)g * N + pos) * a.inner + col]), a.kb_re, a.kb_im)
                     : combine_factor<TM>(lb, __ldg(&a.pb[pbase + pos]));
                 x = mul_factor<TM>(x, f);
-                acc[1] += (double)x.x * x.x + (double)x.y * x.y;
+                acc[1] += abs_sq(x);
             }
             v[0][m] = x;
         }

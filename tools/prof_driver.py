@@ -15,7 +15,8 @@ mesh = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 mode = sys.argv[3] if len(sys.argv) > 3 else 'imag'
 ps = bench.build_problem(mesh)
-pl = Plan(mesh, mesh, 1)
+cdtype = torch.complex64 if os.environ.get('SGPE_PREC', 'c128') == 'c64' else torch.complex128
+pl = Plan(mesh, mesh, 1, cdtype, torch.device('cuda', 0))
 pl.set_grid(ps.space['dr'][0], ps.space['dr'][1], ps.space['dv_r'], ps.space['dv_k'], ps.atom_num)
 pl.set_interactions(ps.g_sc['uu'], ps.g_sc['dd'], ps.g_sc['ud'])
 pl.set_kinetic(ps.kin_eng_spin[0], ps.kin_eng_spin[1])
@@ -31,7 +32,7 @@ for kv in filter(None, os.environ.get('SGPE_OPTS', '').split(',')):      # e.g. 
     pl.set_option(k, int(v))
 pl.set_coupling(_capi.SGPE_COUPLING_NONE)
 pl.set_time(mode, 1 / 50 if mode == 'imag' else 1 / 5000)
-pl.load(np.array(ps.psik)[None])
+pl.load(np.array(ps.psik)[None].astype(np.complex64 if cdtype == torch.complex64 else np.complex128))
 pops = torch.zeros((1, steps, 2), dtype=torch.float64, device='cuda')
 pl.full_steps(steps, pops)
 torch.cuda.synchronize()
