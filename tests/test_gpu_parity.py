@@ -230,6 +230,15 @@ def test_headline_config_against_oracle():
     assert abs(res.pops['vals'][-1].sum() / ps.atom_num - 1) < TOL_SCALAR
     np.testing.assert_allclose(res.eng_final[2:], want['energy'][2:], rtol=TOL_SCALAR)
     np.testing.assert_allclose(res.eng_final, want['energy'], rtol=TOL_SCALAR)
+    # the energy of every step on the same configuration (the "energy tracking" of configs[2]): six steps, i.e. the polar
+    # side chain (persistent inverse column pass, polar row pass, shuffle stencils) launched normally AND replayed from the
+    # captured graph; step 3 against the oracle, the last step against the stand-alone evaluation of the final state
+    ps3 = bench.build_problem(2048)
+    res3, prop3 = ps3.imaginary(1 / 50, 6, 'cuda', unwrap='none', track_energy=True)
+    np.testing.assert_allclose(res3.eng_history[2], want['energy'], rtol=TOL_SCALAR)
+    np.testing.assert_allclose(res3.pops['vals'][:3], want['pops_vals'], rtol=TOL_SCALAR)
+    np.testing.assert_allclose(res3.eng_history[-1], res3.eng_final, rtol=TOL_SCALAR)
+    assert np.all(np.diff(res3.eng_history[:, 0]) < 0)          # imaginary time: the energy goes down every step
     # the general (dense-operator) kernels on the same configuration
     ps2 = bench.build_problem(2048)
     res2, prop2 = ps2.imaginary(1 / 50, n, 'cuda', unwrap='none', separable=False)
