@@ -33,11 +33,14 @@ for mesh, mode, prec, opts in cases:
     ps = build(mesh)
     for sep in ((True, False) if opts.get('col_kernel', 2) == 2 else (True,)):
         prop = TensorPropagator(ps, 1 / 2000 if mode == 'real' else 1 / 50, 6, 'cuda', time=mode, precision=prec,
-                                separable=sep, unwrap='none', track_energy=(prec == 'c128'))
+                                separable=sep, unwrap='none', track_energy=True)
         for k, v in opts.items():
             prop._plan.set_option(k, v)
         res = prop.prop_loop(6)
         print(mesh, mode, prec, opts, 'separable' if sep else 'dense', res.pops['vals'][-1], res.eng_final[0], flush=True)
+from spinor_gpe_b200 import tensor_tools as tt  # noqa: E402
+g = tt.grad([torch.as_tensor(np.asarray(p)).cuda() for p in build((96, 80)).psi], (0.1, 0.2))
+print('gradient', float(g[0][0].abs().sum()), flush=True)
 ps = build((128, 64))
 prop = TensorPropagator(ps, 1 / 50, 2, 'cuda', time='imag')
 print('unwrapped energy', prop.prop_loop(2).eng_final, flush=True)
