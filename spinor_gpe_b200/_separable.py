@@ -20,27 +20,30 @@ def split_separable(grids, rtol=RTOL):
     gx carries the rest: the factor tables exp(-gx tau), exp(-gy tau) then stay as well scaled as the
     operator itself (anchoring at a corner would make one table overflow in imaginary time on fine meshes,
     where k_max^2 tau / 2 exceeds 709)."""
-    g = np.asarray(grids, dtype=np.float64)
-    gx = np.empty((g.shape[0], g.shape[2]))
-    gy = np.empty((g.shape[0], g.shape[1]))
-    for c in range(g.shape[0]):
-        col = g[c, :, 0]
+    # (a list of per-component grids is taken as it is: stacking two 2048^2 grids costs more than the whole check)
+    g = [np.asarray(c, dtype=np.float64) for c in grids]
+    nc, (ny, nx) = len(g), g[0].shape
+    gx = np.empty((nc, nx))
+    gy = np.empty((nc, ny))
+    for c in range(nc):
+        col = g[c][:, 0]
         i0 = int(np.argmin(col))
         gy[c] = col - col[i0]
-        gx[c] = g[c, i0, :]
+        gx[c] = g[c][i0, :]
     # a cheap look at a coarse sub-grid rejects most non-separable grids before the full check
-    sy, sx = max(1, g.shape[1] // 64), max(1, g.shape[2] // 64)
-    coarse = g[:, ::sy, ::sx]
-    scale = max(float(np.abs(coarse).max()), 1e-300)
-    if np.abs(coarse - (gx[:, None, ::sx] + gy[:, ::sy, None])).max() > rtol * scale * 4:
-        return None
+    sy, sx = max(1, ny // 64), max(1, nx // 64)
+    for c in range(nc):
+        coarse = g[c][::sy, ::sx]
+        scale = max(float(np.abs(coarse).max()), 1e-300)
+        if np.abs(coarse - (gx[c, None, ::sx] + gy[c, ::sy, None])).max() > rtol * scale * 4:
+            return None
     # full check in cache-sized row blocks (no full-size temporaries), a few host threads (NumPy releases the GIL)
-    rows = max(1, (1 << 19) // max(1, g.shape[2]))
-    blocks = [(c, r) for c in range(g.shape[0]) for r in range(0, g.shape[1], rows)]
+    rows = max(1, (1 << 19) // max(1, nx))
+    blocks = [(c, r) for c in range(nc) for r in range(0, ny, rows)]
 
     def check(job):
         c, r = job
-        blk = g[c, r:r + rows]
+        blk = g[c][r:r + rows]
         return (float(np.abs(blk - gx[c] - gy[c, r:r + rows, None]).max()), float(np.abs(blk).max()))
 
     if len(blocks) > 4:

@@ -261,8 +261,8 @@ class TensorPropagator:
         self.separable = {'kin': False, 'pot': False}
         ksep = psep = None
         if self._separable_opt:
-            ksep = split_separable(np.stack(self._kin_np))
-            psep = split_separable(np.stack(self._pot_np))
+            ksep = split_separable(self._kin_np)
+            psep = split_separable(self._pot_np)
         # the plan borrows the device pointers of the dense grids: it keeps the tensors alive itself, so rebinding
         # the public attributes (prop.pot_eng_spin = ...) cannot leave it with a dangling pointer
         if ksep is not None:
