@@ -165,11 +165,18 @@ int sgpe_energy_real_space(sgpe_plan* p, const void* psi_dev, int unwrap_mode, d
  *             atan2(im, re), np.angle at :529), kind 1 = float64 wrapped angles
  *   mask    : != 0 (kind 0 only) zeroes the result where |psi|^2 < 1e-6 * max |psi|^2 of the plane (:538)
  *   out_dev : nplanes x [ny][nx] float64 = wrapped phase + 2 pi * integer
- * Angles, per-pixel reliabilities, edge keys, the radix sort of the edges and the final pass run on the device; the
- * region merging, sequential by construction, runs on the host between two copies (4 B per edge down, 4 B per pixel
- * up), one host thread per plane.  Border pixels get the fixed reliability value 9999999 (scikit-image adds rand()),
- * equal keys keep edge order (horizontal edges row by row, then vertical).  Synchronises st.
- * Option "unwrap_sort" = 1 (sgpe_set_option) sorts the edges on the host instead (same order, for cross-checks). */
+ * Everything but a short tail runs on the device: angles, per-pixel reliabilities, edge keys, the radix sort of the
+ * edges, the region merging (the minimum spanning tree of the pixel grid under the edge ranks with the relative
+ * multiples of 2 pi along it — Boruvka rounds over an offset-carrying union-find — then the one pixel group whose
+ * values the published merge rules never move, found level by level with a bisection over the rank threshold and a
+ * lock-free union-find; groups of at most "unwrap_tail" = 16384 tree edges finish on the host) and the final pass.
+ * The integer field equals the sequential edge-by-edge merging's bit for bit, global offset included.  Border pixels
+ * get the fixed reliability value 9999999 (scikit-image adds rand()), equal keys keep edge order (horizontal edges
+ * row by row, then vertical).  Synchronises st.
+ * Options (sgpe_set_option), all for cross-checks: "unwrap_sort" = 1 sorts the edges on the host (same order);
+ * "unwrap_merge" = 1 runs the whole merging on the host (sequential offset-carrying union-find over all edges, one
+ * thread per plane); "unwrap_anchor" = 0 finds the surviving group by a sequential host pass over the tree edges
+ * (default for more than 4 planes or fewer than 65536 pixels: one plane per core), 1 by the device bisection. */
 int sgpe_unwrap_phase(sgpe_plan* p, const void* in_dev, int kind, int nplanes, int mask, double* out_dev,
                       sgpe_stream st);
 

@@ -22,6 +22,7 @@
 
 #ifndef SGPE_EMU
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
 #endif
 
 #include "../../include/sgpe.h"
@@ -97,9 +98,13 @@ struct sgpe_plan {
     struct TileMap { const void* ptr = nullptr; int w = 0; SgpeTileMap* map = nullptr; };
     std::vector<TileMap> tile_maps;   // column-tile descriptors of the buffers the persistent pass has run on
     int unwrap_sort = 0;           // edge sort of the phase unwrapping: 0 device radix sort, 1 host (option "unwrap_sort")
+    int unwrap_merge = 0;          // region merging: 0 spanning tree on the device, 1 all on the host
+    int unwrap_tail = 16384;       // device anchor search: groups of at most this many tree edges finish on the host (option "unwrap_tail")
+    int unwrap_anchor = -1;        // pixel group that keeps its values: 0 host pass over the tree edges, 1 device bisection, -1 by plane count
     struct UnwrapCache {           // scratch of the phase unwrapping, kept between evaluations (unwrap_scratch)
         double* rel = nullptr; unsigned long long* keys = nullptr; unsigned long long* keys_sorted = nullptr;
         unsigned* vals = nullptr; unsigned* vals_sorted = nullptr; void* tmp = nullptr; size_t tmp_bytes = 0;
+        unsigned* counters = nullptr;   // [0] groups hooked in a Boruvka round, [1] tree edges selected, [8..15] anchor search
         uint32_t* order_host = nullptr; int32_t* inc_host = nullptr;
         int nplanes = 0; size_t plane = 0; bool device_sort = false;
     } unwrap;
@@ -832,30 +837,41 @@ static void host_pinned_free(void* q) { free(q); }
 
 void unwrap_release(sgpe_plan::UnwrapCache& w) {
     cudaFree(w.rel); cudaFree(w.keys); cudaFree(w.keys_sorted); cudaFree(w.vals); cudaFree(w.vals_sorted); cudaFree(w.tmp);
+    cudaFree(w.counters);
     host_pinned_free(w.order_host); host_pinned_free(w.inc_host);
     w = sgpe_plan::UnwrapCache();
 }
 
-// the scratch of the phase unwrapping lives with the plan (device buffers, the sort's work space, page-locked staging
-// for the edge order going down and the increments coming up): nothing is allocated per evaluation
+#ifndef SGPE_EMU
+struct UnwrapIsTreeEdge { __device__ bool operator()(unsigned x) const { return x != sgpe::kUnwrapNoEdge; } };
+#endif
+
+// the scratch of the phase unwrapping lives with the plan (device buffers, the sort's and the selection's work space,
+// host staging for the edge order going down and the increments coming up): nothing is allocated per evaluation.
+// The device-side merging reuses the sort's buffers once the order is known: keys -> forest nodes, then the tree-edge
+// list; keys_sorted -> pending hooks, then the flagged candidates; vals -> rank of every edge; rel -> best edge per group.
 static int unwrap_scratch(sgpe_plan* p, int nplanes, size_t plane, size_t n_edges, bool device_sort, cudaStream_t st) {
     sgpe_plan::UnwrapCache& w = p->unwrap;
     if (w.nplanes >= nplanes && w.plane == plane && w.device_sort == device_sort && w.rel) return 0;
     unwrap_release(w);
     if (cudaMalloc((void**)&w.rel, plane * sizeof(double)) != cudaSuccess ||
         cudaMalloc((void**)&w.keys, n_edges * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMalloc((void**)&w.vals, n_edges * sizeof(unsigned)) != cudaSuccess)
+        cudaMalloc((void**)&w.vals, n_edges * sizeof(unsigned)) != cudaSuccess ||
+        cudaMalloc((void**)&w.keys_sorted, n_edges * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc((void**)&w.vals_sorted, n_edges * sizeof(unsigned)) != cudaSuccess ||
+        cudaMalloc((void**)&w.counters, 16 * sizeof(unsigned)) != cudaSuccess)
         return fail(SGPE_ENOMEM, "unwrap scratch allocation failed");
 #ifndef SGPE_EMU
-    if (device_sort) {
-        if (cudaMalloc((void**)&w.keys_sorted, n_edges * sizeof(unsigned long long)) != cudaSuccess ||
-            cudaMalloc((void**)&w.vals_sorted, n_edges * sizeof(unsigned)) != cudaSuccess)
-            return fail(SGPE_ENOMEM, "unwrap scratch allocation failed");
+    size_t select_bytes = 0;
+    SGPE_CUDA(cub::DeviceSelect::If(nullptr, select_bytes, w.vals, w.vals_sorted, w.counters, (long long)n_edges,
+                                    UnwrapIsTreeEdge(), st));
+    w.tmp_bytes = 0;
+    if (device_sort)
         SGPE_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, w.tmp_bytes, w.keys, w.keys_sorted, w.vals, w.vals_sorted,
                                                   (long long)n_edges, 0, 64, st));
-        if (cudaMalloc(&w.tmp, w.tmp_bytes ? w.tmp_bytes : 1) != cudaSuccess)
-            return fail(SGPE_ENOMEM, "unwrap scratch allocation failed");
-    }
+    w.tmp_bytes = std::max(w.tmp_bytes, select_bytes);
+    if (cudaMalloc(&w.tmp, w.tmp_bytes ? w.tmp_bytes : 1) != cudaSuccess)
+        return fail(SGPE_ENOMEM, "unwrap scratch allocation failed");
 #else
     (void)st;
 #endif
@@ -866,14 +882,151 @@ static int unwrap_scratch(sgpe_plan* p, int nplanes, size_t plane, size_t n_edge
     return 0;
 }
 
+// The pixel whose group never moved: Kruskal over the spanning tree's edges in rank order with the published rules for
+// who absorbs whom (see UnwrapForest above), sizes only — the absorbed root hangs below the surviving one, so the
+// root of the final tree IS a pixel of the group that kept its values throughout.  tree[k] = first pixel of the k-th
+// tree edge, bit 31 set for a vertical edge (unwrap_tree_edges_pass).
+int64_t unwrap_anchor(int nx, const uint32_t* tree, size_t n_tree, size_t plane) {
+    struct Node { int32_t parent, size; };
+    std::vector<Node> nd(plane);
+    for (size_t i = 0; i < plane; i++) nd[i] = {(int32_t)i, 1};
+    Node* n = nd.data();
+    auto find = [n](int32_t x) {
+        while (n[x].parent != x) { const int32_t g = n[n[x].parent].parent; n[x].parent = g; x = g; }   // path halving
+        return x;
+    };
+    constexpr size_t kAhead = 24;
+    for (size_t k = 0; k < n_tree; k++) {
+        if (k + kAhead < n_tree) {
+            const uint32_t t = tree[k + kAhead];
+            const uint32_t q = t & 0x7fffffffu;
+            __builtin_prefetch(&n[q]);
+            if (t >> 31) __builtin_prefetch(&n[q + (uint32_t)nx]);
+        }
+        const uint32_t t = tree[k];
+        const int32_t p1 = (int32_t)(t & 0x7fffffffu), p2 = p1 + ((t >> 31) ? nx : 1);
+        const int32_t r1 = find(p1), r2 = find(p2);
+        if (r1 == r2) continue;                                  // (cannot happen for tree edges)
+        const int32_t s1 = n[r1].size, s2 = n[r2].size;
+        const bool second_joins = (s2 == 1) || (s1 != 1 && s1 > s2);
+        if (second_joins) { n[r2].parent = r1; n[r1].size = s1 + s2; }
+        else              { n[r1].parent = r2; n[r2].size = s1 + s2; }
+    }
+    return find(0);
+}
+
+// The same pixel found on the device (unwrap.cuh, "the pixel group that never moves"): per level a bisection over the
+// rank threshold with a lock-free union-find, until the group is small enough for the host pass above.  The tree-edge
+// list is in w.keys (as left by the selection); forests, pixel lists and edge lists live in the sort's buffers.
+static int unwrap_anchor_device(sgpe_plan* p, int nx, size_t plane, cudaStream_t st, int64_t* anchor, int* levels, int* probes) {
+    sgpe_plan::UnwrapCache& w = p->unwrap;
+    unsigned* tree = reinterpret_cast<unsigned*>(w.keys);
+    unsigned* cnt = tree + plane;
+    unsigned* snap = reinterpret_cast<unsigned*>(w.rel);
+    unsigned* work = snap + plane;
+    unsigned* vl[2] = {w.vals, w.vals + plane};
+    sgpe::UnwrapEdge* el[2] = {reinterpret_cast<sgpe::UnwrapEdge*>(w.keys_sorted), reinterpret_cast<sgpe::UnwrapEdge*>(w.keys_sorted) + plane};
+    unsigned* result = w.counters + 8;
+    unsigned host_result[8];
+    const dim3 block(256);
+    long long nv = (long long)plane, ne = nv - 1, bound = ne;
+    int cur = 0;
+    SGPE_LAUNCH((sgpe::unwrap_level0_pass), dim3(unwrap_blocks(nv)), block, 0, st, tree, nv, vl[0], el[0]);
+    p->launches++;
+    while (ne > (long long)p->unwrap_tail) {
+        const dim3 grid_v(unwrap_blocks(nv)), grid_e(unwrap_blocks(ne));
+        SGPE_LAUNCH((sgpe::unwrap_level_reset_pass), grid_v, block, 0, st, vl[cur], nv, (const unsigned*)nullptr, snap, cnt);
+        p->launches++;
+        long long lo = -1, hi = bound - 1;          // no group of more than nv / 2 pixels with the edges <= lo, one with those <= hi
+        while (hi - lo > 1) {
+            const long long mid = lo + (hi - lo) / 2;
+            SGPE_CUDA(cudaMemsetAsync(result, 0, sizeof(unsigned), st));
+            SGPE_LAUNCH((sgpe::unwrap_level_reset_pass), grid_v, block, 0, st, vl[cur], nv, (const unsigned*)snap, work, cnt);
+            SGPE_LAUNCH((sgpe::unwrap_level_union_pass), grid_e, block, 0, st, el[cur], ne, lo, mid, nx, work);
+            SGPE_LAUNCH((sgpe::unwrap_level_count_pass), grid_v, block, 256 * sizeof(unsigned), st, vl[cur], nv, work, cnt, result);
+            p->launches += 3;
+            SGPE_CUDA(cudaMemcpyAsync(host_result, result, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            SGPE_CUDA(cudaStreamSynchronize(st));
+            (*probes)++;
+            if (2ll * host_result[0] > nv) hi = mid;
+            else { lo = mid; std::swap(snap, work); }
+        }
+        // edge `hi` creates the majority group; snap holds the forest just before it
+        SGPE_CUDA(cudaMemsetAsync(result, 0, 8 * sizeof(unsigned), st));
+        SGPE_LAUNCH((sgpe::unwrap_level_reset_pass), grid_v, block, 0, st, vl[cur], nv, (const unsigned*)snap, snap, cnt);
+        SGPE_LAUNCH((sgpe::unwrap_level_count_pass), grid_v, block, 256 * sizeof(unsigned), st, vl[cur], nv, snap, cnt, result);
+        SGPE_LAUNCH((sgpe::unwrap_level_sides_pass), grid_e, block, 0, st, el[cur], ne, (unsigned)hi, nx, snap, cnt, result);
+        p->launches += 3;
+        SGPE_CUDA(cudaMemcpyAsync(host_result, result, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        SGPE_CUDA(cudaStreamSynchronize(st));
+        const long long s1 = host_result[2], s2 = host_result[4];
+        if (s1 < 1 || s2 < 1 || 2 * (s1 + s2) <= nv || 2 * s1 > nv || 2 * s2 > nv)
+            return fail(SGPE_ECUDA, "phase unwrapping: anchor bisection lost its edge (internal error)");
+        const bool second_joins = (s2 == 1) || (s1 != 1 && s1 > s2);
+        const unsigned keep = second_joins ? host_result[1] : host_result[3];
+        const long long keep_size = second_joins ? s1 : s2;
+        SGPE_LAUNCH((sgpe::unwrap_level_select_pass), dim3(unwrap_blocks(nv)), block, 0, st, vl[cur], nv, el[cur], ne, (unsigned)hi, keep,
+                    snap, vl[1 - cur], el[1 - cur], result);
+        p->launches++;
+        SGPE_CUDA(cudaMemcpyAsync(host_result, result, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        SGPE_CUDA(cudaStreamSynchronize(st));
+        if ((long long)host_result[5] != keep_size || (long long)host_result[6] != keep_size - 1)
+            return fail(SGPE_ECUDA, "phase unwrapping: anchor bisection selected a wrong group (internal error)");
+        nv = keep_size; ne = nv - 1; bound = hi; cur ^= 1;
+        (*levels)++;
+    }
+    if (ne == 0) {
+        unsigned v = 0;
+        SGPE_CUDA(cudaMemcpyAsync(&v, vl[cur], sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        SGPE_CUDA(cudaStreamSynchronize(st));
+        *anchor = (int64_t)v;
+        return 0;
+    }
+    // the rest on the host: the group's tree edges in rank order, pixels renumbered densely
+    std::vector<sgpe::UnwrapEdge> edges((size_t)ne);
+    SGPE_CUDA(cudaMemcpyAsync(edges.data(), el[cur], (size_t)ne * sizeof(sgpe::UnwrapEdge), cudaMemcpyDeviceToHost, st));
+    SGPE_CUDA(cudaStreamSynchronize(st));
+    std::sort(edges.begin(), edges.end(), [](const sgpe::UnwrapEdge& a, const sgpe::UnwrapEdge& b) { return a.k < b.k; });
+    std::vector<uint32_t> pixels;
+    pixels.reserve(2 * (size_t)ne);
+    for (const auto& e : edges) {
+        const uint32_t p1 = e.t & 0x7fffffffu;
+        pixels.push_back(p1);
+        pixels.push_back(p1 + ((e.t >> 31) ? (uint32_t)nx : 1u));
+    }
+    std::sort(pixels.begin(), pixels.end());
+    pixels.erase(std::unique(pixels.begin(), pixels.end()), pixels.end());
+    auto dense = [&pixels](uint32_t v) { return (int32_t)(std::lower_bound(pixels.begin(), pixels.end(), v) - pixels.begin()); };
+    struct Node { int32_t parent, size; };
+    std::vector<Node> nd(pixels.size());
+    for (size_t i = 0; i < nd.size(); i++) nd[i] = {(int32_t)i, 1};
+    auto find = [&nd](int32_t x) { while (nd[x].parent != x) { const int32_t g = nd[nd[x].parent].parent; nd[x].parent = g; x = g; } return x; };
+    for (const auto& e : edges) {
+        const uint32_t p1 = e.t & 0x7fffffffu;
+        const int32_t r1 = find(dense(p1)), r2 = find(dense(p1 + ((e.t >> 31) ? (uint32_t)nx : 1u)));
+        if (r1 == r2) continue;
+        const int32_t s1 = nd[r1].size, s2 = nd[r2].size;
+        const bool second_joins = (s2 == 1) || (s1 != 1 && s1 > s2);
+        if (second_joins) { nd[r2].parent = r1; nd[r1].size = s1 + s2; }
+        else              { nd[r1].parent = r2; nd[r2].size = s1 + s2; }
+    }
+    *anchor = (int64_t)pixels[(size_t)find(0)];
+    return 0;
+}
+
 int unwrap_increments_impl(sgpe_plan* p, const double* phi_dev, int nplanes, int* inc_dev, cudaStream_t st) {
     const int nx = p->nx, ny = p->ny;
     const size_t plane = (size_t)p->plane;
     const size_t n_edges = (size_t)ny * (nx - 1) + (size_t)nx * (ny - 1);
+    if (n_edges >= (1ull << 29)) return fail(SGPE_EINVAL, "phase unwrapping: mesh too large (edge ids are 29 bits)");
     bool device_sort = false;
 #ifndef SGPE_EMU
     device_sort = p->unwrap_sort == 0;
 #endif
+    const bool device_merge = p->unwrap_merge == 0 && plane > 1;
+    // the anchor search on the device handles the planes one after the other; the host pass runs one plane per core
+    const bool device_anchor = device_merge && n_edges >= plane + plane / 2 + 2 &&
+                               (p->unwrap_anchor == 1 || (p->unwrap_anchor < 0 && nplanes <= 4 && plane >= 65536));
     const bool timing = getenv("SGPE_UNWRAP_TIMING") != nullptr;       // dev: phase times on stderr
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now();
@@ -882,17 +1035,18 @@ int unwrap_increments_impl(sgpe_plan* p, const double* phi_dev, int nplanes, int
     if (timing) { cudaStreamSynchronize(st); fprintf(stderr, "unwrap: scratch %.1f ms\n", now() - t_begin); }
     sgpe_plan::UnwrapCache& w = p->unwrap;
     std::vector<unsigned long long> host_keys;
-    // The region merging of a plane (host, sequential) starts as soon as its edge order has arrived and runs beside the
-    // device work of the next plane; the planes are independent.
+    std::vector<int64_t> anchors((size_t)nplanes, 0);
+    // The sequential part of a plane (host) starts as soon as its edges have arrived and runs beside the device work of
+    // the next plane; the planes are independent.
     std::vector<std::thread> pool;
     struct Joiner { std::vector<std::thread>& t; ~Joiner() { for (auto& th : t) if (th.joinable()) th.join(); } } joiner{pool};
     const unsigned max_threads = std::max(1u, std::thread::hardware_concurrency());
+    const dim3 grid_plane(unwrap_blocks((long long)plane)), grid_edges(unwrap_blocks((long long)n_edges)), block(256);
     for (int pl = 0; pl < nplanes; pl++) {
         const double* phi = phi_dev + (size_t)pl * plane;
         uint32_t* order = w.order_host + (size_t)pl * n_edges;
-        SGPE_LAUNCH((sgpe::unwrap_reliab_pass), dim3(unwrap_blocks((long long)plane)), dim3(256), 0, st, phi, nx, ny, w.rel);
-        SGPE_LAUNCH((sgpe::unwrap_edge_pass), dim3(unwrap_blocks((long long)plane)), dim3(256), 0, st, phi, w.rel, nx, ny,
-                    w.keys, w.vals);
+        SGPE_LAUNCH((sgpe::unwrap_reliab_pass), grid_plane, block, 0, st, phi, nx, ny, w.rel);
+        SGPE_LAUNCH((sgpe::unwrap_edge_pass), grid_plane, block, 0, st, phi, w.rel, nx, ny, w.keys, w.vals);
         p->launches += 2;
         SGPE_CUDA(cudaGetLastError());
         if (device_sort) {
@@ -901,8 +1055,10 @@ int unwrap_increments_impl(sgpe_plan* p, const double* phi_dev, int nplanes, int
             SGPE_CUDA(cub::DeviceRadixSort::SortPairs(w.tmp, w.tmp_bytes, w.keys, w.keys_sorted, w.vals, w.vals_sorted,
                                                       (long long)n_edges, 0, 64, st));
             p->launches++;
-            SGPE_CUDA(cudaMemcpyAsync(order, w.vals_sorted, n_edges * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-            SGPE_CUDA(cudaStreamSynchronize(st));
+            if (!device_merge) {
+                SGPE_CUDA(cudaMemcpyAsync(order, w.vals_sorted, n_edges * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+                SGPE_CUDA(cudaStreamSynchronize(st));
+            }
 #endif
         } else {
             host_keys.resize(n_edges);
@@ -915,24 +1071,105 @@ int unwrap_increments_impl(sgpe_plan* p, const double* phi_dev, int nplanes, int
             const unsigned long long* hk = host_keys.data();
             std::sort(perm.begin(), perm.end(), [hk](uint32_t a, uint32_t b) { return hk[a] != hk[b] ? hk[a] < hk[b] : a < b; });
             for (size_t k = 0; k < n_edges; k++) order[k] = vals[perm[k]];
+            if (device_merge)
+                SGPE_CUDA(cudaMemcpyAsync(w.vals_sorted, order, n_edges * sizeof(unsigned), cudaMemcpyHostToDevice, st));
         }
+        if (timing) { cudaStreamSynchronize(st); fprintf(stderr, "unwrap: plane %d order ready at %.1f ms\n", pl, now() - t_begin); }
         int32_t* inc = w.inc_host + (size_t)pl * plane;
-        if (timing) fprintf(stderr, "unwrap: plane %d order on the host at %.1f ms\n", pl, now() - t_begin);
+        if (!device_merge) {
+            if (max_threads > 1 && nplanes > 1) {
+                if (pool.size() >= max_threads) { pool.front().join(); pool.erase(pool.begin()); }
+                pool.emplace_back([=]() {
+                    const double t0 = now();
+                    unwrap_merge(nx, ny, order, n_edges, inc);
+                    if (timing) fprintf(stderr, "unwrap: merge of plane %d %.1f ms\n", pl, now() - t0);
+                });
+            } else {
+                unwrap_merge(nx, ny, order, n_edges, inc);
+            }
+            continue;
+        }
+        // ---- spanning tree and relative increments on the device (unwrap.cuh)
+        unsigned long long* node = w.keys;
+        unsigned long long* pend = w.keys_sorted;
+        unsigned* rank_of = w.vals;
+        unsigned* best = reinterpret_cast<unsigned*>(w.rel);
+        int* raw = inc_dev + (size_t)pl * plane;
+        SGPE_LAUNCH((sgpe::unwrap_rank_pass), grid_edges, block, 0, st, w.vals_sorted, (long long)n_edges, rank_of);
+        SGPE_LAUNCH((sgpe::unwrap_forest_init_pass), grid_plane, block, 0, st, (long long)plane, node, best);
+        p->launches += 2;
+        size_t joined = 0;
+        int rounds = 0;
+        while (joined + 1 < plane) {
+            unsigned hooked = 0;
+            SGPE_CUDA(cudaMemsetAsync(w.counters, 0, sizeof(unsigned), st));
+            SGPE_LAUNCH((sgpe::unwrap_minedge_pass), grid_plane, block, 0, st, node, rank_of, nx, ny, best);
+            SGPE_LAUNCH((sgpe::unwrap_hook_pass), grid_plane, block, 0, st, node, best, w.vals_sorted, nx, ny, pend, w.counters);
+            SGPE_LAUNCH((sgpe::unwrap_adopt_pass), grid_plane, block, 0, st, (long long)plane, pend, node, best);
+            SGPE_LAUNCH((sgpe::unwrap_compress_pass), grid_plane, block, 0, st, (long long)plane, node);
+            p->launches += 4;
+            SGPE_CUDA(cudaMemcpyAsync(&hooked, w.counters, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            SGPE_CUDA(cudaStreamSynchronize(st));
+            rounds++;
+            if (hooked == 0) return fail(SGPE_ECUDA, "phase unwrapping: the spanning tree did not close (internal error)");
+            joined += hooked;
+        }
+        if (joined + 1 != plane) return fail(SGPE_ECUDA, "phase unwrapping: wrong number of tree edges (internal error)");
+        SGPE_LAUNCH((sgpe::unwrap_offsets_pass), grid_plane, block, 0, st, (long long)plane, node, raw);
+        unsigned* cand = reinterpret_cast<unsigned*>(w.keys_sorted);
+        unsigned* tree_dev = reinterpret_cast<unsigned*>(w.keys);
+        SGPE_LAUNCH((sgpe::unwrap_tree_edges_pass), grid_edges, block, 0, st, w.vals_sorted, (long long)n_edges, nx, ny, cand);
+        p->launches += 2;
+        SGPE_CUDA(cudaGetLastError());
+#ifndef SGPE_EMU
+        SGPE_CUDA(cub::DeviceSelect::If(w.tmp, w.tmp_bytes, cand, tree_dev, w.counters + 1, (long long)n_edges,
+                                        UnwrapIsTreeEdge(), st));
+        p->launches++;
+#else
+        { size_t m = 0; for (size_t k = 0; k < n_edges; k++) if (cand[k] != sgpe::kUnwrapNoEdge) tree_dev[m++] = cand[k]; w.counters[1] = (unsigned)m; }
+#endif
+        unsigned n_tree = 0;
+        SGPE_CUDA(cudaMemcpyAsync(&n_tree, w.counters + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        if (!device_anchor)
+            SGPE_CUDA(cudaMemcpyAsync(order, tree_dev, (plane - 1) * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        SGPE_CUDA(cudaStreamSynchronize(st));
+        if ((size_t)n_tree + 1 != plane) return fail(SGPE_ECUDA, "phase unwrapping: tree edge list incomplete (internal error)");
+        if (timing) fprintf(stderr, "unwrap: plane %d tree ready at %.1f ms (%d rounds)\n", pl, now() - t_begin, rounds);
+        if (device_anchor) {
+            int levels = 0, probes = 0;
+            rc = unwrap_anchor_device(p, nx, plane, st, &anchors[(size_t)pl], &levels, &probes);
+            if (rc) return rc;
+            if (timing) fprintf(stderr, "unwrap: plane %d anchor %lld at %.1f ms (%d levels, %d probes)\n", pl,
+                                (long long)anchors[(size_t)pl], now() - t_begin, levels, probes);
+            continue;
+        }
+        int64_t* anchor = &anchors[(size_t)pl];
+        auto work = [=]() {
+            const double t0 = now();
+            *anchor = unwrap_anchor(nx, order, plane - 1, plane);
+            if (timing) fprintf(stderr, "unwrap: anchor pass of plane %d %.1f ms\n", pl, now() - t0);
+        };
         if (max_threads > 1 && nplanes > 1) {
             if (pool.size() >= max_threads) { pool.front().join(); pool.erase(pool.begin()); }
-            pool.emplace_back([=]() {
-                const double t0 = now();
-                unwrap_merge(nx, ny, order, n_edges, inc);
-                if (timing) fprintf(stderr, "unwrap: merge of plane %d %.1f ms\n", pl, now() - t0);
-            });
+            pool.emplace_back(work);
         } else {
-            unwrap_merge(nx, ny, order, n_edges, inc);
+            work();
         }
     }
     for (auto& th : pool) th.join();
     pool.clear();
     if (timing) fprintf(stderr, "unwrap: merged at %.1f ms\n", now() - t_begin);
-    SGPE_CUDA(cudaMemcpyAsync(inc_dev, w.inc_host, (size_t)nplanes * plane * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (!device_merge) {
+        SGPE_CUDA(cudaMemcpyAsync(inc_dev, w.inc_host, (size_t)nplanes * plane * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    } else {
+        for (int pl = 0; pl < nplanes; pl++) {
+            int* raw = inc_dev + (size_t)pl * plane;
+            SGPE_LAUNCH((sgpe::unwrap_anchor_pass), grid_plane, block, 0, st, (long long)plane, (long long)anchors[(size_t)pl], raw);
+            SGPE_LAUNCH((sgpe::unwrap_anchor_zero_pass), dim3(1), dim3(32), 0, st, (long long)anchors[(size_t)pl], raw);
+            p->launches += 2;
+        }
+        SGPE_CUDA(cudaGetLastError());
+    }
     SGPE_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
@@ -1339,6 +1576,21 @@ int sgpe_set_option(sgpe_plan* p, const char* name, int value) {
         return 0;
     }
     if (std::strcmp(name, "prefetch") == 0) { p->prefetch = value ? 1 : 0; return 0; }
+    if (std::strcmp(name, "unwrap_merge") == 0) {
+        if (value != 0 && value != 1) return fail(SGPE_EINVAL, "unwrap_merge: 0 (spanning tree on the device) or 1 (all on the host)");
+        p->unwrap_merge = value;
+        return 0;
+    }
+    if (std::strcmp(name, "unwrap_tail") == 0) {
+        if (value < 0) return fail(SGPE_EINVAL, "unwrap_tail: a non-negative number of edges");
+        p->unwrap_tail = value;
+        return 0;
+    }
+    if (std::strcmp(name, "unwrap_anchor") == 0) {
+        if (value < -1 || value > 1) return fail(SGPE_EINVAL, "unwrap_anchor: -1 (by plane count), 0 (host pass) or 1 (device bisection)");
+        p->unwrap_anchor = value;
+        return 0;
+    }
     if (std::strcmp(name, "unwrap_sort") == 0) {
         if (value != 0 && value != 1) return fail(SGPE_EINVAL, "unwrap_sort: 0 (device radix sort) or 1 (host sort)");
         p->unwrap_sort = value;

@@ -13,8 +13,18 @@
 //   (radix sort of the edges by key: cub, in sgpe_api.cu)
 //   unwrap_apply_pass  : phi + 2 pi * increment, optionally zeroed where the density is below 1e-6 of its maximum
 //                        (tensor_tools.py:538)
-// The region merging between sort and apply is inherently sequential (every merge depends on all the earlier ones)
-// and runs on the host: an offset-carrying union-find in sgpe_api.cu.
+// The region merging between sort and apply is Kruskal's algorithm on the reliability-sorted edges.  Its RESULT splits
+// into two parts of very different nature:
+//   * the minimum spanning tree of the pixel grid under the (unique) edge ranks and, along its edges, the relative
+//     multiples of 2 pi of every pixel pair — independent of the order in which the tree is grown, so it is built on
+//     the device by Boruvka rounds over an offset-carrying union-find (unwrap_minedge_pass / unwrap_hook_pass /
+//     unwrap_adopt_pass / unwrap_compress_pass below; the tree is the same one Kruskal finds because ranks are unique);
+//   * the ONE pixel group that never moves (the published merge rules let the larger group keep its values: the global
+//     2 pi offset of the field, visible at the mask edge of the energy) — this depends on the group sizes at every merge
+//     in rank order and stays a sequential pass, on the host, over the N - 1 tree edges only and without any offset
+//     bookkeeping (unwrap_anchor in sgpe_api.cu).
+// Option "unwrap_merge" = 1 keeps the whole merging on the host (offset-carrying union-find over all edges), for
+// cross-checks.
 //
 // The arithmetic that decides the ORDER of the edges is written with explicit round-to-nearest multiplies and adds
 // (no FMA contraction) so that keys are bit-identical to a plain C evaluation of the same expressions.
@@ -139,6 +149,298 @@ __global__ void __launch_bounds__(256) unwrap_apply_pass(const typename cx_of<T>
             if (n < thr) v = 0.0;
         }
         out[i] = v;
+    }
+}
+
+// ---- region merging on the device: Boruvka rounds over an offset-carrying union-find --------------------------------
+// node[v] = parent(v) in the low word, increment(v) - increment(parent(v)) in the high word (one 64-bit word, so a
+// reader always sees a consistent pair).  Between rounds every pixel points at the root of its group (a star).
+constexpr unsigned kUnwrapNoEdge = 0xffffffffu;
+constexpr unsigned kUnwrapTreeBit = 0x80000000u;     // set in the sorted payload of an edge once it joins the tree
+
+SGPE_DI unsigned long long unwrap_pack(unsigned parent, int off) {
+    return ((unsigned long long)(unsigned)off << 32) | parent;
+}
+SGPE_DI unsigned unwrap_parent(unsigned long long n) { return (unsigned)(n & 0xffffffffull); }
+SGPE_DI int unwrap_off(unsigned long long n) { return (int)(unsigned)(n >> 32); }
+// the two pixels of edge e (numbering of unwrap_edge_pass)
+SGPE_DI void unwrap_edge_ends(unsigned e, int nx, unsigned n_horizontal, unsigned* p1, unsigned* p2) {
+    if (e < n_horizontal) {
+        const unsigned i = e / (unsigned)(nx - 1), j = e - i * (unsigned)(nx - 1);
+        *p1 = i * (unsigned)nx + j; *p2 = *p1 + 1u;
+    } else {
+        *p1 = e - n_horizontal; *p2 = *p1 + (unsigned)nx;
+    }
+}
+
+// rank_of[e] = position of edge e in the sorted order (ranks are unique: ties were broken by edge id in the sort)
+__global__ void __launch_bounds__(256) unwrap_rank_pass(const unsigned* sorted, long long n_edges, unsigned* rank_of) {
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n_edges;
+         k += (long long)gridDim.x * blockDim.x)
+        rank_of[(sorted[k] & ~kUnwrapTreeBit) >> 2] = (unsigned)k;
+}
+
+__global__ void __launch_bounds__(256) unwrap_forest_init_pass(long long plane, unsigned long long* node, unsigned* best) {
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < plane;
+         v += (long long)gridDim.x * blockDim.x) {
+        node[v] = unwrap_pack((unsigned)v, 0);
+        best[v] = kUnwrapNoEdge;
+    }
+}
+
+// every pixel offers the lowest-ranked of its (up to four) edges that leave its group to the group's root
+__global__ void __launch_bounds__(256) unwrap_minedge_pass(const unsigned long long* node, const unsigned* rank_of,
+                                                           int nx, int ny, unsigned* best) {
+    const long long plane = (long long)nx * ny;
+    const unsigned n_horizontal = (unsigned)ny * (unsigned)(nx - 1);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < plane;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / nx), j = (int)(idx - (long long)i * nx);
+        const unsigned root = unwrap_parent(node[idx]);
+        unsigned m = kUnwrapNoEdge;
+        if (j < nx - 1 && unwrap_parent(node[idx + 1]) != root) { const unsigned r = rank_of[(unsigned)i * (unsigned)(nx - 1) + j]; m = r < m ? r : m; }
+        if (j > 0 && unwrap_parent(node[idx - 1]) != root) { const unsigned r = rank_of[(unsigned)i * (unsigned)(nx - 1) + j - 1]; m = r < m ? r : m; }
+        if (i < ny - 1 && unwrap_parent(node[idx + nx]) != root) { const unsigned r = rank_of[n_horizontal + (unsigned)idx]; m = r < m ? r : m; }
+        if (i > 0 && unwrap_parent(node[idx - nx]) != root) { const unsigned r = rank_of[n_horizontal + (unsigned)(idx - nx)]; m = r < m ? r : m; }
+        if (m != kUnwrapNoEdge && m < best[root]) atomicMin(&best[root], m);
+    }
+}
+
+// every root with an outgoing edge hangs itself below the root on the other side of its lowest-ranked one (written to
+// pend[], adopted by the next pass: node[] stays a forest of stars while this pass reads it).  Two groups that chose
+// the same edge: the root with the smaller index stays.  Ranks are unique, so there is no longer cycle.
+__global__ void __launch_bounds__(256) unwrap_hook_pass(const unsigned long long* node, const unsigned* best,
+                                                        unsigned* sorted, int nx, int ny, unsigned long long* pend,
+                                                        unsigned* hooked) {
+    const long long plane = (long long)nx * ny;
+    const unsigned n_horizontal = (unsigned)ny * (unsigned)(nx - 1);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < plane;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const unsigned v = (unsigned)idx;
+        if (unwrap_parent(node[idx]) != v) continue;
+        unsigned long long out = unwrap_pack(v, 0);
+        const unsigned k = best[idx];
+        if (k != kUnwrapNoEdge) {
+            const unsigned payload = sorted[k] & ~kUnwrapTreeBit;
+            const int wraps = (int)(payload & 3u) - 1;            // increment(p1) - increment(p2)
+            unsigned p1, p2;
+            unwrap_edge_ends(payload >> 2, nx, n_horizontal, &p1, &p2);
+            const unsigned long long n1 = node[p1], n2 = node[p2];
+            const bool first_is_mine = unwrap_parent(n1) == v;
+            const unsigned other_root = first_is_mine ? unwrap_parent(n2) : unwrap_parent(n1);
+            const int a_mine = first_is_mine ? unwrap_off(n1) : unwrap_off(n2);
+            const int a_other = first_is_mine ? unwrap_off(n2) : unwrap_off(n1);
+            if (!(best[other_root] == k && v < other_root)) {
+                // increment(v) - increment(other_root)
+                out = unwrap_pack(other_root, (first_is_mine ? wraps : -wraps) + a_other - a_mine);
+                atomicOr(&sorted[k], kUnwrapTreeBit);
+                atomicAdd(hooked, 1u);
+            }
+        }
+        pend[idx] = out;
+    }
+}
+
+__global__ void __launch_bounds__(256) unwrap_adopt_pass(long long plane, const unsigned long long* pend,
+                                                         unsigned long long* node, unsigned* best) {
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < plane;
+         v += (long long)gridDim.x * blockDim.x) {
+        if (unwrap_parent(node[v]) == (unsigned)v) node[v] = pend[v];
+        best[v] = kUnwrapNoEdge;
+    }
+}
+
+// pointer jumping until every pixel points at a root again.  Each thread rewrites only its own word, and every word is
+// at all times a true statement "increment(v) - increment(parent) = off" about SOME ancestor, so concurrent readers
+// may see any mixture of old and new words.
+__global__ void __launch_bounds__(256) unwrap_compress_pass(long long plane, unsigned long long* node) {
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < plane;
+         v += (long long)gridDim.x * blockDim.x) {
+        unsigned long long mine = node[v];
+        for (;;) {
+            const unsigned p = unwrap_parent(mine);
+            const unsigned long long up = __ldcg(&node[p]);
+            if (unwrap_parent(up) == p) break;
+            mine = unwrap_pack(unwrap_parent(up), unwrap_off(mine) + unwrap_off(up));
+            node[v] = mine;
+        }
+    }
+}
+
+// raw[v] = increment(v) - increment(root of the tree)
+__global__ void __launch_bounds__(256) unwrap_offsets_pass(long long plane, const unsigned long long* node, int* raw) {
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < plane;
+         v += (long long)gridDim.x * blockDim.x)
+        raw[v] = unwrap_off(node[v]);
+}
+
+// the tree edges in rank order for the host's anchor pass: first pixel, bit 31 = vertical edge; others kUnwrapNoEdge
+__global__ void __launch_bounds__(256) unwrap_tree_edges_pass(const unsigned* sorted, long long n_edges, int nx, int ny,
+                                                              unsigned* cand) {
+    const unsigned n_horizontal = (unsigned)ny * (unsigned)(nx - 1);
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n_edges;
+         k += (long long)gridDim.x * blockDim.x) {
+        const unsigned s = sorted[k];
+        unsigned out = kUnwrapNoEdge;
+        if (s & kUnwrapTreeBit) {
+            unsigned p1, p2;
+            const unsigned e = (s & ~kUnwrapTreeBit) >> 2;
+            unwrap_edge_ends(e, nx, n_horizontal, &p1, &p2);
+            out = p1 | (e >= n_horizontal ? kUnwrapTreeBit : 0u);
+        }
+        cand[k] = out;
+    }
+}
+
+// inc[v] -= inc[anchor]: the anchor pixel's group is the one that never moved.  The anchor's own entry is left alone
+// here (every thread of the grid reads it) and zeroed by unwrap_anchor_zero_pass afterwards.
+__global__ void __launch_bounds__(256) unwrap_anchor_pass(long long plane, long long anchor, int* inc) {
+    const int base = inc[anchor];
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < plane;
+         v += (long long)gridDim.x * blockDim.x)
+        if (v != anchor) inc[v] -= base;
+}
+__global__ void unwrap_anchor_zero_pass(long long anchor, int* inc) { if (threadIdx.x == 0) inc[anchor] = 0; }
+
+// ---- the pixel group that never moves, found on the device ----------------------------------------------------------
+// Kruskal keeps the values of the LARGER group at every merge, so inside any group X that Kruskal ever formed (a
+// connected piece of the spanning tree whose inner edges all rank below its outer ones) the surviving lineage is settled
+// by one merge: the first one that creates a group of more than |X| / 2 pixels.  From then on that group outweighs
+// everything else in X and wins every merge; before, it did not exist.  Its two halves A and B (each at most |X| / 2)
+// are again groups Kruskal formed, and the published rule for (|A|, |B|) names the half whose values survive: recurse
+// into it.  The size at least halves per level, and "does a group of more than |X| / 2 pixels exist once the edges up
+// to rank T are in" is monotone in T, so each level is a bisection over T with a lock-free union-find over the tree
+// edges of X (ECL-CC style hooking by index) and a counting pass.  The bisection keeps the forest of its lower bound
+// and only adds the edges between the bounds.  Small X go to the host (a few thousand edges).
+struct UnwrapEdge { unsigned k, t; };      // position in the rank-sorted tree-edge list; first pixel | vertical << 31
+
+SGPE_DI unsigned unwrap_uf_find(unsigned* parent, unsigned x) {
+    unsigned curr = __ldcg(&parent[x]);
+    if (curr != x) {
+        unsigned prev = x, next;
+        while (curr != (next = __ldcg(&parent[curr]))) { parent[prev] = next; prev = curr; curr = next; }
+    }
+    return curr;
+}
+SGPE_DI void unwrap_uf_union(unsigned* parent, unsigned a, unsigned b) {
+    a = unwrap_uf_find(parent, a);
+    b = unwrap_uf_find(parent, b);
+    while (a != b) {
+        if (a < b) { const unsigned t = a; a = b; b = t; }        // the larger index hangs below the smaller
+        const unsigned seen = atomicCAS(&parent[a], a, b);
+        if (seen == a) break;
+        a = seen;                                                 // someone else moved a: climb and retry
+    }
+}
+
+__global__ void __launch_bounds__(256) unwrap_level0_pass(const unsigned* tree, long long plane, unsigned* vl, UnwrapEdge* el) {
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < plane;
+         v += (long long)gridDim.x * blockDim.x) {
+        vl[v] = (unsigned)v;
+        if (v + 1 < plane) { UnwrapEdge e; e.k = (unsigned)v; e.t = tree[v]; el[v] = e; }
+    }
+}
+// dst[v] = src ? src[v] : v, cnt[v] = 0 over the pixels of the level
+__global__ void __launch_bounds__(256) unwrap_level_reset_pass(const unsigned* vl, long long nv, const unsigned* src,
+                                                               unsigned* dst, unsigned* cnt) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned v = vl[i];
+        dst[v] = src ? src[v] : v;
+        cnt[v] = 0;
+    }
+}
+// joins the ends of the level's edges with lo < k <= hi (signed bounds: lo = -1 means "from the first edge")
+__global__ void __launch_bounds__(256) unwrap_level_union_pass(const UnwrapEdge* el, long long ne, long long lo, long long hi,
+                                                               int nx, unsigned* parent) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ne; i += (long long)gridDim.x * blockDim.x) {
+        const UnwrapEdge e = el[i];
+        if ((long long)e.k <= lo || (long long)e.k > hi) continue;
+        const unsigned p1 = e.t & ~kUnwrapTreeBit;
+        unwrap_uf_union(parent, p1, p1 + ((e.t & kUnwrapTreeBit) ? (unsigned)nx : 1u));
+    }
+}
+// group sizes at the roots and the largest of them (result[0], zeroed by the caller)
+__global__ void __launch_bounds__(256) unwrap_level_count_pass(const unsigned* vl, long long nv, unsigned* parent,
+                                                               unsigned* cnt, unsigned* result) {
+    SGPE_DYN_SMEM(smem_raw);                 // blockDim.x unsigned
+    unsigned* red = reinterpret_cast<unsigned*>(smem_raw);
+    unsigned mx = 0;
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < nv; base += (long long)gridDim.x * blockDim.x) {
+        const long long i = base + threadIdx.x;
+        const bool live = i < nv;
+        unsigned root = 0;
+        if (live) {
+            const unsigned v = vl[i];
+            root = unwrap_uf_find(parent, v);
+            if (root != v) parent[v] = root;
+        }
+#ifdef SGPE_EMU
+        if (live) { const unsigned c = atomicAdd(&cnt[root], 1u) + 1u; mx = c > mx ? c : mx; }
+#else
+        // neighbouring pixels mostly share their root: one atomic per distinct root of a warp
+        const unsigned active = __ballot_sync(0xffffffffu, live);
+        if (live) {
+            const unsigned peers = __match_any_sync(active, root);
+            if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) {
+                const unsigned n = (unsigned)__popc(peers);
+                const unsigned c = atomicAdd(&cnt[root], n) + n;
+                mx = c > mx ? c : mx;
+            }
+        }
+#endif
+    }
+    red[threadIdx.x] = mx;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] = red[threadIdx.x] > red[threadIdx.x + s] ? red[threadIdx.x] : red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && red[0]) atomicMax(result, red[0]);
+}
+// the two groups edge T joins: result[1..4] = root and size on the first pixel's side, root and size on the second's
+__global__ void __launch_bounds__(256) unwrap_level_sides_pass(const UnwrapEdge* el, long long ne, unsigned T, int nx,
+                                                               unsigned* parent, const unsigned* cnt, unsigned* result) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ne; i += (long long)gridDim.x * blockDim.x) {
+        const UnwrapEdge e = el[i];
+        if (e.k != T) continue;
+        const unsigned p1 = e.t & ~kUnwrapTreeBit;
+        const unsigned a = unwrap_uf_find(parent, p1);
+        const unsigned b = unwrap_uf_find(parent, p1 + ((e.t & kUnwrapTreeBit) ? (unsigned)nx : 1u));
+        result[1] = a; result[2] = cnt[a]; result[3] = b; result[4] = cnt[b];
+    }
+}
+// next level: the pixels of group `keep` and the edges below rank T inside it (appended in any order;
+// result[5] / result[6] count them)
+SGPE_DI unsigned unwrap_append_slot(bool take, unsigned* counter) {
+#ifdef SGPE_EMU
+    return take ? atomicAdd(counter, 1u) : 0u;
+#else
+    const unsigned votes = __ballot_sync(0xffffffffu, take);
+    if (!take) return 0u;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned leader = (unsigned)(__ffs(votes) - 1);
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned)__popc(votes));
+    base = __shfl_sync(votes, base, (int)leader);
+    return base + (unsigned)__popc(votes & ((1u << lane) - 1u));
+#endif
+}
+__global__ void __launch_bounds__(256) unwrap_level_select_pass(const unsigned* vl, long long nv, const UnwrapEdge* el,
+                                                                long long ne, unsigned T, unsigned keep, unsigned* parent,
+                                                                unsigned* vl_out, UnwrapEdge* el_out, unsigned* result) {
+    const long long span = nv > ne ? nv : ne;
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < span; base += (long long)gridDim.x * blockDim.x) {
+        const long long i = base + threadIdx.x;
+        bool take = false;
+        unsigned v = 0;
+        if (i < nv) { v = vl[i]; take = unwrap_uf_find(parent, v) == keep; }
+        unsigned slot = unwrap_append_slot(take, &result[5]);
+        if (take) vl_out[slot] = v;
+        take = false;
+        UnwrapEdge e; e.k = 0; e.t = 0;
+        if (i < ne) { e = el[i]; take = e.k < T && unwrap_uf_find(parent, e.t & ~kUnwrapTreeBit) == keep; }
+        slot = unwrap_append_slot(take, &result[6]);
+        if (take) el_out[slot] = e;
     }
 }
 

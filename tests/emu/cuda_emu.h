@@ -176,6 +176,10 @@ inline long long __double_as_longlong(double x) { long long r; std::memcpy(&r, &
 inline double __longlong_as_double(long long x) { double r; std::memcpy(&r, &x, 8); return r; }
 template <typename T> inline T __ldcg(const T* p) { return *p; }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
+inline unsigned atomicMin(unsigned* p, unsigned v) { unsigned o = *p; if (v < o) *p = v; return o; }
+inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
+inline unsigned atomicCAS(unsigned* p, unsigned expect, unsigned v) { unsigned o = *p; if (o == expect) *p = v; return o; }
+inline unsigned atomicOr(unsigned* p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
 inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; if (v > o) *p = v; return o; }
 inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }

@@ -98,6 +98,32 @@ def test_emulated_unwrap_equals_oracle_on_same_angles(shape):
     pl.close()
 
 
+@pytest.mark.parametrize('shape', [(32, 32), (48, 80), (64, 128)])
+def test_emulated_device_merging_equals_host_merging(shape):
+    """Spanning tree by Boruvka rounds on the device + anchor pass over the tree edges (the default) against the
+    offset-carrying union-find over ALL edges on the host (option unwrap_merge = 1): the same integer field, global
+    offset included — also when every reliability ties (flat / exactly linear phase: rank = edge id)."""
+    from tests.emu_harness import EmuPlan
+    ny, nx = shape
+    pl = EmuPlan(nx, ny)
+    fs = fields(ny, nx, 5 * ny + nx)
+    y, x = np.mgrid[0:ny, 0:nx].astype(np.float64)
+    planes = [np.angle(f) for f in fs.values()] + [np.zeros((ny, nx)), wrap(0.25 * x), wrap(0.5 * x - 0.25 * y)]
+    ang = np.stack(planes)
+    got = pl.unwrap_phase(ang)
+    pl.set_option('unwrap_anchor', 1)         # the surviving group by bisection on the device, down to single pixels
+    pl.set_option('unwrap_tail', 0)
+    np.testing.assert_array_equal(pl.unwrap_phase(ang), got)
+    pl.set_option('unwrap_tail', 100)         # ... and with the last levels on the host
+    np.testing.assert_array_equal(pl.unwrap_phase(ang), got)
+    pl.set_option('unwrap_merge', 1)
+    host = pl.unwrap_phase(ang)
+    np.testing.assert_array_equal(got, host)
+    for k in range(len(planes)):
+        np.testing.assert_array_equal(got[k], oracle_unwrap(ang[k]), err_msg=str(k))
+    pl.close()
+
+
 def test_emulated_unwrap_of_complex_field_and_mask():
     from tests.emu_harness import EmuPlan
     ny, nx = 64, 64
@@ -245,4 +271,36 @@ def test_gpu_unwrap_at_full_size_properties():
     assert float((k - torch.round(k)).abs().max()) < 1e-9
     d = (out - true) / TWO_PI
     assert float((d - torch.round(d[0, 0])).abs().max()) < 1e-9
+    pl.close()
+
+
+@pytest.mark.gpu
+def test_gpu_device_merging_equals_host_merging_at_full_size():
+    """2048^2, noise + vortices + a smooth ramp: the device-built spanning tree with the anchor pass gives the integer
+    field of the all-host merging (option unwrap_merge = 1) bit for bit, global offset included."""
+    import torch
+    from spinor_gpe_b200.plan import Plan
+    n = 2048
+    pl = Plan(n, n)
+    g = torch.Generator(device='cuda').manual_seed(7)
+    y, x = torch.meshgrid(torch.arange(n, dtype=torch.float64, device='cuda'),
+                          torch.arange(n, dtype=torch.float64, device='cuda'), indexing='ij')
+    noise = torch.complex(torch.randn(n, n, generator=g, device='cuda', dtype=torch.float64),
+                          torch.randn(n, n, generator=g, device='cuda', dtype=torch.float64))
+    vort = torch.complex(x - 0.31 * n, y - 0.37 * n) * torch.complex(x - 0.62 * n, -(y - 0.71 * n))
+    envelope = torch.exp(-((x - n / 2) ** 2 + (y - n / 2) ** 2) / (0.05 * n * n))
+    planes = torch.stack([noise, vort * torch.exp(0.02j * x) + 30.0 * noise,
+                          torch.polar(envelope, 0.011 * x + 0.007 * y), torch.ones_like(noise)])
+    got = pl.unwrap_phase(planes)             # 4 planes: spanning tree and anchor bisection on the device
+    pl.set_option('unwrap_anchor', 0)         # anchor pass over the tree edges on the host
+    assert torch.equal(pl.unwrap_phase(planes), got)
+    pl.set_option('unwrap_anchor', 1)
+    pl.set_option('unwrap_tail', 0)           # bisection all the way down
+    assert torch.equal(pl.unwrap_phase(planes), got)
+    pl.set_option('unwrap_merge', 1)
+    host = pl.unwrap_phase(planes)
+    assert torch.equal(got, host)
+    k = (got - torch.angle(planes)) / TWO_PI
+    assert float((k - torch.round(k)).abs().max()) < 1e-9
+    assert int(torch.round(k[1]).max() - torch.round(k[1]).min()) >= 2
     pl.close()
