@@ -612,13 +612,17 @@ def run_ours(args, rank, world, local_rank):
         for unwrap in ('herraez', 'none'):
             q = build_problem(mesh, g_ud=1.04 + 0.002 * rank, tag=f'pub{rank}{unwrap}')
             q.imaginary(DT['imag'], 2, dev, unwrap=unwrap)                    # warm-up
-            q = build_problem(mesh, g_ud=1.04 + 0.002 * rank, tag=f'pub{rank}{unwrap}b')
-            ctx.barrier()
-            t0 = time.perf_counter()
-            res, _ = q.imaginary(DT['imag'], args.steps, dev, unwrap=unwrap)
-            torch.cuda.synchronize(dev)
-            ms = ctx.max_over_ranks((time.perf_counter() - t0) * 1e3)
+            passes = []
+            for rep in range(3):                                              # host-side work: median of three runs
+                q = build_problem(mesh, g_ud=1.04 + 0.002 * rank, tag=f'pub{rank}{unwrap}b{rep}')
+                ctx.barrier()
+                t0 = time.perf_counter()
+                res, _ = q.imaginary(DT['imag'], args.steps, dev, unwrap=unwrap)
+                torch.cuda.synchronize(dev)
+                passes.append(ctx.max_over_ranks((time.perf_counter() - t0) * 1e3))
+            ms = sorted(passes)[1]
             out[unwrap] = {'value': world * args.steps * 1e3 / ms, 'unit': 'steps/s', 'ms_total': ms,
+                           'ms_per_pass': [round(v, 1) for v in passes],
                            'eng_final': [float(v) for v in res.eng_final]}
         out['what'] = (f'PSpinor.imaginary(1/50, {args.steps}, "cuda"): host NumPy state and grids in, PropResult (psi, '
                        'psik, populations, final energy) out; herraez = phase-unwrapped energy as the reference defines it')
