@@ -104,6 +104,7 @@ struct sgpe_plan {
     struct UnwrapCache {           // scratch of the phase unwrapping, kept between evaluations (unwrap_scratch)
         double* rel = nullptr; unsigned long long* keys = nullptr; unsigned long long* keys_sorted = nullptr;
         unsigned* vals = nullptr; unsigned* vals_sorted = nullptr; void* tmp = nullptr; size_t tmp_bytes = 0;
+        long long* ctrl = nullptr;      // bisection state of the anchor search (unwrap.cuh)
         unsigned* counters = nullptr;   // [0] groups hooked in a Boruvka round, [1] tree edges selected, [8..15] anchor search
         uint32_t* order_host = nullptr; int32_t* inc_host = nullptr;
         int nplanes = 0; size_t plane = 0; bool device_sort = false;
@@ -837,7 +838,7 @@ static void host_pinned_free(void* q) { free(q); }
 
 void unwrap_release(sgpe_plan::UnwrapCache& w) {
     cudaFree(w.rel); cudaFree(w.keys); cudaFree(w.keys_sorted); cudaFree(w.vals); cudaFree(w.vals_sorted); cudaFree(w.tmp);
-    cudaFree(w.counters);
+    cudaFree(w.counters); cudaFree(w.ctrl);
     host_pinned_free(w.order_host); host_pinned_free(w.inc_host);
     w = sgpe_plan::UnwrapCache();
 }
@@ -859,7 +860,8 @@ static int unwrap_scratch(sgpe_plan* p, int nplanes, size_t plane, size_t n_edge
         cudaMalloc((void**)&w.vals, n_edges * sizeof(unsigned)) != cudaSuccess ||
         cudaMalloc((void**)&w.keys_sorted, n_edges * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc((void**)&w.vals_sorted, n_edges * sizeof(unsigned)) != cudaSuccess ||
-        cudaMalloc((void**)&w.counters, 16 * sizeof(unsigned)) != cudaSuccess)
+        cudaMalloc((void**)&w.counters, 16 * sizeof(unsigned)) != cudaSuccess ||
+        cudaMalloc((void**)&w.ctrl, 4 * sizeof(long long)) != cudaSuccess)
         return fail(SGPE_ENOMEM, "unwrap scratch allocation failed");
 #ifndef SGPE_EMU
     size_t select_bytes = 0;
@@ -927,7 +929,8 @@ static int unwrap_anchor_device(sgpe_plan* p, int nx, size_t plane, cudaStream_t
     unsigned* vl[2] = {w.vals, w.vals + plane};
     sgpe::UnwrapEdge* el[2] = {reinterpret_cast<sgpe::UnwrapEdge*>(w.keys_sorted), reinterpret_cast<sgpe::UnwrapEdge*>(w.keys_sorted) + plane};
     unsigned* result = w.counters + 8;
-    unsigned host_result[8];
+    long long* ctrl = w.ctrl;
+    struct { long long ctrl[3]; unsigned result[8]; } back;
     const dim3 block(256);
     long long nv = (long long)plane, ne = nv - 1, bound = ne;
     int cur = 0;
@@ -935,42 +938,43 @@ static int unwrap_anchor_device(sgpe_plan* p, int nx, size_t plane, cudaStream_t
     p->launches++;
     while (ne > (long long)p->unwrap_tail) {
         const dim3 grid_v(unwrap_blocks(nv)), grid_e(unwrap_blocks(ne));
-        SGPE_LAUNCH((sgpe::unwrap_level_reset_pass), grid_v, block, 0, st, vl[cur], nv, (const unsigned*)nullptr, snap, cnt);
-        p->launches++;
-        long long lo = -1, hi = bound - 1;          // no group of more than nv / 2 pixels with the edges <= lo, one with those <= hi
-        while (hi - lo > 1) {
-            const long long mid = lo + (hi - lo) / 2;
-            SGPE_CUDA(cudaMemsetAsync(result, 0, sizeof(unsigned), st));
-            SGPE_LAUNCH((sgpe::unwrap_level_reset_pass), grid_v, block, 0, st, vl[cur], nv, (const unsigned*)snap, work, cnt);
-            SGPE_LAUNCH((sgpe::unwrap_level_union_pass), grid_e, block, 0, st, el[cur], ne, lo, mid, nx, work);
-            SGPE_LAUNCH((sgpe::unwrap_level_count_pass), grid_v, block, 256 * sizeof(unsigned), st, vl[cur], nv, work, cnt, result);
-            p->launches += 3;
-            SGPE_CUDA(cudaMemcpyAsync(host_result, result, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-            SGPE_CUDA(cudaStreamSynchronize(st));
-            (*probes)++;
-            if (2ll * host_result[0] > nv) hi = mid;
-            else { lo = mid; std::swap(snap, work); }
+        const size_t count_smem = (256 + 16) * sizeof(unsigned);
+        // no group of more than nv / 2 pixels with the edges <= lo (none at all: lo = -1), one with those <= hi
+        SGPE_LAUNCH((sgpe::unwrap_level_begin_pass), dim3(1), dim3(32), 0, st, -1ll, bound - 1, ctrl, result);
+        SGPE_LAUNCH((sgpe::unwrap_level_reset_pass), grid_v, block, 0, st, vl[cur], nv, (const long long*)nullptr, snap, work, 0, cnt);
+        p->launches += 2;
+        int enqueued = 0;
+        for (long long len = bound; len > 1; len = (len + 1) / 2) {        // the interval shrinks to ceil(len / 2) at worst
+            SGPE_LAUNCH((sgpe::unwrap_level_reset_pass), grid_v, block, 0, st, vl[cur], nv, (const long long*)ctrl, snap, work, 0, cnt);
+            SGPE_LAUNCH((sgpe::unwrap_level_union_pass), grid_e, block, 0, st, el[cur], ne, (const long long*)ctrl, nx, snap, work);
+            SGPE_LAUNCH((sgpe::unwrap_level_count_pass), grid_v, block, count_smem, st, vl[cur], nv, (const long long*)ctrl, snap, work, 0, cnt, result);
+            SGPE_LAUNCH((sgpe::unwrap_level_step_pass), dim3(1), dim3(32), 0, st, nv, ctrl, result);
+            p->launches += 4;
+            enqueued++;
         }
-        // edge `hi` creates the majority group; snap holds the forest just before it
-        SGPE_CUDA(cudaMemsetAsync(result, 0, 8 * sizeof(unsigned), st));
-        SGPE_LAUNCH((sgpe::unwrap_level_reset_pass), grid_v, block, 0, st, vl[cur], nv, (const unsigned*)snap, snap, cnt);
-        SGPE_LAUNCH((sgpe::unwrap_level_count_pass), grid_v, block, 256 * sizeof(unsigned), st, vl[cur], nv, snap, cnt, result);
-        SGPE_LAUNCH((sgpe::unwrap_level_sides_pass), grid_e, block, 0, st, el[cur], ne, (unsigned)hi, nx, snap, cnt, result);
+        *probes += enqueued;
+        // edge `hi` creates the majority group; the forest at lo = hi - 1 is the state just before it
+        SGPE_LAUNCH((sgpe::unwrap_level_reset_pass), grid_v, block, 0, st, vl[cur], nv, (const long long*)nullptr, snap, work, 1, cnt);
+        SGPE_LAUNCH((sgpe::unwrap_level_count_pass), grid_v, block, count_smem, st, vl[cur], nv, (const long long*)ctrl, snap, work, 1, cnt, result);
+        SGPE_LAUNCH((sgpe::unwrap_level_sides_pass), grid_e, block, 0, st, el[cur], ne, (const long long*)ctrl, nx, snap, work, (const unsigned*)cnt, result);
         p->launches += 3;
-        SGPE_CUDA(cudaMemcpyAsync(host_result, result, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        SGPE_CUDA(cudaGetLastError());
+        SGPE_CUDA(cudaMemcpyAsync(back.ctrl, ctrl, sizeof(back.ctrl), cudaMemcpyDeviceToHost, st));
+        SGPE_CUDA(cudaMemcpyAsync(back.result, result, sizeof(back.result), cudaMemcpyDeviceToHost, st));
         SGPE_CUDA(cudaStreamSynchronize(st));
-        const long long s1 = host_result[2], s2 = host_result[4];
-        if (s1 < 1 || s2 < 1 || 2 * (s1 + s2) <= nv || 2 * s1 > nv || 2 * s2 > nv)
+        const long long hi = back.ctrl[1];
+        const long long s1 = back.result[2], s2 = back.result[4];
+        if (back.ctrl[1] - back.ctrl[0] != 1 || s1 < 1 || s2 < 1 || 2 * (s1 + s2) <= nv || 2 * s1 > nv || 2 * s2 > nv)
             return fail(SGPE_ECUDA, "phase unwrapping: anchor bisection lost its edge (internal error)");
         const bool second_joins = (s2 == 1) || (s1 != 1 && s1 > s2);
-        const unsigned keep = second_joins ? host_result[1] : host_result[3];
+        const unsigned keep = second_joins ? back.result[1] : back.result[3];
         const long long keep_size = second_joins ? s1 : s2;
         SGPE_LAUNCH((sgpe::unwrap_level_select_pass), dim3(unwrap_blocks(nv)), block, 0, st, vl[cur], nv, el[cur], ne, (unsigned)hi, keep,
-                    snap, vl[1 - cur], el[1 - cur], result);
+                    back.ctrl[2] ? work : snap, vl[1 - cur], el[1 - cur], result);
         p->launches++;
-        SGPE_CUDA(cudaMemcpyAsync(host_result, result, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        SGPE_CUDA(cudaMemcpyAsync(back.result, result, sizeof(back.result), cudaMemcpyDeviceToHost, st));
         SGPE_CUDA(cudaStreamSynchronize(st));
-        if ((long long)host_result[5] != keep_size || (long long)host_result[6] != keep_size - 1)
+        if ((long long)back.result[5] != keep_size || (long long)back.result[6] != keep_size - 1)
             return fail(SGPE_ECUDA, "phase unwrapping: anchor bisection selected a wrong group (internal error)");
         nv = keep_size; ne = nv - 1; bound = hi; cur ^= 1;
         (*levels)++;

@@ -333,6 +333,36 @@ SGPE_DI void unwrap_uf_union(unsigned* parent, unsigned a, unsigned b) {
     }
 }
 
+// The bisection of a level runs without the host: ctrl = {lo, hi, which forest holds the state at lo} lives on the
+// device, the passes of a probe read it (and do nothing once hi - lo <= 1), unwrap_level_step_pass moves a bound after
+// each probe.  The host enqueues ceil(log2(hi - lo)) probes and reads the outcome once per level.
+struct UnwrapProbe { long long lo, mid; unsigned* snap; unsigned* work; bool live; };
+SGPE_DI UnwrapProbe unwrap_probe(const long long* ctrl, unsigned* forest_a, unsigned* forest_b) {
+    UnwrapProbe q;
+    const long long hi = ctrl[1];
+    q.lo = ctrl[0];
+    q.live = hi - q.lo > 1;
+    q.mid = q.lo + (hi - q.lo) / 2;
+    q.snap = ctrl[2] ? forest_b : forest_a;
+    q.work = ctrl[2] ? forest_a : forest_b;
+    return q;
+}
+__global__ void unwrap_level_begin_pass(long long lo, long long hi, long long* ctrl, unsigned* result) {
+    if (threadIdx.x == 0) { ctrl[0] = lo; ctrl[1] = hi; ctrl[2] = 0; }
+    if (threadIdx.x < 8) result[threadIdx.x] = 0;
+}
+// after a probe: result[0] = size of the largest group with the edges up to mid in
+__global__ void unwrap_level_step_pass(long long nv, long long* ctrl, unsigned* result) {
+    if (threadIdx.x != 0) return;
+    const long long lo = ctrl[0], hi = ctrl[1];
+    if (hi - lo > 1) {
+        const long long mid = lo + (hi - lo) / 2;
+        if (2ll * (long long)result[0] > nv) ctrl[1] = mid;
+        else { ctrl[0] = mid; ctrl[2] ^= 1; }
+    }
+    result[0] = 0;
+}
+
 __global__ void __launch_bounds__(256) unwrap_level0_pass(const unsigned* tree, long long plane, unsigned* vl, UnwrapEdge* el) {
     for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < plane;
          v += (long long)gridDim.x * blockDim.x) {
@@ -340,31 +370,57 @@ __global__ void __launch_bounds__(256) unwrap_level0_pass(const unsigned* tree, 
         if (v + 1 < plane) { UnwrapEdge e; e.k = (unsigned)v; e.t = tree[v]; el[v] = e; }
     }
 }
-// dst[v] = src ? src[v] : v, cnt[v] = 0 over the pixels of the level
-__global__ void __launch_bounds__(256) unwrap_level_reset_pass(const unsigned* vl, long long nv, const unsigned* src,
-                                                               unsigned* dst, unsigned* cnt) {
+// Outside a probe (ctrl == nullptr): forest_a[v] = v (identity) or, with keep_state, left as is; cnt[v] = 0.
+// In a probe: work forest = copy of the forest at lo, cnt[v] = 0.
+__global__ void __launch_bounds__(256) unwrap_level_reset_pass(const unsigned* vl, long long nv, const long long* ctrl,
+                                                               unsigned* forest_a, unsigned* forest_b, int keep_state,
+                                                               unsigned* cnt) {
+    const unsigned* src = nullptr;
+    unsigned* dst = forest_a;
+    if (ctrl) {
+        const UnwrapProbe q = unwrap_probe(ctrl, forest_a, forest_b);
+        if (!q.live) return;
+        src = q.snap; dst = q.work;
+    } else if (keep_state) {
+        dst = nullptr;
+    }
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
         const unsigned v = vl[i];
-        dst[v] = src ? src[v] : v;
+        if (dst) dst[v] = src ? src[v] : v;
         cnt[v] = 0;
     }
 }
-// joins the ends of the level's edges with lo < k <= hi (signed bounds: lo = -1 means "from the first edge")
-__global__ void __launch_bounds__(256) unwrap_level_union_pass(const UnwrapEdge* el, long long ne, long long lo, long long hi,
-                                                               int nx, unsigned* parent) {
+// a probe: joins the ends of the level's edges with lo < k <= mid in the work forest
+__global__ void __launch_bounds__(256) unwrap_level_union_pass(const UnwrapEdge* el, long long ne, const long long* ctrl,
+                                                               int nx, unsigned* forest_a, unsigned* forest_b) {
+    const UnwrapProbe q = unwrap_probe(ctrl, forest_a, forest_b);
+    if (!q.live) return;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ne; i += (long long)gridDim.x * blockDim.x) {
         const UnwrapEdge e = el[i];
-        if ((long long)e.k <= lo || (long long)e.k > hi) continue;
+        if ((long long)e.k <= q.lo || (long long)e.k > q.mid) continue;
         const unsigned p1 = e.t & ~kUnwrapTreeBit;
-        unwrap_uf_union(parent, p1, p1 + ((e.t & kUnwrapTreeBit) ? (unsigned)nx : 1u));
+        unwrap_uf_union(q.work, p1, p1 + ((e.t & kUnwrapTreeBit) ? (unsigned)nx : 1u));
     }
 }
-// group sizes at the roots and the largest of them (result[0], zeroed by the caller)
-__global__ void __launch_bounds__(256) unwrap_level_count_pass(const unsigned* vl, long long nv, unsigned* parent,
+// group sizes at the roots and the largest of them (result[0], zeroed by the caller).  Late in a bisection most pixels
+// share ONE root: a CTA keeps a running count for the root its first pixel of an iteration has and adds it to the
+// root's counter only when that root changes (a few thousand atomics on the hot address instead of one per warp);
+// pixels with another root go through one atomic per distinct root of their warp.  Every atomic returns the running
+// total of its root, so the largest value seen anywhere is the size of the largest group.
+// use_snap == 0: a probe (work forest; nothing once the bisection has closed), 1: the forest at lo.
+__global__ void __launch_bounds__(256) unwrap_level_count_pass(const unsigned* vl, long long nv, const long long* ctrl,
+                                                               unsigned* forest_a, unsigned* forest_b, int use_snap,
                                                                unsigned* cnt, unsigned* result) {
-    SGPE_DYN_SMEM(smem_raw);                 // blockDim.x unsigned
+    const UnwrapProbe q = unwrap_probe(ctrl, forest_a, forest_b);
+    if (!use_snap && !q.live) return;
+    unsigned* parent = use_snap ? q.snap : q.work;
+    SGPE_DYN_SMEM(smem_raw);                 // blockDim.x + 16 unsigned
     unsigned* red = reinterpret_cast<unsigned*>(smem_raw);
     unsigned mx = 0;
+#ifndef SGPE_EMU
+    unsigned* warp_hits = red + blockDim.x;  // [8] per-warp counts of the CTA's current root, [8] = that root
+    unsigned held_root = kUnwrapNoEdge, held = 0;          // thread 0 only
+#endif
     for (long long base = (long long)blockIdx.x * blockDim.x; base < nv; base += (long long)gridDim.x * blockDim.x) {
         const long long i = base + threadIdx.x;
         const bool live = i < nv;
@@ -377,18 +433,36 @@ __global__ void __launch_bounds__(256) unwrap_level_count_pass(const unsigned* v
 #ifdef SGPE_EMU
         if (live) { const unsigned c = atomicAdd(&cnt[root], 1u) + 1u; mx = c > mx ? c : mx; }
 #else
-        // neighbouring pixels mostly share their root: one atomic per distinct root of a warp
-        const unsigned active = __ballot_sync(0xffffffffu, live);
-        if (live) {
-            const unsigned peers = __match_any_sync(active, root);
+        if (threadIdx.x == 0) warp_hits[8] = root;         // thread 0 of an iteration is always live
+        __syncthreads();
+        const unsigned cta_root = warp_hits[8];
+        const bool common = live && root == cta_root;
+        const unsigned votes = __ballot_sync(0xffffffffu, common);
+        if ((threadIdx.x & 31u) == 0) warp_hits[threadIdx.x >> 5] = (unsigned)__popc(votes);
+        const unsigned others = __ballot_sync(0xffffffffu, live && !common);
+        if (live && !common) {
+            const unsigned peers = __match_any_sync(others, root);
             if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) {
                 const unsigned n = (unsigned)__popc(peers);
                 const unsigned c = atomicAdd(&cnt[root], n) + n;
                 mx = c > mx ? c : mx;
             }
         }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned n = 0;
+            for (unsigned wi = 0; wi < (blockDim.x >> 5); wi++) n += warp_hits[wi];
+            if (cta_root != held_root) {
+                if (held) { const unsigned c = atomicAdd(&cnt[held_root], held) + held; mx = c > mx ? c : mx; }
+                held_root = cta_root; held = 0;
+            }
+            held += n;
+        }
 #endif
     }
+#ifndef SGPE_EMU
+    if (threadIdx.x == 0 && held) { const unsigned c = atomicAdd(&cnt[held_root], held) + held; mx = c > mx ? c : mx; }
+#endif
     red[threadIdx.x] = mx;
     __syncthreads();
     for (int s = blockDim.x / 2; s > 0; s >>= 1) {
@@ -397,15 +471,19 @@ __global__ void __launch_bounds__(256) unwrap_level_count_pass(const unsigned* v
     }
     if (threadIdx.x == 0 && red[0]) atomicMax(result, red[0]);
 }
-// the two groups edge T joins: result[1..4] = root and size on the first pixel's side, root and size on the second's
-__global__ void __launch_bounds__(256) unwrap_level_sides_pass(const UnwrapEdge* el, long long ne, unsigned T, int nx,
-                                                               unsigned* parent, const unsigned* cnt, unsigned* result) {
+// the two groups edge T = hi joins, in the forest at lo = T - 1: result[1..4] = root and size on the first pixel's
+// side, root and size on the second's
+__global__ void __launch_bounds__(256) unwrap_level_sides_pass(const UnwrapEdge* el, long long ne, const long long* ctrl, int nx,
+                                                               unsigned* forest_a, unsigned* forest_b, const unsigned* cnt,
+                                                               unsigned* result) {
+    const UnwrapProbe q = unwrap_probe(ctrl, forest_a, forest_b);
+    const long long T = ctrl[1];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ne; i += (long long)gridDim.x * blockDim.x) {
         const UnwrapEdge e = el[i];
-        if (e.k != T) continue;
+        if ((long long)e.k != T) continue;
         const unsigned p1 = e.t & ~kUnwrapTreeBit;
-        const unsigned a = unwrap_uf_find(parent, p1);
-        const unsigned b = unwrap_uf_find(parent, p1 + ((e.t & kUnwrapTreeBit) ? (unsigned)nx : 1u));
+        const unsigned a = unwrap_uf_find(q.snap, p1);
+        const unsigned b = unwrap_uf_find(q.snap, p1 + ((e.t & kUnwrapTreeBit) ? (unsigned)nx : 1u));
         result[1] = a; result[2] = cnt[a]; result[3] = b; result[4] = cnt[b];
     }
 }
