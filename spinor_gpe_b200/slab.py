@@ -86,8 +86,9 @@ class SeparableProblem:
                  coupling=None, wavel=790.1e-9, kin_shift=False, rot_coupling=True, detuning_slope=0.0):
         import tempfile, os
         from .pspinor import PSpinor
-        tiny = PSpinor(os.path.join(tempfile.mkdtemp(prefix='sgpe_sep_'), 'p') + os.sep, omeg=omeg, g_sc=g_sc,
-                       mesh_points=(32, 32), r_sizes=r_sizes, atom_num=atom_num, pop_frac=pop_frac)
+        with tempfile.TemporaryDirectory(prefix='sgpe_sep_') as scratch:      # PSpinor creates its data directories
+            tiny = PSpinor(os.path.join(scratch, 'p') + os.sep, omeg=omeg, g_sc=g_sc,
+                           mesh_points=(32, 32), r_sizes=r_sizes, atom_num=atom_num, pop_frac=pop_frac)
         self.atom_num, self.g_sc, self.chem_pot, self.pop_frac = atom_num, tiny.g_sc, tiny.chem_pot, pop_frac
         self.omeg = tiny.omeg
         nx, ny = int(mesh_points[0]), int(mesh_points[1])
