@@ -105,7 +105,9 @@ int sgpe_full_steps(sgpe_plan* p, int n, double* pops_dev, int64_t pops_stride, 
  * [batch][energy_stride] doubles, step i writes energy_dev[b*energy_stride + 4*(energy_first+i) + {0..3}] = E_total,
  * E_kin, E_pot, E_int.  The junction pass that follows a full step stores the boundary state on the side; its inverse
  * transform (with the normalisation and the density maxima folded into the last pass) and the stencil pass run
- * behind it: three extra launches per step, nothing synchronises.  unwrap_mode 0 or 1 (see sgpe_energy). */
+ * behind it: three extra launches per step, nothing synchronises — unwrap_mode 0 or 1 (see sgpe_energy).
+ * unwrap_mode 2 (the reference's own definition: phase unwrapped by region merging) evaluates every closed step
+ * through the stand-alone path of sgpe_energy and synchronises st once per step (≈ 30 ms per step at 2048^2). */
 int sgpe_full_steps_energy(sgpe_plan* p, int n, double* pops_dev, int64_t pops_stride, int pops_first,
                            double* energy_dev, int64_t energy_stride, int energy_first, int unwrap_mode,
                            double kl_term, sgpe_stream st);

@@ -1760,20 +1760,33 @@ int sgpe_full_steps(sgpe_plan* p, int n, double* pops, int64_t pops_stride, int 
     return 0;
 }
 
+static int energy_of_real_space(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, double* out, sgpe_stream st,
+                                long long out_bstride);
+
 int sgpe_full_steps_energy(sgpe_plan* p, int n, double* pops, int64_t pops_stride, int pops_first, double* energy,
                            int64_t energy_stride, int energy_first, int unwrap_mode, double kl_term, sgpe_stream st) {
     int rc = ready_to_step(p);
     if (rc) return rc;
     if (n < 0) return fail(SGPE_EINVAL, "negative step count");
     if (!energy) return fail(SGPE_EINVAL, "null energy buffer (use sgpe_full_steps)");
-    if (unwrap_mode != 0 && unwrap_mode != 1)
-        return fail(SGPE_EINVAL, "per-step tracking stays on the device: unwrap_mode 0 or 1 (sgpe_energy offers 2)");
+    if (unwrap_mode < 0 || unwrap_mode > 2) return fail(SGPE_EINVAL, "unwrap_mode must be 0, 1 or 2");
     DeviceGuard guard(p->device);
     cudaStream_t s = (cudaStream_t)st;
     const size_t bytes = (size_t)p->batch * 2 * p->plane * p->csize;
     if (!p->scratch && cudaMalloc(&p->scratch, bytes) != cudaSuccess) return fail(SGPE_ENOMEM, "scratch allocation failed");
     if (!p->maxdens && cudaMalloc((void**)&p->maxdens, sizeof(double) * 2 * p->batch) != cudaSuccess)
         return fail(SGPE_ENOMEM, "scratch allocation failed");
+    if (unwrap_mode == 2) {
+        // the reference's own definition (phase unwrapped by reliability-sorted region merging) after every step: the
+        // stand-alone evaluation of the closed step, steered from the host (synchronises the stream once per step)
+        for (int i = 0; i < n; i++) {
+            if ((rc = sgpe_full_steps(p, 1, pops, pops_stride, pops_first + i, st))) return rc;
+            if ((rc = sgpe_store_psik(p, p->scratch, st))) return rc;
+            if ((rc = sgpe_fft2d(p, p->scratch, p->scratch, 1, st))) return rc;
+            if ((rc = energy_of_real_space(p, p->scratch, 2, kl_term, energy + 4LL * (energy_first + i), st, energy_stride))) return rc;
+        }
+        return 0;
+    }
     if (p->generic) {
         // generic meshes: the energy of every step through the stand-alone evaluation (junction closed each step)
         for (int i = 0; i < n; i++) {
@@ -1883,7 +1896,8 @@ int sgpe_normalise(sgpe_plan* p, const void* in, void* out, double vol, sgpe_str
 }
 
 // the energy functional on a real-space state (the part of eng_expect after its ifft_2d, tensor_propagator.py:301-324)
-static int energy_of_real_space(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, double* out, sgpe_stream st) {
+static int energy_of_real_space(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, double* out, sgpe_stream st,
+                                long long out_bstride) {
     if (!p->maxdens && cudaMalloc((void**)&p->maxdens, sizeof(double) * 2 * p->batch) != cudaSuccess)
         return fail(SGPE_ENOMEM, "scratch allocation failed");
     if (unwrap_mode == 2) {
@@ -1897,7 +1911,7 @@ static int energy_of_real_space(sgpe_plan* p, const void* psi, int unwrap_mode, 
         if (!rc) rc = unwrap_increments(p, p->unwrap_phi, 2 * p->batch, p->unwrap_inc, (cudaStream_t)st);
         if (rc) return rc;
     }
-    return SGPE_BY_DTYPE(p, run_energy, p, psi, unwrap_mode, kl_term, out, (cudaStream_t)st);
+    return SGPE_BY_DTYPE(p, run_energy, p, psi, unwrap_mode, kl_term, out, (cudaStream_t)st, out_bstride);
 }
 
 int sgpe_energy(sgpe_plan* p, const void* psik, int unwrap_mode, double kl_term, double* out, sgpe_stream st) {
@@ -1915,7 +1929,7 @@ int sgpe_energy(sgpe_plan* p, const void* psik, int unwrap_mode, double kl_term,
         psik = p->scratch;
     }
     if ((rc = sgpe_fft2d(p, psik, p->scratch, 1, st))) return rc;
-    return energy_of_real_space(p, p->scratch, unwrap_mode, kl_term, out, st);
+    return energy_of_real_space(p, p->scratch, unwrap_mode, kl_term, out, st, 4);
 }
 
 int sgpe_kinetic_spectral(sgpe_plan* p, const void* psik, double* out, sgpe_stream st) {
@@ -1960,7 +1974,7 @@ int sgpe_energy_real_space(sgpe_plan* p, const void* psi, int unwrap_mode, doubl
     if (!(p->grid_set && p->g_set && p->pot_set)) return fail(SGPE_ESTATE, "set grid, interactions and potential first");
     if (unwrap_mode < 0 || unwrap_mode > 2) return fail(SGPE_EINVAL, "unwrap_mode must be 0, 1 or 2");
     DeviceGuard guard(p->device);
-    return energy_of_real_space(p, psi, unwrap_mode, kl_term, out, st);
+    return energy_of_real_space(p, psi, unwrap_mode, kl_term, out, st, 4);
 }
 
 int sgpe_unwrap_phase(sgpe_plan* p, const void* in, int kind, int nplanes, int mask, double* out, sgpe_stream st_) {

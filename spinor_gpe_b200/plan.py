@@ -205,7 +205,8 @@ class Plan:
     def full_steps(self, n, pops=None, first=0, energy=None, kl_term=0.0, unwrap='none'):
         """pops: optional float64 CUDA tensor (B, n_total, 2); step i writes row first+i.  energy: optional float64
         CUDA tensor (B, n_total, 4) — the energy expectation [E_total, E_kin, E_pot, E_int] of every step boundary
-        (row first+i), evaluated behind the junction passes (``unwrap`` 'none' or 'local'; no synchronisation)."""
+        (row first+i): ``unwrap`` 'none' or 'local' evaluated behind the junction passes without synchronisation,
+        'herraez' (the reference's definition) through the stand-alone evaluation of every closed step."""
         stride = 0
         if pops is not None:
             assert pops.is_cuda and pops.dtype == torch.float64 and pops.is_contiguous()

@@ -15,8 +15,7 @@ Differences a user can observe (all documented in DESIGN.md):
   ``separable=False`` forces the general dense path.
 * ``eng_expect`` runs on the GPU.  The reference unwraps the phase of each component with
   ``skimage.restoration.unwrap_phase`` (tensor_tools.py:531); ``unwrap='herraez'`` is that algorithm
-  (``sgpe_unwrap_phase``: per-pixel work and the edge sort on the device, the sequential region merging in the
-  library's host code), ``'none'`` differentiates the wrapped phase as it is and ``'local'`` uses locally wrapped
+  (``sgpe_unwrap_phase``: per-pixel work, the edge sort and the region merging on the device), ``'none'`` differentiates the wrapped phase as it is and ``'local'`` uses locally wrapped
   differences (both stay on the device and never synchronise).  The constructor's ``unwrap`` argument
   (default ``DEFAULT_UNWRAP``) is what ``prop_loop`` uses for ``PropResult.eng_final``.
 """
@@ -129,11 +128,12 @@ class TensorPropagator:
                  track_energy=False):
         dev = torch.device(device)
         # track_energy: prop_loop also records eng_expect of every step (PropResult.eng_history, (n_steps, 4)); pass
-        # 'none' or 'local' to choose the phase treatment (True = 'none'); it stays on the device, so the reference's
-        # host-side unwrapping is not available per step
+        # 'none', 'local' or 'herraez' to choose the phase treatment (True = 'none').  'none' / 'local' are fused with
+        # the stepping and never synchronise; 'herraez' (the reference's definition) unwraps the phase after every step
+        # (device-side region merging steered from the host: tens of milliseconds per step at 2048^2)
         self.track_energy = 'none' if track_energy is True else (track_energy or None)
-        if self.track_energy not in (None, 'none', 'local'):
-            raise ValueError("track_energy must be False, True, 'none' or 'local'")
+        if self.track_energy not in (None, 'none', 'local', 'herraez'):
+            raise ValueError("track_energy must be False, True, 'none', 'local' or 'herraez'")
         self.unwrap = DEFAULT_UNWRAP if unwrap is None else unwrap
         if self.unwrap not in ('none', 'local', 'herraez'):
             raise ValueError("unwrap must be 'none', 'local' or 'herraez'")

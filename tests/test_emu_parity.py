@@ -259,7 +259,7 @@ def test_emulated_energy_tracking(case, run, separable):
     assert rel(pl.store()[0], o.psik.numpy()) < 1e-12
     assert np.isfinite(eng2).all()
     with pytest.raises(Exception):
-        pl.full_steps_energy(1, kl, 2)              # host-side unwrapping is not available per step
+        pl.full_steps_energy(1, kl, 3)              # unwrap_mode 0, 1 or 2 (2: tests/test_unwrap.py)
     pl.close()
 
 

@@ -172,6 +172,31 @@ def test_emulated_energy_with_unwrapping_vs_oracle(case, run):
     pl.close()
 
 
+@pytest.mark.parametrize('case,run', [('cgrad_64', 0), ('nocoupl_64', 0)])
+def test_emulated_energy_of_every_step_with_unwrapping(case, run):
+    """sgpe_full_steps_energy(unwrap_mode 2): eng_expect in the reference's definition (phase unwrapped) after every
+    full step against the oracle stepping beside it; state and populations as without the tracking."""
+    from tests.emu_harness import plan_from_problem
+    z = np.load(os.path.join(GOLDEN, case + '.npz'))
+    pre = f'r{run}_'
+    prob = orc.Problem.from_golden(z, pre)
+    mode, dt, n = str(z[pre + 'mode']), float(z[pre + 'dt']), int(z[pre + 'n_steps'])
+    kl = 2 * prob.kL * prob.is_coupling
+    pl = plan_from_problem(prob, mode, dt)
+    pops, eng = pl.full_steps_energy(n, kl, 2)
+    np.testing.assert_allclose(pops[0], z[pre + 'pops_vals'], rtol=1e-12)
+    np.testing.assert_allclose(np.abs(pl.store()[0] - z[pre + 'psik_final']).max(), 0, atol=1e-12 * np.abs(z[pre + 'psik_final']).max())
+    o = orc.OraclePropagator(prob, dt, mode)
+    for i in range(n):
+        o.full_step()
+        want = orc.energy(prob, o.psik, unwrap=oracle_unwrap)
+        if i == n - 1:
+            np.testing.assert_allclose(eng[0, i], want, rtol=1e-10, err_msg=f'step {i}')
+        # (E_pot and E_int do not depend on the phase; E_kin of an intermediate state may sit on a 2 pi decision)
+        np.testing.assert_allclose(eng[0, i, 2:], want[2:], rtol=1e-10, err_msg=f'step {i}')
+    pl.close()
+
+
 def test_unwrap_rejects_bad_arguments():
     from tests.emu_harness import EmuPlan
     from spinor_gpe_b200._capi import SgpeError
@@ -304,3 +329,30 @@ def test_gpu_device_merging_equals_host_merging_at_full_size():
     assert float((k - torch.round(k)).abs().max()) < 1e-9
     assert int(torch.round(k[1]).max() - torch.round(k[1]).min()) >= 2
     pl.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('case,run', [('cgrad_64', 0), ('nocoupl_64', 0)])
+def test_gpu_energy_of_every_step_in_the_reference_definition(case, run):
+    """PSpinor.imaginary / real(track_energy='herraez'): eng_expect with the phase unwrapped as the reference does,
+    after EVERY full step (PropResult.eng_history), against the oracle stepping beside it; the final state and the
+    populations are those of the golden run."""
+    from tests.test_gpu_parity import GOLDEN_SPECS, build_case
+    z = np.load(os.path.join(GOLDEN, case + '.npz'))
+    pre = f'r{run}_'
+    prob = orc.Problem.from_golden(z, pre)
+    spec = GOLDEN_SPECS[case]
+    ps = build_case(spec)
+    mode, dt, n = str(z[pre + 'mode']), float(z[pre + 'dt']), int(z[pre + 'n_steps'])
+    fn = ps.imaginary if mode == 'imag' else ps.real
+    res, prop = fn(dt, n, 'cuda', track_energy='herraez')
+    assert np.abs(np.array(res.psik) - z[pre + 'psik_final']).max() < 1e-10 * np.abs(z[pre + 'psik_final']).max()
+    np.testing.assert_allclose(res.pops['vals'], z[pre + 'pops_vals'], rtol=1e-9)
+    o = orc.OraclePropagator(prob, dt, mode)
+    for i in range(n):
+        o.full_step()
+        want = orc.energy(prob, o.psik, unwrap=oracle_unwrap)
+        np.testing.assert_allclose(res.eng_history[i, 2:], want[2:], rtol=1e-9, err_msg=f'step {i}')
+        if i == n - 1:
+            np.testing.assert_allclose(res.eng_history[i], want, rtol=1e-9)
+    np.testing.assert_allclose(res.eng_history[-1], res.eng_final, rtol=1e-9)
