@@ -172,8 +172,10 @@ class TensorPropagator:
         cdtype = {'c128': torch.complex128, 'c64': torch.complex64}[precision]
         self._cdtype = cdtype
 
-        psik0 = np.asarray(spin.psik)
-        ny, nx = psik0.shape[-2:]
+        psik0 = [np.asarray(spin.psik[0]), np.asarray(spin.psik[1])]      # (no stacked host copy: 134 MB at 2048^2)
+        ny, nx = psik0[0].shape[-2:]
+        if psik0[1].shape != psik0[0].shape or psik0[0].ndim != 2:
+            raise ValueError("psik must be two (Ny, Nx) arrays")
         check_mesh(nx, ny)
         # the kernels read row-major (Ny, Nx) float64 grids through raw pointers: whatever layout the user's arrays
         # have (Fortran order, transposed views, other dtypes), the device copies are C-contiguous float64
@@ -262,7 +264,12 @@ class TensorPropagator:
         ksep = psep = None
         if self._separable_opt:
             ksep = split_separable(self._kin_np)
-            psep = split_separable(self._pot_np)
+            if self._pot_np[0] is self._pot_np[1]:              # one grid for both components: checked once
+                psep = split_separable(self._pot_np[:1])
+                if psep is not None:
+                    psep = (np.repeat(psep[0], 2, axis=0), np.repeat(psep[1], 2, axis=0))
+            else:
+                psep = split_separable(self._pot_np)
         # the plan borrows the device pointers of the dense grids: it keeps the tensors alive itself, so rebinding
         # the public attributes (prop.pot_eng_spin = ...) cannot leave it with a dangling pointer
         if ksep is not None:
