@@ -277,8 +277,14 @@ void invalidate_tables(sgpe_plan::FactorTable* slots, int n) { for (int i = 0; i
 // measured on B200 (profiles/r02_kernel_sweep.jsonl) — complex128: the persistent pass with TMA-staged tiles and the
 // split inverse exchange wins from 1024-point columns on (+5 % at 2048, +13 % at 4096; +12..17 % in real time) and for
 // batched plans (+6..8 % at 8 / 64 x 512^2); complex64: half-width persistent tiles, two CTAs per SM (+12..19 % at 2048).
+// With the plan's 32 KiB twiddle tables copied to shared memory (selector 4) the imaginary-time pass of ONE 2048-point
+// trajectory gains another 0.7 % (109.9 -> 108.6 us); in real time, at 1024 points and for batches it loses 1.6-5 %, at
+// 4096 points the tables do not fit beside the tile images (profiles/r02_variants.md).
 int default_col_kernel(const sgpe_plan* p) {
-    if (p->dtype == SGPE_C128) return (p->ny >= 1024 || (p->batch >= 2 && p->ny >= 512)) ? 1 : 0;
+    if (p->dtype == SGPE_C128) {
+        if (p->ny == 2048 && p->batch == 1 && p->tm == SGPE_TIME_IMAG && p->kin_mode == 1) return 4;   // (factor tables only)
+        return (p->ny >= 1024 || (p->batch >= 2 && p->ny >= 512)) ? 1 : 0;
+    }
     return p->ny >= 1024 ? 5 : 0;
 }
 
