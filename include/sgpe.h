@@ -171,7 +171,7 @@ int sgpe_energy_real_space(sgpe_plan* p, const void* psi_dev, int unwrap_mode, d
  * edges, the region merging (the minimum spanning tree of the pixel grid under the edge ranks with the relative
  * multiples of 2 pi along it — Boruvka rounds over an offset-carrying union-find — then the one pixel group whose
  * values the published merge rules never move, found level by level with a bisection over the rank threshold and a
- * lock-free union-find; groups of at most "unwrap_tail" = 16384 tree edges finish on the host) and the final pass.
+ * lock-free, size-carrying union-find; groups of at most "unwrap_tail" = 16384 tree edges finish on the host) and the final pass.
  * The integer field equals the sequential edge-by-edge merging's bit for bit, global offset included.  Border pixels
  * get the fixed reliability value 9999999 (scikit-image adds rand()), equal keys keep edge order (horizontal edges
  * row by row, then vertical).  Synchronises st.

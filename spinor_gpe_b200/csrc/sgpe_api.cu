@@ -929,14 +929,15 @@ int64_t unwrap_anchor(int nx, const uint32_t* tree, size_t n_tree, size_t plane)
 static int unwrap_anchor_device(sgpe_plan* p, int nx, size_t plane, cudaStream_t st, int64_t* anchor, int* levels, int* probes) {
     sgpe_plan::UnwrapCache& w = p->unwrap;
     unsigned* tree = reinterpret_cast<unsigned*>(w.keys);
-    unsigned* cnt = tree + plane;
-    unsigned* snap = reinterpret_cast<unsigned*>(w.rel);
-    unsigned* work = snap + plane;
+    unsigned* size_a = tree + plane;                 // group sizes at the roots of forest a / b
+    unsigned* size_b = size_a + plane;
+    unsigned* forest_a = reinterpret_cast<unsigned*>(w.rel);
+    unsigned* forest_b = forest_a + plane;
     unsigned* vl[2] = {w.vals, w.vals + plane};
     sgpe::UnwrapEdge* el[2] = {reinterpret_cast<sgpe::UnwrapEdge*>(w.keys_sorted), reinterpret_cast<sgpe::UnwrapEdge*>(w.keys_sorted) + plane};
     unsigned* result = w.counters + 8;
     long long* ctrl = w.ctrl;
-    struct { long long ctrl[3]; unsigned result[8]; } back;
+    struct { long long ctrl[4]; unsigned result[8]; } back;
     const dim3 block(256);
     long long nv = (long long)plane, ne = nv - 1, bound = ne;
     int cur = 0;
@@ -944,26 +945,22 @@ static int unwrap_anchor_device(sgpe_plan* p, int nx, size_t plane, cudaStream_t
     p->launches++;
     while (ne > (long long)p->unwrap_tail) {
         const dim3 grid_v(unwrap_blocks(nv)), grid_e(unwrap_blocks(ne));
-        const size_t count_smem = (256 + 16) * sizeof(unsigned);
         // no group of more than nv / 2 pixels with the edges <= lo (none at all: lo = -1), one with those <= hi
         SGPE_LAUNCH((sgpe::unwrap_level_begin_pass), dim3(1), dim3(32), 0, st, -1ll, bound - 1, ctrl, result);
-        SGPE_LAUNCH((sgpe::unwrap_level_reset_pass), grid_v, block, 0, st, vl[cur], nv, (const long long*)nullptr, snap, work, 0, cnt);
+        SGPE_LAUNCH((sgpe::unwrap_level_reset_pass), grid_v, block, 0, st, vl[cur], nv, (const long long*)nullptr, forest_a, forest_b, size_a, size_b);
         p->launches += 2;
         int enqueued = 0;
         for (long long len = bound; len > 1; len = (len + 1) / 2) {        // the interval shrinks to ceil(len / 2) at worst
-            SGPE_LAUNCH((sgpe::unwrap_level_reset_pass), grid_v, block, 0, st, vl[cur], nv, (const long long*)ctrl, snap, work, 0, cnt);
-            SGPE_LAUNCH((sgpe::unwrap_level_union_pass), grid_e, block, 0, st, el[cur], ne, (const long long*)ctrl, nx, snap, work);
-            SGPE_LAUNCH((sgpe::unwrap_level_count_pass), grid_v, block, count_smem, st, vl[cur], nv, (const long long*)ctrl, snap, work, 0, cnt, result);
+            SGPE_LAUNCH((sgpe::unwrap_level_reset_pass), grid_v, block, 0, st, vl[cur], nv, (const long long*)ctrl, forest_a, forest_b, size_a, size_b);
+            SGPE_LAUNCH((sgpe::unwrap_level_union_pass), grid_e, block, 0, st, el[cur], ne, (const long long*)ctrl, nx, forest_a, forest_b, size_a, size_b, nv, result);
             SGPE_LAUNCH((sgpe::unwrap_level_step_pass), dim3(1), dim3(32), 0, st, nv, ctrl, result);
-            p->launches += 4;
+            p->launches += 3;
             enqueued++;
         }
         *probes += enqueued;
         // edge `hi` creates the majority group; the forest at lo = hi - 1 is the state just before it
-        SGPE_LAUNCH((sgpe::unwrap_level_reset_pass), grid_v, block, 0, st, vl[cur], nv, (const long long*)nullptr, snap, work, 1, cnt);
-        SGPE_LAUNCH((sgpe::unwrap_level_count_pass), grid_v, block, count_smem, st, vl[cur], nv, (const long long*)ctrl, snap, work, 1, cnt, result);
-        SGPE_LAUNCH((sgpe::unwrap_level_sides_pass), grid_e, block, 0, st, el[cur], ne, (const long long*)ctrl, nx, snap, work, (const unsigned*)cnt, result);
-        p->launches += 3;
+        SGPE_LAUNCH((sgpe::unwrap_level_sides_pass), grid_e, block, 0, st, el[cur], ne, (const long long*)ctrl, nx, forest_a, forest_b, size_a, size_b, result);
+        p->launches++;
         SGPE_CUDA(cudaGetLastError());
         SGPE_CUDA(cudaMemcpyAsync(back.ctrl, ctrl, sizeof(back.ctrl), cudaMemcpyDeviceToHost, st));
         SGPE_CUDA(cudaMemcpyAsync(back.result, result, sizeof(back.result), cudaMemcpyDeviceToHost, st));
@@ -976,7 +973,7 @@ static int unwrap_anchor_device(sgpe_plan* p, int nx, size_t plane, cudaStream_t
         const unsigned keep = second_joins ? back.result[1] : back.result[3];
         const long long keep_size = second_joins ? s1 : s2;
         SGPE_LAUNCH((sgpe::unwrap_level_select_pass), dim3(unwrap_blocks(nv)), block, 0, st, vl[cur], nv, el[cur], ne, (unsigned)hi, keep,
-                    back.ctrl[2] ? work : snap, vl[1 - cur], el[1 - cur], result);
+                    back.ctrl[2] ? forest_b : forest_a, vl[1 - cur], el[1 - cur], result);
         p->launches++;
         SGPE_CUDA(cudaMemcpyAsync(back.result, result, sizeof(back.result), cudaMemcpyDeviceToHost, st));
         SGPE_CUDA(cudaStreamSynchronize(st));
@@ -1035,7 +1032,7 @@ int unwrap_increments_impl(sgpe_plan* p, const double* phi_dev, int nplanes, int
 #endif
     const bool device_merge = p->unwrap_merge == 0 && plane > 1;
     // the anchor search on the device handles the planes one after the other; the host pass runs one plane per core
-    const bool device_anchor = device_merge && n_edges >= plane + plane / 2 + 2 &&
+    const bool device_anchor = device_merge && n_edges >= plane + plane / 2 + 2 &&       // (room for the lists in the sort's buffers)
                                (p->unwrap_anchor == 1 || (p->unwrap_anchor < 0 && nplanes <= 4 && plane >= 65536));
     const bool timing = getenv("SGPE_UNWRAP_TIMING") != nullptr;       // dev: phase times on stderr
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };

@@ -310,8 +310,8 @@ __global__ void unwrap_anchor_zero_pass(long long anchor, int* inc) { if (thread
 // are again groups Kruskal formed, and the published rule for (|A|, |B|) names the half whose values survive: recurse
 // into it.  The size at least halves per level, and "does a group of more than |X| / 2 pixels exist once the edges up
 // to rank T are in" is monotone in T, so each level is a bisection over T with a lock-free union-find over the tree
-// edges of X (ECL-CC style hooking by index) and a counting pass.  The bisection keeps the forest of its lower bound
-// and only adds the edges between the bounds.  Small X go to the host (a few thousand edges).
+// edges of X (ECL-CC style hooking by index) that carries the group sizes along.  The bisection keeps the forest of its
+// lower bound and only adds the edges between the bounds.  Small X go to the host (a few thousand edges).
 struct UnwrapEdge { unsigned k, t; };      // position in the rank-sorted tree-edge list; first pixel | vertical << 31
 
 SGPE_DI unsigned unwrap_uf_find(unsigned* parent, unsigned x) {
@@ -322,36 +322,60 @@ SGPE_DI unsigned unwrap_uf_find(unsigned* parent, unsigned x) {
     }
     return curr;
 }
-SGPE_DI void unwrap_uf_union(unsigned* parent, unsigned a, unsigned b) {
+// Lock-free union (the larger root index hangs below the smaller, ECL-CC style) with group sizes kept at the roots.
+// A root that has just been hung below another hands over what it
+// holds with an atomic exchange; whoever adds to a node afterwards looks again whether that node is still a root and,
+// if not, takes back what sits there and passes it on.  Either the absorbing thread's exchange comes after an addition
+// (and carries it along) or the adder sees the node absorbed (and forwards it itself): pixels are never lost or counted
+// twice, and when the pass has ended every size sits at a root.  An addition that lands on a root and lifts it above
+// `report_above` reports the new total (the last one to land on a group reports its final size).
+SGPE_DI void unwrap_uf_union_sized(unsigned* parent, unsigned* size, unsigned a, unsigned b, unsigned* largest,
+                                   unsigned report_above) {
     a = unwrap_uf_find(parent, a);
     b = unwrap_uf_find(parent, b);
     while (a != b) {
-        if (a < b) { const unsigned t = a; a = b; b = t; }        // the larger index hangs below the smaller
+        if (a < b) { const unsigned t = a; a = b; b = t; }
         const unsigned seen = atomicCAS(&parent[a], a, b);
-        if (seen == a) break;
-        a = seen;                                                 // someone else moved a: climb and retry
+        if (seen == a) {
+            unsigned carry = atomicExch(&size[a], 0u);
+            unsigned to = b;
+            while (carry) {
+                const unsigned now = atomicAdd(&size[to], carry) + carry;
+                __threadfence();                                  // the addition is out before the look at the parent
+                const unsigned up = __ldcg(&parent[to]);
+                if (up == to) { if (now > report_above) atomicMax(largest, now); break; }
+                carry = atomicExch(&size[to], 0u);
+                to = up;
+            }
+            break;
+        }
+        a = seen;
     }
 }
 
 // The bisection of a level runs without the host: ctrl = {lo, hi, which forest holds the state at lo} lives on the
-// device, the passes of a probe read it (and do nothing once hi - lo <= 1), unwrap_level_step_pass moves a bound after
-// each probe.  The host enqueues ceil(log2(hi - lo)) probes and reads the outcome once per level.
-struct UnwrapProbe { long long lo, mid; unsigned* snap; unsigned* work; bool live; };
-SGPE_DI UnwrapProbe unwrap_probe(const long long* ctrl, unsigned* forest_a, unsigned* forest_b) {
+// device, the passes of a probe read it (and do nothing once hi - lo <= 1), unwrap_level_step_pass
+// moves a bound after each probe.  The host enqueues ceil(log2(hi - lo)) probes and reads the outcome once per level.
+struct UnwrapProbe { long long lo, mid; unsigned* snap; unsigned* work; unsigned* snap_size; unsigned* work_size; bool live; };
+SGPE_DI UnwrapProbe unwrap_probe(const long long* ctrl, unsigned* forest_a, unsigned* forest_b, unsigned* size_a, unsigned* size_b) {
     UnwrapProbe q;
     const long long hi = ctrl[1];
     q.lo = ctrl[0];
     q.live = hi - q.lo > 1;
     q.mid = q.lo + (hi - q.lo) / 2;
-    q.snap = ctrl[2] ? forest_b : forest_a;
-    q.work = ctrl[2] ? forest_a : forest_b;
+    const bool flipped = ctrl[2] != 0;
+    q.snap = flipped ? forest_b : forest_a;
+    q.work = flipped ? forest_a : forest_b;
+    q.snap_size = flipped ? size_b : size_a;
+    q.work_size = flipped ? size_a : size_b;
     return q;
 }
+// level start: no edge in (lo = -1: every pixel its own group of size 1, in forest_a / size_a)
 __global__ void unwrap_level_begin_pass(long long lo, long long hi, long long* ctrl, unsigned* result) {
-    if (threadIdx.x == 0) { ctrl[0] = lo; ctrl[1] = hi; ctrl[2] = 0; }
-    if (threadIdx.x < 8) result[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { ctrl[0] = lo; ctrl[1] = hi; ctrl[2] = 0; ctrl[3] = 0; }
+    if (threadIdx.x < 8) result[threadIdx.x] = 0u;
 }
-// after a probe: result[0] = size of the largest group with the edges up to mid in
+// after a probe: result[0] = size of the group of more than nv / 2 pixels with the edges up to mid in, or 0
 __global__ void unwrap_level_step_pass(long long nv, long long* ctrl, unsigned* result) {
     if (threadIdx.x != 0) return;
     const long long lo = ctrl[0], hi = ctrl[1];
@@ -370,113 +394,48 @@ __global__ void __launch_bounds__(256) unwrap_level0_pass(const unsigned* tree, 
         if (v + 1 < plane) { UnwrapEdge e; e.k = (unsigned)v; e.t = tree[v]; el[v] = e; }
     }
 }
-// Outside a probe (ctrl == nullptr): forest_a[v] = v (identity) or, with keep_state, left as is; cnt[v] = 0.
-// In a probe: work forest = copy of the forest at lo, cnt[v] = 0.
+// ctrl == nullptr: forest_a[v] = v, size_a[v] = 1.  In a probe: work forest and sizes = copy of those at lo.
 __global__ void __launch_bounds__(256) unwrap_level_reset_pass(const unsigned* vl, long long nv, const long long* ctrl,
-                                                               unsigned* forest_a, unsigned* forest_b, int keep_state,
-                                                               unsigned* cnt) {
-    const unsigned* src = nullptr;
-    unsigned* dst = forest_a;
-    if (ctrl) {
-        const UnwrapProbe q = unwrap_probe(ctrl, forest_a, forest_b);
-        if (!q.live) return;
-        src = q.snap; dst = q.work;
-    } else if (keep_state) {
-        dst = nullptr;
+                                                               unsigned* forest_a, unsigned* forest_b, unsigned* size_a,
+                                                               unsigned* size_b) {
+    if (!ctrl) {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+            const unsigned v = vl[i];
+            forest_a[v] = v;
+            size_a[v] = 1u;
+        }
+        return;
     }
+    const UnwrapProbe q = unwrap_probe(ctrl, forest_a, forest_b, size_a, size_b);
+    if (!q.live) return;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
         const unsigned v = vl[i];
-        if (dst) dst[v] = src ? src[v] : v;
-        cnt[v] = 0;
+        q.work[v] = q.snap[v];
+        q.work_size[v] = q.snap_size[v];
     }
 }
-// a probe: joins the ends of the level's edges with lo < k <= mid in the work forest
+// a probe: joins the ends of the level's edges with lo < k <= mid in the work forest, sizes carried along;
+// result[0] (preset to 0) becomes the size of the group of more than nv / 2 pixels, if the probe creates one
 __global__ void __launch_bounds__(256) unwrap_level_union_pass(const UnwrapEdge* el, long long ne, const long long* ctrl,
-                                                               int nx, unsigned* forest_a, unsigned* forest_b) {
-    const UnwrapProbe q = unwrap_probe(ctrl, forest_a, forest_b);
+                                                               int nx, unsigned* forest_a, unsigned* forest_b,
+                                                               unsigned* size_a, unsigned* size_b, long long nv,
+                                                               unsigned* result) {
+    const UnwrapProbe q = unwrap_probe(ctrl, forest_a, forest_b, size_a, size_b);
     if (!q.live) return;
+    const unsigned half = (unsigned)(nv / 2);                // 2 * size > nv  <=>  size > floor(nv / 2)
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ne; i += (long long)gridDim.x * blockDim.x) {
         const UnwrapEdge e = el[i];
         if ((long long)e.k <= q.lo || (long long)e.k > q.mid) continue;
         const unsigned p1 = e.t & ~kUnwrapTreeBit;
-        unwrap_uf_union(q.work, p1, p1 + ((e.t & kUnwrapTreeBit) ? (unsigned)nx : 1u));
+        unwrap_uf_union_sized(q.work, q.work_size, p1, p1 + ((e.t & kUnwrapTreeBit) ? (unsigned)nx : 1u), result, half);
     }
-}
-// group sizes at the roots and the largest of them (result[0], zeroed by the caller).  Late in a bisection most pixels
-// share ONE root: a CTA keeps a running count for the root its first pixel of an iteration has and adds it to the
-// root's counter only when that root changes (a few thousand atomics on the hot address instead of one per warp);
-// pixels with another root go through one atomic per distinct root of their warp.  Every atomic returns the running
-// total of its root, so the largest value seen anywhere is the size of the largest group.
-// use_snap == 0: a probe (work forest; nothing once the bisection has closed), 1: the forest at lo.
-__global__ void __launch_bounds__(256) unwrap_level_count_pass(const unsigned* vl, long long nv, const long long* ctrl,
-                                                               unsigned* forest_a, unsigned* forest_b, int use_snap,
-                                                               unsigned* cnt, unsigned* result) {
-    const UnwrapProbe q = unwrap_probe(ctrl, forest_a, forest_b);
-    if (!use_snap && !q.live) return;
-    unsigned* parent = use_snap ? q.snap : q.work;
-    SGPE_DYN_SMEM(smem_raw);                 // blockDim.x + 16 unsigned
-    unsigned* red = reinterpret_cast<unsigned*>(smem_raw);
-    unsigned mx = 0;
-#ifndef SGPE_EMU
-    unsigned* warp_hits = red + blockDim.x;  // [8] per-warp counts of the CTA's current root, [8] = that root
-    unsigned held_root = kUnwrapNoEdge, held = 0;          // thread 0 only
-#endif
-    for (long long base = (long long)blockIdx.x * blockDim.x; base < nv; base += (long long)gridDim.x * blockDim.x) {
-        const long long i = base + threadIdx.x;
-        const bool live = i < nv;
-        unsigned root = 0;
-        if (live) {
-            const unsigned v = vl[i];
-            root = unwrap_uf_find(parent, v);
-            if (root != v) parent[v] = root;
-        }
-#ifdef SGPE_EMU
-        if (live) { const unsigned c = atomicAdd(&cnt[root], 1u) + 1u; mx = c > mx ? c : mx; }
-#else
-        if (threadIdx.x == 0) warp_hits[8] = root;         // thread 0 of an iteration is always live
-        __syncthreads();
-        const unsigned cta_root = warp_hits[8];
-        const bool common = live && root == cta_root;
-        const unsigned votes = __ballot_sync(0xffffffffu, common);
-        if ((threadIdx.x & 31u) == 0) warp_hits[threadIdx.x >> 5] = (unsigned)__popc(votes);
-        const unsigned others = __ballot_sync(0xffffffffu, live && !common);
-        if (live && !common) {
-            const unsigned peers = __match_any_sync(others, root);
-            if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) {
-                const unsigned n = (unsigned)__popc(peers);
-                const unsigned c = atomicAdd(&cnt[root], n) + n;
-                mx = c > mx ? c : mx;
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned n = 0;
-            for (unsigned wi = 0; wi < (blockDim.x >> 5); wi++) n += warp_hits[wi];
-            if (cta_root != held_root) {
-                if (held) { const unsigned c = atomicAdd(&cnt[held_root], held) + held; mx = c > mx ? c : mx; }
-                held_root = cta_root; held = 0;
-            }
-            held += n;
-        }
-#endif
-    }
-#ifndef SGPE_EMU
-    if (threadIdx.x == 0 && held) { const unsigned c = atomicAdd(&cnt[held_root], held) + held; mx = c > mx ? c : mx; }
-#endif
-    red[threadIdx.x] = mx;
-    __syncthreads();
-    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) red[threadIdx.x] = red[threadIdx.x] > red[threadIdx.x + s] ? red[threadIdx.x] : red[threadIdx.x + s];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0 && red[0]) atomicMax(result, red[0]);
 }
 // the two groups edge T = hi joins, in the forest at lo = T - 1: result[1..4] = root and size on the first pixel's
 // side, root and size on the second's
 __global__ void __launch_bounds__(256) unwrap_level_sides_pass(const UnwrapEdge* el, long long ne, const long long* ctrl, int nx,
-                                                               unsigned* forest_a, unsigned* forest_b, const unsigned* cnt,
-                                                               unsigned* result) {
-    const UnwrapProbe q = unwrap_probe(ctrl, forest_a, forest_b);
+                                                               unsigned* forest_a, unsigned* forest_b, unsigned* size_a,
+                                                               unsigned* size_b, unsigned* result) {
+    const UnwrapProbe q = unwrap_probe(ctrl, forest_a, forest_b, size_a, size_b);
     const long long T = ctrl[1];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ne; i += (long long)gridDim.x * blockDim.x) {
         const UnwrapEdge e = el[i];
@@ -484,7 +443,7 @@ __global__ void __launch_bounds__(256) unwrap_level_sides_pass(const UnwrapEdge*
         const unsigned p1 = e.t & ~kUnwrapTreeBit;
         const unsigned a = unwrap_uf_find(q.snap, p1);
         const unsigned b = unwrap_uf_find(q.snap, p1 + ((e.t & kUnwrapTreeBit) ? (unsigned)nx : 1u));
-        result[1] = a; result[2] = cnt[a]; result[3] = b; result[4] = cnt[b];
+        result[1] = a; result[2] = q.snap_size[a]; result[3] = b; result[4] = q.snap_size[b];
     }
 }
 // next level: the pixels of group `keep` and the edges below rank T inside it (appended in any order;
