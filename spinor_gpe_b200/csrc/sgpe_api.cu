@@ -769,8 +769,9 @@ int run_energy(sgpe_plan* p, const void* psi, int unwrap_mode, double kl_term, d
 }
 
 // ---- two-dimensional phase unwrapping (Herraez et al. 2002; skimage.restoration.unwrap_phase at the reference's
-// tensor_tools.py:531).  Device: angle, reliabilities, edge keys, radix sort, apply (unwrap.cuh).  Host: the region
-// merging below, which is sequential by construction — edge k's merge depends on the groups all earlier edges built.
+// tensor_tools.py:531).  Device: angle, reliabilities, edge keys, radix sort, the region merging (spanning tree and
+// surviving group, unwrap.cuh) and the final pass, steered from unwrap_increments_impl below.  The sequential
+// edge-by-edge merging that defines the result is kept as the cross-check (option "unwrap_merge" = 1):
 //
 // Groups are an offset-carrying union-find: pot[x] = increment(x) - increment(parent[x]); a root keeps the
 // increments of its group fixed (its own is 0) and the absorbed root receives the shift of its whole group, which is

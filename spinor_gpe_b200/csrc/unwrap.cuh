@@ -21,8 +21,11 @@
 //     unwrap_adopt_pass / unwrap_compress_pass below; the tree is the same one Kruskal finds because ranks are unique);
 //   * the ONE pixel group that never moves (the published merge rules let the larger group keep its values: the global
 //     2 pi offset of the field, visible at the mask edge of the energy) — this depends on the group sizes at every merge
-//     in rank order and stays a sequential pass, on the host, over the N - 1 tree edges only and without any offset
-//     bookkeeping (unwrap_anchor in sgpe_api.cu).
+//     in rank order.  Taken literally that is a sequential pass over the N - 1 tree edges (unwrap_anchor in
+//     sgpe_api.cu: sizes only, no offset bookkeeping; used when there are many planes, one per host core); on the
+//     device it is found level by level — the first merge that creates a group of more than half the pixels decides,
+//     recursively inside the winning half — by a bisection over the rank threshold with a size-carrying lock-free
+//     union-find (unwrap_level_*_pass at the end of this file).
 // Option "unwrap_merge" = 1 keeps the whole merging on the host (offset-carrying union-find over all edges), for
 // cross-checks.
 //
