@@ -337,7 +337,11 @@ SGPE_DI void unwrap_uf_union_sized(unsigned* parent, unsigned* size, unsigned a,
     a = unwrap_uf_find(parent, a);
     b = unwrap_uf_find(parent, b);
     while (a != b) {
-        if (a < b) { const unsigned t = a; a = b; b = t; }
+        // who hangs below whom is decided by a scrambled index (a bijection of 32-bit integers: still a strict total
+        // order, so no cycle can form): pixel indices follow the rows of the image, and on smooth fields so do the
+        // groups — linking by the plain index grows long chains there, linking by the scrambled one behaves like
+        // random linking
+        if (a * 2654435761u < b * 2654435761u) { const unsigned t = a; a = b; b = t; }
         const unsigned seen = atomicCAS(&parent[a], a, b);
         if (seen == a) {
             unsigned carry = atomicExch(&size[a], 0u);
